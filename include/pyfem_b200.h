@@ -1,0 +1,171 @@
+/*
+ * pyfem_b200.h -- C ABI of the B200-native finite-element assembly engine.
+ *
+ * The reference (aaronyicongfu/pyfem_gpu_testflight) is pure Python and has no FFI; its
+ * boundary for this path is the physics-model API in pyfem.py (ModelBase and subclasses).
+ * Each entry point below names the reference interface it replaces (file:line relative to
+ * the reference root).  The Python host mirror (pyfem_gpu_testflight_b200/) binds these
+ * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; every *_dev pointer is a CUDA device pointer owned by the caller
+ *     (torch tensor.data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - calls enqueue work on `stream` and return without synchronising, except
+ *     pfg_mesh_create (synchronises: it sizes allocations from device results).
+ *   - return value: PFG_OK or a negative pfg_status; pfg_last_error() gives the message for
+ *     the calling thread's most recent failure.
+ *   - a handle is used by one host thread at a time (the reference's models are not
+ *     re-entrant either: they mutate shared scratch, pyfem.py:705-756).
+ *   - float64 throughout; node / element ids are int64 at the boundary as in the reference
+ *     (pyfem.py:660, utils.py:290-292).
+ */
+#ifndef PYFEM_B200_H
+#define PYFEM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFG_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define PFG_API __attribute__((visibility("default")))
+#else
+#define PFG_API
+#endif
+
+typedef struct pfg_mesh pfg_mesh; /* opaque: device copies of the mesh, CSR pattern, scatter/gather plans */
+
+typedef enum pfg_status {
+    PFG_OK = 0,
+    PFG_ERR_INVALID = -1,     /* bad argument (reference: ValueError) */
+    PFG_ERR_CUDA = -2,        /* CUDA runtime failure (reference: RuntimeError) */
+    PFG_ERR_UNSUPPORTED = -3, /* element / physics combination not implemented on the device */
+    PFG_ERR_MESH = -4,        /* conn.min() != 0 or conn.max() != nnodes-1 (reference asserts, pyfem.py:680-681) */
+    PFG_ERR_NOMEM = -5
+} pfg_status;
+
+typedef enum pfg_elem {
+    PFG_QUAD4 = 4, /* BasisBilinear2D + QuadratureBilinear2D (pyfem.py:83-95, 253-284) */
+    PFG_HEX8 = 8   /* BasisBlock3D + QuadratureBlock3D (pyfem.py:97-112, 287-338) */
+} pfg_elem;
+
+typedef enum pfg_mode {
+    PFG_MODE_AUTO = 0,   /* gather when the mesh has a gather plan, else atomic */
+    PFG_MODE_ATOMIC = 1, /* element-per-thread, slot-indexed red.global.add.f64 scatter */
+    PFG_MODE_GATHER = 2  /* owner-computes: element matrices staged in shared memory, every CSR value
+                            summed in a fixed order and written exactly once (no atomics, deterministic) */
+} pfg_mode;
+
+typedef enum pfg_info {
+    PFG_INFO_NNZ = 0,        /* CSR nnz of the owned rows */
+    PFG_INFO_NROWS = 1,      /* owned dof rows = ndof_per_node * (own_end - own_begin) */
+    PFG_INFO_NCOLS = 2,      /* global dof columns */
+    PFG_INFO_IDX_BYTES = 3,  /* 4 or 8: the index width scipy's coo->csr would pick (scipy _coo.py:59-61,419) */
+    PFG_INFO_NCHUNKS = 4,    /* row chunks of the gather plan (0 = no plan) */
+    PFG_INFO_CHUNK_ELEMS = 5,/* sum over chunks of elements touching the chunk (>= nelems: halo recompute) */
+    PFG_INFO_PLAN_BYTES = 6, /* device bytes of plan metadata read per assembly */
+    PFG_INFO_DEVICE_BYTES = 7,/* device bytes held by the handle */
+    PFG_INFO_MAX_ROW_BLOCKS = 8, /* largest number of neighbour nodes of any owned node */
+    PFG_INFO_MAX_VALENCE = 9     /* largest number of elements around any node */
+} pfg_info;
+
+PFG_API int pfg_abi_version(void);
+PFG_API const char* pfg_last_error(void);
+
+/*
+ * Once per mesh.  Replaces the device-relevant part of ModelBase.__init__ (pyfem.py:640-757):
+ * casts + sanity asserts (:659-681), utils.create_dof (utils.py:267-298), the COO pattern of
+ * ModelBase._compute_nz_pattern (pyfem.py:837-858) -- here turned directly into the CSR pattern
+ * that coo_matrix(...).tocsr() (pyfem.py:930-931) would produce, plus the element->slot map
+ * and the row-chunk gather plans used by every later assembly.
+ *
+ *   X_dev     (nnodes, ndims) float64 row-major, ndims = 2 for QUAD4, 3 for HEX8
+ *   conn_dev  (nelems, nnodes_per_elem) int64 row-major, values in [0, nnodes)
+ *   own_begin/own_end   node rows [own_begin, own_end) this handle assembles (0, nnodes for
+ *             a single GPU).  Multi-GPU: each rank passes its element block plus one layer of
+ *             ghost elements and owns a contiguous slab of node rows.
+ *   node_gid_dev  NULL, or (nnodes,) int64 strictly increasing local->global node ids used for
+ *             the column indices the pattern reports; ncols_global_nodes = global node count
+ *             (ignored when node_gid_dev is NULL).
+ *   flags     0, or PFG_CREATE_NO_GATHER_PLAN to skip building the gather plan.
+ */
+#define PFG_CREATE_NO_GATHER_PLAN 1
+#define PFG_CREATE_NO_REORDER 2 /* chunk nodes in id order instead of the coordinate tiling */
+PFG_API int pfg_mesh_create(pfg_mesh** out, int elem_type, int ndof_per_node, int64_t nnodes, int64_t nelems,
+                    const double* X_dev, const int64_t* conn_dev, int64_t own_begin, int64_t own_end,
+                    const int64_t* node_gid_dev, int64_t ncols_global_nodes, int flags, void* stream);
+PFG_API int pfg_mesh_destroy(pfg_mesh* mesh);
+PFG_API int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value);
+
+/*
+ * CSR pattern of the owned rows, identical to K.indptr / K.indices of the reference's
+ * ModelBase._assemble_jacobian (pyfem.py:920-931): sorted unique columns, explicit zeros kept.
+ *   indptr_dev  (nrows + 1) entries, indices_dev (nnz) entries, each idx_bytes (4 or 8) wide.
+ */
+PFG_API int pfg_mesh_pattern(const pfg_mesh* mesh, void* indptr_dev, void* indices_dev, int idx_bytes, void* stream);
+
+/*
+ * LinearPoisson.compute_jacobian(rho) (pyfem.py:1005-1030): RAMP material update (:1278-1301),
+ * element matrices (:1175-1217) and CSR scatter (:920-931) in one pass.
+ *   rho_dev  (nnodes,) nodal density or NULL for the constant rho_const (pyfem.py:1015-1016)
+ *   vals_dev (nnz,) CSR values, overwritten.
+ */
+PFG_API int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double* vals_dev,
+                         int mode, void* stream);
+
+/*
+ * LinearElasticity.compute_jacobian(rho) (pyfem.py:1770-1795): plane stress for QUAD4
+ * (ndof_per_node 2), 3-D for HEX8 (ndof_per_node 3); C0 from E, nu as pyfem.py:1746-1757.
+ */
+PFG_API int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double E,
+                            double nu, double* vals_dev, int mode, void* stream);
+
+/*
+ * Helmholtz.__init__ assembly (pyfem.py:2084-2097, element kernels :2126-2177):
+ * K = r0^2 stiffness + mass and R = mass on one pattern.  Either output may be NULL.
+ */
+PFG_API int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_dev, double* R_vals_dev, int mode,
+                           void* stream);
+
+/*
+ * NonlinearPoisson2D.compute_jacobian(xdv, u) (pyfem.py:1390-1404, :1541-1610) and
+ * compute_rhs(xdv, u) = residual (pyfem.py:1375-1388, :1474-1539) in one pass over the
+ * elements.  xdv_host is a HOST array of nxdv (<= 32) design variables.  Either output may be
+ * NULL.  res_dev has one entry per owned dof row.
+ */
+PFG_API int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, int nxdv, const double* u_dev,
+                           double* K_vals_dev, double* res_dev, int mode, void* stream);
+
+/*
+ * LinearPoisson.compute_rhs (pyfem.py:996-1003, :1125-1173, scatter :860-875), split in two
+ * because the source term gfunc is a user Python callable (pyfem.py:957,1127):
+ *   pfg_quad_points  writes Xq (nelems, nquads, ndims), the physical quadrature coordinates
+ *                    (utils.compute_elem_interp, utils.py:203-221) the callable is evaluated on;
+ *   pfg_poisson_rhs  takes g at those points, (nelems, nquads), and writes
+ *                    rhs[i] = sum_e sum_q detJ w N g for the owned rows.
+ */
+PFG_API int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream);
+PFG_API int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs_dev, int mode, void* stream);
+
+/*
+ * ModelBase.apply_dirichlet_bcs (pyfem.py:780-835) on the device CSR, keeping the pattern
+ * (no eliminate_zeros): rows of fixed dofs zeroed, columns too when enforce_symmetric != 0,
+ * unit diagonal, rhs[fixed] = vals (0 when fixed_vals_dev is NULL) and, in the symmetric
+ * case with values, rhs[free] -= K_free,fixed . vals (uses the values before zeroing).
+ *   fixed_dofs_dev (nfixed,) int64 global dof ids; rhs_dev may be NULL.
+ */
+PFG_API int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, const double* fixed_vals_dev,
+                        int64_t nfixed, int enforce_symmetric, double* vals_dev, double* rhs_dev, void* stream);
+
+/*
+ * y = A x on the device CSR of the owned rows (Helmholtz.compute_rhs = R.dot(x), pyfem.py:2117-2120).
+ */
+PFG_API int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYFEM_B200_H */

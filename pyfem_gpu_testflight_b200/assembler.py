@@ -1,0 +1,56 @@
+"""Assembler: the callers of the assembly path (pyfem.py:2286-2423) -- linear solve and Newton loop.
+
+The solver itself is outside the hot path: the assembled scipy CSR goes to
+scipy's direct solver, or to cg / gmres (preconditioned with pyamg smoothed aggregation when pyamg is
+installed, as in the reference, else unpreconditioned).
+"""
+import numpy as np
+from scipy.sparse.linalg import cg, gmres, spsolve
+
+
+class Assembler:
+    def __init__(self, model):
+        self.model = model
+
+    def solve(self, method="gmres"):
+        """Static analysis (pyfem.py:2299-2317)."""
+        assert method in ("direct", "cg", "gmres")
+        K = self.model.compute_jacobian()
+        rhs = self.model.compute_rhs()
+        K, rhs = self.model.apply_dirichlet_bcs(K, rhs, enforce_symmetric_K=True)
+        return self._solve_linear_system(K, rhs, method)
+
+    def solve_nonlinear(self, method="gmres", xdv=None, u0=None, tol=1e-10, atol=1e-12, max_iter=10):
+        """Newton iteration with Jacobian + residual re-assembled every step (pyfem.py:2319-2355)."""
+        assert method in ("direct", "cg", "gmres")
+        u = np.zeros(self.model.nnodes) if u0 is None else u0
+        res_norm_init = None
+        for k in range(max_iter):
+            K = self.model.compute_jacobian(xdv, u)
+            res = self.model.compute_rhs(xdv, u)
+            self.model.apply_dirichlet_bcs(K, res, enforce_symmetric_K=False)
+            res_norm = np.sqrt(np.dot(res, res))
+            print("pyfem", "{0:5d} {1:25.15e}".format(k, res_norm))
+            if k == 0:
+                res_norm_init = res_norm
+            elif res_norm < tol * res_norm_init or res_norm < atol:
+                break
+            u -= self._solve_linear_system(K, res, method)
+        return u
+
+    def _setup_amg(self, K):
+        try:
+            import pyamg
+        except ImportError:
+            return None
+        return pyamg.smoothed_aggregation_solver(K).aspreconditioner()
+
+    def _solve_linear_system(self, K, rhs, method):
+        if method == "direct":
+            return spsolve(K, rhs)
+        M = self._setup_amg(K)
+        solver = cg if method == "cg" else gmres
+        u, fail = solver(K, rhs, rtol=1e-8, M=M, atol=0.0)
+        if fail:
+            raise RuntimeError(f"{method} failed with code {fail}")
+        return u

@@ -1,0 +1,662 @@
+// Assembly kernels and their C-ABI entry points.
+//
+// Two scatter strategies share the element routines of pfg_elem.cuh:
+//   atomic  one thread per element, every entry added with red.global.add.f64 at the slot the
+//           rank map gives (the reference's coo->csr duplicates-summed scatter, pyfem.py:930-931,
+//           and np.add.at for vectors, pyfem.py:872-874);
+//   gather  one CTA per row chunk: phase A integrates every element touching the chunk once and
+//           stages the row blocks of chunk nodes in shared memory, phase B sums each CSR block's
+//           contributions in plan order and writes it exactly once.  No atomics, no zero-fill,
+//           bitwise reproducible.
+#include <algorithm>
+
+#include "pfg_elem.cuh"
+
+namespace pfg {
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory row-block stride (doubles) per incidence; odd multiples of the access width keep
+// element-per-thread stores and plan-ordered loads spread over the banks
+// ---------------------------------------------------------------------------------------------
+template <class Op>
+struct Layout {
+    static constexpr int BLK = Op::M * Op::M;
+    static constexpr int RAW = Op::NMAT * Op::NNE * BLK;
+    static constexpr int RB = (RAW == 0) ? 0 : ((Op::M == 2) ? RAW + 2 : RAW + 1);
+    static constexpr int VEC = Op::NVEC;  // doubles per incidence for the vector output
+};
+
+struct Outputs {
+    double* vals[2];  // CSR values per matrix (may be null)
+    double* vec;      // owned-row vector (may be null)
+};
+
+// ---------------------------------------------------------------------------------------------
+// sinks
+// ---------------------------------------------------------------------------------------------
+template <class Op>
+struct AtomicSink {
+    static constexpr int NNE = Op::NNE, M = Op::M;
+    const Outputs& out;
+    int64_t base[NNE];  // first value slot of the row node's dof rows, -1 when the row is not owned
+    int k[NNE];
+    int row[NNE];
+    const uint8_t* rank_e;  // rank[(e*NNE + a)*NNE + b]
+
+    PFG_DEV AtomicSink(const MeshView& mv, const Outputs& o, const int (&nodes)[NNE], int64_t e) : out(o) {
+        rank_e = mv.rank + e * NNE * NNE;
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) {
+            const int64_t r = nodes[a] - mv.own_begin;
+            if (nodes[a] >= mv.own_begin && nodes[a] < mv.own_end) {
+                const int64_t p0 = __ldg(mv.blk_ptr + r), p1 = __ldg(mv.blk_ptr + r + 1);
+                base[a] = p0 * M * M;
+                k[a] = (int)(p1 - p0);
+                row[a] = (int)r;
+            } else {
+                base[a] = -1;
+                k[a] = 0;
+                row[a] = 0;
+            }
+        }
+    }
+    PFG_DEV void block(int mat, int a, int b, const double* blk) const {
+        if (base[a] < 0 || out.vals[mat] == nullptr) return;
+        const int t = rank_e[a * NNE + b];
+        double* dst = out.vals[mat] + base[a] + (int64_t)M * t;
+#pragma unroll
+        for (int al = 0; al < M; ++al)
+#pragma unroll
+            for (int be = 0; be < M; ++be) atomicAdd(dst + (int64_t)al * M * k[a] + be, blk[al * M + be]);
+    }
+    PFG_DEV void vec(int a, double v) const {
+        if (base[a] < 0 || out.vec == nullptr) return;
+        atomicAdd(out.vec + row[a], v);
+    }
+};
+
+template <class Op>
+struct SmemSink {
+    static constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, RB = Layout<Op>::RB;
+    double* rb;    // row-block staging [n_inc][RB]
+    double* vecs;  // vector staging [n_inc]
+    uint16_t dst[NNE];
+    PFG_DEV void block(int mat, int a, int b, const double* blk) const {
+        if (dst[a] == kNoDst) return;
+        double* p = rb + (int)dst[a] * RB + (mat * NNE + b) * BLK;
+        if constexpr (M == 2) {
+            reinterpret_cast<double2*>(p)[0] = make_double2(blk[0], blk[1]);
+            reinterpret_cast<double2*>(p)[1] = make_double2(blk[2], blk[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < BLK; ++i) p[i] = blk[i];
+        }
+    }
+    PFG_DEV void vec(int a, double v) const {
+        if (dst[a] == kNoDst) return;
+        vecs[dst[a]] = v;
+    }
+};
+
+// single-row sinks for the 8-threads-per-element hex8 elasticity kernels (row node fixed per thread)
+struct HexAtomicRowSink {
+    double* dst0;  // values of the row node's first dof row, nullptr when not owned
+    int k;
+    const uint8_t* rank_row;  // rank[(e*8 + a)*8 + b]
+    PFG_DEV void block(int, int, int b, const double* blk) const {
+        double* dst = dst0 + 3 * (int)rank_row[b];
+#pragma unroll
+        for (int al = 0; al < 3; ++al)
+#pragma unroll
+            for (int be = 0; be < 3; ++be) atomicAdd(dst + (int64_t)al * 3 * k + be, blk[al * 3 + be]);
+    }
+};
+
+struct HexSmemRowSink {
+    double* row;  // this incidence's staged row block [b][3][3]
+    PFG_DEV void block(int, int, int b, const double* blk) const {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) row[b * 9 + i] = blk[i];
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// atomic kernels
+// ---------------------------------------------------------------------------------------------
+template <class Op>
+__global__ void __launch_bounds__(128) k_assemble_atomic(MeshView mv, typename Op::Params prm, Outputs out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= mv.nelems) return;
+    constexpr int NNE = Op::NNE;
+    int nodes[NNE];
+    if constexpr (NNE == 4) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(mv.conn) + e);
+        nodes[0] = v.x, nodes[1] = v.y, nodes[2] = v.z, nodes[3] = v.w;
+    } else {
+        const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e);
+        const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e + 1);
+        nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+        nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+    }
+    AtomicSink<Op> sink(mv, out, nodes, e);
+    Op::run(mv, prm, nodes, e, sink);
+}
+
+struct ElasticityHex8Tag {  // layout / sink traits of the octet kernel
+    static constexpr int NNE = 8, M = 3, NMAT = 1, NVEC = 0;
+};
+
+__global__ void __launch_bounds__(128) k_elasticity_hex8_atomic(MeshView mv, ElasticityHex8Params prm, Outputs out) {
+    __shared__ double stage[16 * kHexStageDoubles];
+    const int64_t e = blockIdx.x * 16ll + (threadIdx.x >> 3);
+    const int lane8 = threadIdx.x & 7;
+    const unsigned octet_mask = 0xffu << ((threadIdx.x & 31) & ~7);
+    if (e >= mv.nelems) return;  // whole octets leave together
+    int nodes[8];
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e);
+    const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e + 1);
+    nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+    nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+    HexAtomicRowSink sink{nullptr, 0, mv.rank + (e * 8 + lane8) * 8};
+    int my_node = 0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+        if (a == lane8) my_node = nodes[a];
+    if (my_node >= mv.own_begin && my_node < mv.own_end && out.vals[0] != nullptr) {
+        const int64_t r = my_node - mv.own_begin;
+        const int64_t p0 = __ldg(mv.blk_ptr + r), p1 = __ldg(mv.blk_ptr + r + 1);
+        sink.dst0 = out.vals[0] + p0 * 9;
+        sink.k = (int)(p1 - p0);
+    }
+    elasticity_hex8_octet(mv, prm, nodes, stage + (threadIdx.x >> 3) * kHexStageDoubles, lane8, octet_mask,
+                          sink.dst0 != nullptr, sink);
+}
+
+// ---------------------------------------------------------------------------------------------
+// gather kernels
+// ---------------------------------------------------------------------------------------------
+// phase B: sum plan-ordered contributions of every (chunk node, neighbour) block and store it
+template <class Op>
+PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const double* __restrict__ rb,
+                            const double* __restrict__ vecs, const Outputs& out) {
+    constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, NMAT = Op::NMAT, RB = Layout<Op>::RB;
+    if constexpr (NMAT > 0) {
+        const int kpad = (int)h.kpad;
+        const int items = (int)h.n_nodes * kpad;
+        for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
+            const int p = idx / kpad;
+            const int t = idx - p * kpad;
+            const ChunkNode cn = mv.cnodes[h.node_begin + p];
+            if (t >= cn.k) continue;
+            const uint8_t* rec = mv.plan_pool + (size_t)cn.plan * 4;
+            const int s0 = rec[t], s1 = rec[t + 1];
+            const uint8_t* src = rec + cn.k + 1;
+            double acc[NMAT][BLK];
+#pragma unroll
+            for (int mt = 0; mt < NMAT; ++mt)
+#pragma unroll
+                for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
+            for (int s = s0; s < s1; ++s) {
+                const int code = src[s];
+                const double* q = rb + ((int)cn.inc_base + (code >> 3)) * RB + (code & 7) * BLK;
+#pragma unroll
+                for (int mt = 0; mt < NMAT; ++mt) {
+                    if constexpr (M == 2) {
+                        const double2 v0 = reinterpret_cast<const double2*>(q + mt * NNE * BLK)[0];
+                        const double2 v1 = reinterpret_cast<const double2*>(q + mt * NNE * BLK)[1];
+                        acc[mt][0] += v0.x, acc[mt][1] += v0.y, acc[mt][2] += v1.x, acc[mt][3] += v1.y;
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < BLK; ++i) acc[mt][i] += q[mt * NNE * BLK + i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < NMAT; ++mt) {
+                if (out.vals[mt] == nullptr) continue;
+                double* dst = out.vals[mt] + cn.gslot + (int64_t)M * t;
+#pragma unroll
+                for (int al = 0; al < M; ++al) {
+                    double* row = dst + (int64_t)al * M * cn.k;
+                    if constexpr (M == 2) {
+                        __stcs(reinterpret_cast<double2*>(row), make_double2(acc[mt][al * 2], acc[mt][al * 2 + 1]));
+                    } else {
+#pragma unroll
+                        for (int be = 0; be < M; ++be) __stcs(row + be, acc[mt][al * M + be]);
+                    }
+                }
+            }
+        }
+    }
+    if constexpr (Op::NVEC > 0) {
+        if (out.vec != nullptr) {
+            for (int p = threadIdx.x; p < (int)h.n_nodes; p += blockDim.x) {
+                const ChunkNode cn = mv.cnodes[h.node_begin + p];
+                double s = 0.0;
+                for (int j = 0; j < cn.valence; ++j) s += vecs[(int)cn.inc_base + j];
+                out.vec[mv.cnode_id[h.node_begin + p] - mv.own_begin] = s;
+            }
+        }
+    }
+}
+
+template <class Op, int THREADS>
+__global__ void __launch_bounds__(THREADS) k_assemble_gather(MeshView mv, typename Op::Params prm, Outputs out) {
+    extern __shared__ __align__(16) double smem[];
+    constexpr int NNE = Op::NNE;
+    const ChunkHdr h = mv.chunks[blockIdx.x];
+    double* rb = smem;
+    double* vecs = smem + (size_t)h.n_inc * Layout<Op>::RB;
+    // ---- phase A: one thread per element record
+    for (int r = threadIdx.x; r < (int)h.n_recs; r += THREADS) {
+        const int64_t rr = h.rec_begin + r;
+        int nodes[NNE];
+        SmemSink<Op> sink;
+        sink.rb = rb;
+        sink.vecs = vecs;
+        if constexpr (NNE == 4) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + rr);
+            nodes[0] = v.x, nodes[1] = v.y, nodes[2] = v.z, nodes[3] = v.w;
+            const uint2 d = __ldg(reinterpret_cast<const uint2*>(mv.rec_dst) + rr);
+            sink.dst[0] = d.x & 0xffff, sink.dst[1] = d.x >> 16, sink.dst[2] = d.y & 0xffff, sink.dst[3] = d.y >> 16;
+        } else {
+            const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr);
+            const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr + 1);
+            nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+            nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+            const uint4 d = __ldg(reinterpret_cast<const uint4*>(mv.rec_dst) + rr);
+            sink.dst[0] = d.x & 0xffff, sink.dst[1] = d.x >> 16, sink.dst[2] = d.y & 0xffff, sink.dst[3] = d.y >> 16;
+            sink.dst[4] = d.z & 0xffff, sink.dst[5] = d.z >> 16, sink.dst[6] = d.w & 0xffff, sink.dst[7] = d.w >> 16;
+        }
+        int64_t elem = 0;
+        if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + rr);
+        Op::run(mv, prm, nodes, elem, sink);
+    }
+    __syncthreads();
+    gather_phase_b<Op>(mv, h, rb, vecs, out);
+}
+
+struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv, ElasticityHex8Params prm, Outputs out) {
+    extern __shared__ __align__(16) double smem[];
+    using L = Layout<ElasticityHex8GatherOp>;
+    const ChunkHdr h = mv.chunks[blockIdx.x];
+    double* stage = smem;  // [THREADS/8][kHexStageDoubles]
+    double* rb = smem + (THREADS / 8) * kHexStageDoubles;
+    const int lane8 = threadIdx.x & 7;
+    const unsigned octet_mask = 0xffu << ((threadIdx.x & 31) & ~7);
+    for (int r = threadIdx.x >> 3; r < (int)h.n_recs; r += THREADS / 8) {
+        const int64_t rr = h.rec_begin + r;
+        int nodes[8];
+        const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr);
+        const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr + 1);
+        nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+        nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+        const uint16_t my_dst = __ldg(mv.rec_dst + rr * 8 + lane8);
+        HexSmemRowSink sink{rb + (int)my_dst * L::RB};
+        elasticity_hex8_octet(mv, prm, nodes, stage + (threadIdx.x >> 3) * kHexStageDoubles, lane8, octet_mask,
+                              my_dst != kNoDst, sink);
+    }
+    __syncthreads();
+    gather_phase_b<ElasticityHex8GatherOp>(mv, h, rb, nullptr, out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// auxiliary kernels
+// ---------------------------------------------------------------------------------------------
+template <int NNE>
+__global__ void k_quad_points(MeshView mv, double* __restrict__ Xq) {  // utils.compute_elem_interp (utils.py:203-221)
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= mv.nelems) return;
+    constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    int nodes[NNE];
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
+    double xe[NNE][DIM];
+    load_coords<NNE>(mv.X, nodes, xe);
+    for_each_q<NQ>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+#pragma unroll
+        for (int l = 0; l < DIM; ++l) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) s = fma(Elem<NNE>::N(Q, a), xe[a][l], s);
+            Xq[(e * NQ + Q) * DIM + l] = s;
+        }
+    });
+}
+
+// Dirichlet rows/columns on the device CSR, pattern kept (pyfem.py:780-835 minus eliminate_zeros).
+__global__ void k_mark_fixed(const int64_t* __restrict__ fixed, const double* __restrict__ fixed_vals, int64_t nfixed,
+                             int64_t ncols, uint8_t* __restrict__ is_fixed, double* __restrict__ u0) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nfixed) return;
+    int64_t dof = fixed[i];
+    if (dof < 0 || dof >= ncols) return;
+    is_fixed[dof] = 1;
+    u0[dof] = fixed_vals ? fixed_vals[i] : 0.0;
+}
+
+__global__ void k_apply_dirichlet(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                  const int64_t* __restrict__ gid, int64_t own_begin, int64_t nown, int m,
+                                  const uint8_t* __restrict__ is_fixed, const double* __restrict__ u0, int symmetric,
+                                  int have_vals, double* __restrict__ vals, double* __restrict__ rhs) {
+    // one thread per owned dof row
+    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nown * m) return;
+    int64_t r = row / m;
+    int alpha = (int)(row - r * m);
+    int64_t node = own_begin + r;
+    int64_t grow = (gid ? gid[node] : node) * m + alpha;
+    int64_t p0 = blk_ptr[r], k = blk_ptr[r + 1] - p0;
+    double* v = vals + p0 * m * m + alpha * k * m;
+    const bool row_fixed = is_fixed[grow];
+    double corr = 0.0;
+    for (int64_t t = 0; t < k; ++t) {
+        int64_t cnode = nbr[p0 + t];
+        int64_t gcol0 = (gid ? gid[cnode] : cnode) * m;
+        for (int beta = 0; beta < m; ++beta) {
+            int64_t gcol = gcol0 + beta;
+            double& x = v[t * m + beta];
+            if (row_fixed) {
+                x = (gcol == grow) ? 1.0 : 0.0;
+            } else if (symmetric && is_fixed[gcol]) {
+                if (have_vals) corr = fma(x, u0[gcol], corr);
+                x = 0.0;
+            }
+        }
+    }
+    if (rhs) {
+        if (row_fixed) rhs[row] = u0[grow];
+        else if (symmetric && have_vals) rhs[row] -= corr;
+    }
+}
+
+__global__ void k_spmv(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                       const int64_t* __restrict__ gid, int64_t nown, int m, const double* __restrict__ vals,
+                       const double* __restrict__ x, double* __restrict__ y) {
+    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nown * m) return;
+    int64_t r = row / m;
+    int alpha = (int)(row - r * m);
+    int64_t p0 = blk_ptr[r], k = blk_ptr[r + 1] - p0;
+    const double* v = vals + p0 * m * m + alpha * k * m;
+    double s = 0.0;
+    for (int64_t t = 0; t < k; ++t) {
+        int64_t cnode = nbr[p0 + t];
+        int64_t gcol0 = (gid ? gid[cnode] : cnode) * m;
+        for (int beta = 0; beta < m; ++beta) s = fma(v[t * m + beta], x[gcol0 + beta], s);
+    }
+    y[row] = s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static MeshView view_of(const MeshDev& d) {
+    MeshView mv;
+    mv.X = d.X;
+    mv.own_begin = d.own_begin;
+    mv.own_end = d.own_end;
+    mv.conn = d.conn;
+    mv.blk_ptr = d.blk_ptr;
+    mv.rank = d.rank;
+    mv.nelems = d.nelems;
+    mv.chunks = d.chunks;
+    mv.cnodes = d.cnodes;
+    mv.cnode_id = d.cnode_id;
+    mv.rec_nodes = d.rec_nodes;
+    mv.rec_dst = d.rec_dst;
+    mv.rec_elem = d.rec_elem;
+    mv.plan_pool = d.plan_pool;
+    return mv;
+}
+
+static int resolve_mode(const MeshDev& d, int mode, bool* gather) {
+    if (mode != PFG_MODE_AUTO && mode != PFG_MODE_ATOMIC && mode != PFG_MODE_GATHER) {
+        set_error("unknown scatter mode %d", mode);
+        return PFG_ERR_INVALID;
+    }
+    if (mode == PFG_MODE_GATHER && d.nchunks == 0) {
+        set_error("this mesh has no gather plan (PFG_CREATE_NO_GATHER_PLAN, or node valence > %d)", kMaxValence);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    *gather = (mode == PFG_MODE_GATHER) || (mode == PFG_MODE_AUTO && d.nchunks > 0);
+    return PFG_OK;
+}
+
+static int zero_outputs(const MeshDev& d, const Outputs& out, cudaStream_t st) {
+    for (int i = 0; i < 2; ++i)
+        if (out.vals[i]) PFG_CUDA_TRY(cudaMemsetAsync(out.vals[i], 0, d.nnz * sizeof(double), st));
+    if (out.vec) PFG_CUDA_TRY(cudaMemsetAsync(out.vec, 0, (d.own_end - d.own_begin) * d.m * sizeof(double), st));
+    return PFG_OK;
+}
+
+template <class Op, int THREADS>
+static int launch(const MeshDev& d, const typename Op::Params& prm, const Outputs& out, bool gather,
+                  cudaStream_t st) {
+    const MeshView mv = view_of(d);
+    if (!gather) {
+        PFG_TRY(zero_outputs(d, out, st));
+        const unsigned grid = (unsigned)((d.nelems + 127) / 128);
+        k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
+    } else {
+        const size_t smem = (size_t)d.max_chunk_inc * (Layout<Op>::RB + Layout<Op>::VEC) * sizeof(double);
+        if (smem > 227 * 1024) {
+            set_error("chunk staging of %zu bytes exceeds shared memory", smem);
+            return PFG_ERR_UNSUPPORTED;
+        }
+        auto kern = k_assemble_gather<Op, THREADS>;
+        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)d.nchunks, THREADS, smem, st>>>(mv, prm, out);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+static Material material_of(const double* rho_dev, double rho_const, double p) {
+    Material m;
+    m.rho = rho_dev;
+    m.rho_const = rho_const;
+    m.p = p;
+    return m;
+}
+
+}  // namespace pfg
+
+using namespace pfg;
+
+#define PFG_CHECK_MESH(mesh)                         \
+    if (!(mesh)) {                                   \
+        set_error("%s: mesh is NULL", __func__);     \
+        return PFG_ERR_INVALID;                      \
+    }
+
+extern "C" int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p,
+                                    double* vals_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || !vals_dev) {
+        set_error("pfg_assemble_poisson: needs ndof_per_node == 1 and a values buffer");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    Outputs out{{vals_dev, nullptr}, nullptr};
+    if (d.nne == 4) {
+        PoissonOp<4>::Params prm{material_of(rho_dev, rho_const, p)};
+        return launch<PoissonOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+    }
+    PoissonOp<8>::Params prm{material_of(rho_dev, rho_const, p)};
+    return launch<PoissonOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_dev, double* R_vals_dev, int mode,
+                                      void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || (!K_vals_dev && !R_vals_dev)) {
+        set_error("pfg_assemble_helmholtz: needs ndof_per_node == 1 and at least one output");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    Outputs out{{K_vals_dev, R_vals_dev}, nullptr};
+    if (d.nne == 4) {
+        HelmholtzOp<4>::Params prm{r0 * r0};
+        return launch<HelmholtzOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+    }
+    HelmholtzOp<8>::Params prm{r0 * r0};
+    return launch<HelmholtzOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double E,
+                                       double nu, double* vals_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != d.ndims || !vals_dev) {
+        set_error("pfg_assemble_elasticity: needs ndof_per_node == ndims and a values buffer");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    cudaStream_t st = (cudaStream_t)stream;
+    Outputs out{{vals_dev, nullptr}, nullptr};
+    if (d.nne == 4) {
+        // plane stress C0 (pyfem.py:1746-1750)
+        const double f = E / (1.0 - nu * nu);
+        ElasticityQuad4Op::Params prm{material_of(rho_dev, rho_const, p), f, f * nu, f * 0.5 * (1.0 - nu)};
+        return launch<ElasticityQuad4Op, 192>(d, prm, out, gather, st);
+    }
+    // 3-D C0 (pyfem.py:1752-1757)
+    const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    ElasticityHex8Params prm{material_of(rho_dev, rho_const, p), f * (1.0 - nu), f * nu, f * (0.5 - nu)};
+    const MeshView mv = view_of(d);
+    if (!gather) {
+        PFG_TRY(zero_outputs(d, out, st));
+        const unsigned grid = (unsigned)((d.nelems + 15) / 16);
+        k_elasticity_hex8_atomic<<<grid, 128, 0, st>>>(mv, prm, out);
+    } else {
+        constexpr int THREADS = 128;
+        const size_t smem = ((size_t)(THREADS / 8) * kHexStageDoubles +
+                             (size_t)d.max_chunk_inc * Layout<ElasticityHex8GatherOp>::RB) * sizeof(double);
+        if (smem > 227 * 1024) {
+            set_error("chunk staging of %zu bytes exceeds shared memory", smem);
+            return PFG_ERR_UNSUPPORTED;
+        }
+        auto kern = k_elasticity_hex8_gather<THREADS>;
+        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(unsigned)d.nchunks, THREADS, smem, st>>>(mv, prm, out);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+extern "C" int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, int nxdv, const double* u_dev,
+                                      double* K_vals_dev, double* res_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || d.nne != 4) {
+        set_error("pfg_assemble_nlpoisson: quad4 with ndof_per_node == 1 only (NonlinearPoisson2D)");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    if (!xdv_host || nxdv < 1 || nxdv > kMaxXdv || !u_dev || (!K_vals_dev && !res_dev)) {
+        set_error("pfg_assemble_nlpoisson: need 1..%d design variables, u and at least one output", kMaxXdv);
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    NlPoissonQuad4Op::Params prm;
+    prm.u = u_dev;
+    prm.nxdv = nxdv;
+    // binomial(nxdv-1, k) by the multiplicative recurrence (exact in double for nxdv <= 32)
+    double binom = 1.0;
+    for (int k = 0; k < kMaxXdv; ++k) {
+        prm.coef[k] = (k < nxdv) ? xdv_host[k] * binom : 0.0;
+        if (k < nxdv - 1) binom = binom * (double)(nxdv - 1 - k) / (double)(k + 1);
+    }
+    Outputs out{{K_vals_dev, nullptr}, res_dev};
+    return launch<NlPoissonQuad4Op, 256>(d, prm, out, gather, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!Xq_dev) {
+        set_error("pfg_quad_points: output is NULL");
+        return PFG_ERR_INVALID;
+    }
+    const MeshView mv = view_of(d);
+    const unsigned grid = (unsigned)((d.nelems + 127) / 128);
+    if (d.nne == 4) k_quad_points<4><<<grid, 128, 0, (cudaStream_t)stream>>>(mv, Xq_dev);
+    else k_quad_points<8><<<grid, 128, 0, (cudaStream_t)stream>>>(mv, Xq_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+extern "C" int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || !gq_dev || !rhs_dev) {
+        set_error("pfg_poisson_rhs: needs ndof_per_node == 1, g at the quadrature points and an output");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    Outputs out{{nullptr, nullptr}, rhs_dev};
+    if (d.nne == 4) {
+        PoissonRhsOp<4>::Params prm{gq_dev};
+        return launch<PoissonRhsOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+    }
+    PoissonRhsOp<8>::Params prm{gq_dev};
+    return launch<PoissonRhsOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, const double* fixed_vals_dev,
+                                   int64_t nfixed, int enforce_symmetric, double* vals_dev, double* rhs_dev,
+                                   void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!vals_dev || nfixed < 0 || (nfixed > 0 && !fixed_dofs_dev)) {
+        set_error("pfg_apply_dirichlet: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ncols = d.ncols_nodes * d.m;
+    uint8_t* is_fixed = nullptr;
+    double* u0 = nullptr;
+    PFG_CUDA_TRY(cudaMallocAsync(&is_fixed, ncols, st));
+    PFG_CUDA_TRY(cudaMallocAsync(&u0, ncols * sizeof(double), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(is_fixed, 0, ncols, st));
+    PFG_CUDA_TRY(cudaMemsetAsync(u0, 0, ncols * sizeof(double), st));
+    if (nfixed)
+        k_mark_fixed<<<(unsigned)((nfixed + 255) / 256), 256, 0, st>>>(fixed_dofs_dev, fixed_vals_dev, nfixed, ncols,
+                                                                      is_fixed, u0);
+    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
+    if (nrows)
+        k_apply_dirichlet<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
+            d.blk_ptr, d.nbr, d.gid, d.own_begin, d.own_end - d.own_begin, d.m, is_fixed, u0, enforce_symmetric,
+            fixed_vals_dev != nullptr, vals_dev, rhs_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    PFG_CUDA_TRY(cudaFreeAsync(is_fixed, st));
+    PFG_CUDA_TRY(cudaFreeAsync(u0, st));
+    return PFG_OK;
+}
+
+extern "C" int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!vals_dev || !x_dev || !y_dev) {
+        set_error("pfg_spmv: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
+    if (nrows)
+        k_spmv<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d.blk_ptr, d.nbr, d.gid,
+                                                                                 d.own_end - d.own_begin, d.m, vals_dev,
+                                                                                 x_dev, y_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}

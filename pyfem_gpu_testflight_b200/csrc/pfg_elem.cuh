@@ -1,0 +1,621 @@
+// Per-element quadrature in registers: geometry + element matrices / vectors for quad4 and hex8.
+//
+// Math follows SURVEY.md Appendix A (reference utils.py:171-264 for the geometry; pyfem.py:1177-1185,
+// 1132-1134, 2017-2026, 2127-2136, 1462-1471, 1530-1537, 1595-1609 for the element einsums), restated
+// for one thread per element with everything unrolled so that basis values are immediates:
+//   G_a = det(J) * grad N_a   (adjugate form, one reciprocal per quadrature point instead of
+//                              dividing every inverse entry);
+//   weights collapse to s_q = w_q c_q / det(J_q)  for gradient-gradient terms.
+// Results go to a Sink (atomic scatter or shared-memory staging) one node-pair block at a time.
+#pragma once
+#include <utility>
+
+#include "pfg_internal.cuh"
+
+namespace pfg {
+
+#define PFG_DEV __device__ __forceinline__
+#define PFG_G 0.57735026918962576451  /* 1/sqrt(3) */
+
+// ---------------------------------------------------------------------------------------------
+// Reference element tables as constexpr functions (folded to immediates after unrolling)
+// ---------------------------------------------------------------------------------------------
+template <int NNE>
+struct Elem;
+
+template <>
+struct Elem<4> {  // BasisBilinear2D / QuadratureBilinear2D (pyfem.py:83-95, 253-284)
+    static constexpr int DIM = 2, NQ = 4;
+    PFG_DEV static constexpr double sgn(int a, int k) {  // local node coordinates
+        return k == 0 ? ((a == 1 || a == 2) ? 1.0 : -1.0) : ((a >= 2) ? 1.0 : -1.0);
+    }
+    PFG_DEV static constexpr double qp(int q, int k) {  // quadrature points, CCW order
+        return sgn(q, k) * PFG_G;
+    }
+    PFG_DEV static constexpr double N(int q, int a) {
+        return 0.25 * (1.0 + sgn(a, 0) * qp(q, 0)) * (1.0 + sgn(a, 1) * qp(q, 1));
+    }
+    PFG_DEV static constexpr double dN(int q, int a, int k) {
+        return k == 0 ? 0.25 * sgn(a, 0) * (1.0 + sgn(a, 1) * qp(q, 1))
+                      : 0.25 * sgn(a, 1) * (1.0 + sgn(a, 0) * qp(q, 0));
+    }
+};
+
+template <>
+struct Elem<8> {  // BasisBlock3D / QuadratureBlock3D (pyfem.py:97-112, 287-338)
+    static constexpr int DIM = 3, NQ = 8;
+    PFG_DEV static constexpr double sgn(int a, int k) {
+        return k == 0 ? (((a & 3) == 1 || (a & 3) == 2) ? 1.0 : -1.0)
+                      : (k == 1 ? (((a & 3) >= 2) ? 1.0 : -1.0) : ((a >= 4) ? 1.0 : -1.0));
+    }
+    PFG_DEV static constexpr double qp(int q, int k) {  // x slowest, z fastest
+        return (k == 0 ? ((q & 4) ? 1.0 : -1.0) : (k == 1 ? ((q & 2) ? 1.0 : -1.0) : ((q & 1) ? 1.0 : -1.0))) * PFG_G;
+    }
+    PFG_DEV static constexpr double N(int q, int a) {
+        return 0.125 * (1.0 + sgn(a, 0) * qp(q, 0)) * (1.0 + sgn(a, 1) * qp(q, 1)) * (1.0 + sgn(a, 2) * qp(q, 2));
+    }
+    PFG_DEV static constexpr double dN(int q, int a, int k) {
+        return 0.125 * sgn(a, k) * (1.0 + sgn(a, (k + 1) % 3) * qp(q, (k + 1) % 3)) *
+               (1.0 + sgn(a, (k + 2) % 3) * qp(q, (k + 2) % 3));
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// What a kernel hands the element routines
+// ---------------------------------------------------------------------------------------------
+struct MeshView {
+    const double* X;
+    int64_t own_begin, own_end;
+    // atomic path
+    const int32_t* conn;
+    const int64_t* blk_ptr;
+    const uint8_t* rank;
+    int64_t nelems;
+    // gather path
+    const ChunkHdr* chunks;
+    const ChunkNode* cnodes;
+    const int32_t* cnode_id;
+    const int32_t* rec_nodes;
+    const uint16_t* rec_dst;
+    const int32_t* rec_elem;
+    const uint8_t* plan_pool;
+};
+
+template <int NNE>
+PFG_DEV void load_coords(const double* __restrict__ X, const int (&nodes)[NNE], double (&xe)[NNE][Elem<NNE>::DIM]) {
+    if constexpr (NNE == 4) {
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            double2 v = __ldg(reinterpret_cast<const double2*>(X) + nodes[a]);
+            xe[a][0] = v.x;
+            xe[a][1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            const double* p = X + (int64_t)nodes[a] * 3;
+            xe[a][0] = __ldg(p);
+            xe[a][1] = __ldg(p + 1);
+            xe[a][2] = __ldg(p + 2);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Geometry at one quadrature point: det(J) and G_a = det(J) grad N_a
+// (J[j][k] = sum_a dN_a/dxi_k X_a[j], utils.py:184; adjugate = det * inverse of utils.py:243-260)
+// ---------------------------------------------------------------------------------------------
+struct Quad4Coef {  // dx/dxi = ax + cx*eta, dx/deta = bx + cx*xi (bilinear map), same for y
+    double ax, bx, cx, ay, by, cy;
+};
+
+PFG_DEV Quad4Coef quad4_coef(const double (&xe)[4][2]) {
+    Quad4Coef c;
+    c.ax = 0.25 * ((xe[1][0] - xe[0][0]) + (xe[2][0] - xe[3][0]));
+    c.bx = 0.25 * ((xe[3][0] - xe[0][0]) + (xe[2][0] - xe[1][0]));
+    c.cx = 0.25 * ((xe[0][0] - xe[1][0]) + (xe[2][0] - xe[3][0]));
+    c.ay = 0.25 * ((xe[1][1] - xe[0][1]) + (xe[2][1] - xe[3][1]));
+    c.by = 0.25 * ((xe[3][1] - xe[0][1]) + (xe[2][1] - xe[1][1]));
+    c.cy = 0.25 * ((xe[0][1] - xe[1][1]) + (xe[2][1] - xe[3][1]));
+    return c;
+}
+
+template <int Q>
+PFG_DEV void quad4_geo(const Quad4Coef& c, double& det, double (&G)[4][2]) {
+    constexpr double xi = Elem<4>::qp(Q, 0), eta = Elem<4>::qp(Q, 1);
+    const double xxi = fma(c.cx, eta, c.ax), xeta = fma(c.cx, xi, c.bx);
+    const double yxi = fma(c.cy, eta, c.ay), yeta = fma(c.cy, xi, c.by);
+    det = xxi * yeta - xeta * yxi;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const double dxi = Elem<4>::dN(Q, a, 0), deta = Elem<4>::dN(Q, a, 1);
+        G[a][0] = dxi * yeta - deta * yxi;
+        G[a][1] = deta * xxi - dxi * xeta;
+    }
+}
+
+template <int Q>
+PFG_DEV void hex8_geo(const double (&xe)[8][3], double& det, double (&G)[8][3]) {
+    double J[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double s = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) s = fma(Elem<8>::dN(Q, a, k), xe[a][j], s);
+            J[j][k] = s;
+        }
+    double A[3][3];  // adjugate: A = det * inv(J)
+    A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    A[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+    A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+    A[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+    A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+    A[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+    A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    A[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+    A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int l = 0; l < 3; ++l)
+            G[a][l] = Elem<8>::dN(Q, a, 0) * A[0][l] + Elem<8>::dN(Q, a, 1) * A[1][l] + Elem<8>::dN(Q, a, 2) * A[2][l];
+}
+
+template <int NNE>
+struct GeoCtx;
+template <>
+struct GeoCtx<4> {
+    Quad4Coef c;
+    PFG_DEV explicit GeoCtx(const double (&xe)[4][2]) : c(quad4_coef(xe)) {}
+    template <int Q>
+    PFG_DEV void at(const double (&)[4][2], double& det, double (&G)[4][2]) const {
+        quad4_geo<Q>(c, det, G);
+    }
+};
+template <>
+struct GeoCtx<8> {
+    PFG_DEV explicit GeoCtx(const double (&)[8][3]) {}
+    template <int Q>
+    PFG_DEV void at(const double (&xe)[8][3], double& det, double (&G)[8][3]) const {
+        hex8_geo<Q>(xe, det, G);
+    }
+};
+
+// compile-time loop over quadrature points
+template <class F, int... Qs>
+PFG_DEV void for_each_q_impl(F&& f, std::integer_sequence<int, Qs...>) {
+    (f(std::integral_constant<int, Qs>{}), ...);
+}
+template <int NQ, class F>
+PFG_DEV void for_each_q(F&& f) {
+    for_each_q_impl(f, std::make_integer_sequence<int, NQ>{});
+}
+
+template <int NNE, int Q>
+PFG_DEV double interp(const double (&f)[NNE]) {  // node -> quadrature point (utils.py:218)
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) s = fma(Elem<NNE>::N(Q, a), f[a], s);
+    return s;
+}
+
+// RAMP-penalised material factor at the quadrature points (pyfem.py:1294-1300, 1938-1944)
+struct Material {
+    const double* rho;  // nodal field or nullptr
+    double rho_const, p;
+};
+
+template <int NNE>
+PFG_DEV void material_at_quads(const Material& mat, const int (&nodes)[NNE], double (&cq)[Elem<NNE>::NQ]) {
+    if (mat.rho == nullptr) {
+        const double c = mat.rho_const / (1.0 + mat.p * (1.0 - mat.rho_const));
+#pragma unroll
+        for (int q = 0; q < Elem<NNE>::NQ; ++q) cq[q] = c;
+        return;
+    }
+    double re[NNE];
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) re[a] = __ldg(mat.rho + nodes[a]);
+    for_each_q<Elem<NNE>::NQ>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        const double rq = interp<NNE, Q>(re);
+        cq[Q] = rq / (1.0 + mat.p * (1.0 - rq));
+    });
+}
+
+// emit a symmetric scalar matrix held as upper-triangular accumulators
+template <int NNE, class Sink>
+PFG_DEV void emit_sym_scalar(Sink& sink, int mat, const double (&K)[NNE][NNE]) {
+#pragma unroll
+    for (int a = 0; a < NNE; ++a)
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) {
+            const double v = (a <= b) ? K[a][b] : K[b][a];
+            sink.block(mat, a, b, &v);
+        }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Physics operators, one thread per element.  Op::run(mv, prm, nodes, elem, sink)
+// ---------------------------------------------------------------------------------------------
+template <int NNE_>
+struct PoissonOp {  // LinearPoisson._compute_element_jacobian (pyfem.py:1188-1217, einsum :1177-1185)
+    static constexpr int NNE = NNE_, M = 1, NMAT = 1, NVEC = 0;
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr bool NEEDS_ELEM = false;
+    struct Params {
+        Material mat;
+    };
+    template <class Sink>
+    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t, Sink& sink) {
+        double xe[NNE][DIM];
+        load_coords<NNE>(mv.X, nodes, xe);
+        double cq[NQ];
+        material_at_quads<NNE>(prm.mat, nodes, cq);
+        double K[NNE][NNE];
+#pragma unroll
+        for (int a = 0; a < NNE; ++a)
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) K[a][b] = 0.0;
+        GeoCtx<NNE> geo(xe);
+        for_each_q<NQ>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[NNE][DIM];
+            geo.template at<Q>(xe, det, G);
+            const double s = cq[Q] / det;  // w = 1 (pyfem.py:92,110)
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) {
+                double H[DIM];
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) H[l] = s * G[a][l];
+#pragma unroll
+                for (int b = a; b < NNE; ++b)
+#pragma unroll
+                    for (int l = 0; l < DIM; ++l) K[a][b] = fma(H[l], G[b][l], K[a][b]);
+            }
+        });
+        emit_sym_scalar<NNE>(sink, 0, K);
+    }
+};
+
+template <int NNE_>
+struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2138-2177)
+    static constexpr int NNE = NNE_, M = 1, NMAT = 2, NVEC = 0;  // matrix 0 = K, 1 = R
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr bool NEEDS_ELEM = false;
+    struct Params {
+        double r0sq;
+    };
+    template <class Sink>
+    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t, Sink& sink) {
+        double xe[NNE][DIM];
+        load_coords<NNE>(mv.X, nodes, xe);
+        double K[NNE][NNE], R[NNE][NNE];
+#pragma unroll
+        for (int a = 0; a < NNE; ++a)
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) K[a][b] = R[a][b] = 0.0;
+        GeoCtx<NNE> geo(xe);
+        for_each_q<NQ>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[NNE][DIM];
+            geo.template at<Q>(xe, det, G);
+            const double s = prm.r0sq / det;
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) {
+                double H[DIM];
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) H[l] = s * G[a][l];
+#pragma unroll
+                for (int b = a; b < NNE; ++b) {
+#pragma unroll
+                    for (int l = 0; l < DIM; ++l) K[a][b] = fma(H[l], G[b][l], K[a][b]);
+                    R[a][b] = fma(det, Elem<NNE>::N(Q, a) * Elem<NNE>::N(Q, b), R[a][b]);
+                }
+            }
+        });
+#pragma unroll
+        for (int a = 0; a < NNE; ++a)
+#pragma unroll
+            for (int b = a; b < NNE; ++b) K[a][b] += R[a][b];  // Ke += Re (pyfem.py:2176)
+        emit_sym_scalar<NNE>(sink, 0, K);
+        emit_sym_scalar<NNE>(sink, 1, R);
+    }
+};
+
+struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_jacobian (pyfem.py:2029-2068)
+    static constexpr int NNE = 4, M = 2, NMAT = 1, NVEC = 0, DIM = 2, NQ = 4;
+    static constexpr bool NEEDS_ELEM = false;
+    struct Params {
+        Material mat;
+        double c11, c12, c33;  // C0 entries (pyfem.py:1746-1750)
+    };
+    template <class Sink>
+    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[4], int64_t, Sink& sink) {
+        double xe[4][2];
+        load_coords<4>(mv.X, nodes, xe);
+        double cq[4];
+        material_at_quads<4>(prm.mat, nodes, cq);
+        // per node pair (a <= b): sums over q of s * {GxaGxb, GyaGyb, GxaGyb, GyaGxb}
+        double XX[4][4], YY[4][4], XY[4][4], YX[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) XX[a][b] = YY[a][b] = XY[a][b] = YX[a][b] = 0.0;
+        const Quad4Coef c = quad4_coef(xe);
+        for_each_q<4>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[4][2];
+            quad4_geo<Q>(c, det, G);
+            const double s = cq[Q] / det;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double hx = s * G[a][0], hy = s * G[a][1];
+#pragma unroll
+                for (int b = a; b < 4; ++b) {
+                    XX[a][b] = fma(hx, G[b][0], XX[a][b]);
+                    YY[a][b] = fma(hy, G[b][1], YY[a][b]);
+                    XY[a][b] = fma(hx, G[b][1], XY[a][b]);
+                    if (b != a) YX[a][b] = fma(hy, G[b][0], YX[a][b]);
+                }
+            }
+        });
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = a; b < 4; ++b) {
+                const double yx = (a == b) ? XY[a][b] : YX[a][b];
+                double blk[4];  // [alpha][beta] for (row node a, col node b)
+                blk[0] = fma(prm.c11, XX[a][b], prm.c33 * YY[a][b]);
+                blk[1] = fma(prm.c12, XY[a][b], prm.c33 * yx);
+                blk[2] = fma(prm.c12, yx, prm.c33 * XY[a][b]);
+                blk[3] = fma(prm.c11, YY[a][b], prm.c33 * XX[a][b]);
+                sink.block(0, a, b, blk);
+                if (b != a) {
+                    const double t[4] = {blk[0], blk[2], blk[1], blk[3]};
+                    sink.block(0, b, a, t);
+                }
+            }
+    }
+};
+
+constexpr int kMaxXdv = 32;
+
+struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) + residual (pyfem.py:1474-1539)
+    static constexpr int NNE = 4, M = 1, NMAT = 1, NVEC = 1, DIM = 2, NQ = 4;
+    static constexpr bool NEEDS_ELEM = false;
+    struct Params {
+        const double* u;
+        int nxdv;
+        double coef[kMaxXdv];  // xdv[k] * binom(nxdv-1, k)  (pyfem.py:1466-1470)
+    };
+    PFG_DEV static double hfun(const Params& prm, double x, double y) {
+        // h = 1 + 4y(1-y) sum_k coef_k (1-x)^(n-1-k) x^k, powers by repeated multiplication
+        const int n = prm.nxdv;
+        double om[kMaxXdv];
+        om[0] = 1.0;
+        for (int k = 1; k < n; ++k) om[k] = om[k - 1] * (1.0 - x);
+        double xp = 1.0, s = 0.0;
+        for (int k = 0; k < n; ++k) {
+            s = fma(prm.coef[k] * om[n - 1 - k], xp, s);
+            xp *= x;
+        }
+        return fma(s, 4.0 * y * (1.0 - y), 1.0);
+    }
+    PFG_DEV static double gfun(double x, double y) {  // pyfem.py:1438-1446
+        return 1e4 * x * (1.0 - x) * (1.0 - 2.0 * x) * y * (1.0 - y) * (1.0 - 2.0 * y);
+    }
+    template <class Sink>
+    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[4], int64_t, Sink& sink) {
+        double xe[4][2], ue[4];
+        load_coords<4>(mv.X, nodes, xe);
+#pragma unroll
+        for (int a = 0; a < 4; ++a) ue[a] = __ldg(prm.u + nodes[a]);
+        double K[4][4], res[4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            res[a] = 0.0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) K[a][b] = 0.0;
+        }
+        const Quad4Coef c = quad4_coef(xe);
+        for_each_q<4>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[4][2];
+            quad4_geo<Q>(c, det, G);
+            double xq = 0.0, yq = 0.0, uq = 0.0, gux = 0.0, guy = 0.0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                xq = fma(Elem<4>::N(Q, a), xe[a][0], xq);
+                yq = fma(Elem<4>::N(Q, a), xe[a][1], yq);
+                uq = fma(Elem<4>::N(Q, a), ue[a], uq);
+                gux = fma(G[a][0], ue[a], gux);  // det * du/dx
+                guy = fma(G[a][1], ue[a], guy);
+            }
+            const double h = hfun(prm, xq, yq);
+            const double inv = 1.0 / det;
+            const double c1 = h * fma(uq, uq, 1.0) * inv;  // detJ h (1+u^2) w / det^2
+            const double c2 = 2.0 * h * uq * inv;
+            const double gsrc = det * gfun(xq, yq);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                const double da = fma(G[a][0], gux, G[a][1] * guy);  // det^2 gradN_a . grad u
+                res[a] = fma(c1, da, res[a]);
+                res[a] = fma(-gsrc, Elem<4>::N(Q, a), res[a]);
+                const double hx = c1 * G[a][0], hy = c1 * G[a][1], na = c2 * da;
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    double v = fma(hx, G[b][0], K[a][b]);
+                    v = fma(hy, G[b][1], v);
+                    K[a][b] = fma(na, Elem<4>::N(Q, b), v);
+                }
+            }
+        });
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+#pragma unroll
+            for (int b = 0; b < 4; ++b) sink.block(0, a, b, &K[a][b]);
+            sink.vec(a, res[a]);
+        }
+    }
+};
+
+template <int NNE_>
+struct PoissonRhsOp {  // LinearPoisson._compute_element_rhs (pyfem.py:1137-1173, einsum :1132-1134)
+    static constexpr int NNE = NNE_, M = 1, NMAT = 0, NVEC = 1;
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr bool NEEDS_ELEM = true;
+    struct Params {
+        const double* gq;  // (nelems, NQ) source term at the quadrature points
+    };
+    template <class Sink>
+    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t elem, Sink& sink) {
+        double xe[NNE][DIM];
+        load_coords<NNE>(mv.X, nodes, xe);
+        double f[NNE];
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) f[a] = 0.0;
+        GeoCtx<NNE> geo(xe);
+        const double* g = prm.gq + elem * NQ;
+        for_each_q<NQ>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[NNE][DIM];
+            geo.template at<Q>(xe, det, G);
+            const double wg = det * __ldg(g + Q);
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) f[a] = fma(wg, Elem<NNE>::N(Q, a), f[a]);
+        });
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) sink.vec(a, f[a]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// hex8 3-D elasticity: 8 threads per element.  Thread t first acts as quadrature point t (geometry
+// into shared staging), then as local row node t (3 x 24 row block from 72 accumulators).
+// LinearElasticity._compute_element_jacobian, 3-D branch (pyfem.py:2000-2011, 2017-2026, 1752-1757).
+// ---------------------------------------------------------------------------------------------
+struct ElasticityHex8Params {
+    Material mat;
+    double c11, c12, c44;
+};
+
+constexpr int kHexStageDoubles = 8 * 25 + 2;  // per element: [q][8 nodes x 3 + s_q], padded against bank conflicts
+
+// `stage` points at this element's staging area; `lane8` is the thread's index inside its octet.
+// All 8 threads of an octet must call this together (uses __syncwarp on the octet's lanes).
+template <class Sink>
+PFG_DEV void elasticity_hex8_octet(const MeshView& mv, const ElasticityHex8Params& prm, const int (&nodes)[8],
+                                   double* __restrict__ stage, int lane8, unsigned octet_mask, bool row_wanted,
+                                   Sink& sink) {
+    // ---- role 1: quadrature point `lane8` (x slowest, z fastest; basis evaluated at run time so the
+    //      eight lanes of an octet execute one instruction stream)
+    double xe[8][3];
+    load_coords<8>(mv.X, nodes, xe);
+    const double qx = (lane8 & 4) ? PFG_G : -PFG_G, qy = (lane8 & 2) ? PFG_G : -PFG_G, qz = (lane8 & 1) ? PFG_G : -PFG_G;
+    const double fx[2] = {1.0 - qx, 1.0 + qx}, fy[2] = {1.0 - qy, 1.0 + qy}, fz[2] = {1.0 - qz, 1.0 + qz};
+    double det, G[8][3], cq;
+    {
+        double dn[8][3], shape[8];
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+            constexpr double e8 = 0.125;
+            const int ix = Elem<8>::sgn(a, 0) > 0 ? 1 : 0, iy = Elem<8>::sgn(a, 1) > 0 ? 1 : 0, iz = Elem<8>::sgn(a, 2) > 0 ? 1 : 0;
+            dn[a][0] = (Elem<8>::sgn(a, 0) * e8) * (fy[iy] * fz[iz]);
+            dn[a][1] = (Elem<8>::sgn(a, 1) * e8) * (fx[ix] * fz[iz]);
+            dn[a][2] = (Elem<8>::sgn(a, 2) * e8) * (fx[ix] * fy[iy]);
+            shape[a] = e8 * fx[ix] * (fy[iy] * fz[iz]);
+        }
+        double J[3][3];
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                double s = 0.0;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) s = fma(dn[a][k], xe[a][j], s);
+                J[j][k] = s;
+            }
+        double A[3][3];
+        A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+        A[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+        A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+        A[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+        A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+        A[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+        A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+        A[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+        A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+        det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
+#pragma unroll
+        for (int a = 0; a < 8; ++a)
+#pragma unroll
+            for (int l = 0; l < 3; ++l) G[a][l] = dn[a][0] * A[0][l] + dn[a][1] * A[1][l] + dn[a][2] * A[2][l];
+        if (prm.mat.rho == nullptr) {
+            cq = prm.mat.rho_const / (1.0 + prm.mat.p * (1.0 - prm.mat.rho_const));
+        } else {
+            double rq = 0.0;
+#pragma unroll
+            for (int a = 0; a < 8; ++a) rq = fma(shape[a], __ldg(prm.mat.rho + nodes[a]), rq);
+            cq = rq / (1.0 + prm.mat.p * (1.0 - rq));
+        }
+    }
+    double* mine = stage + lane8 * 25;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int l = 0; l < 3; ++l) mine[b * 3 + l] = G[b][l];
+    mine[24] = cq / det;
+    __syncwarp(octet_mask);
+    // ---- role 2: row node `lane8`
+    if (row_wanted) {
+        double P[8][3][3];
+#pragma unroll
+        for (int b = 0; b < 8; ++b)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) P[b][i][j] = 0.0;
+#pragma unroll 1
+        for (int q = 0; q < 8; ++q) {
+            const double* gq = stage + q * 25;
+            const double s = gq[24];
+            const double h0 = s * gq[lane8 * 3 + 0], h1 = s * gq[lane8 * 3 + 1], h2 = s * gq[lane8 * 3 + 2];
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const double g0 = gq[b * 3 + 0], g1 = gq[b * 3 + 1], g2 = gq[b * 3 + 2];
+                P[b][0][0] = fma(h0, g0, P[b][0][0]);
+                P[b][0][1] = fma(h0, g1, P[b][0][1]);
+                P[b][0][2] = fma(h0, g2, P[b][0][2]);
+                P[b][1][0] = fma(h1, g0, P[b][1][0]);
+                P[b][1][1] = fma(h1, g1, P[b][1][1]);
+                P[b][1][2] = fma(h1, g2, P[b][1][2]);
+                P[b][2][0] = fma(h2, g0, P[b][2][0]);
+                P[b][2][1] = fma(h2, g1, P[b][2][1]);
+                P[b][2][2] = fma(h2, g2, P[b][2][2]);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+            double blk[9];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    if (i == j) {
+                        const int l1 = (i + 1) % 3, l2 = (i + 2) % 3;
+                        blk[i * 3 + j] = fma(prm.c11, P[b][i][i], prm.c44 * (P[b][l1][l1] + P[b][l2][l2]));
+                    } else {
+                        blk[i * 3 + j] = fma(prm.c12, P[b][i][j], prm.c44 * P[b][j][i]);
+                    }
+                }
+            sink.block(0, lane8, b, blk);
+        }
+    }
+    __syncwarp(octet_mask);  // staging may be reused by the caller's next element
+}
+
+}  // namespace pfg

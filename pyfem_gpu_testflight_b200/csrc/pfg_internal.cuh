@@ -1,0 +1,110 @@
+// Internal definitions shared by the setup (pattern / plan builder) and assembly kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/pyfem_b200.h"
+
+namespace pfg {
+
+// ---------------------------------------------------------------------------------------------
+// error plumbing: status codes out, message kept per host thread (pfg_last_error)
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define PFG_CUDA_TRY(expr)                                                                     \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            pfg::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return (_e == cudaErrorMemoryAllocation) ? PFG_ERR_NOMEM : PFG_ERR_CUDA;            \
+        }                                                                                      \
+    } while (0)
+
+#define PFG_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != PFG_OK) return _s; \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Gather-plan layout (see DESIGN.md "Data layout in HBM")
+//
+// Owned node rows are grouped into chunks; one CTA assembles one chunk:
+//   phase A  every element touching the chunk is integrated once by one thread (hex8 elasticity:
+//            8 threads) and the row blocks that belong to chunk nodes are staged in shared memory,
+//            one "incidence" slot per (chunk node, adjacent element) pair, node-major;
+//   phase B  one thread per (chunk node, neighbour node) block sums the <= valence contributions
+//            listed in the node's plan in a fixed order and stores the m x m block to CSR.
+// ---------------------------------------------------------------------------------------------
+struct ChunkHdr {        // 32 bytes
+    uint32_t node_begin; // first chunk-ordered node slot
+    uint32_t n_nodes;
+    int64_t rec_begin;   // first element record
+    uint32_t n_recs;
+    uint32_t n_inc;      // incidences = sum of valence over chunk nodes
+    uint32_t kpad;       // max neighbour count over chunk nodes
+    uint32_t pad_;
+};
+
+struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
+    int64_t gslot;       // offset of the node's first dof row in the owned CSR values
+    uint32_t plan;       // offset of the node's plan record in the plan pool, 4-byte units
+    uint16_t inc_base;   // first incidence slot of this node inside the chunk
+    uint8_t k;           // neighbour nodes (row length in node blocks)
+    uint8_t valence;     // adjacent elements
+};
+// plan record of a node: uint8 start[k+1] (prefix of contribution counts per neighbour),
+// then uint8 src[valence*nne] sorted by neighbour rank, src = (adjacent-element ordinal << 3) | local column node.
+
+constexpr int kMaxValence = 31;      // 5-bit ordinal; start[] must fit uint8 (31*8 = 248)
+constexpr int kMaxRowBlocks = 255;   // rank fits uint8
+constexpr uint16_t kNoDst = 0xFFFF;
+
+struct MeshDev {
+    // dimensions
+    int elem_type = 0, nne = 0, ndims = 0, m = 0, nquads = 0;
+    int64_t nnodes = 0, nelems = 0, own_begin = 0, own_end = 0, ncols_nodes = 0;
+    int64_t nblocks = 0;      // node-level nnz of owned rows
+    int64_t nnz = 0;          // dof-level nnz of owned rows = m*m*nblocks
+    int idx_bytes = 4;
+    int max_k = 0, max_valence = 0;
+    int flags = 0;
+
+    // mesh (device)
+    double* X = nullptr;        // (nnodes, ndims)
+    int32_t* conn = nullptr;    // (nelems, nne)
+    int64_t* gid = nullptr;     // optional local->global node id
+
+    // node -> element incidences (all local nodes), sorted by (node, element, local index)
+    int64_t* inc_ptr = nullptr;   // (nnodes+1)
+    uint32_t* inc_list = nullptr; // (nelems*nne) values e*nne + a
+
+    // node-level CSR pattern of the owned rows
+    int64_t* blk_ptr = nullptr;   // (nown+1) prefix of neighbour counts
+    int32_t* nbr = nullptr;       // (nblocks) sorted neighbour (local) node ids
+    uint8_t* rank = nullptr;      // (nelems*nne*nne) rank of conn[e][b] in the row of conn[e][a] (garbage for non-owned rows)
+
+    // gather plan
+    int64_t nchunks = 0, nrecs = 0, plan_bytes = 0;
+    ChunkHdr* chunks = nullptr;
+    ChunkNode* cnodes = nullptr;  // (nown)
+    int32_t* cnode_id = nullptr;  // (nown) local node id of each chunk-ordered slot
+    int32_t* rec_nodes = nullptr; // (nrecs, nne)
+    uint16_t* rec_dst = nullptr;  // (nrecs, nne)
+    int32_t* rec_elem = nullptr;  // (nrecs)
+    uint8_t* plan_pool = nullptr;
+    int max_chunk_inc = 0, max_chunk_nodes = 0, max_chunk_recs = 0, max_kpad = 0;
+
+    int64_t device_bytes = 0;
+    int sm_count = 148;
+    int device = 0;
+};
+
+}  // namespace pfg
+
+struct pfg_mesh {
+    pfg::MeshDev d;
+};

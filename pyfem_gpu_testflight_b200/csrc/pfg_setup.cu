@@ -1,0 +1,898 @@
+// Once-per-mesh setup on the device: CSR pattern builder, element->slot rank map and the
+// row-chunk gather plans.  Replaces ModelBase.__init__'s pattern work (reference pyfem.py:640-757,
+// :837-858) and the sort/unique that scipy's coo->csr redoes on every assembly (pyfem.py:930-931).
+//
+// Everything here is integer work on device arrays; sorts and scans use CUB (the CUDA toolkit's
+// header-only primitives), the rest are small hand-written kernels.
+#include <cub/cub.cuh>
+#include <stdarg.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <vector>
+
+#include "pfg_internal.cuh"
+
+namespace pfg {
+
+static thread_local std::string g_last_error;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small RAII device buffer + CUB temp storage
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct DBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DBuf() = default;
+    DBuf(const DBuf&) = delete;
+    DBuf& operator=(const DBuf&) = delete;
+    ~DBuf() { release(); }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        return cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    }
+    T* take() {
+        T* r = p;
+        p = nullptr;
+        n = 0;
+        return r;
+    }
+};
+
+struct Scratch {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~Scratch() {
+        if (p) cudaFree(p);
+    }
+    cudaError_t reserve(size_t need) {
+        if (need <= bytes) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        cudaError_t e = cudaMalloc(&p, need);
+        if (e == cudaSuccess) bytes = need;
+        return e;
+    }
+};
+
+#define PFG_CUB(scratch, stream, call_with_temp)                                      \
+    do {                                                                              \
+        void* d_temp_storage = nullptr;                                               \
+        size_t temp_storage_bytes = 0;                                                \
+        PFG_CUDA_TRY(call_with_temp);                                                 \
+        PFG_CUDA_TRY((scratch).reserve(temp_storage_bytes + 16));                     \
+        d_temp_storage = (scratch).p;                                                 \
+        PFG_CUDA_TRY(call_with_temp);                                                 \
+    } while (0)
+
+static inline int bits_for(uint64_t maxval) {
+    int b = 1;
+    while (b < 64 && (maxval >> b)) ++b;
+    return b;
+}
+
+constexpr int kThreads = 256;
+static inline unsigned grid_for(int64_t n, int threads = kThreads) {
+    return (unsigned)std::max<int64_t>(1, (n + threads - 1) / threads);
+}
+
+// ---------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void k_conn_to_i32(const int64_t* __restrict__ conn, int32_t* __restrict__ out, int64_t n,
+                              long long* __restrict__ minmax) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    if (i < n) {
+        long long v = conn[i];
+        out[i] = (int32_t)v;
+        lo = hi = v;
+    }
+    for (int o = 16; o; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&minmax[0], lo);
+        atomicMax(&minmax[1], hi);
+    }
+}
+
+__global__ void k_iota_u32(uint32_t* out, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint32_t)i;
+}
+
+__global__ void k_count_nodes(const int32_t* __restrict__ conn, unsigned* __restrict__ counts, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) atomicAdd(&counts[conn[i]], 1u);
+}
+
+// Sorted-unique neighbour list of one node in thread-local memory.
+struct NbrList {
+    int32_t v[kMaxRowBlocks + 1];
+    int n = 0;
+    bool overflow = false;
+    __device__ void insert(int32_t c) {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            if (v[mid] < c) lo = mid + 1; else hi = mid;
+        }
+        if (lo < n && v[lo] == c) return;
+        if (n >= kMaxRowBlocks) { overflow = true; return; }
+        for (int s = n; s > lo; --s) v[s] = v[s - 1];
+        v[lo] = c;
+        ++n;
+    }
+};
+
+// pass 0: count neighbours of every owned node; pass 1: write them.
+template <int NNE>
+__global__ void k_node_neighbours(const int32_t* __restrict__ conn, const int64_t* __restrict__ inc_ptr,
+                                  const uint32_t* __restrict__ inc_list, int64_t own_begin, int64_t nown,
+                                  int* __restrict__ kcount, const int64_t* __restrict__ blk_ptr,
+                                  int32_t* __restrict__ nbr, int* __restrict__ err) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    int64_t node = own_begin + r;
+    NbrList L;
+    for (int64_t s = inc_ptr[node]; s < inc_ptr[node + 1]; ++s) {
+        int64_t e = inc_list[s] / NNE;
+        const int32_t* c = conn + e * NNE;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) L.insert(c[b]);
+    }
+    if (L.overflow) atomicExch(err, 1);
+    if (nbr == nullptr) {
+        kcount[r] = L.n;
+    } else {
+        int64_t base = blk_ptr[r];
+        for (int t = 0; t < L.n; ++t) nbr[base + t] = L.v[t];
+    }
+}
+
+template <int NNE>
+__global__ void k_rank_map(const int32_t* __restrict__ conn, const int64_t* __restrict__ blk_ptr,
+                           const int32_t* __restrict__ nbr, int64_t own_begin, int64_t own_end, int64_t ninc,
+                           uint8_t* __restrict__ rank) {
+    int64_t ia = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // e*NNE + a
+    if (ia >= ninc) return;
+    int64_t e = ia / NNE;
+    int32_t node = conn[ia];
+    if (node < own_begin || node >= own_end) return;
+    int64_t lo0 = blk_ptr[node - own_begin], hi0 = blk_ptr[node - own_begin + 1];
+    const int32_t* c = conn + e * NNE;
+#pragma unroll
+    for (int b = 0; b < NNE; ++b) {
+        int32_t col = c[b];
+        int64_t lo = lo0, hi = hi0;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (nbr[mid] < col) lo = mid + 1; else hi = mid;
+        }
+        rank[ia * NNE + b] = (uint8_t)(lo - lo0);
+    }
+}
+
+template <class IdxT>
+__global__ void k_write_indptr(const int64_t* __restrict__ blk_ptr, int64_t nown, int m, IdxT* __restrict__ indptr) {
+    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;  // dof row, inclusive of the last+1
+    int64_t nrows = nown * m;
+    if (row > nrows) return;
+    if (row == nrows) {
+        indptr[row] = (IdxT)(blk_ptr[nown] * m * m);
+        return;
+    }
+    int64_t r = row / m;
+    int alpha = (int)(row - r * m);
+    int64_t k = blk_ptr[r + 1] - blk_ptr[r];
+    indptr[row] = (IdxT)(blk_ptr[r] * m * m + alpha * k * m);
+}
+
+template <class IdxT>
+__global__ void k_write_indices(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                const int64_t* __restrict__ gid, int64_t nown, int m, IdxT* __restrict__ indices) {
+    // one thread per (owned node, neighbour) block; writes m rows x m columns of column indices
+    int64_t r = blockIdx.y * (int64_t)gridDim.x * blockDim.x + blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    // r indexes node blocks; find the row by binary search on blk_ptr
+    int64_t nblocks = blk_ptr[nown];
+    if (r >= nblocks) return;
+    int64_t lo = 0, hi = nown;  // last row with blk_ptr[row] <= r
+    while (hi - lo > 1) {
+        int64_t mid = (lo + hi) >> 1;
+        if (blk_ptr[mid] <= r) lo = mid; else hi = mid;
+    }
+    int64_t row = lo;
+    int64_t k = blk_ptr[row + 1] - blk_ptr[row];
+    int64_t t = r - blk_ptr[row];
+    int64_t col = nbr[r];
+    if (gid) col = gid[col];
+    int64_t base = blk_ptr[row] * m * m;
+    for (int alpha = 0; alpha < m; ++alpha)
+        for (int beta = 0; beta < m; ++beta)
+            indices[base + alpha * k * m + t * m + beta] = (IdxT)(col * m + beta);
+}
+
+// ---- chunking (sort-tile-recursive with tie-aware cuts) ---------------------------------------
+__device__ __forceinline__ uint64_t sortable_f64(double x) {
+    uint64_t b = (uint64_t)__double_as_longlong(x + 0.0);  // +0.0 folds -0 into +0
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__global__ void k_coord_keys(const double* __restrict__ X, int ndims, int axis, int64_t own_begin, int64_t nown,
+                             uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    keys[r] = sortable_f64(X[(own_begin + r) * ndims + axis]);
+    vals[r] = (uint32_t)r;
+}
+
+__global__ void k_gather_u32(const uint32_t* __restrict__ table, const uint32_t* __restrict__ idx, int64_t n,
+                             uint32_t* __restrict__ out) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) out[r] = table[idx[r]];
+}
+
+// Along the order (group, coord, id): mark the start position of each group and of each run of
+// equal coordinate inside a group (as "r+1", 0 elsewhere) for the two max-scans.
+__global__ void k_mark_starts(const uint32_t* __restrict__ group_sorted, const uint32_t* __restrict__ order,
+                              const double* __restrict__ X, int ndims, int axis, int64_t own_begin, int64_t n,
+                              int64_t* __restrict__ gstart, int64_t* __restrict__ vstart) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    bool newg = (r == 0) || (group_sorted[r] != group_sorted[r - 1]);
+    bool newv = newg;
+    if (!newv) {
+        double a = X[(own_begin + order[r]) * ndims + axis];
+        double b = X[(own_begin + order[r - 1]) * ndims + axis];
+        newv = !(a == b);
+    }
+    gstart[r] = newg ? r + 1 : 0;
+    vstart[r] = newv ? r + 1 : 0;
+}
+
+// cut id inside the group; then flag where (group, cut) changes.
+__global__ void k_cut_flags(const uint32_t* __restrict__ group_sorted, const int64_t* __restrict__ gstart,
+                            const int64_t* __restrict__ vstart, int64_t n, int64_t target,
+                            uint32_t* __restrict__ cut, uint32_t* __restrict__ flag) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    auto cut_of = [&](int64_t q) -> uint32_t {
+        int64_t g0 = gstart[q] - 1, v0 = vstart[q] - 1;
+        int64_t pos = q - g0, vpos = v0 - g0;
+        // keep runs of equal coordinate together unless the run itself is long
+        int64_t basis = (pos - vpos >= (target + 3) / 4) ? pos : vpos;
+        return (uint32_t)(basis / target);
+    };
+    uint32_t c = cut_of(r);
+    cut[r] = c;
+    bool f = (r == 0) || (group_sorted[r] != group_sorted[r - 1]) || (cut_of(r - 1) != c);
+    flag[r] = f ? 1u : 0u;
+}
+
+__global__ void k_scatter_group(const uint32_t* __restrict__ order, const uint32_t* __restrict__ dense_incl,
+                                int64_t n, uint32_t* __restrict__ group_of_node) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) group_of_node[order[r]] = dense_incl[r] - 1;
+}
+
+__global__ void k_chunk_by_id(int64_t n, int64_t target, uint32_t* __restrict__ group_of_node) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r < n) group_of_node[r] = (uint32_t)(r / target);
+}
+
+// chunk-ordered node slots: per-slot valence / k, chunk boundaries
+__global__ void k_slot_counts(const uint32_t* __restrict__ slot_node, const int64_t* __restrict__ inc_ptr,
+                              const int64_t* __restrict__ blk_ptr, int64_t own_begin, int64_t n,
+                              uint32_t* __restrict__ valence, uint32_t* __restrict__ kk) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int64_t r = slot_node[p];
+    valence[p] = (uint32_t)(inc_ptr[own_begin + r + 1] - inc_ptr[own_begin + r]);
+    kk[p] = (uint32_t)(blk_ptr[r + 1] - blk_ptr[r]);
+}
+
+__global__ void k_chunk_node_begin(const uint32_t* __restrict__ slot_chunk, int64_t n, int64_t nchunks,
+                                   ChunkHdr* __restrict__ chunks) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    uint32_t c = slot_chunk[p];
+    if (p == 0 || slot_chunk[p - 1] != c) chunks[c].node_begin = (uint32_t)p;
+    if (p == n - 1 || slot_chunk[p + 1] != c) chunks[c].n_nodes = (uint32_t)(p + 1);  // fixed up below
+}
+
+__global__ void k_chunk_finish(int64_t nchunks, const int64_t* __restrict__ inc_excl, const uint32_t* __restrict__ kk,
+                               ChunkHdr* __restrict__ chunks, int64_t nslots, int* __restrict__ maxima) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    ChunkHdr h = chunks[c];
+    uint32_t end = h.n_nodes;  // holds end slot
+    h.n_nodes = end - h.node_begin;
+    int64_t inc0 = inc_excl[h.node_begin];
+    int64_t inc1 = (end == nslots) ? inc_excl[nslots] : inc_excl[end];
+    h.n_inc = (uint32_t)(inc1 - inc0);
+    uint32_t kp = 0;
+    for (uint32_t p = h.node_begin; p < end; ++p) kp = max(kp, kk[p]);
+    h.kpad = kp;
+    h.pad_ = 0;
+    chunks[c] = h;
+    atomicMax(&maxima[0], (int)h.n_inc);
+    atomicMax(&maxima[1], (int)h.n_nodes);
+    atomicMax(&maxima[2], (int)kp);
+}
+
+// one key per owned incidence: (chunk << 32) | element
+template <int NNE>
+__global__ void k_inc_keys(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
+                           const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
+                           const int64_t* __restrict__ inc_excl, int64_t own_begin, int64_t nslots,
+                           uint64_t* __restrict__ keys) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    int64_t node = own_begin + slot_node[p];
+    int64_t o = inc_excl[p];
+    uint64_t c = slot_chunk[p];
+    for (int64_t s = inc_ptr[node]; s < inc_ptr[node + 1]; ++s) keys[o++] = (c << 32) | (uint64_t)(inc_list[s] / NNE);
+}
+
+template <int NNE>
+__global__ void k_fill_records(const uint64_t* __restrict__ rec_keys, int64_t nrecs, const int32_t* __restrict__ conn,
+                               int32_t* __restrict__ rec_nodes, uint16_t* __restrict__ rec_dst,
+                               int32_t* __restrict__ rec_elem, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nrecs) return;
+    uint64_t key = rec_keys[r];
+    uint32_t c = (uint32_t)(key >> 32);
+    int64_t e = (int64_t)(key & 0xffffffffull);
+    rec_elem[r] = (int32_t)e;
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) {
+        rec_nodes[r * NNE + a] = conn[e * NNE + a];
+        rec_dst[r * NNE + a] = kNoDst;
+    }
+    bool first = (r == 0) || ((uint32_t)(rec_keys[r - 1] >> 32) != c);
+    bool last = (r == nrecs - 1) || ((uint32_t)(rec_keys[r + 1] >> 32) != c);
+    if (first) chunks[c].rec_begin = r;
+    if (last) chunks[c].n_recs = (uint32_t)(r + 1);  // end index (fits: checked on host), fixed up below
+}
+
+__global__ void k_chunk_rec_finish(int64_t nchunks, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    uint32_t n = (uint32_t)((int64_t)chunks[c].n_recs - chunks[c].rec_begin);
+    chunks[c].n_recs = n;
+    atomicMax(&maxima[3], (int)n);
+}
+
+template <int NNE>
+__global__ void k_fill_dst(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
+                           const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
+                           const int64_t* __restrict__ inc_excl, const ChunkHdr* __restrict__ chunks,
+                           const uint64_t* __restrict__ rec_keys, int64_t own_begin, int64_t nslots,
+                           uint16_t* __restrict__ rec_dst) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    uint32_t c = slot_chunk[p];
+    ChunkHdr h = chunks[c];
+    int64_t node = own_begin + slot_node[p];
+    int64_t inc_local = inc_excl[p] - inc_excl[h.node_begin];
+    int j = 0;
+    for (int64_t s = inc_ptr[node]; s < inc_ptr[node + 1]; ++s, ++j) {
+        uint32_t ia = inc_list[s];
+        uint64_t key = ((uint64_t)c << 32) | (uint64_t)(ia / NNE);
+        int64_t lo = h.rec_begin, hi = h.rec_begin + h.n_recs;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (rec_keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        rec_dst[lo * NNE + (ia % NNE)] = (uint16_t)(inc_local + j);
+    }
+}
+
+__global__ void k_plan_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne,
+                             int64_t nslots, uint32_t* __restrict__ words) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    uint32_t bytes = kk[p] + 1 + valence[p] * nne;
+    words[p] = (bytes + 3) / 4;
+}
+
+template <int NNE>
+__global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64_t* __restrict__ inc_ptr,
+                             const uint32_t* __restrict__ inc_list, const uint8_t* __restrict__ rank,
+                             const int64_t* __restrict__ blk_ptr, const int64_t* __restrict__ inc_excl,
+                             const ChunkHdr* __restrict__ chunks, const uint32_t* __restrict__ slot_chunk,
+                             const int64_t* __restrict__ plan_off, int64_t own_begin, int64_t nslots, int m,
+                             ChunkNode* __restrict__ cnodes, int32_t* __restrict__ cnode_id,
+                             uint8_t* __restrict__ pool) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    int64_t r = slot_node[p];
+    int64_t node = own_begin + r;
+    int k = (int)(blk_ptr[r + 1] - blk_ptr[r]);
+    int64_t s0 = inc_ptr[node], s1 = inc_ptr[node + 1];
+    int val = (int)(s1 - s0);
+    uint8_t* rec = pool + plan_off[p] * 4;
+    uint8_t* start = rec;
+    uint8_t* src = rec + k + 1;
+    // counting sort of the valence*NNE contributions by neighbour rank
+    uint8_t cnt[kMaxRowBlocks + 1];
+    for (int t = 0; t <= k; ++t) cnt[t] = 0;
+    for (int64_t s = s0; s < s1; ++s) {
+        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
+    }
+    for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
+    for (int t = 0; t <= k; ++t) start[t] = cnt[t];
+    int j = 0;
+    for (int64_t s = s0; s < s1; ++s, ++j) {
+        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) src[cnt[rk[b]]++] = (uint8_t)((j << 3) | b);
+    }
+    ChunkNode cn;
+    cn.gslot = blk_ptr[r] * m * m;
+    cn.plan = (uint32_t)plan_off[p];
+    cn.inc_base = (uint16_t)(inc_excl[p] - inc_excl[chunks[slot_chunk[p]].node_begin]);
+    cn.k = (uint8_t)k;
+    cn.valence = (uint8_t)val;
+    cnodes[p] = cn;
+    cnode_id[p] = (int32_t)node;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host orchestration
+// ---------------------------------------------------------------------------------------------
+template <int NNE>
+static int build_pattern(MeshDev& d, cudaStream_t st, Scratch& scratch) {
+    const int64_t ninc = d.nelems * NNE;
+    const int64_t nown = d.own_end - d.own_begin;
+
+    // node -> incidence lists (stable radix sort of (node, e*NNE+a))
+    DBuf<uint32_t> vals_in, keys_out;
+    DBuf<unsigned> counts;
+    PFG_CUDA_TRY(vals_in.alloc(ninc));
+    PFG_CUDA_TRY(keys_out.alloc(ninc));
+    PFG_CUDA_TRY(counts.alloc(d.nnodes + 1));
+    PFG_CUDA_TRY(cudaMalloc(&d.inc_list, std::max<int64_t>(ninc, 1) * sizeof(uint32_t)));
+    PFG_CUDA_TRY(cudaMalloc(&d.inc_ptr, (d.nnodes + 1) * sizeof(int64_t)));
+    k_iota_u32<<<grid_for(ninc), kThreads, 0, st>>>(vals_in.p, ninc);
+    PFG_CUB(scratch, st,
+            cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint32_t*)d.conn, keys_out.p,
+                                            (const uint32_t*)vals_in.p, d.inc_list, ninc, 0,
+                                            bits_for((uint64_t)d.nnodes), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(counts.p, 0, (d.nnodes + 1) * sizeof(unsigned), st));
+    k_count_nodes<<<grid_for(ninc), kThreads, 0, st>>>(d.conn, counts.p, ninc);
+    PFG_CUB(scratch, st,
+            cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, counts.p, d.inc_ptr, d.nnodes + 1, st));
+    DBuf<unsigned> maxval;
+    PFG_CUDA_TRY(maxval.alloc(1));
+    PFG_CUB(scratch, st,
+            cub::DeviceReduce::Max(d_temp_storage, temp_storage_bytes, counts.p, maxval.p, d.nnodes, st));
+    unsigned h_maxval = 0;
+    PFG_CUDA_TRY(cudaMemcpyAsync(&h_maxval, maxval.p, sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+
+    // neighbour counts -> blk_ptr -> neighbour lists
+    DBuf<int> kcount, err;
+    PFG_CUDA_TRY(kcount.alloc(nown + 1));
+    PFG_CUDA_TRY(err.alloc(1));
+    PFG_CUDA_TRY(cudaMemsetAsync(err.p, 0, sizeof(int), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(kcount.p, 0, (nown + 1) * sizeof(int), st));
+    PFG_CUDA_TRY(cudaMalloc(&d.blk_ptr, (nown + 1) * sizeof(int64_t)));
+    k_node_neighbours<NNE><<<grid_for(nown, 128), 128, 0, st>>>(d.conn, d.inc_ptr, d.inc_list, d.own_begin, nown,
+                                                               kcount.p, nullptr, nullptr, err.p);
+    PFG_CUB(scratch, st,
+            cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, kcount.p, d.blk_ptr, nown + 1, st));
+    DBuf<int> maxk;
+    PFG_CUDA_TRY(maxk.alloc(1));
+    PFG_CUB(scratch, st, cub::DeviceReduce::Max(d_temp_storage, temp_storage_bytes, kcount.p, maxk.p, nown, st));
+    int h_err = 0, h_maxk = 0;
+    PFG_CUDA_TRY(cudaMemcpyAsync(&h_err, err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(&h_maxk, maxk.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(&d.nblocks, d.blk_ptr + nown, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error("a node has more than %d neighbour nodes; mesh valence too high for the device pattern builder",
+                  kMaxRowBlocks);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    d.max_k = h_maxk;
+    d.max_valence = (int)h_maxval;
+    d.nnz = d.nblocks * d.m * d.m;
+    PFG_CUDA_TRY(cudaMalloc(&d.nbr, std::max<int64_t>(d.nblocks, 1) * sizeof(int32_t)));
+    k_node_neighbours<NNE><<<grid_for(nown, 128), 128, 0, st>>>(d.conn, d.inc_ptr, d.inc_list, d.own_begin, nown,
+                                                               nullptr, d.blk_ptr, d.nbr, err.p);
+    // element -> slot rank map
+    PFG_CUDA_TRY(cudaMalloc(&d.rank, std::max<int64_t>(ninc * NNE, 1)));
+    k_rank_map<NNE><<<grid_for(ninc), kThreads, 0, st>>>(d.conn, d.blk_ptr, d.nbr, d.own_begin, d.own_end, ninc,
+                                                         d.rank);
+    PFG_CUDA_TRY(cudaGetLastError());
+    d.device_bytes += ninc * 4 + (d.nnodes + 1) * 8 + (nown + 1) * 8 + d.nblocks * 4 + ninc * NNE;
+    return PFG_OK;
+}
+
+static int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// shared-memory doubles staged per incidence, worst case over the physics a handle with this
+// (element, ndof_per_node) can run: m == 1 -> Helmholtz (two matrices) or nonlinear Poisson
+// (matrix + residual); m > 1 -> elasticity.  Must match rb_stride() in pfg_assemble.cu.
+static int worst_rb_doubles(int nne, int m) {
+    if (m == 1) return 2 * nne + 2;
+    return nne * m * m + 2;
+}
+
+template <int NNE>
+static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
+    const int64_t nown = d.own_end - d.own_begin;
+    if (nown == 0 || d.nelems == 0) return PFG_OK;
+    if (d.max_valence > kMaxValence || d.max_k > kMaxRowBlocks) return PFG_OK;  // atomic path only
+
+    // ---- chunk size from the shared-memory budget
+    int budget = env_int("PFG_CHUNK_SMEM_BYTES", (d.m == 3) ? 160 * 1024 : 72 * 1024);
+    int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
+    int64_t C = budget / per_node * 4 / 5;  // tie-aware cuts may overshoot the target by up to 1/4
+    C = env_int("PFG_CHUNK_NODES", (int)C);
+    C = std::max<int64_t>(4, std::min<int64_t>(C, 1024));
+
+    // ---- chunk id per owned node
+    DBuf<uint32_t> group;  // per owned node (index r = node - own_begin)
+    PFG_CUDA_TRY(group.alloc(nown));
+    PFG_CUDA_TRY(cudaMemsetAsync(group.p, 0, nown * sizeof(uint32_t), st));
+    int64_t ngroups = 1;
+    if (d.flags & PFG_CREATE_NO_REORDER) {
+        k_chunk_by_id<<<grid_for(nown), kThreads, 0, st>>>(nown, C, group.p);
+        ngroups = (nown + C - 1) / C;
+    } else {
+        DBuf<uint64_t> ckeys, ckeys2;
+        DBuf<uint32_t> ord0, ord1, ord2, gsorted, gtmp, cut, flag, dense;
+        DBuf<int64_t> gstart, vstart;
+        PFG_CUDA_TRY(ckeys.alloc(nown));
+        PFG_CUDA_TRY(ckeys2.alloc(nown));
+        PFG_CUDA_TRY(ord0.alloc(nown));
+        PFG_CUDA_TRY(ord1.alloc(nown));
+        PFG_CUDA_TRY(ord2.alloc(nown));
+        PFG_CUDA_TRY(gsorted.alloc(nown));
+        PFG_CUDA_TRY(gtmp.alloc(nown));
+        PFG_CUDA_TRY(cut.alloc(nown));
+        PFG_CUDA_TRY(flag.alloc(nown));
+        PFG_CUDA_TRY(dense.alloc(nown));
+        PFG_CUDA_TRY(gstart.alloc(nown));
+        PFG_CUDA_TRY(vstart.alloc(nown));
+        double avg_group = (double)nown;
+        for (int level = 0; level < d.ndims; ++level) {
+            int remaining = d.ndims - level;
+            int64_t target;
+            if (remaining == 1) {
+                target = C;
+            } else {
+                double splits = std::ceil(std::pow(std::max(1.0, avg_group / (double)C), 1.0 / remaining) - 1e-9);
+                target = (int64_t)std::ceil(avg_group / std::max(1.0, splits));
+            }
+            target = std::max<int64_t>(1, target);
+            // order (group, coord[level], id): stable sort by coord, then stable sort by group
+            k_coord_keys<<<grid_for(nown), kThreads, 0, st>>>(d.X, d.ndims, level, d.own_begin, nown, ckeys.p, ord0.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint64_t*)ckeys.p,
+                                                    ckeys2.p, (const uint32_t*)ord0.p, ord1.p, nown, 0, 64, st));
+            k_gather_u32<<<grid_for(nown), kThreads, 0, st>>>(group.p, ord1.p, nown, gtmp.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint32_t*)gtmp.p,
+                                                    gsorted.p, (const uint32_t*)ord1.p, ord2.p, nown, 0,
+                                                    bits_for((uint64_t)ngroups), st));
+            k_mark_starts<<<grid_for(nown), kThreads, 0, st>>>(gsorted.p, ord2.p, d.X, d.ndims, level, d.own_begin,
+                                                              nown, gstart.p, vstart.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceScan::InclusiveScan(d_temp_storage, temp_storage_bytes, gstart.p, gstart.p,
+                                                   cub::Max(), nown, st));
+            PFG_CUB(scratch, st,
+                    cub::DeviceScan::InclusiveScan(d_temp_storage, temp_storage_bytes, vstart.p, vstart.p,
+                                                   cub::Max(), nown, st));
+            k_cut_flags<<<grid_for(nown), kThreads, 0, st>>>(gsorted.p, gstart.p, vstart.p, nown, target, cut.p,
+                                                            flag.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceScan::InclusiveSum(d_temp_storage, temp_storage_bytes, flag.p, dense.p, nown, st));
+            k_scatter_group<<<grid_for(nown), kThreads, 0, st>>>(ord2.p, dense.p, nown, group.p);
+            uint32_t h_ng = 0;
+            PFG_CUDA_TRY(cudaMemcpyAsync(&h_ng, dense.p + (nown - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            PFG_CUDA_TRY(cudaStreamSynchronize(st));
+            ngroups = h_ng;
+            avg_group = (double)nown / (double)ngroups;
+        }
+    }
+    d.nchunks = ngroups;
+
+    // ---- chunk-ordered node slots: stable sort of id-ordered nodes by chunk id
+    DBuf<uint32_t> ids, slot_node, slot_chunk, valence, kk, words;
+    PFG_CUDA_TRY(ids.alloc(nown));
+    PFG_CUDA_TRY(slot_node.alloc(nown));
+    PFG_CUDA_TRY(slot_chunk.alloc(nown));
+    PFG_CUDA_TRY(valence.alloc(nown + 1));
+    PFG_CUDA_TRY(kk.alloc(nown + 1));
+    PFG_CUDA_TRY(words.alloc(nown + 1));
+    k_iota_u32<<<grid_for(nown), kThreads, 0, st>>>(ids.p, nown);
+    PFG_CUB(scratch, st,
+            cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint32_t*)group.p, slot_chunk.p,
+                                            (const uint32_t*)ids.p, slot_node.p, nown, 0,
+                                            bits_for((uint64_t)d.nchunks), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(valence.p, 0, (nown + 1) * sizeof(uint32_t), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(kk.p, 0, (nown + 1) * sizeof(uint32_t), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(words.p, 0, (nown + 1) * sizeof(uint32_t), st));
+    k_slot_counts<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, d.inc_ptr, d.blk_ptr, d.own_begin, nown,
+                                                      valence.p, kk.p);
+    DBuf<int64_t> inc_excl, plan_off;
+    PFG_CUDA_TRY(inc_excl.alloc(nown + 1));
+    PFG_CUDA_TRY(plan_off.alloc(nown + 1));
+    PFG_CUB(scratch, st,
+            cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, valence.p, inc_excl.p, nown + 1, st));
+    k_plan_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, NNE, nown, words.p);
+    PFG_CUB(scratch, st,
+            cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, words.p, plan_off.p, nown + 1, st));
+
+    PFG_CUDA_TRY(cudaMalloc(&d.chunks, d.nchunks * sizeof(ChunkHdr)));
+    PFG_CUDA_TRY(cudaMemsetAsync(d.chunks, 0, d.nchunks * sizeof(ChunkHdr), st));
+    DBuf<int> maxima;
+    PFG_CUDA_TRY(maxima.alloc(4));
+    PFG_CUDA_TRY(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int), st));
+    k_chunk_node_begin<<<grid_for(nown), kThreads, 0, st>>>(slot_chunk.p, nown, d.nchunks, d.chunks);
+    k_chunk_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, inc_excl.p, kk.p, d.chunks, nown, maxima.p);
+
+    // ---- element records: unique (chunk, element) over the owned incidences
+    int64_t h_ninc_own = 0, h_plan_words = 0;
+    PFG_CUDA_TRY(cudaMemcpyAsync(&h_ninc_own, inc_excl.p + nown, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(&h_plan_words, plan_off.p + nown, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_plan_words >= (int64_t)0xffffffffll) {
+        set_error("gather plan pool exceeds 16 GiB");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    DBuf<uint64_t> ikeys, ikeys_sorted, rec_keys;
+    DBuf<int64_t> nsel;
+    PFG_CUDA_TRY(ikeys.alloc(h_ninc_own));
+    PFG_CUDA_TRY(ikeys_sorted.alloc(h_ninc_own));
+    PFG_CUDA_TRY(rec_keys.alloc(h_ninc_own));
+    PFG_CUDA_TRY(nsel.alloc(1));
+    k_inc_keys<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,
+                                                        d.own_begin, nown, ikeys.p);
+    PFG_CUB(scratch, st,
+            cub::DeviceRadixSort::SortKeys(d_temp_storage, temp_storage_bytes, (const uint64_t*)ikeys.p,
+                                           ikeys_sorted.p, h_ninc_own, 0, 32 + bits_for((uint64_t)d.nchunks), st));
+    PFG_CUB(scratch, st,
+            cub::DeviceSelect::Unique(d_temp_storage, temp_storage_bytes, ikeys_sorted.p, rec_keys.p, nsel.p,
+                                      h_ninc_own, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(&d.nrecs, nsel.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    ikeys.release();
+    ikeys_sorted.release();
+    if (d.nrecs >= (int64_t)0xffffffffll) {
+        set_error("too many element records for the gather plan");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t)));
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t)));
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_elem, d.nrecs * sizeof(int32_t)));
+    k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, d.rec_nodes, d.rec_dst,
+                                                               d.rec_elem, d.chunks, maxima.p);
+    k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
+    k_fill_dst<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,
+                                                        d.chunks, rec_keys.p, d.own_begin, nown, d.rec_dst);
+
+    // ---- per-node plans
+    d.plan_bytes = h_plan_words * 4;
+    PFG_CUDA_TRY(cudaMalloc(&d.plan_pool, std::max<int64_t>(d.plan_bytes, 4)));
+    PFG_CUDA_TRY(cudaMemsetAsync(d.plan_pool, 0, std::max<int64_t>(d.plan_bytes, 4), st));
+    PFG_CUDA_TRY(cudaMalloc(&d.cnodes, nown * sizeof(ChunkNode)));
+    PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
+    k_fill_plans<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, d.inc_ptr, d.inc_list, d.rank, d.blk_ptr,
+                                                          inc_excl.p, d.chunks, slot_chunk.p, plan_off.p, d.own_begin,
+                                                          nown, d.m, d.cnodes, d.cnode_id, d.plan_pool);
+    int h_max[4] = {0, 0, 0, 0};
+    PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    PFG_CUDA_TRY(cudaGetLastError());
+    d.max_chunk_inc = h_max[0];
+    d.max_chunk_nodes = h_max[1];
+    d.max_kpad = h_max[2];
+    d.max_chunk_recs = h_max[3];
+    if (d.max_chunk_inc > 0xFFFE) {
+        set_error("chunk with %d incidences exceeds the 16-bit slot range", d.max_chunk_inc);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    d.device_bytes += d.nchunks * sizeof(ChunkHdr) + nown * (sizeof(ChunkNode) + 4) + d.nrecs * (NNE * 6 + 4) +
+                      d.plan_bytes;
+    return PFG_OK;
+}
+
+static void free_all(MeshDev& d) {
+    void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
+                    d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool};
+    for (void* p : ptrs)
+        if (p) cudaFree(p);
+}
+
+template <int NNE>
+static int create_impl(MeshDev& d, const double* X_dev, const int64_t* conn_dev, const int64_t* gid_dev,
+                       cudaStream_t st) {
+    Scratch scratch;
+    const int64_t ninc = d.nelems * NNE;
+    PFG_CUDA_TRY(cudaMalloc(&d.X, std::max<int64_t>(d.nnodes * d.ndims, 1) * sizeof(double)));
+    PFG_CUDA_TRY(cudaMalloc(&d.conn, std::max<int64_t>(ninc, 1) * sizeof(int32_t)));
+    PFG_CUDA_TRY(cudaMemcpyAsync(d.X, X_dev, d.nnodes * d.ndims * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if (gid_dev) {
+        PFG_CUDA_TRY(cudaMalloc(&d.gid, d.nnodes * sizeof(int64_t)));
+        PFG_CUDA_TRY(cudaMemcpyAsync(d.gid, gid_dev, d.nnodes * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    }
+    d.device_bytes += d.nnodes * d.ndims * 8 + ninc * 4 + (gid_dev ? d.nnodes * 8 : 0);
+    DBuf<long long> minmax;
+    PFG_CUDA_TRY(minmax.alloc(2));
+    long long init[2] = {LLONG_MAX, LLONG_MIN};
+    PFG_CUDA_TRY(cudaMemcpyAsync(minmax.p, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    k_conn_to_i32<<<grid_for(ninc), kThreads, 0, st>>>(conn_dev, d.conn, ninc, minmax.p);
+    long long h_mm[2];
+    PFG_CUDA_TRY(cudaMemcpyAsync(h_mm, minmax.p, sizeof(h_mm), cudaMemcpyDeviceToHost, st));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    if (h_mm[0] != 0 || h_mm[1] != d.nnodes - 1) {
+        // the reference asserts exactly this (pyfem.py:680-681)
+        set_error("conn.min() == %lld, conn.max() == %lld; expected 0 and nnodes-1 == %lld", h_mm[0], h_mm[1],
+                  (long long)(d.nnodes - 1));
+        return PFG_ERR_MESH;
+    }
+    PFG_TRY(build_pattern<NNE>(d, st, scratch));
+    if (!(d.flags & PFG_CREATE_NO_GATHER_PLAN)) PFG_TRY(build_gather_plan<NNE>(d, st, scratch));
+    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+}  // namespace pfg
+
+using namespace pfg;
+
+extern "C" int pfg_abi_version(void) { return PFG_ABI_VERSION; }
+
+extern "C" const char* pfg_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" int pfg_mesh_create(pfg_mesh** out, int elem_type, int ndof_per_node, int64_t nnodes, int64_t nelems,
+                               const double* X_dev, const int64_t* conn_dev, int64_t own_begin, int64_t own_end,
+                               const int64_t* node_gid_dev, int64_t ncols_global_nodes, int flags, void* stream) {
+    if (!out) {
+        set_error("pfg_mesh_create: out is NULL");
+        return PFG_ERR_INVALID;
+    }
+    *out = nullptr;
+    if (elem_type != PFG_QUAD4 && elem_type != PFG_HEX8) {
+        set_error("unsupported element type %d (device path covers quad4 and hex8)", elem_type);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    int ndims = (elem_type == PFG_QUAD4) ? 2 : 3;
+    if (ndof_per_node != 1 && ndof_per_node != ndims) {
+        set_error("ndof_per_node must be 1 or %d for this element, got %d", ndims, ndof_per_node);
+        return PFG_ERR_INVALID;
+    }
+    if (nnodes <= 0 || nelems <= 0 || !X_dev || !conn_dev) {
+        set_error("empty mesh: nnodes=%lld nelems=%lld", (long long)nnodes, (long long)nelems);
+        return PFG_ERR_INVALID;
+    }
+    if (nnodes > 0x7fffffffll || nelems * elem_type > 0xffffffffll) {
+        set_error("mesh too large for 32-bit node / incidence ids");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    if (own_begin < 0 || own_end > nnodes || own_begin > own_end) {
+        set_error("invalid owned row range [%lld, %lld)", (long long)own_begin, (long long)own_end);
+        return PFG_ERR_INVALID;
+    }
+    pfg_mesh* mesh = new pfg_mesh();
+    MeshDev& d = mesh->d;
+    d.elem_type = elem_type;
+    d.nne = elem_type;
+    d.ndims = ndims;
+    d.nquads = elem_type;
+    d.m = ndof_per_node;
+    d.nnodes = nnodes;
+    d.nelems = nelems;
+    d.own_begin = own_begin;
+    d.own_end = own_end;
+    d.ncols_nodes = node_gid_dev ? ncols_global_nodes : nnodes;
+    d.flags = flags;
+    cudaGetDevice(&d.device);
+    cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device);
+    int rc = (elem_type == PFG_QUAD4) ? create_impl<4>(d, X_dev, conn_dev, node_gid_dev, (cudaStream_t)stream)
+                                      : create_impl<8>(d, X_dev, conn_dev, node_gid_dev, (cudaStream_t)stream);
+    if (rc != PFG_OK) {
+        free_all(d);
+        delete mesh;
+        return rc;
+    }
+    // scipy's index-width rule for coo->csr: int32 iff max(coo nnz, ncols) fits (scipy/sparse/_coo.py:59-61,419)
+    int64_t D = (int64_t)d.nne * d.m;
+    int64_t coo_nnz = d.nelems * D * D;
+    int64_t ncols = d.ncols_nodes * d.m;
+    d.idx_bytes = (std::max(coo_nnz, ncols) <= 0x7fffffffll) ? 4 : 8;
+    *out = mesh;
+    return PFG_OK;
+}
+
+extern "C" int pfg_mesh_destroy(pfg_mesh* mesh) {
+    if (!mesh) return PFG_OK;
+    free_all(mesh->d);
+    delete mesh;
+    return PFG_OK;
+}
+
+extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
+    if (!mesh || !value) {
+        set_error("pfg_mesh_get: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    const MeshDev& d = mesh->d;
+    switch (what) {
+        case PFG_INFO_NNZ: *value = d.nnz; break;
+        case PFG_INFO_NROWS: *value = (d.own_end - d.own_begin) * d.m; break;
+        case PFG_INFO_NCOLS: *value = d.ncols_nodes * d.m; break;
+        case PFG_INFO_IDX_BYTES: *value = d.idx_bytes; break;
+        case PFG_INFO_NCHUNKS: *value = d.nchunks; break;
+        case PFG_INFO_CHUNK_ELEMS: *value = d.nrecs; break;
+        case PFG_INFO_PLAN_BYTES:
+            *value = d.nchunks ? (int64_t)(d.nchunks * sizeof(ChunkHdr) + (d.own_end - d.own_begin) * sizeof(ChunkNode) +
+                                           d.nrecs * (d.nne * 6) + d.plan_bytes)
+                               : 0;
+            break;
+        case PFG_INFO_DEVICE_BYTES: *value = d.device_bytes; break;
+        case PFG_INFO_MAX_ROW_BLOCKS: *value = d.max_k; break;
+        case PFG_INFO_MAX_VALENCE: *value = d.max_valence; break;
+        default:
+            set_error("pfg_mesh_get: unknown query %d", what);
+            return PFG_ERR_INVALID;
+    }
+    return PFG_OK;
+}
+
+extern "C" int pfg_mesh_pattern(const pfg_mesh* mesh, void* indptr_dev, void* indices_dev, int idx_bytes,
+                                void* stream) {
+    if (!mesh || !indptr_dev || !indices_dev || (idx_bytes != 4 && idx_bytes != 8)) {
+        set_error("pfg_mesh_pattern: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    const MeshDev& d = mesh->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nown = d.own_end - d.own_begin;
+    if (idx_bytes == 4 && (d.nnz > 0x7fffffffll || d.ncols_nodes * d.m > 0x7fffffffll)) {
+        set_error("pattern does not fit 32-bit indices (nnz=%lld)", (long long)d.nnz);
+        return PFG_ERR_INVALID;
+    }
+    int64_t nrows1 = nown * d.m + 1;
+    unsigned gx = 65535u * 16u;
+    int64_t nb = (d.nblocks + kThreads - 1) / kThreads;
+    dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(nb, gx)), (unsigned)std::max<int64_t>(1, (nb + gx - 1) / gx));
+    if (idx_bytes == 4) {
+        k_write_indptr<int32_t><<<grid_for(nrows1), kThreads, 0, st>>>(d.blk_ptr, nown, d.m, (int32_t*)indptr_dev);
+        if (d.nblocks) k_write_indices<int32_t><<<grid, kThreads, 0, st>>>(d.blk_ptr, d.nbr, d.gid, nown, d.m, (int32_t*)indices_dev);
+    } else {
+        k_write_indptr<int64_t><<<grid_for(nrows1), kThreads, 0, st>>>(d.blk_ptr, nown, d.m, (int64_t*)indptr_dev);
+        if (d.nblocks) k_write_indices<int64_t><<<grid, kThreads, 0, st>>>(d.blk_ptr, d.nbr, d.gid, nown, d.m, (int64_t*)indices_dev);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}

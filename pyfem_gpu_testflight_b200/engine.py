@@ -1,0 +1,240 @@
+"""DeviceMesh: the once-per-mesh device handle (pfg_mesh) with torch tensors as buffer plumbing.
+
+torch supplies device memory, the current stream and host<->device copies; all arithmetic happens in
+libpyfem_b200.so.  One DeviceMesh belongs to one GPU / rank.
+"""
+import ctypes
+from ctypes import byref, c_double, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyfem_gpu_testflight_b200 needs a CUDA device: the assembly path is "
+                           "hand-written sm_100a CUDA and has no CPU fallback")
+    return torch
+
+
+def _ptr(t):
+    return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
+
+
+class DeviceMesh:
+    """Device copies of the mesh, CSR pattern, element->slot map and gather plan (pfg_mesh_create).
+
+    X (nnodes, ndims) float64; conn (nelems, nnodes_per_elem) integer; numpy arrays or torch tensors.
+    own_range = (begin, end) node rows this handle assembles (default all); node_gid = strictly increasing
+    local->global node ids for the reported column indices (multi-GPU slabs).
+    """
+
+    def __init__(self, X, conn, ndof_per_node, device=None, own_range=None, node_gid=None, ncols_nodes=None,
+                 build_gather_plan=True, reorder=True):
+        torch = _torch()
+        self._lib = _lib.load()
+        self._handle = None
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        Xd = torch.as_tensor(X).to(device=self.device, dtype=torch.float64).contiguous()
+        cd = torch.as_tensor(conn).to(device=self.device, dtype=torch.int64).contiguous()
+        if Xd.dim() != 2 or cd.dim() != 2:
+            raise ValueError("X must be (nnodes, ndims) and conn (nelems, nnodes_per_elem)")
+        self.nnodes, self.ndims = int(Xd.shape[0]), int(Xd.shape[1])
+        self.nelems, self.nnodes_per_elem = int(cd.shape[0]), int(cd.shape[1])
+        self.ndof_per_node = int(ndof_per_node)
+        if (self.nnodes_per_elem, self.ndims) not in ((4, 2), (8, 3)):
+            raise NotImplementedError(
+                f"no device path for {self.nnodes_per_elem}-node elements in {self.ndims}-D "
+                "(quad4 and hex8 only; no CPU fallback)")
+        begin, end = (0, self.nnodes) if own_range is None else (int(own_range[0]), int(own_range[1]))
+        gid = None
+        if node_gid is not None:
+            gid = torch.as_tensor(node_gid).to(device=self.device, dtype=torch.int64).contiguous()
+            if ncols_nodes is None:
+                raise ValueError("ncols_nodes (global node count) is required with node_gid")
+        flags = (0 if build_gather_plan else _lib.CREATE_NO_GATHER_PLAN) | (0 if reorder else _lib.CREATE_NO_REORDER)
+        handle = c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_mesh_create(
+                byref(handle), self.nnodes_per_elem, self.ndof_per_node, self.nnodes, self.nelems, _ptr(Xd), _ptr(cd),
+                begin, end, _ptr(gid), int(ncols_nodes or 0), flags, self._stream()))
+        self._handle = handle
+        self.own_begin, self.own_end = begin, end
+        self.nnz = self.info(_lib.INFO_NNZ)
+        self.nrows = self.info(_lib.INFO_NROWS)
+        self.ncols = self.info(_lib.INFO_NCOLS)
+        self.idx_bytes = self.info(_lib.INFO_IDX_BYTES)
+        self.nchunks = self.info(_lib.INFO_NCHUNKS)
+        self.chunk_elems = self.info(_lib.INFO_CHUNK_ELEMS)
+        self.plan_bytes = self.info(_lib.INFO_PLAN_BYTES)
+        self._pattern = None
+        self._pattern_host = None
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def _stream(self):
+        torch = _torch()
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def info(self, what):
+        v = c_int64()
+        _lib.check(self._lib.pfg_mesh_get(self._handle, what, byref(v)))
+        return int(v.value)
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.pfg_mesh_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def index_dtype(self):
+        return np.int32 if self.idx_bytes == 4 else np.int64
+
+    def new_values(self):
+        torch = _torch()
+        return torch.empty(self.nnz, dtype=torch.float64, device=self.device)
+
+    def new_vector(self):
+        torch = _torch()
+        return torch.empty(self.nrows, dtype=torch.float64, device=self.device)
+
+    def _dev_f64(self, a, n, what):
+        torch = _torch()
+        t = torch.as_tensor(a)
+        if t.is_complex():
+            raise NotImplementedError(f"complex {what} (complex-step verification) has no device path")
+        t = t.to(device=self.device, dtype=torch.float64, non_blocking=True).contiguous()
+        if t.numel() != n:
+            raise ValueError(f"{what} must have {n} entries, got {t.numel()}")
+        return t
+
+    # ---- pattern --------------------------------------------------------------------------------
+    def pattern(self, idx_bytes=None):
+        """(indptr, indices) device tensors: K.indptr / K.indices of the reference's tocsr()."""
+        torch = _torch()
+        idx_bytes = idx_bytes or self.idx_bytes
+        if self._pattern is not None and self._pattern[0] == idx_bytes:
+            return self._pattern[1], self._pattern[2]
+        dt = torch.int32 if idx_bytes == 4 else torch.int64
+        indptr = torch.empty(self.nrows + 1, dtype=dt, device=self.device)
+        indices = torch.empty(self.nnz, dtype=dt, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_mesh_pattern(self._handle, _ptr(indptr), _ptr(indices), idx_bytes, self._stream()))
+        self._pattern = (idx_bytes, indptr, indices)
+        return indptr, indices
+
+    def pattern_host(self):
+        if self._pattern_host is None:
+            indptr, indices = self.pattern()
+            self._pattern_host = (indptr.cpu().numpy(), indices.cpu().numpy())
+        return self._pattern_host
+
+    # ---- assembly -------------------------------------------------------------------------------
+    def _rho(self, rho):
+        """nodal density tensor or (None, scalar) -- scalar rho is a constant field (pyfem.py:1015-1016)."""
+        if rho is None:
+            return None, 1.0
+        if not hasattr(rho, "__len__") and not hasattr(rho, "shape"):
+            if isinstance(rho, complex):
+                raise NotImplementedError("complex rho (complex-step verification) has no device path")
+            return None, float(rho)
+        return self._dev_f64(rho, self.nnodes, "rho"), 0.0
+
+    def assemble_poisson(self, rho=1.0, p=0.0, out=None, mode="auto"):
+        torch = _torch()
+        rho_t, rho_c = self._rho(rho)
+        out = self.new_values() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_assemble_poisson(self._handle, _ptr(rho_t), rho_c, float(p), _ptr(out),
+                                                      _lib.MODES[mode], self._stream()))
+        return out
+
+    def assemble_elasticity(self, rho=1.0, p=0.0, E=10.0, nu=0.3, out=None, mode="auto"):
+        torch = _torch()
+        rho_t, rho_c = self._rho(rho)
+        out = self.new_values() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_assemble_elasticity(self._handle, _ptr(rho_t), rho_c, float(p), float(E),
+                                                         float(nu), _ptr(out), _lib.MODES[mode], self._stream()))
+        return out
+
+    def assemble_helmholtz(self, r0, out_K=None, out_R=None, mode="auto"):
+        torch = _torch()
+        out_K = self.new_values() if out_K is None else out_K
+        out_R = self.new_values() if out_R is None else out_R
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_assemble_helmholtz(self._handle, float(r0), _ptr(out_K), _ptr(out_R),
+                                                        _lib.MODES[mode], self._stream()))
+        return out_K, out_R
+
+    def assemble_nlpoisson(self, xdv, u, want_K=True, want_res=True, out_K=None, out_res=None, mode="auto"):
+        torch = _torch()
+        xdv = np.ascontiguousarray(np.asarray(xdv, dtype=np.float64).reshape(-1))
+        u_t = self._dev_f64(u, self.nnodes, "u")
+        if want_K and out_K is None:
+            out_K = self.new_values()
+        if want_res and out_res is None:
+            out_res = self.new_vector()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_assemble_nlpoisson(
+                self._handle, xdv.ctypes.data_as(ctypes.POINTER(c_double)), int(xdv.size), _ptr(u_t),
+                _ptr(out_K if want_K else None), _ptr(out_res if want_res else None), _lib.MODES[mode],
+                self._stream()))
+        return (out_K if want_K else None), (out_res if want_res else None)
+
+    def quad_points(self):
+        """Physical coordinates of the quadrature points, (nelems, nquads, ndims) on the device."""
+        torch = _torch()
+        Xq = torch.empty((self.nelems, self.nnodes_per_elem, self.ndims), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_quad_points(self._handle, _ptr(Xq), self._stream()))
+        return Xq
+
+    def poisson_rhs(self, gq, out=None, mode="auto"):
+        torch = _torch()
+        gq = self._dev_f64(gq, self.nelems * self.nnodes_per_elem, "g at the quadrature points")
+        out = self.new_vector() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_poisson_rhs(self._handle, _ptr(gq), _ptr(out), _lib.MODES[mode], self._stream()))
+        return out
+
+    def apply_dirichlet(self, vals, rhs, dof_fixed, dof_fixed_vals=None, enforce_symmetric=True):
+        """Device-side ModelBase.apply_dirichlet_bcs with the pattern kept (explicit zeros stay)."""
+        torch = _torch()
+        fixed = torch.as_tensor(np.asarray(dof_fixed, dtype=np.int64)).to(self.device)
+        fv = None
+        if dof_fixed_vals is not None:
+            fv = self._dev_f64(dof_fixed_vals, fixed.numel(), "dof_fixed_vals")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_apply_dirichlet(self._handle, _ptr(fixed), _ptr(fv), int(fixed.numel()),
+                                                     1 if enforce_symmetric else 0, _ptr(vals), _ptr(rhs),
+                                                     self._stream()))
+        return vals, rhs
+
+    def spmv(self, vals, x, out=None):
+        torch = _torch()
+        x = self._dev_f64(x, self.ncols, "x")
+        out = self.new_vector() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_spmv(self._handle, _ptr(vals), _ptr(x), _ptr(out), self._stream()))
+        return out
+
+    # ---- host views -------------------------------------------------------------------------------
+    def to_scipy(self, vals, copy_pattern=True):
+        """scipy.sparse.csr_matrix on the host from device values (one D2H copy of nnz doubles)."""
+        from scipy import sparse
+        indptr, indices = self.pattern_host()
+        data = vals.cpu().numpy()
+        if copy_pattern:
+            indptr, indices = indptr.copy(), indices.copy()
+        K = sparse.csr_matrix((data, indices, indptr), shape=(self.nrows, self.ncols), copy=False)
+        K.has_sorted_indices = True
+        K.has_canonical_format = True
+        return K

@@ -1,0 +1,263 @@
+"""Physics models with the reference's constructor / method surface (pyfem.py:634-2177), assembling on
+the GPU.  `compute_jacobian` returns the same scipy CSR matrix (pattern bit-exact, values to 1e-12 of
+max|K|) and `compute_rhs` the same persistent rhs vector as the reference; `*_device` variants keep the
+result in HBM for GPU consumers.
+
+What stays on the host is glue the reference also does in Python: argument casting, the persistent
+`rhs` array, point loads, Dirichlet conditions on a host CSR.  There is no CPU assembly path: element
+families / dtypes without a kernel raise NotImplementedError.
+"""
+import numpy as np
+from scipy import sparse
+
+from .engine import DeviceMesh, _torch
+from .fem import BasisBase, QuadratureBase
+
+
+class ModelBase:
+    """Mesh arrays, dof maps, device handle and the scatter (pyfem.py:634-931)."""
+
+    def __init__(self, ndof_per_node, X, conn, dof_fixed, dof_fixed_vals, quadrature: QuadratureBase,
+                 basis: BasisBase, device=None, scatter="auto"):
+        self.ndof_per_node = int(ndof_per_node)
+        self.X = np.array(X, dtype=float)
+        self.conn = np.array(conn, dtype=int)
+        self.dof_fixed = np.array(dof_fixed, dtype=int)
+        self.dof_fixed_vals = None if dof_fixed_vals is None else np.array(dof_fixed_vals, dtype=float)
+        self.quadrature = quadrature
+        self.basis = basis
+        self.scatter = scatter
+
+        self.nelems, self.nnodes_per_elem = self.conn.shape
+        self.nnodes, self.ndims = self.X.shape
+        self.nquads = quadrature.get_nquads()
+        if getattr(quadrature, "device_elem", None) != self.nnodes_per_elem or \
+                getattr(basis, "device_elem", None) != self.nnodes_per_elem:
+            raise NotImplementedError("quadrature / basis / connectivity combination has no device path "
+                                      "(bilinear quad4 and trilinear hex8 with their 2-point Gauss rules only)")
+        self.nodes = np.arange(self.nnodes)
+        self.ndof = self.nnodes * self.ndof_per_node
+
+        # device: H2D of X / conn, the conn.min()/max() asserts of pyfem.py:680-681, CSR pattern, plans
+        self.mesh = DeviceMesh(self.X, self.conn, self.ndof_per_node, device=device)
+
+        # persistent right-hand side (pyfem.py:756; survey trap T7)
+        self.rhs = np.zeros(self.ndof)
+        self._dof = self._dof_each_node = self._conn_dof = self._dof_free = None
+
+    # ---- dof maps (utils.create_dof, utils.py:267-298), built on first use ---------------------------
+    def _make_dof(self):
+        m = self.ndof_per_node
+        if m == 1:
+            self._dof, self._dof_each_node, self._conn_dof = self.nodes, self.nodes, self.conn
+        else:
+            self._dof = np.arange(self.ndof)
+            self._dof_each_node = self._dof.reshape(self.nnodes, m)
+            self._conn_dof = (m * self.conn[:, :, None] + np.arange(m)[None, None, :]).reshape(self.nelems, -1)
+
+    @property
+    def dof(self):
+        if self._dof is None:
+            self._make_dof()
+        return self._dof
+
+    @property
+    def dof_each_node(self):
+        if self._dof_each_node is None:
+            self._make_dof()
+        return self._dof_each_node
+
+    @property
+    def conn_dof(self):
+        if self._conn_dof is None:
+            self._make_dof()
+        return self._conn_dof
+
+    @property
+    def dof_free(self):
+        if self._dof_free is None:
+            mask = np.ones(self.ndof, dtype=bool)
+            mask[self.dof_fixed] = False
+            self._dof_free = np.nonzero(mask)[0]  # == np.setdiff1d(dof, dof_fixed), pyfem.py:699
+        return self._dof_free
+
+    # ---- abstract interface --------------------------------------------------------------------------
+    def compute_rhs(self):
+        return self.rhs
+
+    def compute_jacobian(self):
+        raise NotImplementedError
+
+    # ---- helpers -------------------------------------------------------------------------------------
+    def _to_scipy(self, vals):
+        return self.mesh.to_scipy(vals)
+
+    def _vec_to_host(self, vec, out):
+        out[:] = vec.cpu().numpy()
+        return out
+
+    def apply_dirichlet_bcs(self, K, rhs, enforce_symmetric_K=True):
+        """Host-side Dirichlet conditions with the reference's semantics (pyfem.py:780-835): rows (and, if
+        asked, columns) of fixed dofs zeroed, unit diagonal, explicit zeros eliminated, rhs updated.
+        K and rhs are edited in place (Assembler.solve_nonlinear relies on that, pyfem.py:2343) and returned.
+        """
+        fixed = self.dof_fixed
+        is_fixed = np.zeros(K.shape[0], dtype=bool)
+        is_fixed[fixed] = True
+        Krb_u0 = None
+        if self.dof_fixed_vals is not None and enforce_symmetric_K:
+            u0 = np.zeros(K.shape[1])
+            u0[fixed] = self.dof_fixed_vals
+            Krb_u0 = (K @ u0)[self.dof_free] - 0.0  # only fixed columns carry non-zero u0
+        diag = K.diagonal()
+        row_of = np.repeat(np.arange(K.shape[0]), np.diff(K.indptr))
+        K.data[is_fixed[row_of]] = 0.0
+        if enforce_symmetric_K:
+            K.data[is_fixed[K.indices]] = 0.0
+        diag[fixed] = 1.0
+        K.setdiag(diag)
+        K.eliminate_zeros()
+        if self.dof_fixed_vals is None:
+            rhs[fixed] = 0.0
+        else:
+            rhs[fixed] = self.dof_fixed_vals[:]
+            if enforce_symmetric_K:
+                rhs[self.dof_free] -= Krb_u0
+        return K, rhs
+
+
+def _check_real(rho):
+    if np.iscomplexobj(rho):
+        raise NotImplementedError("complex rho (complex-step verification, pyfem.py:1019-1020) has no device "
+                                  "path and this engine has no CPU fallback")
+
+
+class LinearPoisson(ModelBase):
+    """-k lap(u) = g with RAMP-penalised conductivity (pyfem.py:934-1329)."""
+
+    def __init__(self, X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, gfunc, kappa0=1.0, p=0.0, **kw):
+        super().__init__(1, X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, **kw)
+        self.gfunc = gfunc
+        self.kappa0 = kappa0  # stored and, as in the reference, never used (pyfem.py:977; survey trap T5)
+        self.p = p
+
+    def compute_jacobian_device(self, rho=1.0, out=None):
+        _check_real(rho)
+        return self.mesh.assemble_poisson(rho, self.p, out=out, mode=self.scatter)
+
+    def compute_jacobian(self, rho=1.0):
+        return self._to_scipy(self.compute_jacobian_device(rho))
+
+    def _source_at_quads(self):
+        """g(x_q): the user callable runs on a CUDA tensor of quadrature coordinates; callables that need
+        numpy get a host array (the callable is user code, not part of the assembly path)."""
+        torch = _torch()
+        Xq = self.mesh.quad_points()
+        try:
+            g = self.gfunc(Xq)
+        except (TypeError, RuntimeError, AttributeError):
+            g = self.gfunc(Xq.cpu().numpy())
+        g = torch.as_tensor(g, dtype=torch.float64, device=self.mesh.device)
+        return g.expand(Xq.shape[:-1]).contiguous() if g.dim() == 0 or g.shape != Xq.shape[:-1] else g.contiguous()
+
+    def compute_rhs_device(self, out=None):
+        return self.mesh.poisson_rhs(self._source_at_quads(), out=out, mode=self.scatter)
+
+    def compute_rhs(self):
+        return self._vec_to_host(self.compute_rhs_device(), self.rhs)
+
+
+class NonlinearPoisson2D(ModelBase):
+    """-div(h(x)(1+u^2) grad u) = g on quad4 meshes (pyfem.py:1332-1664)."""
+
+    def __init__(self, X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, **kw):
+        super().__init__(1, X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, **kw)
+        if self.nnodes_per_elem != 4:
+            raise NotImplementedError("NonlinearPoisson2D is a quad4 model")
+
+    def assemble_device(self, xdv, u, want_K=True, want_res=True):
+        """Jacobian values and residual from ONE pass over the elements (device tensors)."""
+        return self.mesh.assemble_nlpoisson(xdv, u, want_K=want_K, want_res=want_res, mode=self.scatter)
+
+    def compute_jacobian(self, xdv, u):
+        K, _ = self.assemble_device(xdv, u, want_K=True, want_res=False)
+        return self._to_scipy(K)
+
+    def compute_rhs(self, xdv, u):
+        """The residual, as in the reference (pyfem.py:1375-1388)."""
+        _, res = self.assemble_device(xdv, u, want_K=False, want_res=True)
+        return self._vec_to_host(res, self.rhs)
+
+
+class LinearElasticity(ModelBase):
+    """Linear elasticity, plane stress in 2-D (pyfem.py:1667-2068)."""
+
+    def __init__(self, X, conn, dof_fixed, dof_fixed_vals, nodal_force, quadrature, basis, E=10.0, nu=0.3, p=0.0,
+                 **kw):
+        super().__init__(np.asarray(X).shape[1], X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, **kw)
+        self.nodal_force = nodal_force
+        self.E, self.nu, self.p = E, nu, p
+        if self.ndims == 2:  # pyfem.py:1746-1750
+            self.C0 = E / (1.0 - nu ** 2) * np.array([[1.0, nu, 0.0], [nu, 1.0, 0.0], [0.0, 0.0, 0.5 * (1.0 - nu)]])
+        else:  # pyfem.py:1752-1757
+            self.C0 = np.zeros((6, 6))
+            self.C0[:3, :3] = nu
+            self.C0[np.arange(3), np.arange(3)] = 1.0 - nu
+            self.C0[np.arange(3, 6), np.arange(3, 6)] = 0.5 - nu
+            self.C0 *= E / ((1.0 + nu) * (1.0 - 2.0 * nu))
+
+    def compute_rhs(self):
+        """Point loads assigned (not added) into the persistent rhs (pyfem.py:1760-1768)."""
+        nodes = np.array(list(self.nodal_force.keys()), dtype=int)
+        self.rhs[self.dof_each_node[nodes].flatten()] = np.array(list(self.nodal_force.values())).flatten()
+        return self.rhs
+
+    def compute_jacobian_device(self, rho=1.0, out=None):
+        _check_real(rho)
+        return self.mesh.assemble_elasticity(rho, self.p, self.E, self.nu, out=out, mode=self.scatter)
+
+    def compute_jacobian(self, rho=1.0):
+        return self._to_scipy(self.compute_jacobian_device(rho))
+
+
+class Helmholtz(ModelBase):
+    """Helmholtz filter -r^2 lap(rho) + rho = x (pyfem.py:2071-2177): K and R assembled once per mesh."""
+
+    def __init__(self, r0, X, conn, quadrature, basis, **kw):
+        super().__init__(1, X, conn, [], None, quadrature, basis, **kw)
+        self.r0 = r0
+        self.K_device, self.R_device = self.mesh.assemble_helmholtz(r0, mode=self.scatter)
+        self.R = self._to_scipy(self.R_device)
+        self.RT = self.R.transpose()
+        self.K = self._to_scipy(self.K_device)
+        self._Ksolve = None
+
+    @property
+    def Ksolve(self):
+        # The reference builds a pyamg Ruge-Stuben hierarchy here (pyfem.py:2098); the solver is outside
+        # the assembly path, so a sparse factorisation with the same .solve(b, tol) call stands in.
+        if self._Ksolve is None:
+            from scipy.sparse.linalg import splu
+            lu = splu(self.K.tocsc())
+
+            class _Solve:
+                def solve(self, b, tol=1e-8):
+                    return lu.solve(np.asarray(b, dtype=float))
+            self._Ksolve = _Solve()
+        return self._Ksolve
+
+    def apply(self, x):
+        return self.Ksolve.solve(self.compute_rhs(x), tol=1e-8)
+
+    def apply_gradient(self, gradrho):
+        return self.RT.dot(self.Ksolve.solve(gradrho, tol=1e-8))
+
+    def compute_rhs(self, x):
+        self.rhs[:] = self.R.dot(x)
+        return self.rhs
+
+    def compute_rhs_device(self, x, out=None):
+        return self.mesh.spmv(self.R_device, x, out=out)
+
+    def compute_jacobian(self):
+        return self.K
