@@ -485,8 +485,12 @@ struct PoissonRhsOp {  // LinearPoisson._compute_element_rhs (pyfem.py:1137-1173
             double det, G[NNE][DIM];
             geo.template at<Q>(xe, det, G);
             const double wg = det * __ldg(g + Q);
+            // The reference's einsum "ik,k,jk,ik->ij" (pyfem.py:1132-1134) indexes the (nquads, nnodes) table
+            // N as N[j,k] with j the OUTPUT (node) index and k the quadrature index, i.e. it uses
+            // N(quad=j, node=k).  For quad4 the table is symmetric; for hex8 (quadrature order differs from
+            // node order) it is not, and parity means reproducing the reference, so the indices are swapped.
 #pragma unroll
-            for (int a = 0; a < NNE; ++a) f[a] = fma(wg, Elem<NNE>::N(Q, a), f[a]);
+            for (int a = 0; a < NNE; ++a) f[a] = fma(wg, Elem<NNE>::N(a, Q), f[a]);
         });
 #pragma unroll
         for (int a = 0; a < NNE; ++a) sink.vec(a, f[a]);
