@@ -175,10 +175,71 @@ __global__ void __launch_bounds__(128) k_elasticity_hex8_atomic(MeshView mv, Ela
 // ---------------------------------------------------------------------------------------------
 // gather kernels
 // ---------------------------------------------------------------------------------------------
+// TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP) bring the chunk's node table and plan bytes into
+// shared memory while phase A integrates; completion is tracked by one mbarrier.
+PFG_DEV uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+PFG_DEV void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+PFG_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+PFG_DEV void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+PFG_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// shared-memory carve-up of a gather CTA: [mbarrier | chunk node table | chunk plan bytes | row blocks | vectors]
+struct GatherSmem {
+    uint64_t* bar;
+    const ChunkNode* nodes;
+    const uint8_t* plan;  // byte address of the chunk's first plan word
+    double* rb;
+    PFG_DEV GatherSmem(unsigned char* base, const MeshView& mv, const ChunkHdr& h) {
+        bar = reinterpret_cast<uint64_t*>(base);
+        unsigned char* nodes_s = base + 16;
+        unsigned char* plan_s = nodes_s + mv.stage_nodes_bytes;
+        rb = reinterpret_cast<double*>(plan_s + mv.stage_plan_bytes);
+        const size_t plan_lo = (size_t)h.plan_begin * 4;
+        const size_t plan_lo16 = plan_lo & ~(size_t)15;
+        nodes = reinterpret_cast<const ChunkNode*>(nodes_s);
+        plan = plan_s + (plan_lo - plan_lo16);
+        if (threadIdx.x == 0) {
+            const size_t plan_hi16 = ((size_t)(h.plan_begin + h.plan_words) * 4 + 15) & ~(size_t)15;
+            const uint32_t nbytes = h.n_nodes * (uint32_t)sizeof(ChunkNode);
+            const uint32_t pbytes = (uint32_t)(plan_hi16 - plan_lo16);
+            mbar_init(bar, 1);
+            mbar_expect_tx(bar, nbytes + pbytes);
+            tma_load_1d(nodes_s, mv.cnodes + h.node_begin, nbytes, bar);
+            if (pbytes) tma_load_1d(plan_s, mv.plan_pool + plan_lo16, pbytes, bar);
+        }
+    }
+    // call after the __syncthreads that ends phase A (so every thread sees the initialised barrier)
+    PFG_DEV void wait_metadata() const { mbar_wait(bar, 0); }
+};
 // phase B: sum plan-ordered contributions of every (chunk node, neighbour) block and store it
 template <class Op>
-PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const double* __restrict__ rb,
+PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const GatherSmem& sm,
                             const double* __restrict__ vecs, const Outputs& out) {
+    const double* __restrict__ rb = sm.rb;
     constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, NMAT = Op::NMAT, RB = Layout<Op>::RB;
     if constexpr (NMAT > 0) {
         const int kpad = (int)h.kpad;
@@ -186,9 +247,9 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const double*
         for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
             const int p = idx / kpad;
             const int t = idx - p * kpad;
-            const ChunkNode cn = mv.cnodes[h.node_begin + p];
+            const ChunkNode cn = sm.nodes[p];
             if (t >= cn.k) continue;
-            const uint8_t* rec = mv.plan_pool + (size_t)cn.plan * 4;
+            const uint8_t* rec = sm.plan + (size_t)(cn.plan - h.plan_begin) * 4;
             const int s0 = rec[t], s1 = rec[t + 1];
             const uint8_t* src = rec + cn.k + 1;
             double acc[NMAT][BLK];
@@ -231,7 +292,7 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const double*
     if constexpr (Op::NVEC > 0) {
         if (out.vec != nullptr) {
             for (int p = threadIdx.x; p < (int)h.n_nodes; p += blockDim.x) {
-                const ChunkNode cn = mv.cnodes[h.node_begin + p];
+                const ChunkNode cn = sm.nodes[p];
                 double s = 0.0;
                 for (int j = 0; j < cn.valence; ++j) s += vecs[(int)cn.inc_base + j];
                 out.vec[mv.cnode_id[h.node_begin + p] - mv.own_begin] = s;
@@ -242,11 +303,12 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const double*
 
 template <class Op, int THREADS>
 __global__ void __launch_bounds__(THREADS) k_assemble_gather(MeshView mv, typename Op::Params prm, Outputs out) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int NNE = Op::NNE;
     const ChunkHdr h = mv.chunks[blockIdx.x];
-    double* rb = smem;
-    double* vecs = smem + (size_t)h.n_inc * Layout<Op>::RB;
+    const GatherSmem sm(smem_raw, mv, h);
+    double* rb = sm.rb;
+    double* vecs = rb + (size_t)h.n_inc * Layout<Op>::RB;
     // ---- phase A: one thread per element record
     for (int r = threadIdx.x; r < (int)h.n_recs; r += THREADS) {
         const int64_t rr = h.rec_begin + r;
@@ -273,18 +335,20 @@ __global__ void __launch_bounds__(THREADS) k_assemble_gather(MeshView mv, typena
         Op::run(mv, prm, nodes, elem, sink);
     }
     __syncthreads();
-    gather_phase_b<Op>(mv, h, rb, vecs, out);
+    sm.wait_metadata();
+    gather_phase_b<Op>(mv, h, sm, vecs, out);
 }
 
 struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv, ElasticityHex8Params prm, Outputs out) {
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     using L = Layout<ElasticityHex8GatherOp>;
     const ChunkHdr h = mv.chunks[blockIdx.x];
-    double* stage = smem;  // [THREADS/8][kHexStageDoubles]
-    double* rb = smem + (THREADS / 8) * kHexStageDoubles;
+    const GatherSmem sm(smem_raw, mv, h);
+    double* rb = sm.rb;
+    double* stage = rb + (size_t)h.n_inc * L::RB;  // [THREADS/8][kHexStageDoubles]
     const int lane8 = threadIdx.x & 7;
     const unsigned octet_mask = 0xffu << ((threadIdx.x & 31) & ~7);
     for (int r = threadIdx.x >> 3; r < (int)h.n_recs; r += THREADS / 8) {
@@ -300,7 +364,8 @@ __global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv,
                               my_dst != kNoDst, sink);
     }
     __syncthreads();
-    gather_phase_b<ElasticityHex8GatherOp>(mv, h, rb, nullptr, out);
+    sm.wait_metadata();
+    gather_phase_b<ElasticityHex8GatherOp>(mv, h, sm, nullptr, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -411,6 +476,8 @@ static MeshView view_of(const MeshDev& d) {
     mv.rec_dst = d.rec_dst;
     mv.rec_elem = d.rec_elem;
     mv.plan_pool = d.plan_pool;
+    mv.stage_nodes_bytes = d.max_chunk_nodes * (int)sizeof(ChunkNode);
+    mv.stage_plan_bytes = ((d.max_chunk_plan_words * 4 + 15) / 16) * 16 + 32;
     return mv;
 }
 
@@ -443,7 +510,8 @@ static int launch(const MeshDev& d, const typename Op::Params& prm, const Output
         const unsigned grid = (unsigned)((d.nelems + 127) / 128);
         k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
-        const size_t smem = (size_t)d.max_chunk_inc * (Layout<Op>::RB + Layout<Op>::VEC) * sizeof(double);
+        const size_t smem = 16 + mv.stage_nodes_bytes + mv.stage_plan_bytes +
+                            (size_t)d.max_chunk_inc * (Layout<Op>::RB + Layout<Op>::VEC) * sizeof(double);
         if (smem > 227 * 1024) {
             set_error("chunk staging of %zu bytes exceeds shared memory", smem);
             return PFG_ERR_UNSUPPORTED;
@@ -540,7 +608,8 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         k_elasticity_hex8_atomic<<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
         constexpr int THREADS = 128;
-        const size_t smem = ((size_t)(THREADS / 8) * kHexStageDoubles +
+        const size_t smem = 16 + mv.stage_nodes_bytes + mv.stage_plan_bytes +
+                            ((size_t)(THREADS / 8) * kHexStageDoubles +
                              (size_t)d.max_chunk_inc * Layout<ElasticityHex8GatherOp>::RB) * sizeof(double);
         if (smem > 227 * 1024) {
             set_error("chunk staging of %zu bytes exceeds shared memory", smem);

@@ -79,6 +79,8 @@ struct MeshView {
     const uint16_t* rec_dst;
     const int32_t* rec_elem;
     const uint8_t* plan_pool;
+    // shared-memory staging sizes (bytes) for the gather kernels: chunk node table, chunk plan
+    int stage_nodes_bytes, stage_plan_bytes;
 };
 
 template <int NNE>

@@ -39,14 +39,16 @@ void set_error(const char* fmt, ...);
 //   phase B  one thread per (chunk node, neighbour node) block sums the <= valence contributions
 //            listed in the node's plan in a fixed order and stores the m x m block to CSR.
 // ---------------------------------------------------------------------------------------------
-struct ChunkHdr {        // 32 bytes
+struct __align__(16) ChunkHdr {  // 48 bytes
     uint32_t node_begin; // first chunk-ordered node slot
     uint32_t n_nodes;
-    int64_t rec_begin;   // first element record
     uint32_t n_recs;
     uint32_t n_inc;      // incidences = sum of valence over chunk nodes
+    int64_t rec_begin;   // first element record
+    uint32_t plan_begin; // first plan word (4-byte units) of the chunk's nodes in the plan pool
+    uint32_t plan_words; // plan words of the whole chunk (contiguous)
     uint32_t kpad;       // max neighbour count over chunk nodes
-    uint32_t pad_;
+    uint32_t pad_[3];
 };
 
 struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
@@ -96,7 +98,7 @@ struct MeshDev {
     uint16_t* rec_dst = nullptr;  // (nrecs, nne)
     int32_t* rec_elem = nullptr;  // (nrecs)
     uint8_t* plan_pool = nullptr;
-    int max_chunk_inc = 0, max_chunk_nodes = 0, max_chunk_recs = 0, max_kpad = 0;
+    int max_chunk_inc = 0, max_chunk_nodes = 0, max_chunk_recs = 0, max_kpad = 0, max_chunk_plan_words = 0;
 
     int64_t device_bytes = 0;
     int sm_count = 148;

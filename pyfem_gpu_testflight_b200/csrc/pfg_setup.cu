@@ -321,20 +321,23 @@ __global__ void k_chunk_node_begin(const uint32_t* __restrict__ slot_chunk, int6
 }
 
 __global__ void k_chunk_finish(int64_t nchunks, const int64_t* __restrict__ inc_excl, const uint32_t* __restrict__ kk,
-                               ChunkHdr* __restrict__ chunks, int64_t nslots, int* __restrict__ maxima) {
+                               const int64_t* __restrict__ plan_off, ChunkHdr* __restrict__ chunks, int64_t nslots,
+                               int* __restrict__ maxima) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     ChunkHdr h = chunks[c];
     uint32_t end = h.n_nodes;  // holds end slot
     h.n_nodes = end - h.node_begin;
     int64_t inc0 = inc_excl[h.node_begin];
-    int64_t inc1 = (end == nslots) ? inc_excl[nslots] : inc_excl[end];
+    int64_t inc1 = inc_excl[end];
     h.n_inc = (uint32_t)(inc1 - inc0);
     uint32_t kp = 0;
     for (uint32_t p = h.node_begin; p < end; ++p) kp = max(kp, kk[p]);
     h.kpad = kp;
-    h.pad_ = 0;
+    h.plan_begin = (uint32_t)plan_off[h.node_begin];
+    h.plan_words = (uint32_t)(plan_off[end] - plan_off[h.node_begin]);
     chunks[c] = h;
+    atomicMax(&maxima[4], (int)h.plan_words);
     atomicMax(&maxima[0], (int)h.n_inc);
     atomicMax(&maxima[1], (int)h.n_nodes);
     atomicMax(&maxima[2], (int)kp);
@@ -654,10 +657,11 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     PFG_CUDA_TRY(cudaMalloc(&d.chunks, d.nchunks * sizeof(ChunkHdr)));
     PFG_CUDA_TRY(cudaMemsetAsync(d.chunks, 0, d.nchunks * sizeof(ChunkHdr), st));
     DBuf<int> maxima;
-    PFG_CUDA_TRY(maxima.alloc(4));
-    PFG_CUDA_TRY(cudaMemsetAsync(maxima.p, 0, 4 * sizeof(int), st));
+    PFG_CUDA_TRY(maxima.alloc(8));
+    PFG_CUDA_TRY(cudaMemsetAsync(maxima.p, 0, 8 * sizeof(int), st));
     k_chunk_node_begin<<<grid_for(nown), kThreads, 0, st>>>(slot_chunk.p, nown, d.nchunks, d.chunks);
-    k_chunk_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, inc_excl.p, kk.p, d.chunks, nown, maxima.p);
+    k_chunk_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, inc_excl.p, kk.p, plan_off.p, d.chunks, nown,
+                                                             maxima.p);
 
     // ---- element records: unique (chunk, element) over the owned incidences
     int64_t h_ninc_own = 0, h_plan_words = 0;
@@ -701,14 +705,15 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 
     // ---- per-node plans
     d.plan_bytes = h_plan_words * 4;
-    PFG_CUDA_TRY(cudaMalloc(&d.plan_pool, std::max<int64_t>(d.plan_bytes, 4)));
-    PFG_CUDA_TRY(cudaMemsetAsync(d.plan_pool, 0, std::max<int64_t>(d.plan_bytes, 4), st));
+    // +32 bytes: a chunk's plan is fetched with 16-byte aligned bulk copies that may over-read either end
+    PFG_CUDA_TRY(cudaMalloc(&d.plan_pool, d.plan_bytes + 32));
+    PFG_CUDA_TRY(cudaMemsetAsync(d.plan_pool, 0, d.plan_bytes + 32, st));
     PFG_CUDA_TRY(cudaMalloc(&d.cnodes, nown * sizeof(ChunkNode)));
     PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
     k_fill_plans<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, d.inc_ptr, d.inc_list, d.rank, d.blk_ptr,
                                                           inc_excl.p, d.chunks, slot_chunk.p, plan_off.p, d.own_begin,
                                                           nown, d.m, d.cnodes, d.cnode_id, d.plan_pool);
-    int h_max[4] = {0, 0, 0, 0};
+    int h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
     PFG_CUDA_TRY(cudaStreamSynchronize(st));
     PFG_CUDA_TRY(cudaGetLastError());
@@ -716,6 +721,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     d.max_chunk_nodes = h_max[1];
     d.max_kpad = h_max[2];
     d.max_chunk_recs = h_max[3];
+    d.max_chunk_plan_words = h_max[4];
     if (d.max_chunk_inc > 0xFFFE) {
         set_error("chunk with %d incidences exceeds the 16-bit slot range", d.max_chunk_inc);
         return PFG_ERR_UNSUPPORTED;
