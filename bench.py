@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py -- assembled elements/second of the FE assembly hot path (fp64 Ke + CSR scatter).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+
+One "step" = one assembly pass (element quadrature -> CSR values) over the workload's mesh with the mesh,
+pattern and gather plan already resident in HBM (built once per mesh, reported as setup_s).  Default
+workload: BASELINE.json configs[1], 2-D plane-stress elasticity on a 4096 x 4096 quad mesh (16.8 M
+elements, 604 M CSR values = 4.8 GB written per step -- far larger than the 126 MB L2, so no L2 flush
+is needed between iterations).  N > 1: one process per GPU (torchrun), weak scaling -- every rank owns a
+4096 x 4096 slab of a 4096 x (4096 N) mesh plus one ghost element layer; no data-path collective.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's numpy /
+scipy assembly (oracle/pyfem_oracle.py; the reference is pure Python, so there is nothing to compile
+into oracle/_ref) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "assembled elements/sec (fp64 Ke + CSR scatter)"
+UNIT = "elements/s"
+
+# name -> (description, physics, nodes per elem, ndof per node, default elements per side, scaling at N>1)
+WORKLOADS = {
+    "c1": ("2-D linear Poisson, quad 64x64", "poisson", 4, 1, 64, "weak"),
+    "c2": ("2-D plane-stress linear elasticity, quad 4096x4096 (16.8M elements)", "elasticity", 4, 2, 4096, "weak"),
+    "c3": ("Helmholtz filter K and R, quad 4096x2048 (8.4M elements)", "helmholtz", 4, 1, 4096, "weak"),
+    "c4": ("nonlinear Poisson Jacobian + residual, quad 4096x4096 (16.8M elements)", "nlpoisson", 4, 1, 4096, "weak"),
+    "c5": ("3-D hex8 linear elasticity, 256^3 elements partitioned across the ranks", "elasticity", 8, 3, 256, "strong"),
+}
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(nelems, nnodes, nne, ndims, nnz, n_value_arrays=1, nodal_fields=0, rhs_rows=0):
+    """conn as int32 + coordinates + nodal fields + CSR values written once (+ rhs)."""
+    return nelems * nne * 4 + nnodes * ndims * 8 + nodal_fields * nnodes * 8 + n_value_arrays * nnz * 8 + rhs_rows * 8
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.proc = None
+        self.path = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.gpu_index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 10:
+                    continue
+                try:
+                    sm.append(float(parts[2]))
+                    smax.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                     parts[6:10]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(smax), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# ---------------------------------------------------------------------------------------------------
+def oracle_step(physics, nne, n_side):
+    """One CPU assembly of an n_side^d-element sample of the workload; returns (nelems, seconds, cpu_seconds)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyfem_oracle as orc
+    if nne == 4:
+        X, conn = orc.structured_mesh(n_side + 1, n_side + 1)
+    else:
+        X, conn = orc.structured_mesh(n_side + 1, n_side + 1, n_side + 1)
+    t0, c0 = time.perf_counter(), time.process_time()
+    if physics == "elasticity":
+        orc.assemble_elasticity(X, conn)
+    elif physics == "poisson":
+        orc.assemble_poisson(X, conn)
+    elif physics == "helmholtz":
+        orc.assemble_helmholtz(X, conn, 0.05)
+    else:
+        u = np.random.default_rng(0).random(X.shape[0])
+        orc.assemble_nlpoisson(X, conn, np.ones(10) / 10.0, u)
+    return conn.shape[0], time.perf_counter() - t0, time.process_time() - c0
+
+
+def cpu_sample_side(physics, nne, budget_s):
+    """Elements per side of the CPU sample so that one step takes about budget_s seconds."""
+    rate = {"elasticity": 8e4 if nne == 4 else 8e3, "poisson": 1.2e5, "helmholtz": 1e5, "nlpoisson": 3.5e4}[physics]
+    nel = max(64.0, rate * budget_s)
+    if nne == 4:
+        return int(max(32, min(1024, round(nel ** 0.5))))
+    return int(max(8, min(64, round(nel ** (1.0 / 3.0)))))
+
+
+def run_reference(args, desc, physics, nne):
+    budget = max(0.5, min(15.0, 150.0 / max(1, args.steps + args.warmup)))
+    side = cpu_sample_side(physics, nne, budget)
+    for _ in range(args.warmup):
+        oracle_step(physics, nne, side)
+    nel = wall = cpu = 0.0
+    for _ in range(args.steps):
+        n, w, c = oracle_step(physics, nne, side)
+        nel += n
+        wall += w
+        cpu += c
+    value = nel / wall
+    sample = (f"{side}^{2 if nne == 4 else 3} elements of the same structured mesh per step "
+              f"(numpy {np.__version__} einsum + scipy coo->csr, as the reference)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "host_cores_available": os.cpu_count()},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": round(cpu / wall, 2), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# device arm
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="elements per side (default: the workload's named size)")
+    ap.add_argument("--mode", default="auto", choices=["auto", "gather", "atomic"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    desc, physics, nne, m, n_default, scaling = WORKLOADS[args.workload]
+    n_side = args.n or n_default
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank == 0:
+            run_reference(args, desc, physics, nne)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import pyfem_gpu_testflight_b200 as pf
+    from pyfem_gpu_testflight_b200.partition import structured_slab
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- mesh: this rank's slab (+ ghost layer) of the ProblemCreator mesh
+    t_setup = time.perf_counter()
+    if nne == 4:
+        nx = n_side + 1
+        ny_el = (n_side // 2 if args.workload == "c3" else n_side) * (world if scaling == "weak" else 1)
+        part = structured_slab(nx, ny_el + 1, None, rank, world)
+        ndims = 2
+    else:
+        nz_el = n_side * (world if scaling == "weak" else 1)
+        part = structured_slab(n_side + 1, n_side + 1, nz_el + 1, rank, world)
+        ndims = 3
+    mesh = pf.DeviceMesh(part.X, part.conn, m, device=dev, own_range=part.own_range, node_gid=part.node_gid,
+                         ncols_nodes=part.nnodes_global)
+    torch.cuda.synchronize()
+    setup_s = time.perf_counter() - t_setup
+    own_nodes = part.own_range[1] - part.own_range[0]
+    # elements this rank is responsible for (its block, without the ghost layer)
+    total_elems_global = (n_side * (ny_el if nne == 4 else n_side * nz_el))
+    my_elems = total_elems_global // world  # slabs are balanced to within one element layer
+
+    vals = mesh.new_values()
+    vals2 = mesh.new_values() if physics == "helmholtz" else None
+    res = mesh.new_vector() if physics == "nlpoisson" else None
+    u = torch.rand(mesh.nnodes, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(0)) \
+        if physics == "nlpoisson" else None
+    xdv = np.ones(10) / 10.0
+
+    def step(rho=1.0, p=0.0):
+        if physics == "elasticity":
+            mesh.assemble_elasticity(rho, p, out=vals, mode=args.mode)
+        elif physics == "poisson":
+            mesh.assemble_poisson(rho, p, out=vals, mode=args.mode)
+        elif physics == "helmholtz":
+            mesh.assemble_helmholtz(0.05, out_K=vals, out_R=vals2, mode=args.mode)
+        else:
+            mesh.assemble_nlpoisson(xdv, u, out_K=vals, out_res=res, mode=args.mode)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    barrier()
+    # ---- timed region: K steps, CUDA events on the launching stream, one event pair per step as well
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = total_elems_global / (ms_per_step * 1e-3)
+    checksum = float(vals.sum().item())
+
+    # ---- end-to-end through the model API with HOST buffers (rank-local): H2D of the nodal field from
+    # pinned memory + assembly + D2H of the CSR values into a scipy matrix
+    e2e = None
+    h2d = d2h = 0
+    if args.e2e_steps > 0 and physics in ("elasticity", "poisson"):
+        rho_host = torch.from_numpy(0.1 + 0.9 * np.random.default_rng(0).random(mesh.nnodes)).pin_memory()
+        data_host = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory()
+        data_np = data_host.numpy()
+
+        def e2e_step():
+            # the public call path of LinearElasticity.compute_jacobian(rho): host rho in, host scipy CSR out
+            v = (mesh.assemble_elasticity if physics == "elasticity" else mesh.assemble_poisson)(
+                rho_host, 5.0, out=vals, mode=args.mode)
+            return mesh.to_scipy(v, copy_pattern=False, out=data_np)
+
+        mesh.pattern_host()  # pattern fetched once per mesh
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            K = e2e_step()
+        barrier()
+        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = total_elems_global / float(t.item())
+        h2d, d2h = mesh.nnodes * 8, mesh.nnz * 8
+        del K
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (the assembly kernel is the only kernel of a step)
+    peak, peak_src = load_peaks()
+    alg_bytes = algorithmic_bytes(part.conn.shape[0], mesh.nnodes, nne, ndims, mesh.nnz,
+                                  n_value_arrays=2 if physics == "helmholtz" else 1,
+                                  nodal_fields=1 if physics == "nlpoisson" else 0,
+                                  rhs_rows=mesh.nrows if physics == "nlpoisson" else 0)
+    kernel_ms = statistics.mean(per_launch_ms)
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(f"{args.workload}:{'gather' if mesh.nchunks else 'atomic'}")
+        except Exception:
+            traffic = None
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
+                   "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
+                   "csr_nnz_rank0": mesh.nnz, "scatter": "gather" if (args.mode != "atomic" and mesh.nchunks) else "atomic",
+                   "partition": f"row slabs x{world}, ghost-element layer, no data-path collective",
+                   "l2": "outputs (4.8 GB/step for c2) and inputs exceed the 126 MB L2; no flush needed",
+                   "rho": "constant 1.0, p=0 (device-resident headline); e2e uses a host nodal rho field, p=5",
+                   "setup_s_once_per_mesh": round(setup_s, 3), "halo_recompute_factor": round(mesh.chunk_elems / max(1, mesh.nelems), 4),
+                   "plan_bytes": mesh.plan_bytes, "checksum": checksum},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
+                     "peak_source": peak_src},
+        "clocks": clocks,
+        "gpu_launches": args.steps * 1,
+    }
+    if e2e is not None:
+        line["e2e"] = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+    if world == 1 and not args.no_cpu_baseline:
+        side = cpu_sample_side(physics, nne, 12.0)
+        n, w, c = oracle_step(physics, nne, side)
+        line["cpu_baseline"] = {"value": n / w, "unit": UNIT, "cores": round(c / w, 2), "kind": "port",
+                                "sample": f"one assembly of {side}^{2 if nne == 4 else 3} elements of the same mesh "
+                                          f"family with the numpy/scipy oracle ({w:.1f} s)"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -540,7 +540,8 @@ using namespace pfg;
     if (!(mesh)) {                                   \
         set_error("%s: mesh is NULL", __func__);     \
         return PFG_ERR_INVALID;                      \
-    }
+    }                                                \
+    PFG_CUDA_TRY(cudaSetDevice((mesh)->d.device));
 
 extern "C" int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p,
                                     double* vals_dev, int mode, void* stream) {

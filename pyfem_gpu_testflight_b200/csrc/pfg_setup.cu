@@ -822,7 +822,21 @@ extern "C" int pfg_mesh_create(pfg_mesh** out, int elem_type, int ndof_per_node,
     d.own_end = own_end;
     d.ncols_nodes = node_gid_dev ? ncols_global_nodes : nnodes;
     d.flags = flags;
-    cudaGetDevice(&d.device);
+    // the handle lives on the device that owns X_dev (one handle per GPU / rank); this library's CUDA
+    // runtime instance is separate from the caller's, so the device is selected explicitly
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, X_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        set_error("X_dev is not a device pointer");
+        delete mesh;
+        return PFG_ERR_INVALID;
+    }
+    d.device = attr.device;
+    if (cudaSetDevice(d.device) != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed", d.device);
+        delete mesh;
+        return PFG_ERR_CUDA;
+    }
     cudaDeviceGetAttribute(&d.sm_count, cudaDevAttrMultiProcessorCount, d.device);
     int rc = (elem_type == PFG_QUAD4) ? create_impl<4>(d, X_dev, conn_dev, node_gid_dev, (cudaStream_t)stream)
                                       : create_impl<8>(d, X_dev, conn_dev, node_gid_dev, (cudaStream_t)stream);
@@ -882,6 +896,7 @@ extern "C" int pfg_mesh_pattern(const pfg_mesh* mesh, void* indptr_dev, void* in
         return PFG_ERR_INVALID;
     }
     const MeshDev& d = mesh->d;
+    PFG_CUDA_TRY(cudaSetDevice(d.device));
     cudaStream_t st = (cudaStream_t)stream;
     int64_t nown = d.own_end - d.own_begin;
     if (idx_bytes == 4 && (d.nnz > 0x7fffffffll || d.ncols_nodes * d.m > 0x7fffffffll)) {

@@ -227,11 +227,18 @@ class DeviceMesh:
         return out
 
     # ---- host views -------------------------------------------------------------------------------
-    def to_scipy(self, vals, copy_pattern=True):
-        """scipy.sparse.csr_matrix on the host from device values (one D2H copy of nnz doubles)."""
+    def to_scipy(self, vals, copy_pattern=True, out=None):
+        """scipy.sparse.csr_matrix on the host from device values (one D2H copy of nnz doubles).
+
+        copy_pattern=True hands out private copies of indptr / indices, so callers may edit the matrix in
+        place (apply_dirichlet_bcs runs eliminate_zeros on it) without touching the cached pattern.
+        `out` may be a float64 host array (e.g. the numpy view of a pinned torch tensor) to receive the values.
+        """
+        torch = _torch()
         from scipy import sparse
         indptr, indices = self.pattern_host()
-        data = vals.cpu().numpy()
+        data = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        torch.from_numpy(data).copy_(vals)
         if copy_pattern:
             indptr, indices = indptr.copy(), indices.copy()
         K = sparse.csr_matrix((data, indices, indptr), shape=(self.nrows, self.ncols), copy=False)

@@ -191,3 +191,33 @@ def test_bad_inputs_raise(pf):
         pf.LinearPoisson(X, conn, [0], None, q, b, gfunc).compute_jacobian(np.ones(16, dtype=complex))
     with pytest.raises(NotImplementedError):
         pf.LinearPoisson(X, conn[:, :3], [0], None, q, b, gfunc)
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+@pytest.mark.parametrize("size", [2, 3])
+def test_row_slabs_reproduce_global_matrix(pf, three_d, size):
+    """The multi-GPU decomposition, with the ranks emulated one after another on this GPU: each rank's
+    handle owns a row slab and gets its element block + ghost layer; the concatenated slabs are the global
+    CSR (pattern bit-exact incl. global column ids, values to 1e-12)."""
+    from pyfem_gpu_testflight_b200.partition import concat_slabs, partition_mesh
+    if three_d:
+        X, conn = _hex_case(9, 8, 13, seed=4)
+    else:
+        X, conn = _quad_case(41, 57, seed=4)
+    m = X.shape[1]
+    rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+    Kg = orc.assemble_elasticity(X, conn, rho, 3.0)
+    slabs = []
+    for r in range(size):
+        part = partition_mesh(X, conn, r, size)
+        mesh = pf.DeviceMesh(part.X, part.conn, m, own_range=part.own_range, node_gid=part.node_gid,
+                             ncols_nodes=part.nnodes_global)
+        vals = mesh.assemble_elasticity(rho[part.node_gid], 3.0, mode="gather")
+        vals_a = mesh.assemble_elasticity(rho[part.node_gid], 3.0, mode="atomic")
+        assert_values_close(vals_a.cpu().numpy(), vals.cpu().numpy(), 1e-13)
+        indptr, indices = mesh.pattern_host()
+        slabs.append((indptr, indices, vals.cpu().numpy()))
+        assert mesh.ncols == Kg.shape[1]
+    K = concat_slabs(slabs, Kg.shape[1])
+    assert np.array_equal(K.indptr, Kg.indptr) and np.array_equal(K.indices, Kg.indices)
+    assert_values_close(K.data, Kg.data, VAL_TOL)

@@ -1,0 +1,86 @@
+"""The multi-rank host logic under torch.distributed (gloo, world_size 2, CPU): every rank partitions the mesh
+(element block + ghost layer, order-preserving renumbering), assembles its row slab -- here with the numpy oracle
+standing in for the GPU, since this container has none -- and the gathered slabs must reproduce the global
+CSR bit for bit; the distributed residual norm must equal the serial one."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import pyfem_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, three_d, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyfem_gpu_testflight_b200.partition import concat_slabs, global_norm, partition_mesh, structured_slab
+    dims = (6, 5, 7) if three_d else (11, 9, None)
+    X, conn = orc.structured_mesh(*dims)
+    rng = np.random.default_rng(3)
+    X = X + rng.uniform(-0.01, 0.01, size=X.shape)
+    m = X.shape[1]
+    part = partition_mesh(X, conn, rank, world)
+    slab = structured_slab(*dims, rank, world)
+    assert slab.conn.shape[1] == conn.shape[1] and slab.nnodes_global == X.shape[0]
+    # local assembly of the owned rows
+    Kl = orc.assemble_elasticity(part.X, part.conn)
+    lb, le = part.own_range
+    rows = Kl[lb * m: le * m]
+    gcols = m * part.node_gid[rows.indices // m] + rows.indices % m
+    mine = (rows.indptr.astype(np.int64), gcols.astype(np.int64), rows.data)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, mine)
+    # distributed norm of a row-distributed vector
+    v = np.arange(X.shape[0] * m, dtype=float)
+    gb, ge = part.owned_global_range
+    nrm = global_norm(torch.from_numpy(v[gb * m: ge * m]))
+    if rank == 0:
+        Kg = orc.assemble_elasticity(X, conn)
+        K = concat_slabs(gathered, Kg.shape[1])
+        ok = (np.array_equal(K.indptr, Kg.indptr) and np.array_equal(K.indices, Kg.indices)
+              and np.max(np.abs(K.data - Kg.data)) <= 1e-13 * np.max(np.abs(Kg.data))
+              and abs(nrm - np.linalg.norm(v)) <= 1e-9 * np.linalg.norm(v))
+        open(os.path.join(out_dir, "ok"), "w").write("1" if ok else "0")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_row_slab_partition_world2(tmp_path, three_d):
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, three_d, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok").read() == "1"
+
+
+def test_structured_slab_equals_general_partition():
+    from pyfem_gpu_testflight_b200.partition import partition_mesh, split_range, structured_slab
+    for dims in [(7, 9, None), (5, 4, 6)]:
+        nx, ny, nz = dims
+        X, conn = orc.structured_mesh(nx, ny, nz)
+        plane = nx if nz is None else nx * ny
+        nslow = ny if nz is None else nz
+        for size in (1, 2, 3, 4):
+            ranges = [(b * plane, e * plane) for b, e in split_range(nslow, size)]
+            for r in range(size):
+                a = structured_slab(nx, ny, nz, r, size)
+                b = partition_mesh(X, conn, r, size, ranges)
+                assert np.array_equal(a.conn, b.conn) and np.allclose(a.X, b.X)
+                assert a.own_range == b.own_range and np.array_equal(a.node_gid, b.node_gid)
+                assert np.array_equal(a.elem_gid, b.elem_gid)
