@@ -139,7 +139,10 @@ __global__ void __launch_bounds__(128) k_assemble_atomic(MeshView mv, typename O
         nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
     }
     AtomicSink<Op> sink(mv, out, nodes, e);
-    Op::run(mv, prm, nodes, e, sink);
+    double xe[NNE][Elem<NNE>::DIM], fe[NNE];
+    load_coords<NNE>(mv.X, nodes, xe);
+    load_field<NNE>(Op::field(prm), nodes, fe);
+    Op::run(prm, xe, fe, e, sink);
 }
 
 struct ElasticityHex8Tag {  // layout / sink traits of the octet kernel
@@ -237,9 +240,9 @@ struct GatherSmem {
 };
 // phase B: sum plan-ordered contributions of every (chunk node, neighbour) block and store it
 template <class Op>
-PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const GatherSmem& sm,
+PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const ChunkNode* __restrict__ cnodes_s,
+                            const uint8_t* __restrict__ plan_s, const double* __restrict__ rb,
                             const double* __restrict__ vecs, const Outputs& out) {
-    const double* __restrict__ rb = sm.rb;
     constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, NMAT = Op::NMAT, RB = Layout<Op>::RB;
     if constexpr (NMAT > 0) {
         const int kpad = (int)h.kpad;
@@ -247,9 +250,9 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const GatherS
         for (int idx = threadIdx.x; idx < items; idx += blockDim.x) {
             const int p = idx / kpad;
             const int t = idx - p * kpad;
-            const ChunkNode cn = sm.nodes[p];
+            const ChunkNode cn = cnodes_s[p];
             if (t >= cn.k) continue;
-            const uint8_t* rec = sm.plan + (size_t)(cn.plan - h.plan_begin) * 4;
+            const uint8_t* rec = plan_s + (size_t)(cn.plan - h.plan_begin) * 4;
             const int s0 = rec[t], s1 = rec[t + 1];
             const uint8_t* src = rec + cn.k + 1;
             double acc[NMAT][BLK];
@@ -292,7 +295,7 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const GatherS
     if constexpr (Op::NVEC > 0) {
         if (out.vec != nullptr) {
             for (int p = threadIdx.x; p < (int)h.n_nodes; p += blockDim.x) {
-                const ChunkNode cn = sm.nodes[p];
+                const ChunkNode cn = cnodes_s[p];
                 double s = 0.0;
                 for (int j = 0; j < cn.valence; ++j) s += vecs[(int)cn.inc_base + j];
                 out.vec[mv.cnode_id[h.node_begin + p] - mv.own_begin] = s;
@@ -301,42 +304,169 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const GatherS
     }
 }
 
-template <class Op, int THREADS>
-__global__ void __launch_bounds__(THREADS) k_assemble_gather(MeshView mv, typename Op::Params prm, Outputs out) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NNE = Op::NNE;
-    const ChunkHdr h = mv.chunks[blockIdx.x];
-    const GatherSmem sm(smem_raw, mv, h);
-    double* rb = sm.rb;
-    double* vecs = rb + (size_t)h.n_inc * Layout<Op>::RB;
-    // ---- phase A: one thread per element record
-    for (int r = threadIdx.x; r < (int)h.n_recs; r += THREADS) {
-        const int64_t rr = h.rec_begin + r;
-        int nodes[NNE];
-        SmemSink<Op> sink;
-        sink.rb = rb;
-        sink.vecs = vecs;
-        if constexpr (NNE == 4) {
-            const int4 v = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + rr);
-            nodes[0] = v.x, nodes[1] = v.y, nodes[2] = v.z, nodes[3] = v.w;
-            const uint2 d = __ldg(reinterpret_cast<const uint2*>(mv.rec_dst) + rr);
-            sink.dst[0] = d.x & 0xffff, sink.dst[1] = d.x >> 16, sink.dst[2] = d.y & 0xffff, sink.dst[3] = d.y >> 16;
-        } else {
-            const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr);
-            const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.rec_nodes) + 2 * rr + 1);
-            nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
-            nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
-            const uint4 d = __ldg(reinterpret_cast<const uint4*>(mv.rec_dst) + rr);
-            sink.dst[0] = d.x & 0xffff, sink.dst[1] = d.x >> 16, sink.dst[2] = d.y & 0xffff, sink.dst[3] = d.y >> 16;
-            sink.dst[4] = d.z & 0xffff, sink.dst[5] = d.z >> 16, sink.dst[6] = d.w & 0xffff, sink.dst[7] = d.w >> 16;
+// ---- persistent, software-pipelined gather kernel -------------------------------------------------
+// One CTA walks a contiguous range of chunks.  Per chunk i:
+//   TMA bulk copies (issued two chunks ahead) bring the chunk's header, node table, plan bytes and element
+//   records into a 3-deep shared-memory ring, each stage guarded by one mbarrier;
+//   cp.async gathers (issued one chunk ahead) stage the coordinates / nodal field of the chunk's elements;
+//   phase A integrates the elements into the row-block staging, phase B sums and stores the CSR blocks.
+// Global-memory latency is therefore paid once per CTA, not once per chunk.
+struct GatherCfg {
+    int meta_stride;                              // bytes per metadata stage
+    int off_nodes, off_plan, off_recn, off_recd;  // offsets inside a metadata stage (header at 0)
+    int x_stride, off_field;                      // bytes per coordinate stage, offset of the field values in it
+    int off_x, off_rb, off_vec;                   // offsets from the shared-memory base
+    int max_recs;                                 // records per chunk the coordinate stage is sized for
+    int nchunks;
+};
+
+PFG_DEV void cp_async_16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+PFG_DEV void cp_async_8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+PFG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+PFG_DEV void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <int NNE>
+PFG_DEV void load_rec_nodes(const int32_t* __restrict__ recn, int r, int (&nodes)[NNE]) {
+    if constexpr (NNE == 4) {
+        const int4 v = reinterpret_cast<const int4*>(recn)[r];
+        nodes[0] = v.x, nodes[1] = v.y, nodes[2] = v.z, nodes[3] = v.w;
+    } else {
+        const int4 v0 = reinterpret_cast<const int4*>(recn)[2 * r];
+        const int4 v1 = reinterpret_cast<const int4*>(recn)[2 * r + 1];
+        nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+        nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+    }
+}
+
+template <class Op, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
+    k_gather_persistent(MeshView mv, typename Op::Params prm, Outputs out, GatherCfg cfg) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM, RB = Layout<Op>::RB;
+    constexpr int STAGES = 3;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
+    const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
+    const int nloc = (int)(c_end - c_begin);
+    if (nloc <= 0) return;
+    const double* __restrict__ field = Op::field(prm);
+    double* rb = reinterpret_cast<double*>(smem + cfg.off_rb);
+    double* vecs = reinterpret_cast<double*>(smem + cfg.off_vec);
+
+    auto meta = [&](int i) -> unsigned char* { return smem + 64 + (i % STAGES) * cfg.meta_stride; };
+    auto xstage = [&](int i) -> double* { return reinterpret_cast<double*>(smem + cfg.off_x + (i & 1) * cfg.x_stride); };
+    // thread 0 only: start the bulk copies of one chunk's metadata
+    auto issue_meta = [&](int i, const ChunkHdr& h) {
+        unsigned char* m = meta(i);
+        uint64_t* bar = &bars[i % STAGES];
+        const size_t plan_lo = (size_t)h.plan_begin * 4, plan_lo16 = plan_lo & ~(size_t)15;
+        const size_t plan_hi16 = ((size_t)(h.plan_begin + h.plan_words) * 4 + 15) & ~(size_t)15;
+        const size_t recd_lo = (size_t)h.rec_begin * NNE * 2, recd_lo16 = recd_lo & ~(size_t)15;
+        const size_t recd_hi16 = (recd_lo + (size_t)h.n_recs * NNE * 2 + 15) & ~(size_t)15;
+        const uint32_t b_nodes = h.n_nodes * (uint32_t)sizeof(ChunkNode);
+        const uint32_t b_plan = (uint32_t)(plan_hi16 - plan_lo16);
+        const uint32_t b_recn = h.n_recs * NNE * 4u;
+        const uint32_t b_recd = (uint32_t)(recd_hi16 - recd_lo16);
+        mbar_expect_tx(bar, (uint32_t)sizeof(ChunkHdr) + b_nodes + b_plan + b_recn + b_recd);
+        tma_load_1d(m, mv.chunks + c_begin + i, (uint32_t)sizeof(ChunkHdr), bar);
+        tma_load_1d(m + cfg.off_nodes, mv.cnodes + h.node_begin, b_nodes, bar);
+        tma_load_1d(m + cfg.off_plan, mv.plan_pool + plan_lo16, b_plan, bar);
+        tma_load_1d(m + cfg.off_recn, mv.rec_nodes + h.rec_begin * NNE, b_recn, bar);
+        tma_load_1d(m + cfg.off_recd, reinterpret_cast<const unsigned char*>(mv.rec_dst) + recd_lo16, b_recd, bar);
+    };
+    // all threads: gather the coordinates (and nodal field) of chunk i's elements into its stage
+    auto prefetch_x = [&](int i) {
+        const unsigned char* m = meta(i);
+        const ChunkHdr* h = reinterpret_cast<const ChunkHdr*>(m);
+        const int32_t* recn = reinterpret_cast<const int32_t*>(m + cfg.off_recn);
+        double* xs = xstage(i);
+        double* fs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(xs) + cfg.off_field);
+        const int n_recs = (int)h->n_recs;
+        for (int r = threadIdx.x; r < n_recs; r += THREADS) {
+            int nodes[NNE];
+            load_rec_nodes<NNE>(recn, r, nodes);
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) {
+                double* dst = xs + ((size_t)a * cfg.max_recs + r) * DIM;  // [a][r][DIM]: conflict-free reads
+                if constexpr (DIM == 2) {
+                    cp_async_16(dst, mv.X + (size_t)nodes[a] * 2);
+                } else {
+                    cp_async_8(dst, mv.X + (size_t)nodes[a] * 3);
+                    cp_async_8(dst + 1, mv.X + (size_t)nodes[a] * 3 + 1);
+                    cp_async_8(dst + 2, mv.X + (size_t)nodes[a] * 3 + 2);
+                }
+                if (field != nullptr) cp_async_8(fs + (size_t)a * cfg.max_recs + r, field + nodes[a]);
+            }
         }
-        int64_t elem = 0;
-        if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + rr);
-        Op::run(mv, prm, nodes, elem, sink);
+    };
+
+    ChunkHdr hdr_next;  // thread 0: header of the chunk whose copies are issued next
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
+        issue_meta(0, mv.chunks[c_begin]);
+        if (nloc > 1) issue_meta(1, mv.chunks[c_begin + 1]);
+        if (nloc > 2) hdr_next = mv.chunks[c_begin + 2];
     }
     __syncthreads();
-    sm.wait_metadata();
-    gather_phase_b<Op>(mv, h, sm, vecs, out);
+    mbar_wait(&bars[0], 0);
+    prefetch_x(0);
+    cp_async_commit();
+
+    for (int i = 0; i < nloc; ++i) {
+        // one chunk ahead: coordinates; two chunks ahead: metadata
+        if (i + 1 < nloc) {
+            mbar_wait(&bars[(i + 1) % STAGES], ((i + 1) / STAGES) & 1);
+            prefetch_x(i + 1);
+        }
+        cp_async_commit();
+        if (threadIdx.x == 0 && i + 2 < nloc) {
+            issue_meta(i + 2, hdr_next);
+            if (i + 3 < nloc) hdr_next = mv.chunks[c_begin + i + 3];
+        }
+        cp_async_wait<1>();  // this thread's copies for chunk i have landed
+
+        const unsigned char* m = meta(i);
+        const ChunkHdr h = *reinterpret_cast<const ChunkHdr*>(m);
+        const ChunkNode* cnodes_s = reinterpret_cast<const ChunkNode*>(m + cfg.off_nodes);
+        const uint8_t* plan_s = m + cfg.off_plan + (((size_t)h.plan_begin * 4) & 15);
+        const uint16_t* recd = reinterpret_cast<const uint16_t*>(m + cfg.off_recd + (((size_t)h.rec_begin * NNE * 2) & 15));
+        const double* xs = xstage(i);
+        const double* fs = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(xs) + cfg.off_field);
+        // ---- phase A: one thread per element record
+        for (int r = threadIdx.x; r < (int)h.n_recs; r += THREADS) {
+            SmemSink<Op> sink;
+            sink.rb = rb;
+            sink.vecs = vecs;
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) sink.dst[a] = recd[r * NNE + a];
+            double xe[NNE][DIM], fe[NNE];
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) {
+                const double* src = xs + ((size_t)a * cfg.max_recs + r) * DIM;
+                if constexpr (DIM == 2) {
+                    const double2 v = *reinterpret_cast<const double2*>(src);
+                    xe[a][0] = v.x, xe[a][1] = v.y;
+                } else {
+                    xe[a][0] = src[0], xe[a][1] = src[1], xe[a][2] = src[2];
+                }
+                fe[a] = (field != nullptr) ? fs[(size_t)a * cfg.max_recs + r] : 0.0;
+            }
+            int64_t elem = 0;
+            if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + h.rec_begin + r);
+            Op::run(prm, xe, fe, elem, sink);
+        }
+        __syncthreads();
+        // ---- phase B: plan-ordered sums, each CSR block written once
+        gather_phase_b<Op>(mv, h, cnodes_s, plan_s, rb, vecs, out);
+        __syncthreads();
+    }
 }
 
 struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
@@ -365,7 +495,7 @@ __global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv,
     }
     __syncthreads();
     sm.wait_metadata();
-    gather_phase_b<ElasticityHex8GatherOp>(mv, h, sm, nullptr, out);
+    gather_phase_b<ElasticityHex8GatherOp>(mv, h, sm.nodes, sm.plan, sm.rb, nullptr, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -501,7 +631,9 @@ static int zero_outputs(const MeshDev& d, const Outputs& out, cudaStream_t st) {
     return PFG_OK;
 }
 
-template <class Op, int THREADS>
+static inline int align16(int x) { return (x + 15) & ~15; }
+
+template <class Op, int THREADS, int MINB>
 static int launch(const MeshDev& d, const typename Op::Params& prm, const Outputs& out, bool gather,
                   cudaStream_t st) {
     const MeshView mv = view_of(d);
@@ -510,15 +642,33 @@ static int launch(const MeshDev& d, const typename Op::Params& prm, const Output
         const unsigned grid = (unsigned)((d.nelems + 127) / 128);
         k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
-        const size_t smem = 16 + mv.stage_nodes_bytes + mv.stage_plan_bytes +
-                            (size_t)d.max_chunk_inc * (Layout<Op>::RB + Layout<Op>::VEC) * sizeof(double);
+        constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
+        GatherCfg cfg;
+        cfg.off_nodes = 64;
+        cfg.off_plan = cfg.off_nodes + d.max_chunk_nodes * (int)sizeof(ChunkNode);
+        cfg.off_recn = cfg.off_plan + align16(d.max_chunk_plan_words * 4) + 32;
+        cfg.off_recd = cfg.off_recn + d.max_chunk_recs * NNE * 4;
+        cfg.meta_stride = cfg.off_recd + align16(d.max_chunk_recs * NNE * 2) + 32;
+        cfg.max_recs = (d.max_chunk_recs + 1) & ~1;
+        cfg.off_field = cfg.max_recs * NNE * DIM * 8;
+        cfg.x_stride = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
+        cfg.off_x = 64 + 3 * cfg.meta_stride;
+        cfg.off_rb = cfg.off_x + 2 * cfg.x_stride;
+        cfg.off_vec = cfg.off_rb + align16(d.max_chunk_inc * Layout<Op>::RB * 8);
+        cfg.nchunks = (int)d.nchunks;
+        const size_t smem = (size_t)cfg.off_vec + (size_t)d.max_chunk_inc * Layout<Op>::VEC * 8;
         if (smem > 227 * 1024) {
             set_error("chunk staging of %zu bytes exceeds shared memory", smem);
             return PFG_ERR_UNSUPPORTED;
         }
-        auto kern = k_assemble_gather<Op, THREADS>;
+        auto kern = k_gather_persistent<Op, THREADS, MINB>;
         PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(unsigned)d.nchunks, THREADS, smem, st>>>(mv, prm, out);
+        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int per_sm = 1;
+        PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+        per_sm = std::max(1, per_sm);
+        const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
+        kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
     }
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
@@ -556,10 +706,10 @@ extern "C" int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, doubl
     Outputs out{{vals_dev, nullptr}, nullptr};
     if (d.nne == 4) {
         PoissonOp<4>::Params prm{material_of(rho_dev, rho_const, p)};
-        return launch<PoissonOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<PoissonOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
     }
     PoissonOp<8>::Params prm{material_of(rho_dev, rho_const, p)};
-    return launch<PoissonOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<PoissonOp<8>, 128, 1>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_dev, double* R_vals_dev, int mode,
@@ -575,10 +725,10 @@ extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_
     Outputs out{{K_vals_dev, R_vals_dev}, nullptr};
     if (d.nne == 4) {
         HelmholtzOp<4>::Params prm{r0 * r0};
-        return launch<HelmholtzOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<HelmholtzOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
     }
     HelmholtzOp<8>::Params prm{r0 * r0};
-    return launch<HelmholtzOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<HelmholtzOp<8>, 128, 1>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double E,
@@ -597,7 +747,7 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         // plane stress C0 (pyfem.py:1746-1750)
         const double f = E / (1.0 - nu * nu);
         ElasticityQuad4Op::Params prm{material_of(rho_dev, rho_const, p), f, f * nu, f * 0.5 * (1.0 - nu)};
-        return launch<ElasticityQuad4Op, 192>(d, prm, out, gather, st);
+        return launch<ElasticityQuad4Op, 192, 2>(d, prm, out, gather, st);
     }
     // 3-D C0 (pyfem.py:1752-1757)
     const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
@@ -648,7 +798,7 @@ extern "C" int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, in
         if (k < nxdv - 1) binom = binom * (double)(nxdv - 1 - k) / (double)(k + 1);
     }
     Outputs out{{K_vals_dev, nullptr}, res_dev};
-    return launch<NlPoissonQuad4Op, 256>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<NlPoissonQuad4Op, 256, 1>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream) {
@@ -678,10 +828,10 @@ extern "C" int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs
     Outputs out{{nullptr, nullptr}, rhs_dev};
     if (d.nne == 4) {
         PoissonRhsOp<4>::Params prm{gq_dev};
-        return launch<PoissonRhsOp<4>, 256>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<PoissonRhsOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
     }
     PoissonRhsOp<8>::Params prm{gq_dev};
-    return launch<PoissonRhsOp<8>, 128>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<PoissonRhsOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, const double* fixed_vals_dev,

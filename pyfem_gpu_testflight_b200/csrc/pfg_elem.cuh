@@ -211,21 +211,24 @@ struct Material {
 };
 
 template <int NNE>
-PFG_DEV void material_at_quads(const Material& mat, const int (&nodes)[NNE], double (&cq)[Elem<NNE>::NQ]) {
+PFG_DEV void material_at_quads(const Material& mat, const double (&re)[NNE], double (&cq)[Elem<NNE>::NQ]) {
     if (mat.rho == nullptr) {
         const double c = mat.rho_const / (1.0 + mat.p * (1.0 - mat.rho_const));
 #pragma unroll
         for (int q = 0; q < Elem<NNE>::NQ; ++q) cq[q] = c;
         return;
     }
-    double re[NNE];
-#pragma unroll
-    for (int a = 0; a < NNE; ++a) re[a] = __ldg(mat.rho + nodes[a]);
     for_each_q<Elem<NNE>::NQ>([&](auto qc) {
         constexpr int Q = decltype(qc)::value;
         const double rq = interp<NNE, Q>(re);
         cq[Q] = rq / (1.0 + mat.p * (1.0 - rq));
     });
+}
+
+template <int NNE>
+PFG_DEV void load_field(const double* __restrict__ f, const int (&nodes)[NNE], double (&fe)[NNE]) {
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) fe[a] = (f != nullptr) ? __ldg(f + nodes[a]) : 0.0;
 }
 
 // emit a symmetric scalar matrix held as upper-triangular accumulators
@@ -251,12 +254,12 @@ struct PoissonOp {  // LinearPoisson._compute_element_jacobian (pyfem.py:1188-12
     struct Params {
         Material mat;
     };
+    __host__ __device__ __forceinline__ static const double* field(const Params& prm) { return prm.mat.rho; }
     template <class Sink>
-    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t, Sink& sink) {
-        double xe[NNE][DIM];
-        load_coords<NNE>(mv.X, nodes, xe);
+    PFG_DEV static void run(const Params& prm, const double (&xe)[NNE][DIM], const double (&fe)[NNE], int64_t,
+                            Sink& sink) {
         double cq[NQ];
-        material_at_quads<NNE>(prm.mat, nodes, cq);
+        material_at_quads<NNE>(prm.mat, fe, cq);
         double K[NNE][NNE];
 #pragma unroll
         for (int a = 0; a < NNE; ++a)
@@ -291,10 +294,10 @@ struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2
     struct Params {
         double r0sq;
     };
+    __host__ __device__ __forceinline__ static const double* field(const Params&) { return nullptr; }
     template <class Sink>
-    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t, Sink& sink) {
-        double xe[NNE][DIM];
-        load_coords<NNE>(mv.X, nodes, xe);
+    PFG_DEV static void run(const Params& prm, const double (&xe)[NNE][DIM], const double (&)[NNE], int64_t,
+                            Sink& sink) {
         double K[NNE][NNE], R[NNE][NNE];
 #pragma unroll
         for (int a = 0; a < NNE; ++a)
@@ -335,12 +338,11 @@ struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_j
         Material mat;
         double c11, c12, c33;  // C0 entries (pyfem.py:1746-1750)
     };
+    __host__ __device__ __forceinline__ static const double* field(const Params& prm) { return prm.mat.rho; }
     template <class Sink>
-    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[4], int64_t, Sink& sink) {
-        double xe[4][2];
-        load_coords<4>(mv.X, nodes, xe);
+    PFG_DEV static void run(const Params& prm, const double (&xe)[4][2], const double (&fe)[4], int64_t, Sink& sink) {
         double cq[4];
-        material_at_quads<4>(prm.mat, nodes, cq);
+        material_at_quads<4>(prm.mat, fe, cq);
         // per node pair (a <= b): sums over q of s * {GxaGxb, GyaGyb, GxaGyb, GyaGxb}
         double XX[4][4], YY[4][4], XY[4][4], YX[4][4];
 #pragma unroll
@@ -410,12 +412,9 @@ struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) 
     PFG_DEV static double gfun(double x, double y) {  // pyfem.py:1438-1446
         return 1e4 * x * (1.0 - x) * (1.0 - 2.0 * x) * y * (1.0 - y) * (1.0 - 2.0 * y);
     }
+    __host__ __device__ __forceinline__ static const double* field(const Params& prm) { return prm.u; }
     template <class Sink>
-    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[4], int64_t, Sink& sink) {
-        double xe[4][2], ue[4];
-        load_coords<4>(mv.X, nodes, xe);
-#pragma unroll
-        for (int a = 0; a < 4; ++a) ue[a] = __ldg(prm.u + nodes[a]);
+    PFG_DEV static void run(const Params& prm, const double (&xe)[4][2], const double (&ue)[4], int64_t, Sink& sink) {
         double K[4][4], res[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
@@ -473,10 +472,10 @@ struct PoissonRhsOp {  // LinearPoisson._compute_element_rhs (pyfem.py:1137-1173
     struct Params {
         const double* gq;  // (nelems, NQ) source term at the quadrature points
     };
+    __host__ __device__ __forceinline__ static const double* field(const Params&) { return nullptr; }
     template <class Sink>
-    PFG_DEV static void run(const MeshView& mv, const Params& prm, const int (&nodes)[NNE], int64_t elem, Sink& sink) {
-        double xe[NNE][DIM];
-        load_coords<NNE>(mv.X, nodes, xe);
+    PFG_DEV static void run(const Params& prm, const double (&xe)[NNE][DIM], const double (&)[NNE], int64_t elem,
+                            Sink& sink) {
         double f[NNE];
 #pragma unroll
         for (int a = 0; a < NNE; ++a) f[a] = 0.0;

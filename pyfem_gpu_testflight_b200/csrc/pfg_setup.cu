@@ -695,7 +695,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         return PFG_ERR_UNSUPPORTED;
     }
     PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t)));
-    PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t)));
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t) + 32));  // bulk copies may over-read
     PFG_CUDA_TRY(cudaMalloc(&d.rec_elem, d.nrecs * sizeof(int32_t)));
     k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, d.rec_nodes, d.rec_dst,
                                                                d.rec_elem, d.chunks, maxima.p);
