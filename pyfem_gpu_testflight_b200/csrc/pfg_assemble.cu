@@ -304,22 +304,7 @@ PFG_DEV void gather_phase_b(const MeshView& mv, const ChunkHdr& h, const ChunkNo
     }
 }
 
-// ---- persistent, software-pipelined gather kernel -------------------------------------------------
-// One CTA walks a contiguous range of chunks.  Per chunk i:
-//   TMA bulk copies (issued two chunks ahead) bring the chunk's header, node table, plan bytes and element
-//   records into a 3-deep shared-memory ring, each stage guarded by one mbarrier;
-//   cp.async gathers (issued one chunk ahead) stage the coordinates / nodal field of the chunk's elements;
-//   phase A integrates the elements into the row-block staging, phase B sums and stores the CSR blocks.
-// Global-memory latency is therefore paid once per CTA, not once per chunk.
-struct GatherCfg {
-    int meta_stride;                              // bytes per metadata stage
-    int off_nodes, off_plan, off_recn, off_recd;  // offsets inside a metadata stage (header at 0)
-    int x_stride, off_field;                      // bytes per coordinate stage, offset of the field values in it
-    int off_x, off_rb, off_vec;                   // offsets from the shared-memory base
-    int max_recs;                                 // records per chunk the coordinate stage is sized for
-    int nchunks;
-};
-
+// ---- cp.async helpers ------------------------------------------------------------------------------
 PFG_DEV void cp_async_16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -345,56 +330,198 @@ PFG_DEV void load_rec_nodes(const int32_t* __restrict__ recn, int r, int (&nodes
     }
 }
 
+// ---- tile kernel: persistent, software-pipelined owner-computes assembly -----------------------------
+// Staging layout of one element record for operator Op (doubles): NMAT matrices of NB node-pair blocks
+// (upper triangle only when the operator is symmetric), then NVEC*NNE vector entries.  The record stride S
+// is chosen so that consecutive records (= consecutive lanes in phase A) hit different banks with the
+// widest store the operator uses (16 B for 2x2 blocks, 8 B for scalars).
+template <class Op>
+struct TileStage {
+    static constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M;
+    static constexpr bool SYM = Op::SYM;
+    static constexpr int NB = SYM ? NNE * (NNE + 1) / 2 : NNE * NNE;
+    static constexpr int MATD = Op::NMAT * NB * BLK;
+    static constexpr int RAW = MATD + Op::NVEC * NNE;
+    static constexpr bool WIDE = (M == 2 && Op::NMAT > 0);  // 16-byte code units / accesses
+    static constexpr int S = WIDE ? ((((RAW + 1) / 2) % 2 == 1) ? ((RAW + 1) & ~1) : ((RAW + 1) & ~1) + 2) : (RAW | 1);
+    static constexpr int UNIT_D = WIDE ? 2 : 1;  // doubles per code unit
+    PFG_DEV static constexpr int block_index(int a, int b) {
+        return SYM ? (a * (2 * NNE - 1 - a) / 2 + b) : (a * NNE + b);
+    }
+    static TileLayout layout() {
+        TileLayout L;
+        L.nne = NNE;
+        L.unit_shift = WIDE ? 4 : 3;
+        L.rec_units = S / UNIT_D;
+        L.sym = SYM ? 1 : 0;
+        L.blk_units = BLK / UNIT_D;
+        L.has_mat = Op::NMAT > 0 ? 1 : 0;
+        return L;
+    }
+};
+
+template <class Op>
+struct TileSink {
+    using St = TileStage<Op>;
+    static constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M;
+    double* rec;  // this record's staging area
+    PFG_DEV void block(int mat, int a, int b, const double* blk) const {
+        if (St::SYM && a > b) return;  // lower triangle is read transposed in phase B
+        double* p = rec + (mat * St::NB + St::block_index(a, b)) * BLK;
+        if constexpr (M == 2) {
+            reinterpret_cast<double2*>(p)[0] = make_double2(blk[0], blk[1]);
+            reinterpret_cast<double2*>(p)[1] = make_double2(blk[2], blk[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < BLK; ++i) p[i] = blk[i];
+        }
+    }
+    PFG_DEV void vec(int a, double v) const { rec[St::MATD + a] = v; }
+};
+
+struct TileCfg {
+    int off_dir;                  // ring of 8 TileDir entries
+    int off_blob, off_codes;      // chunk blob / codes buffers (one stage each)
+    int off_ids, ids_stride;      // record node ids, two stages
+    int off_x, off_field;         // coordinates / nodal field of the chunk's records (one stage)
+    int off_stage;                // element-record staging
+    int max_recs;                 // records per chunk the stages are sized for
+    int nchunks;
+};
+
+// phase B: one thread per (chunk node, neighbour) block sums the staged contributions in plan order and writes
+// the block's m x m CSR values once; then one thread per chunk node sums the vector entries.
+template <class Op, int THREADS>
+PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ blob,
+                          const uint16_t* __restrict__ codes, const double* __restrict__ stage, const Outputs& out) {
+    using St = TileStage<Op>;
+    constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, NMAT = Op::NMAT;
+    const TileHdr h = *reinterpret_cast<const TileHdr*>(blob);
+    const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
+    if constexpr (NMAT > 0) {
+        const int kpad = (int)h.kpad;
+        const int items = (int)h.n_nodes * kpad;
+        const float inv_kpad = 1.0f / (float)kpad;
+        for (int idx = threadIdx.x; idx < items; idx += THREADS) {
+            const int p = (int)(((float)idx + 0.5f) * inv_kpad);
+            const int t = idx - p * kpad;
+            const TileNode tn = nodes[p];
+            const uint8_t* __restrict__ pl = blob + tn.start_off;
+            const int k = pl[0];
+            if (t >= k) continue;
+            const int s0 = pl[2 + t], s1 = pl[3 + t];
+            const uint16_t* __restrict__ cp = codes + tn.code_off;
+            double acc[NMAT][BLK];
+#pragma unroll
+            for (int mt = 0; mt < NMAT; ++mt)
+#pragma unroll
+                for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
+            for (int s = s0; s < s1; ++s) {
+                const unsigned code = cp[s];
+                const double* __restrict__ q = stage + (code >> 1) * St::UNIT_D;
+#pragma unroll
+                for (int mt = 0; mt < NMAT; ++mt) {
+                    const double* __restrict__ qm = q + mt * St::NB * BLK;
+                    if constexpr (M == 2) {
+                        const double2 v0 = reinterpret_cast<const double2*>(qm)[0];
+                        const double2 v1 = reinterpret_cast<const double2*>(qm)[1];
+                        const bool tr = St::SYM && (code & 1u);
+                        acc[mt][0] += v0.x;
+                        acc[mt][1] += tr ? v1.x : v0.y;
+                        acc[mt][2] += tr ? v0.y : v1.x;
+                        acc[mt][3] += v1.y;
+                    } else {
+                        acc[mt][0] += qm[0];
+                    }
+                }
+            }
+#pragma unroll
+            for (int mt = 0; mt < NMAT; ++mt) {
+                if (out.vals[mt] == nullptr) continue;
+                double* dst = out.vals[mt] + h.gbase + tn.gslot_rel + M * t;
+                if constexpr (M == 2) {
+                    __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[mt][0], acc[mt][1]));
+                    __stcs(reinterpret_cast<double2*>(dst + 2 * k), make_double2(acc[mt][2], acc[mt][3]));
+                } else {
+                    __stcs(dst, acc[mt][0]);
+                }
+            }
+        }
+    }
+    if constexpr (Op::NVEC > 0) {
+        if (out.vec != nullptr) {
+            for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
+                const TileNode tn = nodes[p];
+                const uint8_t* __restrict__ pl = blob + tn.start_off;
+                const int self_t = pl[1];
+                const int s0 = pl[2 + self_t], s1 = pl[3 + self_t];
+                const uint16_t* __restrict__ cp = codes + tn.code_off;
+                double sum = 0.0;
+                for (int s = s0; s < s1; ++s) {  // the diagonal block's contributions are the node's incidences
+                    const int off = (int)(cp[s] >> 1) * St::UNIT_D;  // doubles from the chunk's staging base
+                    const int r = off / St::S;
+                    int a = off - r * St::S;  // vector-only operators address the entry directly
+                    if constexpr (NMAT > 0) {
+                        const int bi = a / BLK;
+                        a = 0;
+#pragma unroll
+                        for (int c = 1; c < NNE; ++c)
+                            if (bi == St::block_index(c, c)) a = c;
+                    }
+                    sum += stage[r * St::S + St::MATD + a];
+                }
+                out.vec[mv.cnode_id[h.node_begin + p] - mv.own_begin] = sum;
+            }
+        }
+    }
+}
+
 template <class Op, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
-    k_gather_persistent(MeshView mv, typename Op::Params prm, Outputs out, GatherCfg cfg) {
+    k_tile(MeshView mv, typename Op::Params prm, Outputs out, TileCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem[];
-    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM, RB = Layout<Op>::RB;
-    constexpr int STAGES = 3;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    using St = TileStage<Op>;
+    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] record ids
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
     const int nloc = (int)(c_end - c_begin);
     if (nloc <= 0) return;
     const double* __restrict__ field = Op::field(prm);
-    double* rb = reinterpret_cast<double*>(smem + cfg.off_rb);
-    double* vecs = reinterpret_cast<double*>(smem + cfg.off_vec);
+    TileDir* dir_s = reinterpret_cast<TileDir*>(smem + cfg.off_dir);
+    unsigned char* blob_s = smem + cfg.off_blob;
+    uint16_t* codes_s = reinterpret_cast<uint16_t*>(smem + cfg.off_codes);
+    double* xs = reinterpret_cast<double*>(smem + cfg.off_x);
+    double* fs = reinterpret_cast<double*>(smem + cfg.off_field);
+    double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
+    const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;  // entries 0..nloc (nloc = next CTA's first / sentinel)
 
-    auto meta = [&](int i) -> unsigned char* { return smem + 64 + (i % STAGES) * cfg.meta_stride; };
-    auto xstage = [&](int i) -> double* { return reinterpret_cast<double*>(smem + cfg.off_x + (i & 1) * cfg.x_stride); };
-    // thread 0 only: start the bulk copies of one chunk's metadata
-    auto issue_meta = [&](int i, const ChunkHdr& h) {
-        unsigned char* m = meta(i);
-        uint64_t* bar = &bars[i % STAGES];
-        const size_t plan_lo = (size_t)h.plan_begin * 4, plan_lo16 = plan_lo & ~(size_t)15;
-        const size_t plan_hi16 = ((size_t)(h.plan_begin + h.plan_words) * 4 + 15) & ~(size_t)15;
-        const size_t recd_lo = (size_t)h.rec_begin * NNE * 2, recd_lo16 = recd_lo & ~(size_t)15;
-        const size_t recd_hi16 = (recd_lo + (size_t)h.n_recs * NNE * 2 + 15) & ~(size_t)15;
-        const uint32_t b_nodes = h.n_nodes * (uint32_t)sizeof(ChunkNode);
-        const uint32_t b_plan = (uint32_t)(plan_hi16 - plan_lo16);
-        const uint32_t b_recn = h.n_recs * NNE * 4u;
-        const uint32_t b_recd = (uint32_t)(recd_hi16 - recd_lo16);
-        mbar_expect_tx(bar, (uint32_t)sizeof(ChunkHdr) + b_nodes + b_plan + b_recn + b_recd);
-        tma_load_1d(m, mv.chunks + c_begin + i, (uint32_t)sizeof(ChunkHdr), bar);
-        tma_load_1d(m + cfg.off_nodes, mv.cnodes + h.node_begin, b_nodes, bar);
-        tma_load_1d(m + cfg.off_plan, mv.plan_pool + plan_lo16, b_plan, bar);
-        tma_load_1d(m + cfg.off_recn, mv.rec_nodes + h.rec_begin * NNE, b_recn, bar);
-        tma_load_1d(m + cfg.off_recd, reinterpret_cast<const unsigned char*>(mv.rec_dst) + recd_lo16, b_recd, bar);
+    auto ids_stage = [&](int j) -> int32_t* { return reinterpret_cast<int32_t*>(smem + cfg.off_ids + (j & 1) * cfg.ids_stride); };
+    auto n_recs_of = [&](int j) -> int { return (int)(dir_s[(j + 1) & 7].rec_begin - dir_s[j & 7].rec_begin); };
+    // thread 0: bulk copies of chunk j's record ids / blob + codes
+    auto issue_ids = [&](int j) {
+        const uint32_t bytes = (uint32_t)n_recs_of(j) * NNE * 4u;
+        uint64_t* bar = &bars[1 + (j & 1)];
+        mbar_expect_tx(bar, bytes);
+        if (bytes) tma_load_1d(ids_stage(j), mv.rec_nodes + (size_t)dir_s[j & 7].rec_begin * NNE, bytes, bar);
     };
-    // all threads: gather the coordinates (and nodal field) of chunk i's elements into its stage
-    auto prefetch_x = [&](int i) {
-        const unsigned char* m = meta(i);
-        const ChunkHdr* h = reinterpret_cast<const ChunkHdr*>(m);
-        const int32_t* recn = reinterpret_cast<const int32_t*>(m + cfg.off_recn);
-        double* xs = xstage(i);
-        double* fs = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(xs) + cfg.off_field);
-        const int n_recs = (int)h->n_recs;
+    auto issue_meta = [&](int j) {
+        const TileDir t = dir_s[j & 7];
+        const uint32_t bb = (uint32_t)t.blob_len16 * 16u, cb = (uint32_t)t.code_len16 * 16u;
+        mbar_expect_tx(&bars[0], bb + cb);
+        tma_load_1d(blob_s, mv.tile_blob + (size_t)t.blob_off16 * 16, bb, &bars[0]);
+        if (cb) tma_load_1d(codes_s, reinterpret_cast<const unsigned char*>(mv.tile_codes) + (size_t)t.code_off16 * 16, cb, &bars[0]);
+    };
+    // all threads: stage the coordinates (and nodal field) of chunk j's records; thread r owns record r
+    auto prefetch_x = [&](int j) {
+        const int32_t* recn = ids_stage(j);
+        const int n_recs = n_recs_of(j);
         for (int r = threadIdx.x; r < n_recs; r += THREADS) {
             int nodes[NNE];
             load_rec_nodes<NNE>(recn, r, nodes);
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
-                double* dst = xs + ((size_t)a * cfg.max_recs + r) * DIM;  // [a][r][DIM]: conflict-free reads
+                double* dst = xs + ((size_t)a * cfg.max_recs + r) * DIM;  // [a][r][DIM]: conflict-free
                 if constexpr (DIM == 2) {
                     cp_async_16(dst, mv.X + (size_t)nodes[a] * 2);
                 } else {
@@ -407,45 +534,27 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
     };
 
-    ChunkHdr hdr_next;  // thread 0: header of the chunk whose copies are issued next
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) mbar_init(&bars[s], 1);
-        issue_meta(0, mv.chunks[c_begin]);
-        if (nloc > 1) issue_meta(1, mv.chunks[c_begin + 1]);
-        if (nloc > 2) hdr_next = mv.chunks[c_begin + 2];
+        for (int s = 0; s < 3; ++s) mbar_init(&bars[s], 1);
+        for (int j = 0; j <= 4 && j <= nloc; ++j) dir_s[j] = dir_g[j];
+        __threadfence_block();
+        issue_ids(0);
+        if (nloc > 1) issue_ids(1);
+        issue_meta(0);
     }
     __syncthreads();
-    mbar_wait(&bars[0], 0);
+    mbar_wait(&bars[1], 0);
     prefetch_x(0);
     cp_async_commit();
 
     for (int i = 0; i < nloc; ++i) {
-        // one chunk ahead: coordinates; two chunks ahead: metadata
-        if (i + 1 < nloc) {
-            mbar_wait(&bars[(i + 1) % STAGES], ((i + 1) / STAGES) & 1);
-            prefetch_x(i + 1);
-        }
+        cp_async_wait<0>();  // this thread's coordinates of chunk i (and thread 0's directory entry) have landed
+        if (threadIdx.x == 0 && i + 5 <= nloc) cp_async_16(&dir_s[(i + 5) & 7], &dir_g[i + 5]);
         cp_async_commit();
-        if (threadIdx.x == 0 && i + 2 < nloc) {
-            issue_meta(i + 2, hdr_next);
-            if (i + 3 < nloc) hdr_next = mv.chunks[c_begin + i + 3];
-        }
-        cp_async_wait<1>();  // this thread's copies for chunk i have landed
-
-        const unsigned char* m = meta(i);
-        const ChunkHdr h = *reinterpret_cast<const ChunkHdr*>(m);
-        const ChunkNode* cnodes_s = reinterpret_cast<const ChunkNode*>(m + cfg.off_nodes);
-        const uint8_t* plan_s = m + cfg.off_plan + (((size_t)h.plan_begin * 4) & 15);
-        const uint16_t* recd = reinterpret_cast<const uint16_t*>(m + cfg.off_recd + (((size_t)h.rec_begin * NNE * 2) & 15));
-        const double* xs = xstage(i);
-        const double* fs = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(xs) + cfg.off_field);
-        // ---- phase A: one thread per element record
-        for (int r = threadIdx.x; r < (int)h.n_recs; r += THREADS) {
-            SmemSink<Op> sink;
-            sink.rb = rb;
-            sink.vecs = vecs;
-#pragma unroll
-            for (int a = 0; a < NNE; ++a) sink.dst[a] = recd[r * NNE + a];
+        // ---- phase A: one thread per element record -> staged element matrices
+        const int n_recs = n_recs_of(i);
+        for (int r = threadIdx.x; r < n_recs; r += THREADS) {
+            TileSink<Op> sink{stage + (size_t)r * St::S};
             double xe[NNE][DIM], fe[NNE];
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
@@ -459,13 +568,22 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 fe[a] = (field != nullptr) ? fs[(size_t)a * cfg.max_recs + r] : 0.0;
             }
             int64_t elem = 0;
-            if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + h.rec_begin + r);
+            if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + dir_s[i & 7].rec_begin + r);
             Op::run(prm, xe, fe, elem, sink);
         }
         __syncthreads();
+        // ---- prefetch: record ids two chunks ahead, coordinates one chunk ahead
+        if (threadIdx.x == 0 && i + 2 < nloc) issue_ids(i + 2);
+        if (i + 1 < nloc) {
+            mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
+            prefetch_x(i + 1);
+        }
+        cp_async_commit();
         // ---- phase B: plan-ordered sums, each CSR block written once
-        gather_phase_b<Op>(mv, h, cnodes_s, plan_s, rb, vecs, out);
+        mbar_wait(&bars[0], i & 1);
+        tile_phase_b<Op, THREADS>(mv, blob_s, codes_s, stage, out);
         __syncthreads();
+        if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
     }
 }
 
@@ -606,6 +724,9 @@ static MeshView view_of(const MeshDev& d) {
     mv.rec_dst = d.rec_dst;
     mv.rec_elem = d.rec_elem;
     mv.plan_pool = d.plan_pool;
+    mv.tile_dir = d.tile_dir;
+    mv.tile_blob = d.tile_blob;
+    mv.tile_codes = d.tile_codes;
     mv.stage_nodes_bytes = d.max_chunk_nodes * (int)sizeof(ChunkNode);
     mv.stage_plan_bytes = ((d.max_chunk_plan_words * 4 + 15) / 16) * 16 + 32;
     return mv;
@@ -634,6 +755,40 @@ static int zero_outputs(const MeshDev& d, const Outputs& out, cudaStream_t st) {
 static inline int align16(int x) { return (x + 15) & ~15; }
 
 template <class Op, int THREADS, int MINB>
+static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params& prm, const Outputs& out,
+                       cudaStream_t st) {
+    using St = TileStage<Op>;
+    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
+    PFG_TRY(tile_prepare_layout(d, St::layout(), st));
+    TileCfg cfg;
+    cfg.max_recs = (d.max_chunk_recs + 1) & ~1;
+    cfg.off_dir = 64;
+    cfg.off_blob = cfg.off_dir + 8 * (int)sizeof(TileDir);
+    cfg.off_codes = cfg.off_blob + align16(d.max_blob_bytes);
+    cfg.off_ids = cfg.off_codes + align16(d.max_code_bytes);
+    cfg.ids_stride = align16(d.max_chunk_recs * NNE * 4);
+    cfg.off_x = cfg.off_ids + 2 * cfg.ids_stride;
+    cfg.off_field = cfg.off_x + cfg.max_recs * NNE * DIM * 8;
+    cfg.off_stage = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
+    cfg.nchunks = (int)d.nchunks;
+    const size_t smem = (size_t)cfg.off_stage + (size_t)d.max_chunk_recs * St::S * 8;
+    if (smem > 227 * 1024) {
+        set_error("chunk staging of %zu bytes exceeds shared memory", smem);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    auto kern = k_tile<Op, THREADS, MINB>;
+    PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    int per_sm = 1;
+    PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
+    per_sm = std::max(1, per_sm);
+    const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
+    kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+template <class Op, int THREADS, int MINB>
 static int launch(const MeshDev& d, const typename Op::Params& prm, const Outputs& out, bool gather,
                   cudaStream_t st) {
     const MeshView mv = view_of(d);
@@ -642,33 +797,8 @@ static int launch(const MeshDev& d, const typename Op::Params& prm, const Output
         const unsigned grid = (unsigned)((d.nelems + 127) / 128);
         k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
-        constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
-        GatherCfg cfg;
-        cfg.off_nodes = 64;
-        cfg.off_plan = cfg.off_nodes + d.max_chunk_nodes * (int)sizeof(ChunkNode);
-        cfg.off_recn = cfg.off_plan + align16(d.max_chunk_plan_words * 4) + 32;
-        cfg.off_recd = cfg.off_recn + d.max_chunk_recs * NNE * 4;
-        cfg.meta_stride = cfg.off_recd + align16(d.max_chunk_recs * NNE * 2) + 32;
-        cfg.max_recs = (d.max_chunk_recs + 1) & ~1;
-        cfg.off_field = cfg.max_recs * NNE * DIM * 8;
-        cfg.x_stride = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
-        cfg.off_x = 64 + 3 * cfg.meta_stride;
-        cfg.off_rb = cfg.off_x + 2 * cfg.x_stride;
-        cfg.off_vec = cfg.off_rb + align16(d.max_chunk_inc * Layout<Op>::RB * 8);
-        cfg.nchunks = (int)d.nchunks;
-        const size_t smem = (size_t)cfg.off_vec + (size_t)d.max_chunk_inc * Layout<Op>::VEC * 8;
-        if (smem > 227 * 1024) {
-            set_error("chunk staging of %zu bytes exceeds shared memory", smem);
-            return PFG_ERR_UNSUPPORTED;
-        }
-        auto kern = k_gather_persistent<Op, THREADS, MINB>;
-        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int per_sm = 1;
-        PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-        per_sm = std::max(1, per_sm);
-        const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
-        kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
+        if (d.tile_threads == 256) return launch_tile<Op, 256, 1>(const_cast<MeshDev&>(d), mv, prm, out, st);
+        return launch_tile<Op, 128, MINB>(const_cast<MeshDev&>(d), mv, prm, out, st);
     }
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
@@ -706,10 +836,10 @@ extern "C" int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, doubl
     Outputs out{{vals_dev, nullptr}, nullptr};
     if (d.nne == 4) {
         PoissonOp<4>::Params prm{material_of(rho_dev, rho_const, p)};
-        return launch<PoissonOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<PoissonOp<4>, 128, 4>(d, prm, out, gather, (cudaStream_t)stream);
     }
     PoissonOp<8>::Params prm{material_of(rho_dev, rho_const, p)};
-    return launch<PoissonOp<8>, 128, 1>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<PoissonOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_dev, double* R_vals_dev, int mode,
@@ -725,10 +855,10 @@ extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_
     Outputs out{{K_vals_dev, R_vals_dev}, nullptr};
     if (d.nne == 4) {
         HelmholtzOp<4>::Params prm{r0 * r0};
-        return launch<HelmholtzOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<HelmholtzOp<4>, 128, 4>(d, prm, out, gather, (cudaStream_t)stream);
     }
     HelmholtzOp<8>::Params prm{r0 * r0};
-    return launch<HelmholtzOp<8>, 128, 1>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<HelmholtzOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double E,
@@ -747,7 +877,7 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         // plane stress C0 (pyfem.py:1746-1750)
         const double f = E / (1.0 - nu * nu);
         ElasticityQuad4Op::Params prm{material_of(rho_dev, rho_const, p), f, f * nu, f * 0.5 * (1.0 - nu)};
-        return launch<ElasticityQuad4Op, 192, 2>(d, prm, out, gather, st);
+        return launch<ElasticityQuad4Op, 128, 3>(d, prm, out, gather, st);
     }
     // 3-D C0 (pyfem.py:1752-1757)
     const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
@@ -798,7 +928,7 @@ extern "C" int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, in
         if (k < nxdv - 1) binom = binom * (double)(nxdv - 1 - k) / (double)(k + 1);
     }
     Outputs out{{K_vals_dev, nullptr}, res_dev};
-    return launch<NlPoissonQuad4Op, 256, 1>(d, prm, out, gather, (cudaStream_t)stream);
+    return launch<NlPoissonQuad4Op, 128, 3>(d, prm, out, gather, (cudaStream_t)stream);
 }
 
 extern "C" int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream) {
@@ -828,7 +958,7 @@ extern "C" int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs
     Outputs out{{nullptr, nullptr}, rhs_dev};
     if (d.nne == 4) {
         PoissonRhsOp<4>::Params prm{gq_dev};
-        return launch<PoissonRhsOp<4>, 256, 2>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<PoissonRhsOp<4>, 128, 4>(d, prm, out, gather, (cudaStream_t)stream);
     }
     PoissonRhsOp<8>::Params prm{gq_dev};
     return launch<PoissonRhsOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);

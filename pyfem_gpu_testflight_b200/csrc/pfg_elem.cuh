@@ -79,6 +79,10 @@ struct MeshView {
     const uint16_t* rec_dst;
     const int32_t* rec_elem;
     const uint8_t* plan_pool;
+    // tile plan (second format)
+    const TileDir* tile_dir;
+    const uint8_t* tile_blob;
+    const uint16_t* tile_codes;
     // shared-memory staging sizes (bytes) for the gather kernels: chunk node table, chunk plan
     int stage_nodes_bytes, stage_plan_bytes;
 };
@@ -250,7 +254,7 @@ template <int NNE_>
 struct PoissonOp {  // LinearPoisson._compute_element_jacobian (pyfem.py:1188-1217, einsum :1177-1185)
     static constexpr int NNE = NNE_, M = 1, NMAT = 1, NVEC = 0;
     static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
-    static constexpr bool NEEDS_ELEM = false;
+    static constexpr bool NEEDS_ELEM = false, SYM = true;
     struct Params {
         Material mat;
     };
@@ -290,7 +294,7 @@ template <int NNE_>
 struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2138-2177)
     static constexpr int NNE = NNE_, M = 1, NMAT = 2, NVEC = 0;  // matrix 0 = K, 1 = R
     static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
-    static constexpr bool NEEDS_ELEM = false;
+    static constexpr bool NEEDS_ELEM = false, SYM = true;
     struct Params {
         double r0sq;
     };
@@ -333,7 +337,7 @@ struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2
 
 struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_jacobian (pyfem.py:2029-2068)
     static constexpr int NNE = 4, M = 2, NMAT = 1, NVEC = 0, DIM = 2, NQ = 4;
-    static constexpr bool NEEDS_ELEM = false;
+    static constexpr bool NEEDS_ELEM = false, SYM = true;
     struct Params {
         Material mat;
         double c11, c12, c33;  // C0 entries (pyfem.py:1746-1750)
@@ -390,7 +394,7 @@ constexpr int kMaxXdv = 32;
 
 struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) + residual (pyfem.py:1474-1539)
     static constexpr int NNE = 4, M = 1, NMAT = 1, NVEC = 1, DIM = 2, NQ = 4;
-    static constexpr bool NEEDS_ELEM = false;
+    static constexpr bool NEEDS_ELEM = false, SYM = false;  // the Newton Jacobian is not symmetric
     struct Params {
         const double* u;
         int nxdv;
@@ -468,7 +472,7 @@ template <int NNE_>
 struct PoissonRhsOp {  // LinearPoisson._compute_element_rhs (pyfem.py:1137-1173, einsum :1132-1134)
     static constexpr int NNE = NNE_, M = 1, NMAT = 0, NVEC = 1;
     static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
-    static constexpr bool NEEDS_ELEM = true;
+    static constexpr bool NEEDS_ELEM = true, SYM = false;
     struct Params {
         const double* gq;  // (nelems, NQ) source term at the quadrature points
     };

@@ -61,6 +61,62 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 // plan record of a node: uint8 start[k+1] (prefix of contribution counts per neighbour),
 // then uint8 src[valence*nne] sorted by neighbour rank, src = (adjacent-element ordinal << 3) | local column node.
 
+// ---------------------------------------------------------------------------------------------
+// Gather plan, second format ("tile plan"): used by every one-thread-per-element physics
+// (quad4 all models, hex8 scalar models).  A chunk's element matrices are staged per element RECORD
+// (upper triangle only for symmetric operators), so phase A needs no destination table, and
+// phase B reads each contribution at a shared-memory offset that is stored ready-made in the plan.
+//
+// Per chunk, three global arrays feed one CTA iteration:
+//   tile_dir[c]      16 B   where the chunk's blob / codes / records live
+//   blob             16 B aligned: TileHdr | TileNode[n_nodes] | per node uint8 start[k+1]
+//   codes            16 B aligned: per node uint16[valence*nne], contributions sorted by neighbour rank
+//   rec_nodes        (n_recs, nne) int32 node ids of the records (shared with the first format)
+// A code is (offset << 1) | transpose, offset in units of the staging block (16 B for 2x2 blocks,
+// 8 B for scalars) from the start of the chunk's staging area.  Codes depend on the staging layout
+// of the operator (record stride, symmetric or full storage); they are stored in the neutral form
+// (record << 2*lb | a << lb | b) beside the working copy, which is re-encoded when an operator with another
+// layout runs.
+// ---------------------------------------------------------------------------------------------
+struct __align__(16) TileDir {  // 16 bytes
+    uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
+    uint32_t code_off16;   // codes offset in the code pool, 16-byte units
+    uint32_t rec_begin;    // first record
+    uint16_t blob_len16;   // blob bytes / 16
+    uint16_t code_len16;   // code bytes / 16
+};
+
+struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
+    int64_t gbase;         // CSR value slot of the chunk's first node (node slots are relative to it)
+    uint32_t rec_begin;
+    uint32_t node_begin;   // first chunk-ordered node slot (row ids of the vector output: cnode_id)
+    uint16_t n_nodes, n_recs;
+    uint16_t kpad;         // max neighbour count over the chunk's nodes
+    uint16_t pad_;
+    uint32_t pad2_[2];
+};
+
+struct __align__(8) TileNode {  // 8 bytes
+    uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileHdr::gbase
+    uint16_t start_off;    // byte offset of start[] inside the blob
+    uint16_t code_off;     // index of the node's first code inside the chunk's code segment
+    // k = number of neighbours and the rank of the node itself are the first two bytes at start_off
+};
+// node plan bytes at start_off: uint8 k, uint8 self_t, uint8 start[k+1]
+
+struct TileLayout {  // how an operator stages one record; decides the code encoding
+    int nne = 0;       // nodes per element
+    int unit_shift = 0;// log2 of bytes per code unit (3 or 4)
+    int rec_units = 0; // record stride in code units
+    int sym = 0;       // upper-triangle storage
+    int blk_units = 0; // units per node-pair block
+    int has_mat = 0;   // 0: vector-only operator, codes address the vector entry of node a
+    bool operator==(const TileLayout& o) const {
+        return nne == o.nne && unit_shift == o.unit_shift && rec_units == o.rec_units && sym == o.sym &&
+               blk_units == o.blk_units && has_mat == o.has_mat;
+    }
+};
+
 constexpr int kMaxValence = 31;      // 5-bit ordinal; start[] must fit uint8 (31*8 = 248)
 constexpr int kMaxRowBlocks = 255;   // rank fits uint8
 constexpr uint16_t kNoDst = 0xFFFF;
@@ -100,10 +156,23 @@ struct MeshDev {
     uint8_t* plan_pool = nullptr;
     int max_chunk_inc = 0, max_chunk_nodes = 0, max_chunk_recs = 0, max_kpad = 0, max_chunk_plan_words = 0;
 
+    // tile plan (second format); present when tile_dir != nullptr
+    TileDir* tile_dir = nullptr;       // (nchunks)
+    uint8_t* tile_blob = nullptr;      // blob pool
+    uint16_t* tile_codes = nullptr;    // working codes, encoded for tile_layout
+    uint16_t* tile_codes_neutral = nullptr;  // (record << 2*lb | a << lb | b), lb = log2(nne)
+    int64_t tile_blob_bytes = 0, tile_ncodes = 0;
+    int max_blob_bytes = 0, max_code_bytes = 0;
+    TileLayout tile_layout;            // encoding of tile_codes (nne == 0: not encoded yet)
+    int tile_threads = 128;            // CTA size of the tile kernels = target element records per chunk
+
     int64_t device_bytes = 0;
     int sm_count = 148;
     int device = 0;
 };
+
+// (re-)encode the working codes of the tile plan for an operator's staging layout
+int tile_prepare_layout(MeshDev& d, const TileLayout& L, cudaStream_t st);
 
 }  // namespace pfg
 

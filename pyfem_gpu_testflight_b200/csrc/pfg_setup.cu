@@ -463,6 +463,173 @@ __global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64
     cnode_id[p] = (int32_t)node;
 }
 
+
+// ---- tile plan (second format) -----------------------------------------------------------------
+__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne,
+                                  int64_t nslots, uint32_t* __restrict__ start_bytes, uint32_t* __restrict__ ncodes) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    start_bytes[p] = kk[p] + 3;  // k, self rank, start[k+1]
+    ncodes[p] = valence[p] * nne;
+}
+
+__global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__ chunks,
+                                   const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl,
+                                   uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
+                                   int* __restrict__ maxima) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const ChunkHdr h = chunks[c];
+    const int64_t p0 = h.node_begin, p1 = p0 + h.n_nodes;
+    const int64_t blob = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes + (sb_excl[p1] - sb_excl[p0]);
+    const int64_t codes = 2 * (nc_excl[p1] - nc_excl[p0]);
+    blob_len16[c] = (uint32_t)((blob + 15) / 16);
+    code_len16[c] = (uint32_t)((codes + 15) / 16);
+    atomicMax(&maxima[5], (int)min((int64_t)INT_MAX, (blob + 15) / 16 * 16));
+    atomicMax(&maxima[6], (int)min((int64_t)INT_MAX, (codes + 15) / 16 * 16));
+}
+
+__global__ void k_tile_dir(int64_t nchunks, const ChunkHdr* __restrict__ chunks, const int64_t* __restrict__ blob_off,
+                           const int64_t* __restrict__ code_off, const uint32_t* __restrict__ blob_len16,
+                           const uint32_t* __restrict__ code_len16, int64_t nrecs, TileDir* __restrict__ dir) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > nchunks) return;
+    TileDir t;
+    if (c == nchunks) {  // sentinel: a chunk's record count is the difference of consecutive rec_begin
+        t.blob_off16 = t.code_off16 = 0;
+        t.rec_begin = (uint32_t)nrecs;
+        t.blob_len16 = t.code_len16 = 0;
+        dir[c] = t;
+        return;
+    }
+    t.blob_off16 = (uint32_t)blob_off[c];
+    t.code_off16 = (uint32_t)code_off[c];
+    t.rec_begin = (uint32_t)chunks[c].rec_begin;
+    t.blob_len16 = (uint16_t)blob_len16[c];
+    t.code_len16 = (uint16_t)code_len16[c];
+    dir[c] = t;
+}
+
+template <int NNE>
+__global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
+                            const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
+                            const uint8_t* __restrict__ rank, const int64_t* __restrict__ blk_ptr,
+                            const int32_t* __restrict__ nbr, const ChunkHdr* __restrict__ chunks,
+                            const TileDir* __restrict__ dir, const uint64_t* __restrict__ rec_keys,
+                            const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl, int64_t own_begin,
+                            int64_t nslots, int m, uint8_t* __restrict__ blob_pool, uint16_t* __restrict__ codes_neutral,
+                            int32_t* __restrict__ cnode_id, int* __restrict__ err) {
+    constexpr int LB = (NNE == 4) ? 2 : 3;
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    const uint32_t c = slot_chunk[p];
+    const ChunkHdr h = chunks[c];
+    const TileDir td = dir[c];
+    const int64_t r = slot_node[p];
+    const int64_t node = own_begin + r;
+    const int64_t r_first = slot_node[h.node_begin];
+    uint8_t* blob = blob_pool + (size_t)td.blob_off16 * 16;
+    const int k = (int)(blk_ptr[r + 1] - blk_ptr[r]);
+    const int64_t s0 = inc_ptr[node], s1 = inc_ptr[node + 1];
+    const int64_t start_off = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes + (sb_excl[p] - sb_excl[h.node_begin]);
+    const int64_t code_off = nc_excl[p] - nc_excl[h.node_begin];
+    const int64_t grel = (blk_ptr[r] - blk_ptr[r_first]) * m * m;
+    if (start_off + k + 3 > 0xFFFF || code_off + (s1 - s0) * NNE > 0xFFFF || grel < 0 || grel > 0xFFFFFFFFll ||
+        h.n_recs > (0xFFFFu >> (2 * LB))) {
+        atomicExch(err, 1);
+        return;
+    }
+    if (p == h.node_begin) {
+        TileHdr th;
+        th.gbase = blk_ptr[r_first] * m * m;
+        th.rec_begin = (uint32_t)h.rec_begin;
+        th.node_begin = h.node_begin;
+        th.n_nodes = (uint16_t)h.n_nodes;
+        th.n_recs = (uint16_t)h.n_recs;
+        th.kpad = (uint16_t)h.kpad;
+        th.pad_ = 0;
+        th.pad2_[0] = th.pad2_[1] = 0;
+        *reinterpret_cast<TileHdr*>(blob) = th;
+    }
+    TileNode tn;
+    tn.gslot_rel = (uint32_t)grel;
+    tn.start_off = (uint16_t)start_off;
+    tn.code_off = (uint16_t)code_off;
+    reinterpret_cast<TileNode*>(blob + sizeof(TileHdr))[p - h.node_begin] = tn;
+    // rank of the node in its own (sorted) neighbour list
+    int self_t = 0;
+    {
+        int64_t lo = blk_ptr[r], hi = blk_ptr[r + 1];
+        const int64_t lo0 = lo;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (nbr[mid] < (int32_t)node) lo = mid + 1; else hi = mid;
+        }
+        self_t = (int)(lo - lo0);
+    }
+    uint8_t* pl = blob + start_off;
+    pl[0] = (uint8_t)k;
+    pl[1] = (uint8_t)self_t;
+    uint8_t* start = pl + 2;
+    // counting sort of the valence*NNE contributions by neighbour rank
+    uint8_t cnt[kMaxRowBlocks + 1];
+    for (int t = 0; t <= k; ++t) cnt[t] = 0;
+    for (int64_t s = s0; s < s1; ++s) {
+        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
+    }
+    for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
+    for (int t = 0; t <= k; ++t) start[t] = cnt[t];
+    uint16_t* codes = codes_neutral + (size_t)td.code_off16 * 8 + code_off;
+    for (int64_t s = s0; s < s1; ++s) {
+        const uint32_t ia = inc_list[s];
+        const uint64_t key = ((uint64_t)c << 32) | (uint64_t)(ia / NNE);
+        int64_t lo = h.rec_begin, hi = h.rec_begin + h.n_recs;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (rec_keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        const uint32_t rloc = (uint32_t)(lo - h.rec_begin);
+        const uint32_t a = ia % NNE;
+        const uint8_t* rk = rank + (int64_t)ia * NNE;
+#pragma unroll
+        for (int b = 0; b < NNE; ++b) codes[cnt[rk[b]]++] = (uint16_t)((rloc << (2 * LB)) | (a << LB) | b);
+    }
+    cnode_id[p] = (int32_t)node;
+}
+
+// neutral (record, a, b) codes -> staging offsets of one operator layout
+__host__ __device__ inline uint32_t tile_encode(const TileLayout& L, uint32_t neutral) {
+    const int lb = (L.nne == 4) ? 2 : 3;
+    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = neutral >> (2 * lb);
+    if (!L.has_mat) return ((r * L.rec_units + a) << 1);
+    if (!L.sym) return ((r * L.rec_units + (a * L.nne + b) * L.blk_units) << 1);
+    const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
+    const uint32_t tri = lo * (2 * L.nne - 1 - lo) / 2 + hi;
+    return ((r * L.rec_units + tri * L.blk_units) << 1) | (a > b ? 1u : 0u);
+}
+
+__global__ void k_tile_encode(const uint16_t* __restrict__ neutral, uint16_t* __restrict__ out, int64_t n, TileLayout L) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (uint16_t)tile_encode(L, neutral[i]);
+}
+
+// (re-)encode the working codes for an operator layout; no-op when they already match
+int tile_prepare_layout(MeshDev& d, const TileLayout& L, cudaStream_t st) {
+    if (d.tile_layout == L) return PFG_OK;
+    const int64_t max_off = (int64_t)d.max_chunk_recs * L.rec_units;
+    if (max_off >= 32768) {
+        set_error("chunk staging of %lld units exceeds the 15-bit code range", (long long)max_off);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    if (d.tile_ncodes)
+        k_tile_encode<<<grid_for(d.tile_ncodes), kThreads, 0, st>>>(d.tile_codes_neutral, d.tile_codes, d.tile_ncodes, L);
+    PFG_CUDA_TRY(cudaGetLastError());
+    d.tile_layout = L;
+    return PFG_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------------------------
@@ -553,10 +720,20 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     if (nown == 0 || d.nelems == 0) return PFG_OK;
     if (d.max_valence > kMaxValence || d.max_k > kMaxRowBlocks) return PFG_OK;  // atomic path only
 
-    // ---- chunk size from the shared-memory budget
-    int budget = env_int("PFG_CHUNK_SMEM_BYTES", (d.m == 3) ? 160 * 1024 : 72 * 1024);
-    int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
-    int64_t C = budget / per_node * 4 / 5;  // tie-aware cuts may overshoot the target by up to 1/4
+    // ---- chunk size
+    d.tile_threads = (env_int("PFG_TILE_THREADS", 128) >= 256) ? 256 : 128;
+    const bool tile = (d.m != 3);  // tile plan for the one-thread-per-element physics, first format for hex8 elasticity
+    int64_t C;
+    if (tile) {
+        // aim at tile_threads element records per chunk: a d-dimensional block of n^d nodes is touched by
+        // (n+1)^d elements; tie-aware cuts vary the block shape, so leave some slack
+        const double side = std::pow((double)d.tile_threads, 1.0 / d.ndims) - 1.0;
+        C = (int64_t)std::floor(std::pow(std::max(1.0, side), (double)d.ndims) * 0.86);
+    } else {
+        int budget = env_int("PFG_CHUNK_SMEM_BYTES", 160 * 1024);
+        int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
+        C = budget / per_node * 4 / 5;  // tie-aware cuts may overshoot the target by up to 1/4
+    }
     C = env_int("PFG_CHUNK_NODES", (int)C);
     C = std::max<int64_t>(4, std::min<int64_t>(C, 1024));
 
@@ -694,12 +871,95 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         set_error("too many element records for the gather plan");
         return PFG_ERR_UNSUPPORTED;
     }
-    PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t)));
-    PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t) + 32));  // bulk copies may over-read
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t) + 64));  // bulk copies may over-read
+    PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t) + 32));
     PFG_CUDA_TRY(cudaMalloc(&d.rec_elem, d.nrecs * sizeof(int32_t)));
     k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, d.rec_nodes, d.rec_dst,
                                                                d.rec_elem, d.chunks, maxima.p);
     k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
+    if (tile) {
+        // ---- tile plan: blob (header, node table, start bytes) and contribution codes per chunk
+        cudaFree(d.rec_dst);
+        d.rec_dst = nullptr;
+        DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16;
+        DBuf<int64_t> sb_excl, nc_excl, blob_off, code_off;
+        DBuf<int> terr;
+        PFG_CUDA_TRY(sbytes.alloc(nown + 1));
+        PFG_CUDA_TRY(ncodes.alloc(nown + 1));
+        PFG_CUDA_TRY(sb_excl.alloc(nown + 1));
+        PFG_CUDA_TRY(nc_excl.alloc(nown + 1));
+        PFG_CUDA_TRY(blob_len16.alloc(d.nchunks + 1));
+        PFG_CUDA_TRY(code_len16.alloc(d.nchunks + 1));
+        PFG_CUDA_TRY(blob_off.alloc(d.nchunks + 1));
+        PFG_CUDA_TRY(code_off.alloc(d.nchunks + 1));
+        PFG_CUDA_TRY(terr.alloc(1));
+        PFG_CUDA_TRY(cudaMemsetAsync(terr.p, 0, sizeof(int), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(sbytes.p, 0, (nown + 1) * sizeof(uint32_t), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(ncodes.p, 0, (nown + 1) * sizeof(uint32_t), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(blob_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(code_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
+        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, NNE, nown, sbytes.p, ncodes.p);
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, sbytes.p, sb_excl.p, nown + 1, st));
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, ncodes.p, nc_excl.p, nown + 1, st));
+        k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, sb_excl.p, nc_excl.p,
+                                                                     blob_len16.p, code_len16.p, maxima.p);
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, blob_len16.p, blob_off.p,
+                                              d.nchunks + 1, st));
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, code_len16.p, code_off.p,
+                                              d.nchunks + 1, st));
+        int64_t h_blob16 = 0, h_code16 = 0;
+        PFG_CUDA_TRY(cudaMemcpyAsync(&h_blob16, blob_off.p + d.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaMemcpyAsync(&h_code16, code_off.p + d.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        if (h_blob16 >= 0xffffffffll || h_code16 >= 0xffffffffll) {
+            set_error("tile plan pools exceed 64 GiB");
+            return PFG_ERR_UNSUPPORTED;
+        }
+        d.tile_blob_bytes = h_blob16 * 16;
+        d.tile_ncodes = h_code16 * 8;
+        PFG_CUDA_TRY(cudaMalloc(&d.tile_dir, (d.nchunks + 1) * sizeof(TileDir)));
+        PFG_CUDA_TRY(cudaMalloc(&d.tile_blob, d.tile_blob_bytes + 64));
+        PFG_CUDA_TRY(cudaMalloc(&d.tile_codes, d.tile_ncodes * 2 + 64));
+        PFG_CUDA_TRY(cudaMalloc(&d.tile_codes_neutral, d.tile_ncodes * 2 + 64));
+        PFG_CUDA_TRY(cudaMemsetAsync(d.tile_blob, 0, d.tile_blob_bytes + 64, st));
+        PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes, 0, d.tile_ncodes * 2 + 64, st));
+        PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes_neutral, 0, d.tile_ncodes * 2 + 64, st));
+        PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
+        k_tile_dir<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.chunks, blob_off.p, code_off.p,
+                                                                 blob_len16.p, code_len16.p, d.nrecs, d.tile_dir);
+        k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, d.rank,
+                                                              d.blk_ptr, d.nbr, d.chunks, d.tile_dir, rec_keys.p,
+                                                              sb_excl.p, nc_excl.p, d.own_begin, nown, d.m, d.tile_blob,
+                                                              d.tile_codes_neutral, d.cnode_id, terr.p);
+        int h_terr = 0, h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        PFG_CUDA_TRY(cudaGetLastError());
+        d.max_chunk_inc = h_max[0];
+        d.max_chunk_nodes = h_max[1];
+        d.max_kpad = h_max[2];
+        d.max_chunk_recs = h_max[3];
+        d.max_blob_bytes = h_max[5];
+        d.max_code_bytes = h_max[6];
+        if (h_terr || d.max_blob_bytes > 0xFFFF * 16 || d.max_code_bytes > 0xFFFF * 16) {
+            // chunk too irregular for the compact tile encoding: assemble with the atomic scatter instead
+            cudaFree(d.tile_dir); d.tile_dir = nullptr;
+            cudaFree(d.tile_blob); d.tile_blob = nullptr;
+            cudaFree(d.tile_codes); d.tile_codes = nullptr;
+            cudaFree(d.tile_codes_neutral); d.tile_codes_neutral = nullptr;
+            d.nchunks = 0;
+            return PFG_OK;
+        }
+        d.plan_bytes = d.tile_blob_bytes + d.tile_ncodes * 2;
+        d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * (NNE * 4 + 4) +
+                          d.tile_blob_bytes + d.tile_ncodes * 4;
+        return PFG_OK;
+    }
     k_fill_dst<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,
                                                         d.chunks, rec_keys.p, d.own_begin, nown, d.rec_dst);
 
@@ -733,7 +993,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 
 static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
-                    d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool};
+                    d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
+                    d.tile_codes, d.tile_codes_neutral};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }
@@ -875,9 +1136,12 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_NCHUNKS: *value = d.nchunks; break;
         case PFG_INFO_CHUNK_ELEMS: *value = d.nrecs; break;
         case PFG_INFO_PLAN_BYTES:
-            *value = d.nchunks ? (int64_t)(d.nchunks * sizeof(ChunkHdr) + (d.own_end - d.own_begin) * sizeof(ChunkNode) +
-                                           d.nrecs * (d.nne * 6) + d.plan_bytes)
-                               : 0;
+            if (d.tile_dir)
+                *value = (int64_t)(d.nchunks * sizeof(TileDir) + d.nrecs * (d.nne * 4) + d.plan_bytes);
+            else
+                *value = d.nchunks ? (int64_t)(d.nchunks * sizeof(ChunkHdr) + (d.own_end - d.own_begin) * sizeof(ChunkNode) +
+                                               d.nrecs * (d.nne * 6) + d.plan_bytes)
+                                   : 0;
             break;
         case PFG_INFO_DEVICE_BYTES: *value = d.device_bytes; break;
         case PFG_INFO_MAX_ROW_BLOCKS: *value = d.max_k; break;
