@@ -391,65 +391,90 @@ struct TileCfg {
 
 // phase B: one thread per (chunk node, neighbour) block sums the staged contributions in plan order and writes
 // the block's m x m CSR values once; then one thread per chunk node sums the vector entries.
+// CP > 0: every block of the chunk has at most CP contributions; the loop is fully unrolled and slots past a
+// block's count read the all-zero record 0 (code 0), so a warp runs one branch-free instruction stream.
+template <class Op, int THREADS, int CP>
+PFG_DEV void tile_phase_b_mat(const TileHdr& h, const unsigned char* __restrict__ blob,
+                              const uint16_t* __restrict__ codes, const double* __restrict__ stage,
+                              const Outputs& out) {
+    using St = TileStage<Op>;
+    constexpr int M = Op::M, BLK = M * M, NMAT = Op::NMAT;
+    const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
+    const int kpad = (int)h.kpad;
+    const int items = (int)h.n_nodes * kpad;
+    const float inv_kpad = 1.0f / (float)kpad;
+    double* vbase[NMAT];
+#pragma unroll
+    for (int mt = 0; mt < NMAT; ++mt) vbase[mt] = out.vals[mt] ? out.vals[mt] + h.gbase : nullptr;
+    for (int idx = threadIdx.x; idx < items; idx += THREADS) {
+        const int p = (int)(((float)idx + 0.5f) * inv_kpad);
+        const int t = idx - p * kpad;
+        const TileNode tn = nodes[p];
+        const uint8_t* __restrict__ pl = blob + tn.start_off;
+        const int k = pl[0];
+        if (t >= k) continue;
+        const int s0 = pl[2 + t], cnt = (int)pl[3 + t] - s0;
+        const uint16_t* __restrict__ cp = codes + tn.code_off + s0;
+        double acc[NMAT][BLK];
+#pragma unroll
+        for (int mt = 0; mt < NMAT; ++mt)
+#pragma unroll
+            for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
+        auto add = [&](unsigned code) {
+            const double* __restrict__ q = stage + (code >> 1) * St::UNIT_D;
+#pragma unroll
+            for (int mt = 0; mt < NMAT; ++mt) {
+                const double* __restrict__ qm = q + mt * St::NB * BLK;
+                if constexpr (M == 2) {
+                    const double2 v0 = reinterpret_cast<const double2*>(qm)[0];
+                    const double2 v1 = reinterpret_cast<const double2*>(qm)[1];
+                    const bool tr = St::SYM && (code & 1u);
+                    acc[mt][0] += v0.x;
+                    acc[mt][1] += tr ? v1.x : v0.y;
+                    acc[mt][2] += tr ? v0.y : v1.x;
+                    acc[mt][3] += v1.y;
+                } else {
+                    acc[mt][0] += qm[0];
+                }
+            }
+        };
+        if constexpr (CP > 0) {
+            unsigned code[CP];
+#pragma unroll
+            for (int j = 0; j < CP; ++j) code[j] = cp[j];  // may read past the block's codes: stays in the padded buffer
+#pragma unroll
+            for (int j = 0; j < CP; ++j) add(j < cnt ? code[j] : 0u);
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < cnt; ++j) add(cp[j]);
+        }
+#pragma unroll
+        for (int mt = 0; mt < NMAT; ++mt) {
+            if (vbase[mt] == nullptr) continue;
+            double* dst = vbase[mt] + (tn.gslot_rel + (unsigned)(M * t));
+            if constexpr (M == 2) {
+                __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[mt][0], acc[mt][1]));
+                __stcs(reinterpret_cast<double2*>(dst + 2 * k), make_double2(acc[mt][2], acc[mt][3]));
+            } else {
+                __stcs(dst, acc[mt][0]);
+            }
+        }
+    }
+}
+
 template <class Op, int THREADS>
 PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ blob,
                           const uint16_t* __restrict__ codes, const double* __restrict__ stage, const Outputs& out) {
     using St = TileStage<Op>;
-    constexpr int NNE = Op::NNE, M = Op::M, BLK = M * M, NMAT = Op::NMAT;
+    constexpr int NNE = Op::NNE, BLK = Op::M * Op::M, NMAT = Op::NMAT;
     const TileHdr h = *reinterpret_cast<const TileHdr*>(blob);
-    const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
     if constexpr (NMAT > 0) {
-        const int kpad = (int)h.kpad;
-        const int items = (int)h.n_nodes * kpad;
-        const float inv_kpad = 1.0f / (float)kpad;
-        for (int idx = threadIdx.x; idx < items; idx += THREADS) {
-            const int p = (int)(((float)idx + 0.5f) * inv_kpad);
-            const int t = idx - p * kpad;
-            const TileNode tn = nodes[p];
-            const uint8_t* __restrict__ pl = blob + tn.start_off;
-            const int k = pl[0];
-            if (t >= k) continue;
-            const int s0 = pl[2 + t], s1 = pl[3 + t];
-            const uint16_t* __restrict__ cp = codes + tn.code_off;
-            double acc[NMAT][BLK];
-#pragma unroll
-            for (int mt = 0; mt < NMAT; ++mt)
-#pragma unroll
-                for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
-            for (int s = s0; s < s1; ++s) {
-                const unsigned code = cp[s];
-                const double* __restrict__ q = stage + (code >> 1) * St::UNIT_D;
-#pragma unroll
-                for (int mt = 0; mt < NMAT; ++mt) {
-                    const double* __restrict__ qm = q + mt * St::NB * BLK;
-                    if constexpr (M == 2) {
-                        const double2 v0 = reinterpret_cast<const double2*>(qm)[0];
-                        const double2 v1 = reinterpret_cast<const double2*>(qm)[1];
-                        const bool tr = St::SYM && (code & 1u);
-                        acc[mt][0] += v0.x;
-                        acc[mt][1] += tr ? v1.x : v0.y;
-                        acc[mt][2] += tr ? v0.y : v1.x;
-                        acc[mt][3] += v1.y;
-                    } else {
-                        acc[mt][0] += qm[0];
-                    }
-                }
-            }
-#pragma unroll
-            for (int mt = 0; mt < NMAT; ++mt) {
-                if (out.vals[mt] == nullptr) continue;
-                double* dst = out.vals[mt] + h.gbase + tn.gslot_rel + M * t;
-                if constexpr (M == 2) {
-                    __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[mt][0], acc[mt][1]));
-                    __stcs(reinterpret_cast<double2*>(dst + 2 * k), make_double2(acc[mt][2], acc[mt][3]));
-                } else {
-                    __stcs(dst, acc[mt][0]);
-                }
-            }
-        }
+        if (h.cpad <= 4) tile_phase_b_mat<Op, THREADS, 4>(h, blob, codes, stage, out);
+        else tile_phase_b_mat<Op, THREADS, 0>(h, blob, codes, stage, out);
     }
     if constexpr (Op::NVEC > 0) {
         if (out.vec != nullptr) {
+            const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
             for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
                 const TileNode tn = nodes[p];
                 const uint8_t* __restrict__ pl = blob + tn.start_off;
@@ -459,7 +484,7 @@ PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ 
                 double sum = 0.0;
                 for (int s = s0; s < s1; ++s) {  // the diagonal block's contributions are the node's incidences
                     const int off = (int)(cp[s] >> 1) * St::UNIT_D;  // doubles from the chunk's staging base
-                    const int r = off / St::S;
+                    const int r = off / St::S;                       // staged record (record 0 is the zero record)
                     int a = off - r * St::S;  // vector-only operators address the entry directly
                     if constexpr (NMAT > 0) {
                         const int bi = a / BLK;
@@ -534,6 +559,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
     };
 
+    for (int i = threadIdx.x; i < St::S; i += THREADS) stage[i] = 0.0;  // record slot 0: zeros (code 0)
     if (threadIdx.x == 0) {
         for (int s = 0; s < 3; ++s) mbar_init(&bars[s], 1);
         for (int j = 0; j <= 4 && j <= nloc; ++j) dir_s[j] = dir_g[j];
@@ -554,7 +580,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         // ---- phase A: one thread per element record -> staged element matrices
         const int n_recs = n_recs_of(i);
         for (int r = threadIdx.x; r < n_recs; r += THREADS) {
-            TileSink<Op> sink{stage + (size_t)r * St::S};
+            TileSink<Op> sink{stage + (size_t)(r + 1) * St::S};  // slot 0 is the all-zero record
             double xe[NNE][DIM], fe[NNE];
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
@@ -765,13 +791,13 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     cfg.off_dir = 64;
     cfg.off_blob = cfg.off_dir + 8 * (int)sizeof(TileDir);
     cfg.off_codes = cfg.off_blob + align16(d.max_blob_bytes);
-    cfg.off_ids = cfg.off_codes + align16(d.max_code_bytes);
+    cfg.off_ids = cfg.off_codes + align16(d.max_code_bytes) + 16;  // slack: phase B may read a few codes past the end
     cfg.ids_stride = align16(d.max_chunk_recs * NNE * 4);
     cfg.off_x = cfg.off_ids + 2 * cfg.ids_stride;
     cfg.off_field = cfg.off_x + cfg.max_recs * NNE * DIM * 8;
     cfg.off_stage = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
     cfg.nchunks = (int)d.nchunks;
-    const size_t smem = (size_t)cfg.off_stage + (size_t)d.max_chunk_recs * St::S * 8;
+    const size_t smem = (size_t)cfg.off_stage + (size_t)(d.max_chunk_recs + 1) * St::S * 8;
     if (smem > 227 * 1024) {
         set_error("chunk staging of %zu bytes exceeds shared memory", smem);
         return PFG_ERR_UNSUPPORTED;

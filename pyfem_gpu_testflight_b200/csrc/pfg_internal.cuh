@@ -92,7 +92,7 @@ struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
     uint32_t node_begin;   // first chunk-ordered node slot (row ids of the vector output: cnode_id)
     uint16_t n_nodes, n_recs;
     uint16_t kpad;         // max neighbour count over the chunk's nodes
-    uint16_t pad_;
+    uint16_t cpad;         // max contributions to one block over the chunk
     uint32_t pad2_[2];
 };
 

@@ -518,7 +518,7 @@ __global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32
                             const TileDir* __restrict__ dir, const uint64_t* __restrict__ rec_keys,
                             const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl, int64_t own_begin,
                             int64_t nslots, int m, uint8_t* __restrict__ blob_pool, uint16_t* __restrict__ codes_neutral,
-                            int32_t* __restrict__ cnode_id, int* __restrict__ err) {
+                            int32_t* __restrict__ cnode_id, int* __restrict__ chunk_cpad, int* __restrict__ err) {
     constexpr int LB = (NNE == 4) ? 2 : 3;
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nslots) return;
@@ -547,7 +547,7 @@ __global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32
         th.n_nodes = (uint16_t)h.n_nodes;
         th.n_recs = (uint16_t)h.n_recs;
         th.kpad = (uint16_t)h.kpad;
-        th.pad_ = 0;
+        th.cpad = 0;  // filled by k_tile_cpad
         th.pad2_[0] = th.pad2_[1] = 0;
         *reinterpret_cast<TileHdr*>(blob) = th;
     }
@@ -579,6 +579,9 @@ __global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32
 #pragma unroll
         for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
     }
+    int cmax = 0;
+    for (int t = 0; t < k; ++t) cmax = max(cmax, (int)cnt[t + 1]);
+    atomicMax(&chunk_cpad[c], cmax);
     for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
     for (int t = 0; t <= k; ++t) start[t] = cnt[t];
     uint16_t* codes = codes_neutral + (size_t)td.code_off16 * 8 + code_off;
@@ -599,10 +602,17 @@ __global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32
     cnode_id[p] = (int32_t)node;
 }
 
-// neutral (record, a, b) codes -> staging offsets of one operator layout
+__global__ void k_tile_cpad(int64_t nchunks, const TileDir* __restrict__ dir, const int* __restrict__ chunk_cpad,
+                            uint8_t* __restrict__ blob_pool) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    reinterpret_cast<TileHdr*>(blob_pool + (size_t)dir[c].blob_off16 * 16)->cpad = (uint16_t)chunk_cpad[c];
+}
+
+// neutral (record, a, b) codes -> staging offsets of one operator layout (record slot 0 is the zero record)
 __host__ __device__ inline uint32_t tile_encode(const TileLayout& L, uint32_t neutral) {
     const int lb = (L.nne == 4) ? 2 : 3;
-    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = neutral >> (2 * lb);
+    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = (neutral >> (2 * lb)) + 1;
     if (!L.has_mat) return ((r * L.rec_units + a) << 1);
     if (!L.sym) return ((r * L.rec_units + (a * L.nne + b) * L.blk_units) << 1);
     const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
@@ -618,7 +628,7 @@ __global__ void k_tile_encode(const uint16_t* __restrict__ neutral, uint16_t* __
 // (re-)encode the working codes for an operator layout; no-op when they already match
 int tile_prepare_layout(MeshDev& d, const TileLayout& L, cudaStream_t st) {
     if (d.tile_layout == L) return PFG_OK;
-    const int64_t max_off = (int64_t)d.max_chunk_recs * L.rec_units;
+    const int64_t max_off = (int64_t)(d.max_chunk_recs + 1) * L.rec_units;
     if (max_off >= 32768) {
         set_error("chunk staging of %lld units exceeds the 15-bit code range", (long long)max_off);
         return PFG_ERR_UNSUPPORTED;
@@ -883,7 +893,9 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.rec_dst = nullptr;
         DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16;
         DBuf<int64_t> sb_excl, nc_excl, blob_off, code_off;
-        DBuf<int> terr;
+        DBuf<int> terr, chunk_cpad;
+        PFG_CUDA_TRY(chunk_cpad.alloc(d.nchunks));
+        PFG_CUDA_TRY(cudaMemsetAsync(chunk_cpad.p, 0, d.nchunks * sizeof(int), st));
         PFG_CUDA_TRY(sbytes.alloc(nown + 1));
         PFG_CUDA_TRY(ncodes.alloc(nown + 1));
         PFG_CUDA_TRY(sb_excl.alloc(nown + 1));
@@ -934,7 +946,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, d.rank,
                                                               d.blk_ptr, d.nbr, d.chunks, d.tile_dir, rec_keys.p,
                                                               sb_excl.p, nc_excl.p, d.own_begin, nown, d.m, d.tile_blob,
-                                                              d.tile_codes_neutral, d.cnode_id, terr.p);
+                                                              d.tile_codes_neutral, d.cnode_id, chunk_cpad.p, terr.p);
+        k_tile_cpad<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.tile_dir, chunk_cpad.p, d.tile_blob);
         int h_terr = 0, h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
