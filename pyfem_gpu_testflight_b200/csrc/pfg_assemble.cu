@@ -210,6 +210,16 @@ PFG_DEV void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
 }
 
+// TMA bulk store shared -> global (SASS UBLKCP.G.S), tracked by the issuing thread's bulk async-group
+PFG_DEV void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)),
+                 "r"(bytes)
+                 : "memory");
+}
+PFG_DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+PFG_DEV void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+PFG_DEV void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // shared-memory carve-up of a gather CTA: [mbarrier | chunk node table | chunk plan bytes | row blocks | vectors]
 struct GatherSmem {
     uint64_t* bar;
@@ -385,18 +395,19 @@ struct TileCfg {
     int off_ids, ids_stride;      // record node ids, two stages
     int off_x, off_field;         // coordinates / nodal field of the chunk's records (one stage)
     int off_stage;                // element-record staging
+    int off_image;                // row format: image of the chunk's CSR values (TMA bulk-store source)
     int max_recs;                 // records per chunk the stages are sized for
     int nchunks;
 };
 
-// phase B: one thread per (chunk node, neighbour) block sums the staged contributions in plan order and writes
-// the block's m x m CSR values once; then one thread per chunk node sums the vector entries.
+// phase B, item format: one thread per (chunk node, neighbour) block sums the staged contributions in plan
+// order and writes the block's m x m CSR values once.
 // CP > 0: every block of the chunk has at most CP contributions; the loop is fully unrolled and slots past a
 // block's count read the all-zero record 0 (code 0), so a warp runs one branch-free instruction stream.
 template <class Op, int THREADS, int CP>
-PFG_DEV void tile_phase_b_mat(const TileHdr& h, const unsigned char* __restrict__ blob,
-                              const uint16_t* __restrict__ codes, const double* __restrict__ stage,
-                              const Outputs& out) {
+PFG_DEV void tile_phase_b_items(const TileHdr& h, const unsigned char* __restrict__ blob,
+                                const uint16_t* __restrict__ codes, const double* __restrict__ stage,
+                                const Outputs& out) {
     using St = TileStage<Op>;
     constexpr int M = Op::M, BLK = M * M, NMAT = Op::NMAT;
     const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
@@ -410,7 +421,7 @@ PFG_DEV void tile_phase_b_mat(const TileHdr& h, const unsigned char* __restrict_
         const int p = (int)(((float)idx + 0.5f) * inv_kpad);
         const int t = idx - p * kpad;
         const TileNode tn = nodes[p];
-        const uint8_t* __restrict__ pl = blob + tn.start_off;
+        const uint8_t* __restrict__ pl = blob + tn.aux;
         const int k = pl[0];
         if (t >= k) continue;
         const int s0 = pl[2 + t], cnt = (int)pl[3 + t] - s0;
@@ -421,7 +432,7 @@ PFG_DEV void tile_phase_b_mat(const TileHdr& h, const unsigned char* __restrict_
 #pragma unroll
             for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
         auto add = [&](unsigned code) {
-            const double* __restrict__ q = stage + (code >> 1) * St::UNIT_D;
+            const double* __restrict__ q = stage + (code >> 2) * St::UNIT_D;
 #pragma unroll
             for (int mt = 0; mt < NMAT; ++mt) {
                 const double* __restrict__ qm = q + mt * St::NB * BLK;
@@ -462,6 +473,53 @@ PFG_DEV void tile_phase_b_mat(const TileHdr& h, const unsigned char* __restrict_
     }
 }
 
+// phase B, row format (2x2 blocks, one matrix): one thread per chunk node walks the node's codes in groups of
+// eight, sums each (node, neighbour) block in plan order and, at the block's end flag, drops its two rows into
+// the shared-memory image of the CSR values.  Neighbouring lanes read the same block of neighbouring records,
+// so on a regular mesh the gather runs at one bank-conflict-free wavefront per 128 bytes.
+template <class Op, int THREADS>
+PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict__ blob,
+                               const uint16_t* __restrict__ codes, const double* __restrict__ stage,
+                               double* __restrict__ image) {
+    using St = TileStage<Op>;
+    static_assert(Op::M == 2 && Op::NMAT == 1, "row format is for one matrix of 2x2 blocks");
+    const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
+    const uint16_t* __restrict__ kn = reinterpret_cast<const uint16_t*>(nodes + h.n_nodes);
+    const unsigned char* __restrict__ stage_b = reinterpret_cast<const unsigned char*>(stage);
+    for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
+        const TileNode tn = nodes[p];
+        const unsigned knv = kn[p];
+        const int row_bytes = (int)(knv & 255u) * 16;  // 2k doubles per dof row
+        const int ngroups = (int)(knv >> 8);
+        const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(codes) + tn.code_off;
+        unsigned char* o = reinterpret_cast<unsigned char*>(image) + (size_t)tn.aux * 16;
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        auto add = [&](unsigned code) {  // code in the low 16 bits
+            const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code & 0xFFFCu) << 2));
+            const double2 v0 = q[0], v1 = q[1];
+            const bool tr = St::SYM && (code & 1u);
+            a00 += v0.x;
+            a01 += tr ? v1.x : v0.y;
+            a10 += tr ? v0.y : v1.x;
+            a11 += v1.y;
+            if (code & 2u) {  // last contribution of this block
+                *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
+                *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
+                o += 16;
+                a00 = a01 = a10 = a11 = 0.0;
+            }
+        };
+#pragma unroll 1
+        for (int g = 0; g < ngroups; ++g) {
+            const uint4 c = cp[g];
+            add(c.x & 0xFFFFu), add(c.x >> 16);
+            add(c.y & 0xFFFFu), add(c.y >> 16);
+            add(c.z & 0xFFFFu), add(c.z >> 16);
+            add(c.w & 0xFFFFu), add(c.w >> 16);
+        }
+    }
+}
+
 template <class Op, int THREADS>
 PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ blob,
                           const uint16_t* __restrict__ codes, const double* __restrict__ stage, const Outputs& out) {
@@ -469,21 +527,21 @@ PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ 
     constexpr int NNE = Op::NNE, BLK = Op::M * Op::M, NMAT = Op::NMAT;
     const TileHdr h = *reinterpret_cast<const TileHdr*>(blob);
     if constexpr (NMAT > 0) {
-        if (h.cpad <= 4) tile_phase_b_mat<Op, THREADS, 4>(h, blob, codes, stage, out);
-        else tile_phase_b_mat<Op, THREADS, 0>(h, blob, codes, stage, out);
+        if (h.cpad <= 4) tile_phase_b_items<Op, THREADS, 4>(h, blob, codes, stage, out);
+        else tile_phase_b_items<Op, THREADS, 0>(h, blob, codes, stage, out);
     }
     if constexpr (Op::NVEC > 0) {
         if (out.vec != nullptr) {
             const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
             for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
                 const TileNode tn = nodes[p];
-                const uint8_t* __restrict__ pl = blob + tn.start_off;
+                const uint8_t* __restrict__ pl = blob + tn.aux;
                 const int self_t = pl[1];
                 const int s0 = pl[2 + self_t], s1 = pl[3 + self_t];
                 const uint16_t* __restrict__ cp = codes + tn.code_off;
                 double sum = 0.0;
                 for (int s = s0; s < s1; ++s) {  // the diagonal block's contributions are the node's incidences
-                    const int off = (int)(cp[s] >> 1) * St::UNIT_D;  // doubles from the chunk's staging base
+                    const int off = (int)(cp[s] >> 2) * St::UNIT_D;  // doubles from the chunk's staging base
                     const int r = off / St::S;                       // staged record (record 0 is the zero record)
                     int a = off - r * St::S;  // vector-only operators address the entry directly
                     if constexpr (NMAT > 0) {
@@ -519,6 +577,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
     double* xs = reinterpret_cast<double*>(smem + cfg.off_x);
     double* fs = reinterpret_cast<double*>(smem + cfg.off_field);
     double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
+    double* image = reinterpret_cast<double*>(smem + cfg.off_image);
+    constexpr bool ROWS = (Op::M == 2);  // row format: handles with two dofs per node
     const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;  // entries 0..nloc (nloc = next CTA's first / sentinel)
 
     auto ids_stage = [&](int j) -> int32_t* { return reinterpret_cast<int32_t*>(smem + cfg.off_ids + (j & 1) * cfg.ids_stride); };
@@ -597,6 +657,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + dir_s[i & 7].rec_begin + r);
             Op::run(prm, xe, fe, elem, sink);
         }
+        if constexpr (ROWS) tma_store_wait_read();  // the previous chunk's bulk stores have read the image
         __syncthreads();
         // ---- prefetch: record ids two chunks ahead, coordinates one chunk ahead
         if (threadIdx.x == 0 && i + 2 < nloc) issue_ids(i + 2);
@@ -607,10 +668,31 @@ __global__ void __launch_bounds__(THREADS, MINB)
         cp_async_commit();
         // ---- phase B: plan-ordered sums, each CSR block written once
         mbar_wait(&bars[0], i & 1);
-        tile_phase_b<Op, THREADS>(mv, blob_s, codes_s, stage, out);
-        __syncthreads();
+        if constexpr (ROWS) {
+            const TileHdr h = *reinterpret_cast<const TileHdr*>(blob_s);
+            tile_phase_b_rows<Op, THREADS>(h, blob_s, codes_s, stage, image);
+            fence_proxy_async();  // image writes (generic proxy) -> visible to the bulk-copy engine
+            __syncthreads();
+            // one TMA bulk store per run of consecutive node ids: image -> CSR values
+            if (out.vals[0] != nullptr) {
+                const TileRun* __restrict__ runs = reinterpret_cast<const TileRun*>(
+                    blob_s + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes + ((2 * (int)h.n_nodes + 7) / 8) * 8);
+                for (int q = threadIdx.x; q < (int)h.n_runs; q += THREADS) {
+                    const TileRun run = runs[q];
+                    tma_store_1d(out.vals[0] + h.gbase + run.gslot_rel,
+                                 reinterpret_cast<const unsigned char*>(image) + (size_t)run.out_off16 * 16,
+                                 (uint32_t)run.len16 * 16u);
+                }
+                tma_store_commit();
+            }
+            __syncthreads();  // every thread has read the blob's run table before the next blob lands
+        } else {
+            tile_phase_b<Op, THREADS>(mv, blob_s, codes_s, stage, out);
+            __syncthreads();
+        }
         if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
     }
+    if constexpr (ROWS) tma_store_wait_read();
 }
 
 struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
@@ -797,7 +879,12 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     cfg.off_field = cfg.off_x + cfg.max_recs * NNE * DIM * 8;
     cfg.off_stage = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
     cfg.nchunks = (int)d.nchunks;
-    const size_t smem = (size_t)cfg.off_stage + (size_t)(d.max_chunk_recs + 1) * St::S * 8;
+    cfg.off_image = align16(cfg.off_stage + (d.max_chunk_recs + 1) * St::S * 8);
+    if ((Op::M == 2) != d.tile_rows) {
+        set_error("tile plan sub-format does not match the operator");
+        return PFG_ERR_INVALID;
+    }
+    const size_t smem = (size_t)cfg.off_image + (Op::M == 2 ? (size_t)d.max_out_bytes : 0);
     if (smem > 227 * 1024) {
         set_error("chunk staging of %zu bytes exceeds shared memory", smem);
         return PFG_ERR_UNSUPPORTED;

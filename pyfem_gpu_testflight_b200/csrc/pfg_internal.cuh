@@ -69,19 +69,31 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 //
 // Per chunk, three global arrays feed one CTA iteration:
 //   tile_dir[c]      16 B   where the chunk's blob / codes / records live
-//   blob             16 B aligned: TileHdr | TileNode[n_nodes] | per node uint8 start[k+1]
-//   codes            16 B aligned: per node uint16[valence*nne], contributions sorted by neighbour rank
+//   blob             16 B aligned: TileHdr | TileNode[n_nodes] | format-specific tables (below)
+//   codes            16 B aligned: per node uint16 contribution codes, sorted by neighbour rank
 //   rec_nodes        (n_recs, nne) int32 node ids of the records (shared with the first format)
-// A code is (offset << 1) | transpose, offset in units of the staging block (16 B for 2x2 blocks,
-// 8 B for scalars) from the start of the chunk's staging area.  Codes depend on the staging layout
-// of the operator (record stride, symmetric or full storage); they are stored in the neutral form
-// (record << 2*lb | a << lb | b) beside the working copy, which is re-encoded when an operator with another
-// layout runs.
+// A code is (offset << 2) | end << 1 | transpose: offset in units of the staging block (16 B for 2x2
+// blocks, 8 B for scalars) from the start of the chunk's staging area, whose record slot 0 is all zeros
+// (code 0 adds nothing); `end` marks the last contribution of a (node, neighbour) block.  Codes depend on
+// the staging layout of the operator (record stride, symmetric or full storage); they are kept in the
+// neutral form (end << 15 | record << 2*lb | a << lb | b, 0xFFFF = padding) beside the working copy, which
+// is re-encoded when an operator with another layout runs.
+//
+// Two sub-formats, chosen by ndof_per_node when the mesh handle is built:
+//   item format (m == 1): one phase-B thread per (node, neighbour) block.  After the node table the blob
+//       holds, per node, uint8 k, uint8 self rank, uint8 start[k+1] (prefix of contribution counts);
+//       TileNode::aux = byte offset of that record, TileNode::code_off = index of the node's first code.
+//   row format (m == 2): one phase-B thread per node walks the node's codes (padded to groups of 8 with
+//       code 0), writes the node's two dof rows into a shared-memory image of the CSR values, and the
+//       image leaves through one TMA bulk store per run of consecutive node ids.  After the node table:
+//       uint16 kn[n_nodes] = k | code groups << 8 (padded to 8 B), then TileRun[n_runs];
+//       TileNode::aux = offset of the node's rows in the image (16 B units), TileNode::code_off = index
+//       of the node's first code group.
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) TileDir {  // 16 bytes
     uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
     uint32_t code_off16;   // codes offset in the code pool, 16-byte units
-    uint32_t rec_begin;    // first record
+    uint32_t rec_begin;    // first record (a chunk's record count is the next entry's rec_begin minus this)
     uint16_t blob_len16;   // blob bytes / 16
     uint16_t code_len16;   // code bytes / 16
 };
@@ -93,16 +105,22 @@ struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
     uint16_t n_nodes, n_recs;
     uint16_t kpad;         // max neighbour count over the chunk's nodes
     uint16_t cpad;         // max contributions to one block over the chunk
-    uint32_t pad2_[2];
+    uint16_t n_runs;       // row format: runs of consecutive node ids
+    uint16_t pad_;
+    uint32_t pad2_;
 };
 
 struct __align__(8) TileNode {  // 8 bytes
     uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileHdr::gbase
-    uint16_t start_off;    // byte offset of start[] inside the blob
-    uint16_t code_off;     // index of the node's first code inside the chunk's code segment
-    // k = number of neighbours and the rank of the node itself are the first two bytes at start_off
+    uint16_t aux;          // item format: byte offset of the node's start record; row format: image offset / 16
+    uint16_t code_off;     // item format: first code index; row format: first code group (8 codes)
 };
-// node plan bytes at start_off: uint8 k, uint8 self_t, uint8 start[k+1]
+
+struct __align__(8) TileRun {  // 8 bytes: one bulk store, image -> CSR values
+    uint32_t gslot_rel;    // first value slot, relative to TileHdr::gbase
+    uint16_t out_off16;    // image offset / 16
+    uint16_t len16;        // bytes / 16
+};
 
 struct TileLayout {  // how an operator stages one record; decides the code encoding
     int nne = 0;       // nodes per element
@@ -162,7 +180,8 @@ struct MeshDev {
     uint16_t* tile_codes = nullptr;    // working codes, encoded for tile_layout
     uint16_t* tile_codes_neutral = nullptr;  // (record << 2*lb | a << lb | b), lb = log2(nne)
     int64_t tile_blob_bytes = 0, tile_ncodes = 0;
-    int max_blob_bytes = 0, max_code_bytes = 0;
+    int max_blob_bytes = 0, max_code_bytes = 0, max_out_bytes = 0;
+    bool tile_rows = false;            // row sub-format (m == 2)
     TileLayout tile_layout;            // encoding of tile_codes (nne == 0: not encoded yet)
     int tile_threads = 128;            // CTA size of the tile kernels = target element records per chunk
 

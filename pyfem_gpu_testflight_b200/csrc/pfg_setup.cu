@@ -465,23 +465,41 @@ __global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64
 
 
 // ---- tile plan (second format) -----------------------------------------------------------------
-__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne,
+__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne, int rows,
                                   int64_t nslots, uint32_t* __restrict__ start_bytes, uint32_t* __restrict__ ncodes) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nslots) return;
-    start_bytes[p] = kk[p] + 3;  // k, self rank, start[k+1]
-    ncodes[p] = valence[p] * nne;
+    const uint32_t n = valence[p] * nne;
+    start_bytes[p] = rows ? 0 : kk[p] + 3;  // item format: k, self rank, start[k+1]
+    ncodes[p] = rows ? ((n + 7) / 8) * 8 : n;
+}
+
+// row format: a run starts where the chunk starts or the node ids stop being consecutive
+__global__ void k_tile_run_flags(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
+                                 int64_t nslots, uint32_t* __restrict__ flag) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    flag[p] = (p == 0 || slot_chunk[p] != slot_chunk[p - 1] || slot_node[p] != slot_node[p - 1] + 1) ? 1u : 0u;
 }
 
 __global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__ chunks,
                                    const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl,
-                                   uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
+                                   const int64_t* __restrict__ kk_excl, const uint32_t* __restrict__ run_id, int rows,
+                                   int m, uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
                                    int* __restrict__ maxima) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const ChunkHdr h = chunks[c];
     const int64_t p0 = h.node_begin, p1 = p0 + h.n_nodes;
-    const int64_t blob = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes + (sb_excl[p1] - sb_excl[p0]);
+    int64_t blob = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
+    if (rows) {
+        const int64_t nruns = (int64_t)run_id[p1 - 1] - run_id[p0] + 1;
+        blob += ((2 * (int64_t)h.n_nodes + 7) / 8) * 8 + (int64_t)sizeof(TileRun) * nruns;
+        const int64_t out_bytes = (kk_excl[p1] - kk_excl[p0]) * m * m * 8;
+        atomicMax(&maxima[7], (int)min((int64_t)INT_MAX, out_bytes));
+    } else {
+        blob += sb_excl[p1] - sb_excl[p0];
+    }
     const int64_t codes = 2 * (nc_excl[p1] - nc_excl[p0]);
     blob_len16[c] = (uint32_t)((blob + 15) / 16);
     code_len16[c] = (uint32_t)((codes + 15) / 16);
@@ -510,96 +528,148 @@ __global__ void k_tile_dir(int64_t nchunks, const ChunkHdr* __restrict__ chunks,
     dir[c] = t;
 }
 
+struct TileFillArgs {
+    const uint32_t *slot_node, *slot_chunk;
+    const int64_t* inc_ptr;
+    const uint32_t* inc_list;
+    const uint8_t* rank;
+    const int64_t* blk_ptr;
+    const int32_t* nbr;
+    const ChunkHdr* chunks;
+    const TileDir* dir;
+    const uint64_t* rec_keys;
+    const int64_t *sb_excl, *nc_excl, *kk_excl;
+    const uint32_t *run_flag, *run_id;
+    int64_t own_begin, nslots;
+    int m, rows;
+    uint8_t* blob_pool;
+    uint16_t* codes_neutral;
+    int32_t* cnode_id;
+    int *chunk_cpad, *err;
+};
+
 template <int NNE>
-__global__ void k_tile_fill(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
-                            const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
-                            const uint8_t* __restrict__ rank, const int64_t* __restrict__ blk_ptr,
-                            const int32_t* __restrict__ nbr, const ChunkHdr* __restrict__ chunks,
-                            const TileDir* __restrict__ dir, const uint64_t* __restrict__ rec_keys,
-                            const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl, int64_t own_begin,
-                            int64_t nslots, int m, uint8_t* __restrict__ blob_pool, uint16_t* __restrict__ codes_neutral,
-                            int32_t* __restrict__ cnode_id, int* __restrict__ chunk_cpad, int* __restrict__ err) {
+__global__ void k_tile_fill(TileFillArgs A) {
     constexpr int LB = (NNE == 4) ? 2 : 3;
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p >= nslots) return;
-    const uint32_t c = slot_chunk[p];
-    const ChunkHdr h = chunks[c];
-    const TileDir td = dir[c];
-    const int64_t r = slot_node[p];
-    const int64_t node = own_begin + r;
-    const int64_t r_first = slot_node[h.node_begin];
-    uint8_t* blob = blob_pool + (size_t)td.blob_off16 * 16;
-    const int k = (int)(blk_ptr[r + 1] - blk_ptr[r]);
-    const int64_t s0 = inc_ptr[node], s1 = inc_ptr[node + 1];
-    const int64_t start_off = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes + (sb_excl[p] - sb_excl[h.node_begin]);
-    const int64_t code_off = nc_excl[p] - nc_excl[h.node_begin];
-    const int64_t grel = (blk_ptr[r] - blk_ptr[r_first]) * m * m;
-    if (start_off + k + 3 > 0xFFFF || code_off + (s1 - s0) * NNE > 0xFFFF || grel < 0 || grel > 0xFFFFFFFFll ||
-        h.n_recs > (0xFFFFu >> (2 * LB))) {
-        atomicExch(err, 1);
+    if (p >= A.nslots) return;
+    const uint32_t c = A.slot_chunk[p];
+    const ChunkHdr h = A.chunks[c];
+    const TileDir td = A.dir[c];
+    const int64_t r = A.slot_node[p];
+    const int64_t node = A.own_begin + r;
+    const int64_t r_first = A.slot_node[h.node_begin];
+    const int64_t p_end = (int64_t)h.node_begin + h.n_nodes;
+    uint8_t* blob = A.blob_pool + (size_t)td.blob_off16 * 16;
+    const int k = (int)(A.blk_ptr[r + 1] - A.blk_ptr[r]);
+    const int64_t s0 = A.inc_ptr[node], s1 = A.inc_ptr[node + 1];
+    const int64_t ncontrib = (s1 - s0) * NNE;
+    const int64_t code_off = A.nc_excl[p] - A.nc_excl[h.node_begin];
+    const int64_t grel = (A.blk_ptr[r] - A.blk_ptr[r_first]) * A.m * A.m;
+    const int64_t tables = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
+    const int64_t nruns = A.rows ? (int64_t)A.run_id[p_end - 1] - A.run_id[h.node_begin] + 1 : 0;
+    int64_t aux, code_index;
+    bool bad = grel < 0 || grel > 0xFFFFFFFFll || h.n_recs >= (0x7FFFu >> (2 * LB));
+    if (A.rows) {
+        aux = (A.kk_excl[p] - A.kk_excl[h.node_begin]) * A.m * A.m * 8 / 16;  // image offset of the node's rows
+        code_index = code_off / 8;
+        bad = bad || (ncontrib + 7) / 8 > 255 || k > 255 || nruns > 0xFFFF;
+    } else {
+        aux = tables + (A.sb_excl[p] - A.sb_excl[h.node_begin]);
+        code_index = code_off;
+        bad = bad || aux + k + 3 > 0xFFFF;
+    }
+    bad = bad || aux > 0xFFFF || code_index > 0xFFFF;
+    if (bad) {
+        atomicExch(A.err, 1);
         return;
     }
     if (p == h.node_begin) {
         TileHdr th;
-        th.gbase = blk_ptr[r_first] * m * m;
+        th.gbase = A.blk_ptr[r_first] * A.m * A.m;
         th.rec_begin = (uint32_t)h.rec_begin;
         th.node_begin = h.node_begin;
         th.n_nodes = (uint16_t)h.n_nodes;
         th.n_recs = (uint16_t)h.n_recs;
         th.kpad = (uint16_t)h.kpad;
         th.cpad = 0;  // filled by k_tile_cpad
-        th.pad2_[0] = th.pad2_[1] = 0;
+        th.n_runs = (uint16_t)nruns;
+        th.pad_ = 0;
+        th.pad2_ = 0;
         *reinterpret_cast<TileHdr*>(blob) = th;
     }
     TileNode tn;
     tn.gslot_rel = (uint32_t)grel;
-    tn.start_off = (uint16_t)start_off;
-    tn.code_off = (uint16_t)code_off;
+    tn.aux = (uint16_t)aux;
+    tn.code_off = (uint16_t)code_index;
     reinterpret_cast<TileNode*>(blob + sizeof(TileHdr))[p - h.node_begin] = tn;
-    // rank of the node in its own (sorted) neighbour list
-    int self_t = 0;
-    {
-        int64_t lo = blk_ptr[r], hi = blk_ptr[r + 1];
-        const int64_t lo0 = lo;
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if (nbr[mid] < (int32_t)node) lo = mid + 1; else hi = mid;
-        }
-        self_t = (int)(lo - lo0);
-    }
-    uint8_t* pl = blob + start_off;
-    pl[0] = (uint8_t)k;
-    pl[1] = (uint8_t)self_t;
-    uint8_t* start = pl + 2;
     // counting sort of the valence*NNE contributions by neighbour rank
     uint8_t cnt[kMaxRowBlocks + 1];
     for (int t = 0; t <= k; ++t) cnt[t] = 0;
     for (int64_t s = s0; s < s1; ++s) {
-        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+        const uint8_t* rk = A.rank + (int64_t)A.inc_list[s] * NNE;
 #pragma unroll
         for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
     }
     int cmax = 0;
     for (int t = 0; t < k; ++t) cmax = max(cmax, (int)cnt[t + 1]);
-    atomicMax(&chunk_cpad[c], cmax);
+    atomicMax(&A.chunk_cpad[c], cmax);
     for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
-    for (int t = 0; t <= k; ++t) start[t] = cnt[t];
-    uint16_t* codes = codes_neutral + (size_t)td.code_off16 * 8 + code_off;
+    if (A.rows) {
+        uint16_t* kn = reinterpret_cast<uint16_t*>(blob + tables);
+        kn[p - h.node_begin] = (uint16_t)(k | (((ncontrib + 7) / 8) << 8));
+        if (A.run_flag[p]) {  // this node starts a run: find its length
+            int64_t len16 = 0, q = p;
+            do {
+                const int64_t rq = A.slot_node[q];
+                len16 += (A.blk_ptr[rq + 1] - A.blk_ptr[rq]) * A.m * A.m * 8 / 16;
+                ++q;
+            } while (q < p_end && !A.run_flag[q]);
+            if (len16 > 0xFFFF) atomicExch(A.err, 1);
+            TileRun run;
+            run.gslot_rel = (uint32_t)grel;
+            run.out_off16 = (uint16_t)aux;
+            run.len16 = (uint16_t)len16;
+            TileRun* runs = reinterpret_cast<TileRun*>(blob + tables + ((2 * (int64_t)h.n_nodes + 7) / 8) * 8);
+            runs[A.run_id[p] - A.run_id[h.node_begin]] = run;
+        }
+    } else {
+        // rank of the node in its own (sorted) neighbour list
+        int64_t lo = A.blk_ptr[r], hi = A.blk_ptr[r + 1];
+        const int64_t lo0 = lo;
+        while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (A.nbr[mid] < (int32_t)node) lo = mid + 1; else hi = mid;
+        }
+        uint8_t* pl = blob + aux;
+        pl[0] = (uint8_t)k;
+        pl[1] = (uint8_t)(lo - lo0);
+        for (int t = 0; t <= k; ++t) pl[2 + t] = cnt[t];
+    }
+    // neutral codes in block order; the last contribution of each block carries the end flag
+    uint16_t* codes = A.codes_neutral + (size_t)td.code_off16 * 8 + code_off;
+    uint8_t end_at[kMaxRowBlocks + 1];  // last code index of block t = start of block t+1 minus one
+    for (int t = 0; t < k; ++t) end_at[t] = (uint8_t)(cnt[t + 1] - 1);
     for (int64_t s = s0; s < s1; ++s) {
-        const uint32_t ia = inc_list[s];
+        const uint32_t ia = A.inc_list[s];
         const uint64_t key = ((uint64_t)c << 32) | (uint64_t)(ia / NNE);
         int64_t lo = h.rec_begin, hi = h.rec_begin + h.n_recs;
         while (lo < hi) {
             int64_t mid = (lo + hi) >> 1;
-            if (rec_keys[mid] < key) lo = mid + 1; else hi = mid;
+            if (A.rec_keys[mid] < key) lo = mid + 1; else hi = mid;
         }
         const uint32_t rloc = (uint32_t)(lo - h.rec_begin);
         const uint32_t a = ia % NNE;
-        const uint8_t* rk = rank + (int64_t)ia * NNE;
+        const uint8_t* rk = A.rank + (int64_t)ia * NNE;
 #pragma unroll
-        for (int b = 0; b < NNE; ++b) codes[cnt[rk[b]]++] = (uint16_t)((rloc << (2 * LB)) | (a << LB) | b);
+        for (int b = 0; b < NNE; ++b) {
+            const int t = rk[b];
+            const int pos = cnt[t]++;
+            const uint32_t end = (pos == end_at[t]) ? 0x8000u : 0u;
+            codes[pos] = (uint16_t)(end | (rloc << (2 * LB)) | (a << LB) | b);
+        }
     }
-    cnode_id[p] = (int32_t)node;
+    A.cnode_id[p] = (int32_t)node;
 }
 
 __global__ void k_tile_cpad(int64_t nchunks, const TileDir* __restrict__ dir, const int* __restrict__ chunk_cpad,
@@ -609,15 +679,17 @@ __global__ void k_tile_cpad(int64_t nchunks, const TileDir* __restrict__ dir, co
     reinterpret_cast<TileHdr*>(blob_pool + (size_t)dir[c].blob_off16 * 16)->cpad = (uint16_t)chunk_cpad[c];
 }
 
-// neutral (record, a, b) codes -> staging offsets of one operator layout (record slot 0 is the zero record)
+// neutral codes -> staging offsets of one operator layout (record slot 0 is the zero record; padding -> 0)
 __host__ __device__ inline uint32_t tile_encode(const TileLayout& L, uint32_t neutral) {
+    if (neutral == 0xFFFFu) return 0;
     const int lb = (L.nne == 4) ? 2 : 3;
-    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = (neutral >> (2 * lb)) + 1;
-    if (!L.has_mat) return ((r * L.rec_units + a) << 1);
-    if (!L.sym) return ((r * L.rec_units + (a * L.nne + b) * L.blk_units) << 1);
+    const uint32_t end = (neutral >> 15) << 1;
+    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = ((neutral & 0x7FFFu) >> (2 * lb)) + 1;
+    if (!L.has_mat) return ((r * L.rec_units + a) << 2) | end;
+    if (!L.sym) return ((r * L.rec_units + (a * L.nne + b) * L.blk_units) << 2) | end;
     const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
     const uint32_t tri = lo * (2 * L.nne - 1 - lo) / 2 + hi;
-    return ((r * L.rec_units + tri * L.blk_units) << 1) | (a > b ? 1u : 0u);
+    return ((r * L.rec_units + tri * L.blk_units) << 2) | end | (a > b ? 1u : 0u);
 }
 
 __global__ void k_tile_encode(const uint16_t* __restrict__ neutral, uint16_t* __restrict__ out, int64_t n, TileLayout L) {
@@ -629,8 +701,8 @@ __global__ void k_tile_encode(const uint16_t* __restrict__ neutral, uint16_t* __
 int tile_prepare_layout(MeshDev& d, const TileLayout& L, cudaStream_t st) {
     if (d.tile_layout == L) return PFG_OK;
     const int64_t max_off = (int64_t)(d.max_chunk_recs + 1) * L.rec_units;
-    if (max_off >= 32768) {
-        set_error("chunk staging of %lld units exceeds the 15-bit code range", (long long)max_off);
+    if (max_off >= 16384) {
+        set_error("chunk staging of %lld units exceeds the 14-bit code range", (long long)max_off);
         return PFG_ERR_UNSUPPORTED;
     }
     if (d.tile_ncodes)
@@ -888,18 +960,23 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                                                                d.rec_elem, d.chunks, maxima.p);
     k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
     if (tile) {
-        // ---- tile plan: blob (header, node table, start bytes) and contribution codes per chunk
+        // ---- tile plan: blob (header, node table, format tables) and contribution codes per chunk
         cudaFree(d.rec_dst);
         d.rec_dst = nullptr;
-        DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16;
-        DBuf<int64_t> sb_excl, nc_excl, blob_off, code_off;
+        const int rows = (d.m == 2) ? 1 : 0;
+        d.tile_rows = rows != 0;
+        DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16, run_flag, run_id;
+        DBuf<int64_t> sb_excl, nc_excl, kk_excl, blob_off, code_off;
         DBuf<int> terr, chunk_cpad;
         PFG_CUDA_TRY(chunk_cpad.alloc(d.nchunks));
         PFG_CUDA_TRY(cudaMemsetAsync(chunk_cpad.p, 0, d.nchunks * sizeof(int), st));
         PFG_CUDA_TRY(sbytes.alloc(nown + 1));
         PFG_CUDA_TRY(ncodes.alloc(nown + 1));
+        PFG_CUDA_TRY(run_flag.alloc(nown + 1));
+        PFG_CUDA_TRY(run_id.alloc(nown + 1));
         PFG_CUDA_TRY(sb_excl.alloc(nown + 1));
         PFG_CUDA_TRY(nc_excl.alloc(nown + 1));
+        PFG_CUDA_TRY(kk_excl.alloc(nown + 1));
         PFG_CUDA_TRY(blob_len16.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(code_len16.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(blob_off.alloc(d.nchunks + 1));
@@ -908,15 +985,22 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(cudaMemsetAsync(terr.p, 0, sizeof(int), st));
         PFG_CUDA_TRY(cudaMemsetAsync(sbytes.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(ncodes.p, 0, (nown + 1) * sizeof(uint32_t), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(run_flag.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(blob_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(code_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
-        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, NNE, nown, sbytes.p, ncodes.p);
+        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, NNE, rows, nown, sbytes.p, ncodes.p);
+        k_tile_run_flags<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, nown, run_flag.p);
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, sbytes.p, sb_excl.p, nown + 1, st));
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, ncodes.p, nc_excl.p, nown + 1, st));
-        k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, sb_excl.p, nc_excl.p,
-                                                                     blob_len16.p, code_len16.p, maxima.p);
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, kk.p, kk_excl.p, nown + 1, st));
+        PFG_CUB(scratch, st,
+                cub::DeviceScan::InclusiveSum(d_temp_storage, temp_storage_bytes, run_flag.p, run_id.p, nown + 1, st));
+        k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, sb_excl.p, nc_excl.p, kk_excl.p,
+                                                                     run_id.p, rows, d.m, blob_len16.p, code_len16.p,
+                                                                     maxima.p);
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, blob_len16.p, blob_off.p,
                                               d.nchunks + 1, st));
@@ -939,14 +1023,20 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(cudaMalloc(&d.tile_codes_neutral, d.tile_ncodes * 2 + 64));
         PFG_CUDA_TRY(cudaMemsetAsync(d.tile_blob, 0, d.tile_blob_bytes + 64, st));
         PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes, 0, d.tile_ncodes * 2 + 64, st));
-        PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes_neutral, 0, d.tile_ncodes * 2 + 64, st));
+        PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes_neutral, 0xFF, d.tile_ncodes * 2 + 64, st));  // 0xFFFF = padding
         PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
         k_tile_dir<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.chunks, blob_off.p, code_off.p,
                                                                  blob_len16.p, code_len16.p, d.nrecs, d.tile_dir);
-        k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, d.rank,
-                                                              d.blk_ptr, d.nbr, d.chunks, d.tile_dir, rec_keys.p,
-                                                              sb_excl.p, nc_excl.p, d.own_begin, nown, d.m, d.tile_blob,
-                                                              d.tile_codes_neutral, d.cnode_id, chunk_cpad.p, terr.p);
+        TileFillArgs fa;
+        fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
+        fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr, fa.nbr = d.nbr;
+        fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p;
+        fa.sb_excl = sb_excl.p, fa.nc_excl = nc_excl.p, fa.kk_excl = kk_excl.p;
+        fa.run_flag = run_flag.p, fa.run_id = run_id.p;
+        fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m, fa.rows = rows;
+        fa.blob_pool = d.tile_blob, fa.codes_neutral = d.tile_codes_neutral, fa.cnode_id = d.cnode_id;
+        fa.chunk_cpad = chunk_cpad.p, fa.err = terr.p;
+        k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(fa);
         k_tile_cpad<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.tile_dir, chunk_cpad.p, d.tile_blob);
         int h_terr = 0, h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -959,6 +1049,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.max_chunk_recs = h_max[3];
         d.max_blob_bytes = h_max[5];
         d.max_code_bytes = h_max[6];
+        d.max_out_bytes = h_max[7];
         if (h_terr || d.max_blob_bytes > 0xFFFF * 16 || d.max_code_bytes > 0xFFFF * 16) {
             // chunk too irregular for the compact tile encoding: assemble with the atomic scatter instead
             cudaFree(d.tile_dir); d.tile_dir = nullptr;
