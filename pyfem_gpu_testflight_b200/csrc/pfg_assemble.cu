@@ -477,6 +477,7 @@ PFG_DEV void tile_phase_b_items(const TileHdr& h, const unsigned char* __restric
 // eight, sums each (node, neighbour) block in plan order and, at the block's end flag, drops its two rows into
 // the shared-memory image of the CSR values.  Neighbouring lanes read the same block of neighbouring records,
 // so on a regular mesh the gather runs at one bank-conflict-free wavefront per 128 bytes.
+// The running sums restart without a branch: acc = fma(acc, keep, v) with keep = 0 after an end flag.
 template <class Op, int THREADS>
 PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict__ blob,
                                const uint16_t* __restrict__ codes, const double* __restrict__ stage,
@@ -484,34 +485,33 @@ PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict
     using St = TileStage<Op>;
     static_assert(Op::M == 2 && Op::NMAT == 1, "row format is for one matrix of 2x2 blocks");
     const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
-    const uint16_t* __restrict__ kn = reinterpret_cast<const uint16_t*>(nodes + h.n_nodes);
     const unsigned char* __restrict__ stage_b = reinterpret_cast<const unsigned char*>(stage);
-    for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
+    const int n_nodes = (int)h.n_nodes, gmax = (int)h.gmax;
+    for (int p = threadIdx.x; p < n_nodes; p += THREADS) {
         const TileNode tn = nodes[p];
-        const unsigned knv = kn[p];
-        const int row_bytes = (int)(knv & 255u) * 16;  // 2k doubles per dof row
-        const int ngroups = (int)(knv >> 8);
-        const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(codes) + tn.code_off;
+        const int row_bytes = (int)tn.code_off * 16;  // k neighbours: 2k doubles per dof row
+        const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(codes) + p;  // [group][node]
         unsigned char* o = reinterpret_cast<unsigned char*>(image) + (size_t)tn.aux * 16;
-        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0;
+        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, keep = 0.0;
         auto add = [&](unsigned code) {  // code in the low 16 bits
             const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code & 0xFFFCu) << 2));
             const double2 v0 = q[0], v1 = q[1];
             const bool tr = St::SYM && (code & 1u);
-            a00 += v0.x;
-            a01 += tr ? v1.x : v0.y;
-            a10 += tr ? v0.y : v1.x;
-            a11 += v1.y;
-            if (code & 2u) {  // last contribution of this block
+            a00 = fma(a00, keep, v0.x);
+            a01 = fma(a01, keep, tr ? v1.x : v0.y);
+            a10 = fma(a10, keep, tr ? v0.y : v1.x);
+            a11 = fma(a11, keep, v1.y);
+            const bool end = (code & 2u) != 0;  // last contribution of this block
+            if (end) {
                 *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
                 *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
                 o += 16;
-                a00 = a01 = a10 = a11 = 0.0;
             }
+            keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
         };
 #pragma unroll 1
-        for (int g = 0; g < ngroups; ++g) {
-            const uint4 c = cp[g];
+        for (int g = 0; g < gmax; ++g) {
+            const uint4 c = cp[(size_t)g * n_nodes];
             add(c.x & 0xFFFFu), add(c.x >> 16);
             add(c.y & 0xFFFFu), add(c.y >> 16);
             add(c.z & 0xFFFFu), add(c.z >> 16);
@@ -671,26 +671,30 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if constexpr (ROWS) {
             const TileHdr h = *reinterpret_cast<const TileHdr*>(blob_s);
             tile_phase_b_rows<Op, THREADS>(h, blob_s, codes_s, stage, image);
+            // runs of consecutive node ids leave as TMA bulk stores, spread over the warps' leading lanes;
+            // the run entry is read before the barrier so that the blob may be overwritten right after it
+            // (a chunk has at most 128 runs: checked when the plan is built)
+            constexpr int NW = THREADS / 32;
+            const int my_run = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
+            TileRun run;
+            run.len16 = 0;
+            if (my_run < (int)h.n_runs)
+                run = reinterpret_cast<const TileRun*>(blob_s + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes)[my_run];
             fence_proxy_async();  // image writes (generic proxy) -> visible to the bulk-copy engine
             __syncthreads();
-            // one TMA bulk store per run of consecutive node ids: image -> CSR values
+            if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
             if (out.vals[0] != nullptr) {
-                const TileRun* __restrict__ runs = reinterpret_cast<const TileRun*>(
-                    blob_s + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes + ((2 * (int)h.n_nodes + 7) / 8) * 8);
-                for (int q = threadIdx.x; q < (int)h.n_runs; q += THREADS) {
-                    const TileRun run = runs[q];
+                if (run.len16)
                     tma_store_1d(out.vals[0] + h.gbase + run.gslot_rel,
                                  reinterpret_cast<const unsigned char*>(image) + (size_t)run.out_off16 * 16,
                                  (uint32_t)run.len16 * 16u);
-                }
                 tma_store_commit();
             }
-            __syncthreads();  // every thread has read the blob's run table before the next blob lands
         } else {
             tile_phase_b<Op, THREADS>(mv, blob_s, codes_s, stage, out);
             __syncthreads();
+            if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
         }
-        if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
     }
     if constexpr (ROWS) tma_store_wait_read();
 }

@@ -83,12 +83,12 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 //   item format (m == 1): one phase-B thread per (node, neighbour) block.  After the node table the blob
 //       holds, per node, uint8 k, uint8 self rank, uint8 start[k+1] (prefix of contribution counts);
 //       TileNode::aux = byte offset of that record, TileNode::code_off = index of the node's first code.
-//   row format (m == 2): one phase-B thread per node walks the node's codes (padded to groups of 8 with
-//       code 0), writes the node's two dof rows into a shared-memory image of the CSR values, and the
-//       image leaves through one TMA bulk store per run of consecutive node ids.  After the node table:
-//       uint16 kn[n_nodes] = k | code groups << 8 (padded to 8 B), then TileRun[n_runs];
-//       TileNode::aux = offset of the node's rows in the image (16 B units), TileNode::code_off = index
-//       of the node's first code group.
+//   row format (m == 2): one phase-B thread per node walks the node's codes, writes the node's two dof
+//       rows into a shared-memory image of the CSR values, and the image leaves through one TMA bulk
+//       store per run of consecutive node ids.  Codes are stored group-major, [group][node][8 codes],
+//       every node padded with code 0 to the chunk's TileHdr::gmax groups, so that a warp's 16-byte code
+//       loads are contiguous.  After the node table: TileRun[n_runs].
+//       TileNode::aux = offset of the node's rows in the image (16 B units), TileNode::code_off = k.
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) TileDir {  // 16 bytes
     uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
@@ -106,14 +106,14 @@ struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
     uint16_t kpad;         // max neighbour count over the chunk's nodes
     uint16_t cpad;         // max contributions to one block over the chunk
     uint16_t n_runs;       // row format: runs of consecutive node ids
-    uint16_t pad_;
+    uint16_t gmax;         // row format: code groups (8 codes) per node, padded to the chunk maximum
     uint32_t pad2_;
 };
 
 struct __align__(8) TileNode {  // 8 bytes
     uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileHdr::gbase
     uint16_t aux;          // item format: byte offset of the node's start record; row format: image offset / 16
-    uint16_t code_off;     // item format: first code index; row format: first code group (8 codes)
+    uint16_t code_off;     // item format: first code index; row format: neighbour count k
 };
 
 struct __align__(8) TileRun {  // 8 bytes: one bulk store, image -> CSR values

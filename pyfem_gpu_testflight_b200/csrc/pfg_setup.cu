@@ -465,13 +465,16 @@ __global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64
 
 
 // ---- tile plan (second format) -----------------------------------------------------------------
-__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne, int rows,
-                                  int64_t nslots, uint32_t* __restrict__ start_bytes, uint32_t* __restrict__ ncodes) {
+__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk,
+                                  const uint32_t* __restrict__ slot_chunk, int nne, int rows, int64_t nslots,
+                                  uint32_t* __restrict__ start_bytes, uint32_t* __restrict__ ncodes,
+                                  int* __restrict__ chunk_gmax) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nslots) return;
     const uint32_t n = valence[p] * nne;
     start_bytes[p] = rows ? 0 : kk[p] + 3;  // item format: k, self rank, start[k+1]
-    ncodes[p] = rows ? ((n + 7) / 8) * 8 : n;
+    ncodes[p] = rows ? 0 : n;               // row format: codes are group-major per chunk (gmax * n_nodes groups)
+    if (rows) atomicMax(&chunk_gmax[slot_chunk[p]], (int)((n + 7) / 8));
 }
 
 // row format: a run starts where the chunk starts or the node ids stop being consecutive
@@ -484,23 +487,26 @@ __global__ void k_tile_run_flags(const uint32_t* __restrict__ slot_node, const u
 
 __global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__ chunks,
                                    const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl,
-                                   const int64_t* __restrict__ kk_excl, const uint32_t* __restrict__ run_id, int rows,
-                                   int m, uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
+                                   const int64_t* __restrict__ kk_excl, const uint32_t* __restrict__ run_id,
+                                   const int* __restrict__ chunk_gmax, int rows, int m,
+                                   uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
                                    int* __restrict__ maxima) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const ChunkHdr h = chunks[c];
     const int64_t p0 = h.node_begin, p1 = p0 + h.n_nodes;
     int64_t blob = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
+    int64_t codes;
     if (rows) {
         const int64_t nruns = (int64_t)run_id[p1 - 1] - run_id[p0] + 1;
-        blob += ((2 * (int64_t)h.n_nodes + 7) / 8) * 8 + (int64_t)sizeof(TileRun) * nruns;
+        blob += (int64_t)sizeof(TileRun) * nruns;
         const int64_t out_bytes = (kk_excl[p1] - kk_excl[p0]) * m * m * 8;
         atomicMax(&maxima[7], (int)min((int64_t)INT_MAX, out_bytes));
+        codes = 16 * (int64_t)chunk_gmax[c] * h.n_nodes;  // group-major: [group][node] 8 codes
     } else {
         blob += sb_excl[p1] - sb_excl[p0];
+        codes = 2 * (nc_excl[p1] - nc_excl[p0]);
     }
-    const int64_t codes = 2 * (nc_excl[p1] - nc_excl[p0]);
     blob_len16[c] = (uint32_t)((blob + 15) / 16);
     code_len16[c] = (uint32_t)((codes + 15) / 16);
     atomicMax(&maxima[5], (int)min((int64_t)INT_MAX, (blob + 15) / 16 * 16));
@@ -546,6 +552,7 @@ struct TileFillArgs {
     uint16_t* codes_neutral;
     int32_t* cnode_id;
     int *chunk_cpad, *err;
+    const int* chunk_gmax;
 };
 
 template <int NNE>
@@ -563,7 +570,6 @@ __global__ void k_tile_fill(TileFillArgs A) {
     uint8_t* blob = A.blob_pool + (size_t)td.blob_off16 * 16;
     const int k = (int)(A.blk_ptr[r + 1] - A.blk_ptr[r]);
     const int64_t s0 = A.inc_ptr[node], s1 = A.inc_ptr[node + 1];
-    const int64_t ncontrib = (s1 - s0) * NNE;
     const int64_t code_off = A.nc_excl[p] - A.nc_excl[h.node_begin];
     const int64_t grel = (A.blk_ptr[r] - A.blk_ptr[r_first]) * A.m * A.m;
     const int64_t tables = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
@@ -572,8 +578,8 @@ __global__ void k_tile_fill(TileFillArgs A) {
     bool bad = grel < 0 || grel > 0xFFFFFFFFll || h.n_recs >= (0x7FFFu >> (2 * LB));
     if (A.rows) {
         aux = (A.kk_excl[p] - A.kk_excl[h.node_begin]) * A.m * A.m * 8 / 16;  // image offset of the node's rows
-        code_index = code_off / 8;
-        bad = bad || (ncontrib + 7) / 8 > 255 || k > 255 || nruns > 0xFFFF;
+        code_index = k;  // row format keeps the neighbour count here; codes are addressed [group][node]
+        bad = bad || A.chunk_gmax[c] > 0xFFFF || nruns > 128;
     } else {
         aux = tables + (A.sb_excl[p] - A.sb_excl[h.node_begin]);
         code_index = code_off;
@@ -594,7 +600,7 @@ __global__ void k_tile_fill(TileFillArgs A) {
         th.kpad = (uint16_t)h.kpad;
         th.cpad = 0;  // filled by k_tile_cpad
         th.n_runs = (uint16_t)nruns;
-        th.pad_ = 0;
+        th.gmax = (uint16_t)(A.rows ? A.chunk_gmax[c] : 0);
         th.pad2_ = 0;
         *reinterpret_cast<TileHdr*>(blob) = th;
     }
@@ -616,8 +622,6 @@ __global__ void k_tile_fill(TileFillArgs A) {
     atomicMax(&A.chunk_cpad[c], cmax);
     for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
     if (A.rows) {
-        uint16_t* kn = reinterpret_cast<uint16_t*>(blob + tables);
-        kn[p - h.node_begin] = (uint16_t)(k | (((ncontrib + 7) / 8) << 8));
         if (A.run_flag[p]) {  // this node starts a run: find its length
             int64_t len16 = 0, q = p;
             do {
@@ -630,7 +634,7 @@ __global__ void k_tile_fill(TileFillArgs A) {
             run.gslot_rel = (uint32_t)grel;
             run.out_off16 = (uint16_t)aux;
             run.len16 = (uint16_t)len16;
-            TileRun* runs = reinterpret_cast<TileRun*>(blob + tables + ((2 * (int64_t)h.n_nodes + 7) / 8) * 8);
+            TileRun* runs = reinterpret_cast<TileRun*>(blob + tables);
             runs[A.run_id[p] - A.run_id[h.node_begin]] = run;
         }
     } else {
@@ -647,7 +651,8 @@ __global__ void k_tile_fill(TileFillArgs A) {
         for (int t = 0; t <= k; ++t) pl[2 + t] = cnt[t];
     }
     // neutral codes in block order; the last contribution of each block carries the end flag
-    uint16_t* codes = A.codes_neutral + (size_t)td.code_off16 * 8 + code_off;
+    uint16_t* codes = A.codes_neutral + (size_t)td.code_off16 * 8 + (A.rows ? 0 : code_off);
+    const int64_t pl = p - h.node_begin;  // row format: code s of this node sits at [s / 8][node][s % 8]
     uint8_t end_at[kMaxRowBlocks + 1];  // last code index of block t = start of block t+1 minus one
     for (int t = 0; t < k; ++t) end_at[t] = (uint8_t)(cnt[t + 1] - 1);
     for (int64_t s = s0; s < s1; ++s) {
@@ -666,7 +671,8 @@ __global__ void k_tile_fill(TileFillArgs A) {
             const int t = rk[b];
             const int pos = cnt[t]++;
             const uint32_t end = (pos == end_at[t]) ? 0x8000u : 0u;
-            codes[pos] = (uint16_t)(end | (rloc << (2 * LB)) | (a << LB) | b);
+            const int64_t at = A.rows ? (((int64_t)(pos >> 3) * h.n_nodes + pl) * 8 + (pos & 7)) : pos;
+            codes[at] = (uint16_t)(end | (rloc << (2 * LB)) | (a << LB) | b);
         }
     }
     A.cnode_id[p] = (int32_t)node;
@@ -967,9 +973,11 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.tile_rows = rows != 0;
         DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16, run_flag, run_id;
         DBuf<int64_t> sb_excl, nc_excl, kk_excl, blob_off, code_off;
-        DBuf<int> terr, chunk_cpad;
+        DBuf<int> terr, chunk_cpad, chunk_gmax;
         PFG_CUDA_TRY(chunk_cpad.alloc(d.nchunks));
+        PFG_CUDA_TRY(chunk_gmax.alloc(d.nchunks));
         PFG_CUDA_TRY(cudaMemsetAsync(chunk_cpad.p, 0, d.nchunks * sizeof(int), st));
+        PFG_CUDA_TRY(cudaMemsetAsync(chunk_gmax.p, 0, d.nchunks * sizeof(int), st));
         PFG_CUDA_TRY(sbytes.alloc(nown + 1));
         PFG_CUDA_TRY(ncodes.alloc(nown + 1));
         PFG_CUDA_TRY(run_flag.alloc(nown + 1));
@@ -988,7 +996,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(cudaMemsetAsync(run_flag.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(blob_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(code_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
-        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, NNE, rows, nown, sbytes.p, ncodes.p);
+        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, slot_chunk.p, NNE, rows, nown, sbytes.p,
+                                                               ncodes.p, chunk_gmax.p);
         k_tile_run_flags<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, nown, run_flag.p);
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, sbytes.p, sb_excl.p, nown + 1, st));
@@ -999,8 +1008,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUB(scratch, st,
                 cub::DeviceScan::InclusiveSum(d_temp_storage, temp_storage_bytes, run_flag.p, run_id.p, nown + 1, st));
         k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, sb_excl.p, nc_excl.p, kk_excl.p,
-                                                                     run_id.p, rows, d.m, blob_len16.p, code_len16.p,
-                                                                     maxima.p);
+                                                                     run_id.p, chunk_gmax.p, rows, d.m, blob_len16.p,
+                                                                     code_len16.p, maxima.p);
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, blob_len16.p, blob_off.p,
                                               d.nchunks + 1, st));
@@ -1035,7 +1044,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         fa.run_flag = run_flag.p, fa.run_id = run_id.p;
         fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m, fa.rows = rows;
         fa.blob_pool = d.tile_blob, fa.codes_neutral = d.tile_codes_neutral, fa.cnode_id = d.cnode_id;
-        fa.chunk_cpad = chunk_cpad.p, fa.err = terr.p;
+        fa.chunk_cpad = chunk_cpad.p, fa.err = terr.p, fa.chunk_gmax = chunk_gmax.p;
         k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(fa);
         k_tile_cpad<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.tile_dir, chunk_cpad.p, d.tile_blob);
         int h_terr = 0, h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
