@@ -9,6 +9,7 @@
 //           contributions in plan order and writes it exactly once.  No atomics, no zero-fill,
 //           bitwise reproducible.
 #include <algorithm>
+#include <cstdlib>
 
 #include "pfg_elem.cuh"
 
@@ -392,11 +393,11 @@ struct TileSink {
 struct TileCfg {
     int off_dir;                  // ring of 8 TileDir entries
     int off_blob, off_codes;      // chunk blob / codes buffers (one stage each)
-    int off_ids, ids_stride;      // record node ids, two stages
-    int off_x, off_field;         // coordinates / nodal field of the chunk's records (one stage)
+    int off_win, win_stride;      // node-window ids, two stages
+    int off_loc;                  // window indices of the record corners (one stage)
+    int off_x, off_field;         // coordinates / nodal field of the window nodes (one stage)
     int off_stage;                // element-record staging
     int off_image;                // row format: image of the chunk's CSR values (TMA bulk-store source)
-    int max_recs;                 // records per chunk the stages are sized for
     int nchunks;
 };
 
@@ -559,13 +560,26 @@ PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ 
     }
 }
 
+PFG_DEV void cp_async_mbar_arrive(uint64_t* bar) {  // the mbarrier sees this thread's earlier cp.async copies land
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// Persistent CTA over a contiguous range of chunks.  Per chunk i:
+//   phase A  one thread per element record: coordinates (and nodal field) come from the chunk's node window in
+//            shared memory, the element matrices go to the record staging;
+//   phase B  plan-ordered sums -> CSR values (row format: shared-memory image + TMA bulk stores).
+// Everything a chunk needs is in flight one or two chunks ahead and is tracked by mbarriers, never by
+// register scoreboards: TMA bulk copies bring the directory-addressed blob + codes (one ahead), the corner
+// indices (one ahead) and the window's node ids (two ahead); cp.async gathers the window's coordinates one
+// chunk ahead and reports to an mbarrier.
 template <class Op, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
     k_tile(MeshView mv, typename Op::Params prm, Outputs out, TileCfg cfg) {
     extern __shared__ __align__(128) unsigned char smem[];
     using St = TileStage<Op>;
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] record ids
+    constexpr bool ROWS = (Op::M == 2);  // row format: handles with two dofs per node
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] window ids, [3] corner indices, [4] window data
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
     const int nloc = (int)(c_end - c_begin);
@@ -574,84 +588,102 @@ __global__ void __launch_bounds__(THREADS, MINB)
     TileDir* dir_s = reinterpret_cast<TileDir*>(smem + cfg.off_dir);
     unsigned char* blob_s = smem + cfg.off_blob;
     uint16_t* codes_s = reinterpret_cast<uint16_t*>(smem + cfg.off_codes);
+    unsigned char* loc_s = smem + cfg.off_loc;
     double* xs = reinterpret_cast<double*>(smem + cfg.off_x);
     double* fs = reinterpret_cast<double*>(smem + cfg.off_field);
     double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
     double* image = reinterpret_cast<double*>(smem + cfg.off_image);
-    constexpr bool ROWS = (Op::M == 2);  // row format: handles with two dofs per node
     const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;  // entries 0..nloc (nloc = next CTA's first / sentinel)
 
-    auto ids_stage = [&](int j) -> int32_t* { return reinterpret_cast<int32_t*>(smem + cfg.off_ids + (j & 1) * cfg.ids_stride); };
     auto n_recs_of = [&](int j) -> int { return (int)(dir_s[(j + 1) & 7].rec_begin - dir_s[j & 7].rec_begin); };
-    // thread 0: bulk copies of chunk j's record ids / blob + codes
-    auto issue_ids = [&](int j) {
-        const uint32_t bytes = (uint32_t)n_recs_of(j) * NNE * 4u;
+    auto n_win_of = [&](int j) -> int { return (int)(dir_s[(j + 1) & 7].win_begin - dir_s[j & 7].win_begin); };
+    auto win_stage = [&](int j) -> unsigned char* { return smem + cfg.off_win + (j & 1) * cfg.win_stride; };
+    // thread 0: bulk copies.  Sources are only 4- or 8-byte aligned, so each copy starts at the enclosing 16-byte
+    // boundary and the readers skip the same number of bytes (the pools are padded at both ends).
+    auto issue_win = [&](int j) {
+        const size_t lo = (size_t)dir_s[j & 7].win_begin * 4, lo16 = lo & ~(size_t)15;
+        const uint32_t bytes = (uint32_t)(((lo + (size_t)n_win_of(j) * 4 + 15) & ~(size_t)15) - lo16);
         uint64_t* bar = &bars[1 + (j & 1)];
         mbar_expect_tx(bar, bytes);
-        if (bytes) tma_load_1d(ids_stage(j), mv.rec_nodes + (size_t)dir_s[j & 7].rec_begin * NNE, bytes, bar);
+        if (bytes) tma_load_1d(win_stage(j), reinterpret_cast<const unsigned char*>(mv.win_nodes) + lo16, bytes, bar);
+    };
+    auto issue_loc = [&](int j) {
+        const size_t lo = (size_t)dir_s[j & 7].rec_begin * NNE * 2, lo16 = lo & ~(size_t)15;
+        const uint32_t bytes = (uint32_t)(((lo + (size_t)n_recs_of(j) * NNE * 2 + 15) & ~(size_t)15) - lo16);
+        mbar_expect_tx(&bars[3], bytes);
+        if (bytes) tma_load_1d(loc_s, reinterpret_cast<const unsigned char*>(mv.rec_local) + lo16, bytes, &bars[3]);
     };
     auto issue_meta = [&](int j) {
-        const TileDir t = dir_s[j & 7];
-        const uint32_t bb = (uint32_t)t.blob_len16 * 16u, cb = (uint32_t)t.code_len16 * 16u;
+        const TileDir t = dir_s[j & 7], t1 = dir_s[(j + 1) & 7];
+        const uint32_t bb = (t1.blob_off16 - t.blob_off16) * 16u, cb = (t1.code_off16 - t.code_off16) * 16u;
         mbar_expect_tx(&bars[0], bb + cb);
         tma_load_1d(blob_s, mv.tile_blob + (size_t)t.blob_off16 * 16, bb, &bars[0]);
         if (cb) tma_load_1d(codes_s, reinterpret_cast<const unsigned char*>(mv.tile_codes) + (size_t)t.code_off16 * 16, cb, &bars[0]);
     };
-    // all threads: stage the coordinates (and nodal field) of chunk j's records; thread r owns record r
-    auto prefetch_x = [&](int j) {
-        const int32_t* recn = ids_stage(j);
-        const int n_recs = n_recs_of(j);
-        for (int r = threadIdx.x; r < n_recs; r += THREADS) {
-            int nodes[NNE];
-            load_rec_nodes<NNE>(recn, r, nodes);
-#pragma unroll
-            for (int a = 0; a < NNE; ++a) {
-                double* dst = xs + ((size_t)a * cfg.max_recs + r) * DIM;  // [a][r][DIM]: conflict-free
-                if constexpr (DIM == 2) {
-                    cp_async_16(dst, mv.X + (size_t)nodes[a] * 2);
-                } else {
-                    cp_async_8(dst, mv.X + (size_t)nodes[a] * 3);
-                    cp_async_8(dst + 1, mv.X + (size_t)nodes[a] * 3 + 1);
-                    cp_async_8(dst + 2, mv.X + (size_t)nodes[a] * 3 + 2);
-                }
-                if (field != nullptr) cp_async_8(fs + (size_t)a * cfg.max_recs + r, field + nodes[a]);
+    // all threads: gather the coordinates (and nodal field) of chunk j's window nodes, one node per thread
+    auto gather_window = [&](int j) {
+        const uint32_t* __restrict__ win =
+            reinterpret_cast<const uint32_t*>(win_stage(j) + (((size_t)dir_s[j & 7].win_begin * 4) & 15));
+        const int n_win = n_win_of(j);
+        for (int t = threadIdx.x; t < n_win; t += THREADS) {
+            const size_t node = win[t];
+            double* dst = xs + (size_t)t * DIM;
+            if constexpr (DIM == 2) {
+                cp_async_16(dst, mv.X + node * 2);
+            } else {
+                cp_async_8(dst, mv.X + node * 3);
+                cp_async_8(dst + 1, mv.X + node * 3 + 1);
+                cp_async_8(dst + 2, mv.X + node * 3 + 2);
             }
+            if (field != nullptr) cp_async_8(fs + t, field + node);
         }
+        cp_async_mbar_arrive(&bars[4]);
     };
 
     for (int i = threadIdx.x; i < St::S; i += THREADS) stage[i] = 0.0;  // record slot 0: zeros (code 0)
     if (threadIdx.x == 0) {
-        for (int s = 0; s < 3; ++s) mbar_init(&bars[s], 1);
+        for (int s = 0; s < 4; ++s) mbar_init(&bars[s], 1);
+        mbar_init(&bars[4], THREADS);
         for (int j = 0; j <= 4 && j <= nloc; ++j) dir_s[j] = dir_g[j];
         __threadfence_block();
-        issue_ids(0);
-        if (nloc > 1) issue_ids(1);
+        issue_win(0);
+        if (nloc > 1) issue_win(1);
+        issue_loc(0);
         issue_meta(0);
     }
     __syncthreads();
     mbar_wait(&bars[1], 0);
-    prefetch_x(0);
-    cp_async_commit();
+    gather_window(0);
 
     for (int i = 0; i < nloc; ++i) {
-        cp_async_wait<0>();  // this thread's coordinates of chunk i (and thread 0's directory entry) have landed
-        if (threadIdx.x == 0 && i + 5 <= nloc) cp_async_16(&dir_s[(i + 5) & 7], &dir_g[i + 5]);
-        cp_async_commit();
+        if (threadIdx.x == 0 && i + 5 <= nloc) cp_async_16(&dir_s[(i + 5) & 7], &dir_g[i + 5]);  // rides on the next arrive
+        mbar_wait(&bars[4], i & 1);  // the window's coordinates have landed (all threads' copies)
+        mbar_wait(&bars[3], i & 1);  // and so have the corner indices
         // ---- phase A: one thread per element record -> staged element matrices
         const int n_recs = n_recs_of(i);
+        const unsigned char* loc_i = loc_s + (((size_t)dir_s[i & 7].rec_begin * NNE * 2) & 15);
         for (int r = threadIdx.x; r < n_recs; r += THREADS) {
             TileSink<Op> sink{stage + (size_t)(r + 1) * St::S};  // slot 0 is the all-zero record
+            unsigned loc[NNE];
+            if constexpr (NNE == 4) {
+                const uint2 v = reinterpret_cast<const uint2*>(loc_i)[r];
+                loc[0] = v.x & 0xFFFFu, loc[1] = v.x >> 16, loc[2] = v.y & 0xFFFFu, loc[3] = v.y >> 16;
+            } else {
+                const uint4 v = reinterpret_cast<const uint4*>(loc_i)[r];
+                loc[0] = v.x & 0xFFFFu, loc[1] = v.x >> 16, loc[2] = v.y & 0xFFFFu, loc[3] = v.y >> 16;
+                loc[4] = v.z & 0xFFFFu, loc[5] = v.z >> 16, loc[6] = v.w & 0xFFFFu, loc[7] = v.w >> 16;
+            }
             double xe[NNE][DIM], fe[NNE];
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
-                const double* src = xs + ((size_t)a * cfg.max_recs + r) * DIM;
+                const double* src = xs + (size_t)loc[a] * DIM;
                 if constexpr (DIM == 2) {
                     const double2 v = *reinterpret_cast<const double2*>(src);
                     xe[a][0] = v.x, xe[a][1] = v.y;
                 } else {
                     xe[a][0] = src[0], xe[a][1] = src[1], xe[a][2] = src[2];
                 }
-                fe[a] = (field != nullptr) ? fs[(size_t)a * cfg.max_recs + r] : 0.0;
+                fe[a] = (field != nullptr) ? fs[loc[a]] : 0.0;
             }
             int64_t elem = 0;
             if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + dir_s[i & 7].rec_begin + r);
@@ -659,13 +691,15 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         if constexpr (ROWS) tma_store_wait_read();  // the previous chunk's bulk stores have read the image
         __syncthreads();
-        // ---- prefetch: record ids two chunks ahead, coordinates one chunk ahead
-        if (threadIdx.x == 0 && i + 2 < nloc) issue_ids(i + 2);
+        // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
+        if (threadIdx.x == 0) {
+            if (i + 2 < nloc) issue_win(i + 2);
+            if (i + 1 < nloc) issue_loc(i + 1);
+        }
         if (i + 1 < nloc) {
             mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
-            prefetch_x(i + 1);
+            gather_window(i + 1);
         }
-        cp_async_commit();
         // ---- phase B: plan-ordered sums, each CSR block written once
         mbar_wait(&bars[0], i & 1);
         if constexpr (ROWS) {
@@ -839,6 +873,8 @@ static MeshView view_of(const MeshDev& d) {
     mv.tile_dir = d.tile_dir;
     mv.tile_blob = d.tile_blob;
     mv.tile_codes = d.tile_codes;
+    mv.win_nodes = d.win_nodes;
+    mv.rec_local = d.rec_local;
     mv.stage_nodes_bytes = d.max_chunk_nodes * (int)sizeof(ChunkNode);
     mv.stage_plan_bytes = ((d.max_chunk_plan_words * 4 + 15) / 16) * 16 + 32;
     return mv;
@@ -873,15 +909,15 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
     PFG_TRY(tile_prepare_layout(d, St::layout(), st));
     TileCfg cfg;
-    cfg.max_recs = (d.max_chunk_recs + 1) & ~1;
     cfg.off_dir = 64;
     cfg.off_blob = cfg.off_dir + 8 * (int)sizeof(TileDir);
     cfg.off_codes = cfg.off_blob + align16(d.max_blob_bytes);
-    cfg.off_ids = cfg.off_codes + align16(d.max_code_bytes) + 16;  // slack: phase B may read a few codes past the end
-    cfg.ids_stride = align16(d.max_chunk_recs * NNE * 4);
-    cfg.off_x = cfg.off_ids + 2 * cfg.ids_stride;
-    cfg.off_field = cfg.off_x + cfg.max_recs * NNE * DIM * 8;
-    cfg.off_stage = align16(cfg.off_field + (Op::field(prm) ? cfg.max_recs * NNE * 8 : 0));
+    cfg.off_win = cfg.off_codes + align16(d.max_code_bytes) + 16;  // slack: phase B may read a few codes past the end
+    cfg.win_stride = align16(d.max_chunk_win * 4) + 16;            // copies start at the enclosing 16-byte boundary
+    cfg.off_loc = cfg.off_win + 2 * cfg.win_stride;
+    cfg.off_x = cfg.off_loc + align16(d.max_chunk_recs * NNE * 2) + 16;
+    cfg.off_field = cfg.off_x + align16(d.max_chunk_win * DIM * 8);
+    cfg.off_stage = cfg.off_field + (Op::field(prm) ? align16(d.max_chunk_win * 8) : 0);
     cfg.nchunks = (int)d.nchunks;
     cfg.off_image = align16(cfg.off_stage + (d.max_chunk_recs + 1) * St::S * 8);
     if ((Op::M == 2) != d.tile_rows) {
@@ -900,6 +936,11 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
     per_sm = std::max(1, per_sm);
     const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
+    static const bool debug = getenv("PFG_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "[pfg] k_tile: %d threads, %zu B smem (stage %d, image %d, blob %d, codes %d, win %d, recs<=%d), %d CTA/SM, grid %u\n",
+                THREADS, smem, (d.max_chunk_recs + 1) * St::S * 8, Op::M == 2 ? d.max_out_bytes : 0, d.max_blob_bytes,
+                d.max_code_bytes, d.max_chunk_win, d.max_chunk_recs, per_sm, grid);
     kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;

@@ -95,6 +95,8 @@ struct MeshView {
     const TileDir* tile_dir;
     const uint8_t* tile_blob;
     const uint16_t* tile_codes;
+    const uint32_t* win_nodes;
+    const uint16_t* rec_local;
     // shared-memory staging sizes (bytes) for the gather kernels: chunk node table, chunk plan
     int stage_nodes_bytes, stage_plan_bytes;
 };

@@ -71,7 +71,9 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 //   tile_dir[c]      16 B   where the chunk's blob / codes / records live
 //   blob             16 B aligned: TileHdr | TileNode[n_nodes] | format-specific tables (below)
 //   codes            16 B aligned: per node uint16 contribution codes, sorted by neighbour rank
-//   rec_nodes        (n_recs, nne) int32 node ids of the records (shared with the first format)
+//   win_nodes        uint32 sorted unique node ids of the chunk's records (the "node window": coordinates and
+//                    nodal fields are gathered once per window node into shared memory)
+//   rec_local        (n_recs, nne) uint16 window index of every record corner
 // A code is (offset << 2) | end << 1 | transpose: offset in units of the staging block (16 B for 2x2
 // blocks, 8 B for scalars) from the start of the chunk's staging area, whose record slot 0 is all zeros
 // (code 0 adds nothing); `end` marks the last contribution of a (node, neighbour) block.  Codes depend on
@@ -90,12 +92,11 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 //       loads are contiguous.  After the node table: TileRun[n_runs].
 //       TileNode::aux = offset of the node's rows in the image (16 B units), TileNode::code_off = k.
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) TileDir {  // 16 bytes
+struct __align__(16) TileDir {  // 16 bytes; entry nchunks is a sentinel, so every length is a difference of neighbours
     uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
     uint32_t code_off16;   // codes offset in the code pool, 16-byte units
-    uint32_t rec_begin;    // first record (a chunk's record count is the next entry's rec_begin minus this)
-    uint16_t blob_len16;   // blob bytes / 16
-    uint16_t code_len16;   // code bytes / 16
+    uint32_t rec_begin;    // first record
+    uint32_t win_begin;    // first entry of the chunk's node window (sorted unique node ids of its records)
 };
 
 struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
@@ -179,6 +180,10 @@ struct MeshDev {
     uint8_t* tile_blob = nullptr;      // blob pool
     uint16_t* tile_codes = nullptr;    // working codes, encoded for tile_layout
     uint16_t* tile_codes_neutral = nullptr;  // (record << 2*lb | a << lb | b), lb = log2(nne)
+    uint32_t* win_nodes = nullptr;     // node windows, chunk after chunk
+    uint16_t* rec_local = nullptr;     // (nrecs, nne) window index of every record corner
+    int64_t nwin = 0;
+    int max_chunk_win = 0;
     int64_t tile_blob_bytes = 0, tile_ncodes = 0;
     int max_blob_bytes = 0, max_code_bytes = 0, max_out_bytes = 0;
     bool tile_rows = false;            // row sub-format (m == 2)

@@ -514,24 +514,60 @@ __global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__
 }
 
 __global__ void k_tile_dir(int64_t nchunks, const ChunkHdr* __restrict__ chunks, const int64_t* __restrict__ blob_off,
-                           const int64_t* __restrict__ code_off, const uint32_t* __restrict__ blob_len16,
-                           const uint32_t* __restrict__ code_len16, int64_t nrecs, TileDir* __restrict__ dir) {
+                           const int64_t* __restrict__ code_off, const uint32_t* __restrict__ win_begin, int64_t nrecs,
+                           int64_t nwin, TileDir* __restrict__ dir) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c > nchunks) return;
     TileDir t;
-    if (c == nchunks) {  // sentinel: a chunk's record count is the difference of consecutive rec_begin
-        t.blob_off16 = t.code_off16 = 0;
-        t.rec_begin = (uint32_t)nrecs;
-        t.blob_len16 = t.code_len16 = 0;
-        dir[c] = t;
-        return;
-    }
-    t.blob_off16 = (uint32_t)blob_off[c];
+    t.blob_off16 = (uint32_t)blob_off[c];  // exclusive scans have nchunks + 1 entries: entry nchunks is the total
     t.code_off16 = (uint32_t)code_off[c];
-    t.rec_begin = (uint32_t)chunks[c].rec_begin;
-    t.blob_len16 = (uint16_t)blob_len16[c];
-    t.code_len16 = (uint16_t)code_len16[c];
+    t.rec_begin = (c == nchunks) ? (uint32_t)nrecs : (uint32_t)chunks[c].rec_begin;
+    t.win_begin = (c == nchunks) ? (uint32_t)nwin : win_begin[c];
     dir[c] = t;
+}
+
+// ---- node windows: sorted unique node ids per chunk, and every record corner's index into its window
+template <int NNE>
+__global__ void k_win_keys(const uint64_t* __restrict__ rec_keys, const int32_t* __restrict__ rec_nodes, int64_t ncorners,
+                           uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ncorners) return;
+    keys[i] = (rec_keys[i / NNE] & 0xffffffff00000000ull) | (uint32_t)rec_nodes[i];
+}
+
+__global__ void k_win_fill(const uint64_t* __restrict__ win_keys, int64_t nwin, uint32_t* __restrict__ win_nodes,
+                           uint32_t* __restrict__ win_begin, int* __restrict__ max_win_scratch) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nwin) return;
+    const uint64_t k = win_keys[i];
+    win_nodes[i] = (uint32_t)k;
+    if (i == 0 || (win_keys[i - 1] >> 32) != (k >> 32)) win_begin[k >> 32] = (uint32_t)i;
+}
+
+__global__ void k_win_max(int64_t nchunks, const uint32_t* __restrict__ win_begin, int64_t nwin, int* __restrict__ maxima) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const int64_t e = (c + 1 < nchunks) ? win_begin[c + 1] : nwin;
+    atomicMax(&maxima[8], (int)(e - win_begin[c]));
+}
+
+template <int NNE>
+__global__ void k_rec_local(const uint64_t* __restrict__ rec_keys, const int32_t* __restrict__ rec_nodes,
+                            const uint64_t* __restrict__ win_keys, const uint32_t* __restrict__ win_begin, int64_t nchunks,
+                            int64_t nwin, int64_t ncorners, uint16_t* __restrict__ rec_local, int* __restrict__ err) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= ncorners) return;
+    const uint64_t ck = rec_keys[i / NNE] & 0xffffffff00000000ull;
+    const uint64_t c = ck >> 32;
+    const uint64_t key = ck | (uint32_t)rec_nodes[i];
+    int64_t lo = win_begin[c], hi = ((int64_t)c + 1 < nchunks) ? win_begin[c + 1] : nwin;
+    const int64_t base = lo;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (win_keys[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    if (lo - base > 0xFFFF) atomicExch(err, 1);
+    rec_local[i] = (uint16_t)(lo - base);
 }
 
 struct TileFillArgs {
@@ -817,6 +853,15 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         // (n+1)^d elements; tie-aware cuts vary the block shape, so leave some slack
         const double side = std::pow((double)d.tile_threads, 1.0 / d.ndims) - 1.0;
         C = (int64_t)std::floor(std::pow(std::max(1.0, side), (double)d.ndims) * 0.86);
+        if (d.m == 2) {
+            // row format: three CTAs per SM need <= ~75 KB each.  Per node: staged records (42 doubles each,
+            // (n+1)^2 / n^2 records per node), the two image rows (4 k doubles), codes, window and corner tables.
+            const double recs_per_node = std::pow((side + 1.0) / side, (double)d.ndims);
+            const double per_node = recs_per_node * (42 * 8 + NNE * 2 + 20) + 4.0 * 8 * std::max(1, d.max_k) +
+                                    2.0 * NNE * std::max(1, d.max_valence) + 16;
+            const int64_t c_smem = (int64_t)(env_int("PFG_TILE_SMEM_BYTES", 75 * 1024) * 0.86 / per_node);
+            C = std::min(C, c_smem);
+        }
     } else {
         int budget = env_int("PFG_CHUNK_SMEM_BYTES", 160 * 1024);
         int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
@@ -922,8 +967,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     PFG_CUDA_TRY(cudaMalloc(&d.chunks, d.nchunks * sizeof(ChunkHdr)));
     PFG_CUDA_TRY(cudaMemsetAsync(d.chunks, 0, d.nchunks * sizeof(ChunkHdr), st));
     DBuf<int> maxima;
-    PFG_CUDA_TRY(maxima.alloc(8));
-    PFG_CUDA_TRY(cudaMemsetAsync(maxima.p, 0, 8 * sizeof(int), st));
+    PFG_CUDA_TRY(maxima.alloc(12));
+    PFG_CUDA_TRY(cudaMemsetAsync(maxima.p, 0, 12 * sizeof(int), st));
     k_chunk_node_begin<<<grid_for(nown), kThreads, 0, st>>>(slot_chunk.p, nown, d.nchunks, d.chunks);
     k_chunk_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, inc_excl.p, kk.p, plan_off.p, d.chunks, nown,
                                                              maxima.p);
@@ -971,9 +1016,47 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.rec_dst = nullptr;
         const int rows = (d.m == 2) ? 1 : 0;
         d.tile_rows = rows != 0;
+        DBuf<uint32_t> win_begin;
+        DBuf<int> terr;
+        PFG_CUDA_TRY(terr.alloc(1));
+        PFG_CUDA_TRY(cudaMemsetAsync(terr.p, 0, sizeof(int), st));
+        PFG_CUDA_TRY(win_begin.alloc(d.nchunks + 1));
+        {   // node windows
+            const int64_t ncorners = d.nrecs * NNE;
+            DBuf<uint64_t> wkeys, wsorted, wuniq;
+            DBuf<int64_t> nsel2;
+            PFG_CUDA_TRY(wkeys.alloc(ncorners));
+            PFG_CUDA_TRY(wsorted.alloc(ncorners));
+            PFG_CUDA_TRY(nsel2.alloc(1));
+            k_win_keys<NNE><<<grid_for(ncorners), kThreads, 0, st>>>(rec_keys.p, d.rec_nodes, ncorners, wkeys.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceRadixSort::SortKeys(d_temp_storage, temp_storage_bytes, (const uint64_t*)wkeys.p, wsorted.p,
+                                                   ncorners, 0, 32 + bits_for((uint64_t)d.nchunks), st));
+            wkeys.release();
+            PFG_CUDA_TRY(wuniq.alloc(ncorners));
+            PFG_CUB(scratch, st,
+                    cub::DeviceSelect::Unique(d_temp_storage, temp_storage_bytes, wsorted.p, wuniq.p, nsel2.p, ncorners,
+                                              st));
+            PFG_CUDA_TRY(cudaMemcpyAsync(&d.nwin, nsel2.p, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+            PFG_CUDA_TRY(cudaStreamSynchronize(st));
+            wsorted.release();
+            if (d.nwin >= (int64_t)0xffffffffll) {
+                set_error("node windows exceed the 32-bit index range");
+                return PFG_ERR_UNSUPPORTED;
+            }
+            PFG_CUDA_TRY(cudaMalloc(&d.win_nodes, d.nwin * sizeof(uint32_t) + 64));
+            PFG_CUDA_TRY(cudaMalloc(&d.rec_local, ncorners * sizeof(uint16_t) + 64));
+            PFG_CUDA_TRY(cudaMemsetAsync(win_begin.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
+            k_win_fill<<<grid_for(d.nwin), kThreads, 0, st>>>(wuniq.p, d.nwin, d.win_nodes, win_begin.p, nullptr);
+            k_win_max<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, win_begin.p, d.nwin, maxima.p);
+            k_rec_local<NNE><<<grid_for(ncorners), kThreads, 0, st>>>(rec_keys.p, d.rec_nodes, wuniq.p, win_begin.p,
+                                                                     d.nchunks, d.nwin, ncorners, d.rec_local, terr.p);
+            PFG_CUDA_TRY(cudaStreamSynchronize(st));
+            PFG_CUDA_TRY(cudaGetLastError());
+        }
         DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16, run_flag, run_id;
         DBuf<int64_t> sb_excl, nc_excl, kk_excl, blob_off, code_off;
-        DBuf<int> terr, chunk_cpad, chunk_gmax;
+        DBuf<int> chunk_cpad, chunk_gmax;
         PFG_CUDA_TRY(chunk_cpad.alloc(d.nchunks));
         PFG_CUDA_TRY(chunk_gmax.alloc(d.nchunks));
         PFG_CUDA_TRY(cudaMemsetAsync(chunk_cpad.p, 0, d.nchunks * sizeof(int), st));
@@ -989,8 +1072,6 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(code_len16.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(blob_off.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(code_off.alloc(d.nchunks + 1));
-        PFG_CUDA_TRY(terr.alloc(1));
-        PFG_CUDA_TRY(cudaMemsetAsync(terr.p, 0, sizeof(int), st));
         PFG_CUDA_TRY(cudaMemsetAsync(sbytes.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(ncodes.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(run_flag.p, 0, (nown + 1) * sizeof(uint32_t), st));
@@ -1035,7 +1116,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes_neutral, 0xFF, d.tile_ncodes * 2 + 64, st));  // 0xFFFF = padding
         PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
         k_tile_dir<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.chunks, blob_off.p, code_off.p,
-                                                                 blob_len16.p, code_len16.p, d.nrecs, d.tile_dir);
+                                                                 win_begin.p, d.nrecs, d.nwin, d.tile_dir);
         TileFillArgs fa;
         fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
         fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr, fa.nbr = d.nbr;
@@ -1047,7 +1128,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         fa.chunk_cpad = chunk_cpad.p, fa.err = terr.p, fa.chunk_gmax = chunk_gmax.p;
         k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(fa);
         k_tile_cpad<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.tile_dir, chunk_cpad.p, d.tile_blob);
-        int h_terr = 0, h_max[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int h_terr = 0, h_max[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaStreamSynchronize(st));
@@ -1059,18 +1140,23 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.max_blob_bytes = h_max[5];
         d.max_code_bytes = h_max[6];
         d.max_out_bytes = h_max[7];
+        d.max_chunk_win = h_max[8];
         if (h_terr || d.max_blob_bytes > 0xFFFF * 16 || d.max_code_bytes > 0xFFFF * 16) {
             // chunk too irregular for the compact tile encoding: assemble with the atomic scatter instead
             cudaFree(d.tile_dir); d.tile_dir = nullptr;
             cudaFree(d.tile_blob); d.tile_blob = nullptr;
             cudaFree(d.tile_codes); d.tile_codes = nullptr;
             cudaFree(d.tile_codes_neutral); d.tile_codes_neutral = nullptr;
+            cudaFree(d.win_nodes); d.win_nodes = nullptr;
+            cudaFree(d.rec_local); d.rec_local = nullptr;
             d.nchunks = 0;
             return PFG_OK;
         }
+        cudaFree(d.rec_nodes);  // the tile kernels address record corners through the node windows
+        d.rec_nodes = nullptr;
         d.plan_bytes = d.tile_blob_bytes + d.tile_ncodes * 2;
-        d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * (NNE * 4 + 4) +
-                          d.tile_blob_bytes + d.tile_ncodes * 4;
+        d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * (NNE * 2 + 4) +
+                          d.nwin * 4 + d.tile_blob_bytes + d.tile_ncodes * 4;
         return PFG_OK;
     }
     k_fill_dst<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,
@@ -1107,7 +1193,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
-                    d.tile_codes, d.tile_codes_neutral};
+                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }
@@ -1250,7 +1336,7 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_CHUNK_ELEMS: *value = d.nrecs; break;
         case PFG_INFO_PLAN_BYTES:
             if (d.tile_dir)
-                *value = (int64_t)(d.nchunks * sizeof(TileDir) + d.nrecs * (d.nne * 4) + d.plan_bytes);
+                *value = (int64_t)(d.nchunks * sizeof(TileDir) + d.nrecs * (d.nne * 2) + d.nwin * 4 + d.plan_bytes);
             else
                 *value = d.nchunks ? (int64_t)(d.nchunks * sizeof(ChunkHdr) + (d.own_end - d.own_begin) * sizeof(ChunkNode) +
                                                d.nrecs * (d.nne * 6) + d.plan_bytes)
