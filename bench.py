@@ -279,7 +279,8 @@ def main():
     # pinned memory + assembly + D2H of the CSR values into a scipy matrix
     e2e = None
     h2d = d2h = 0
-    if args.e2e_steps > 0 and physics in ("elasticity", "poisson"):
+    # (skipped when the CSR values alone exceed 8 GB: the full 256^3 hex case would pin > 60 GB of host memory)
+    if args.e2e_steps > 0 and physics in ("elasticity", "poisson") and mesh.nnz * 8 <= 8e9:
         rho_host = torch.from_numpy(0.1 + 0.9 * np.random.default_rng(0).random(mesh.nnodes)).pin_memory()
         data_host = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory()
         data_np = data_host.numpy()

@@ -415,15 +415,14 @@ struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) 
         double coef[kMaxXdv];  // xdv[k] * binom(nxdv-1, k)  (pyfem.py:1466-1470)
     };
     PFG_DEV static double hfun(const Params& prm, double x, double y) {
-        // h = 1 + 4y(1-y) sum_k coef_k (1-x)^(n-1-k) x^k, powers by repeated multiplication
+        // h = 1 + 4y(1-y) sum_k coef_k (1-x)^(n-1-k) x^k.  Two-variable Horner: S_k = (1-x) S_{k-1} + coef_k x^k
+        // needs no power table (three flops per term, coefficients straight from the constant bank).
         const int n = prm.nxdv;
-        double om[kMaxXdv];
-        om[0] = 1.0;
-        for (int k = 1; k < n; ++k) om[k] = om[k - 1] * (1.0 - x);
-        double xp = 1.0, s = 0.0;
-        for (int k = 0; k < n; ++k) {
-            s = fma(prm.coef[k] * om[n - 1 - k], xp, s);
+        const double om = 1.0 - x;
+        double s = prm.coef[0], xp = 1.0;
+        for (int k = 1; k < n; ++k) {
             xp *= x;
+            s = fma(s, om, prm.coef[k] * xp);
         }
         return fma(s, 4.0 * y * (1.0 - y), 1.0);
     }
