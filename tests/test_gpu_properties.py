@@ -1,0 +1,223 @@
+"""GPU parity on irregular / degenerate meshes, and size-independent properties at BASELINE's full sizes.
+
+The oracle cannot assemble 16 M elements on the host, so the full-size checks use properties the
+domain offers: rigid-body null space, symmetry, exact linearity in rho for p = 0, translation invariance of the
+stencil, bitwise reproducibility, agreement of the two scatter strategies, and the pattern's closed-form size.
+"""
+import numpy as np
+import pytest
+
+import pyfem_oracle as orc
+from make_golden import test_gfunc as gfunc
+from parity import VAL_TOL, assert_csr_matches, assert_values_close
+
+pytestmark = pytest.mark.gpu
+MODES = ["atomic", "gather"]
+
+
+@pytest.fixture(scope="module")
+def pf():
+    import pyfem_gpu_testflight_b200 as pf
+    return pf
+
+
+def _objs(pf):
+    q = pf.QuadratureBilinear2D()
+    return q, pf.BasisBilinear2D(q)
+
+
+# ---- irregular quad meshes -------------------------------------------------------------------------
+def three_patch_mesh(n, seed=0):
+    """Three n x n quad patches glued around a centre node (a 'Y' block mesh): the centre has valence 3, the patch
+    seams valence 4 with irregular neighbour sets, element numbering follows the patches (no global structure)."""
+    ang = [np.pi / 2, np.pi / 2 + 2 * np.pi / 3, np.pi / 2 + 4 * np.pi / 3]
+    d = [np.array([np.cos(a), np.sin(a)]) for a in ang]
+    node_id, X, conn = {}, [], []
+
+    def node(key, xy):
+        if key not in node_id:
+            node_id[key] = len(X)
+            X.append(xy)
+        return node_id[key]
+
+    for p in range(3):
+        e1, e2 = d[p], d[(p + 1) % 3]
+
+        def key(i, j):
+            # nodes on the seam (j == 0 of patch p) coincide with (i == 0) nodes of the previous patch
+            if i == 0 and j == 0:
+                return ("c",)
+            if j == 0:
+                return ("s", p, i)
+            if i == 0:
+                return ("s", (p + 1) % 3, j)
+            return ("p", p, i, j)
+
+        for j in range(n):
+            for i in range(n):
+                ids = []
+                for (a, b) in ((i, j), (i + 1, j), (i + 1, j + 1), (i, j + 1)):
+                    ids.append(node(key(a, b), (a * e1 + b * e2) / n))
+                conn.append(ids)
+    X = np.array(X)
+    rng = np.random.default_rng(seed)
+    X = X + rng.uniform(-0.15, 0.15, size=X.shape) / n
+    X = (X - X.min(axis=0)) / (X.max(axis=0) - X.min(axis=0))  # nonlinear Poisson wants [0,1]^2
+    conn = np.array(conn, dtype=np.int64)
+    # make every element counter-clockwise
+    x = X[conn]
+    area = 0.5 * np.sum(x[:, :, 0] * np.roll(x[:, :, 1], -1, axis=1) - np.roll(x[:, :, 0], -1, axis=1) * x[:, :, 1], axis=1)
+    conn[area < 0] = conn[area < 0][:, ::-1]
+    return X, conn
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n", [3, 17])
+def test_three_patch_mesh_all_physics(pf, mode, n):
+    X, conn = three_patch_mesh(n, seed=n)
+    conn = conn[np.random.default_rng(1).permutation(conn.shape[0])]
+    q, b = _objs(pf)
+    rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+    m = pf.LinearElasticity(X, conn, [0], None, {0: [0.0, 0.0]}, q, b, p=4.0, scatter=mode)
+    Kr = orc.assemble_elasticity(X, conn, rho, 4.0)
+    assert_csr_matches(m.compute_jacobian(rho), Kr.indptr, Kr.indices, Kr.data)
+    m = pf.LinearPoisson(X, conn, [0], None, q, b, gfunc, p=1.5, scatter=mode)
+    Kr = orc.assemble_poisson(X, conn, rho, 1.5)
+    assert_csr_matches(m.compute_jacobian(rho), Kr.indptr, Kr.indices, Kr.data)
+    assert_values_close(m.compute_rhs(), orc.assemble_poisson_rhs(X, conn, gfunc), VAL_TOL, "rhs")
+    m = pf.Helmholtz(0.1, X, conn, q, b, scatter=mode)
+    Kr, Rr = orc.assemble_helmholtz(X, conn, 0.1)
+    assert_csr_matches(m.K, Kr.indptr, Kr.indices, Kr.data)
+    assert_csr_matches(m.R, Rr.indptr, Rr.indices, Rr.data)
+    m = pf.NonlinearPoisson2D(X, conn, [0], None, q, b, scatter=mode)
+    xdv = np.linspace(0.02, 0.2, 10)
+    u = np.random.default_rng(5).random(X.shape[0]) - 0.4
+    Kr, rr = orc.assemble_nlpoisson(X, conn, xdv, u)
+    assert_csr_matches(m.compute_jacobian(xdv, u), Kr.indptr, Kr.indices, Kr.data)
+    assert_values_close(m.compute_rhs(xdv, u), rr, VAL_TOL, "residual")
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_fan_mesh_high_valence(pf, mode):
+    """Eight quads sharing one node (valence 8): more contributions per block than the unrolled fast path holds."""
+    k = 8
+    X = [[0.0, 0.0]]
+    for i in range(2 * k):
+        a = 2 * np.pi * i / (2 * k)
+        r = 1.0 if i % 2 == 0 else 1.3
+        X.append([r * np.cos(a), r * np.sin(a)])
+    conn = [[0, 1 + 2 * i, 1 + (2 * i + 1) % (2 * k), 1 + (2 * i + 2) % (2 * k)] for i in range(k)]
+    X, conn = np.array(X), np.array(conn, dtype=np.int64)
+    q, b = _objs(pf)
+    Kr = orc.assemble_elasticity(X, conn, 0.7, 2.0)
+    m = pf.LinearElasticity(X, conn, [0], None, {0: [0.0, 0.0]}, q, b, p=2.0, scatter=mode)
+    assert_csr_matches(m.compute_jacobian(0.7), Kr.indptr, Kr.indices, Kr.data)
+    Kr = orc.assemble_poisson(X, conn)
+    m = pf.LinearPoisson(X, conn, [0], None, q, b, gfunc, scatter=mode)
+    assert_csr_matches(m.compute_jacobian(), Kr.indptr, Kr.indices, Kr.data)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_degenerate_sizes(pf, mode):
+    """One element; a strip of elements; a mesh with a node no element references (empty CSR rows, as scipy gives)."""
+    q, b = _objs(pf)
+    for nx, ny in ((2, 2), (2, 9), (33, 2)):
+        X, conn = orc.structured_mesh(nx, ny)
+        Kr = orc.assemble_elasticity(X, conn)
+        m = pf.LinearElasticity(X, conn, [0], None, {0: [0.0, 0.0]}, q, b, scatter=mode)
+        assert_csr_matches(m.compute_jacobian(), Kr.indptr, Kr.indices, Kr.data)
+    X, conn = orc.structured_mesh(6, 5)
+    # add an unreferenced node in the middle of the numbering: renumber nodes >= 7 up by one
+    X2 = np.insert(X, 7, [[0.33, 0.77]], axis=0)
+    conn2 = np.where(conn >= 7, conn + 1, conn)
+    Kr = orc.assemble_poisson(X2, conn2)
+    m = pf.LinearPoisson(X2, conn2, [0], None, q, b, gfunc, scatter=mode)
+    K = m.compute_jacobian()
+    assert_csr_matches(K, Kr.indptr, Kr.indices, Kr.data)
+    assert K.indptr[7] == K.indptr[8]  # the unreferenced node's row is empty
+    Kr = orc.assemble_elasticity(X2, conn2)
+    m = pf.LinearElasticity(X2, conn2, [0], None, {0: [0.0, 0.0]}, q, b, scatter=mode)
+    assert_csr_matches(m.compute_jacobian(), Kr.indptr, Kr.indices, Kr.data)
+
+
+# ---- full-size properties (BASELINE configs[1] and [3]) ---------------------------------------------
+@pytest.fixture(scope="module")
+def big_quad(pf):
+    import torch
+    n = 4096
+    c = pf.ProblemCreator(n + 1, n + 1)
+    mesh = pf.DeviceMesh(c.X, c.conn, 2)
+    torch.cuda.synchronize()
+    return n, c, mesh
+
+
+def test_full_size_elasticity_properties(pf, big_quad):
+    import torch
+    n, c, mesh = big_quad
+    nn = (n + 1) ** 2
+    assert mesh.nelems == n * n == 16777216
+    assert mesh.nnz == 4 * (3 * (n + 1) - 2) ** 2 == 604078084  # closed form m^2 * prod(3 nn_k - 2)
+    assert mesh.idx_bytes == 4                                   # scipy's rule: COO nnz = 2^30 fits int32
+    K = mesh.assemble_elasticity(1.0, 0.0, mode="gather")
+    # bitwise reproducible; exactly linear in a constant rho when p = 0 (scaling by a power of two is exact)
+    assert torch.equal(K, mesh.assemble_elasticity(1.0, 0.0, mode="gather"))
+    assert torch.equal(2.0 * K, mesh.assemble_elasticity(2.0, 0.0, mode="gather"))
+    scale = float(K.abs().max())
+    # the two scatter strategies agree
+    Ka = mesh.assemble_elasticity(1.0, 0.0, mode="atomic")
+    assert float((Ka - K).abs().max()) <= 1e-13 * scale
+    del Ka
+    # rigid-body translations are in the null space: K [1,0,1,0,...] = K [0,1,0,1,...] = 0
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for axis in (0, 1):
+        t = torch.zeros(2 * nn, dtype=torch.float64, device="cuda")
+        t[axis::2] = 1.0
+        assert float(mesh.spmv(K, t).abs().max()) <= 1e-12 * scale
+    # symmetry: x' K y == y' K x
+    x = torch.rand(2 * nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    y = torch.rand(2 * nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    a, b = float(x @ mesh.spmv(K, y)), float(y @ mesh.spmv(K, x))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b), scale)
+    # translation invariance: interior nodes of the uniform mesh carry the same 2 x 18 row values
+    indptr, _ = mesh.pattern()
+    rows = [2 * (j * (n + 1) + i) for (i, j) in ((7, 9), (2048, 2048), (4000, 123))]
+    ref = K[int(indptr[rows[0]]):int(indptr[rows[0] + 2])]
+    for r in rows[1:]:
+        got = K[int(indptr[r]):int(indptr[r + 2])]
+        assert float((got - ref).abs().max()) <= 1e-12 * scale
+    # the sub-mesh the oracle can afford: rows of a 33 x 33-node corner patch equal the oracle's rows
+    Xs, cs = orc.structured_mesh(40, 40, Lx=39.0 / n * c.X[:, 0].max(), Ly=39.0 / n * c.X[:, 1].max())
+    Ks = orc.assemble_elasticity(Xs, cs)
+    for (i, j) in ((0, 0), (5, 0), (17, 30)):
+        rs, rb = 2 * (j * 40 + i), 2 * (j * (n + 1) + i)
+        got = K[int(indptr[rb]):int(indptr[rb + 1])].cpu().numpy()
+        want = Ks.data[Ks.indptr[rs]:Ks.indptr[rs + 1]]
+        assert_values_close(got, want, VAL_TOL, f"row of node ({i},{j})")
+
+
+def test_full_size_nlpoisson_properties(pf):
+    import torch
+    n = 4096
+    c = pf.ProblemCreator(n + 1, n + 1)
+    X = c.X / c.X.max(axis=0)
+    mesh = pf.DeviceMesh(X, c.conn, 1)
+    nn = (n + 1) ** 2
+    assert mesh.nnz == (3 * (n + 1) - 2) ** 2 == 151019521
+    xdv = np.ones(10) / 10.0
+    g = torch.Generator(device="cuda").manual_seed(0)
+    u = torch.rand(nn, dtype=torch.float64, device="cuda", generator=g)
+    K, res = mesh.assemble_nlpoisson(xdv, u, mode="gather")
+    K2, res2 = mesh.assemble_nlpoisson(xdv, u, mode="gather")
+    assert torch.equal(K, K2) and torch.equal(res, res2)
+    Ka, resa = mesh.assemble_nlpoisson(xdv, u, mode="atomic")
+    assert float((Ka - K).abs().max()) <= 1e-13 * float(K.abs().max())
+    assert float((resa - res).abs().max()) <= 1e-13 * float(res.abs().max())
+    # the Jacobian is the derivative of the residual: res(u + eps v) - res(u - eps v) ~ 2 eps K v
+    v = torch.rand(nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    eps = 1e-6
+    _, rp = mesh.assemble_nlpoisson(xdv, u + eps * v, want_K=False, mode="gather")
+    rp = rp.clone()
+    _, rm = mesh.assemble_nlpoisson(xdv, u - eps * v, want_K=False, mode="gather")
+    fd = (rp - rm) / (2 * eps)
+    Kv = mesh.spmv(K, v)
+    assert float((fd - Kv).abs().max()) <= 1e-6 * float(Kv.abs().max())
