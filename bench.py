@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="elements per side (default: the workload's named size)")
     ap.add_argument("--mode", default="auto", choices=["auto", "gather", "atomic"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--halo", default="ghost", choices=["ghost", "reduce"],
+                    help="N > 1: 'ghost' integrates the ghost element layer on both neighbours (no exchange); "
+                         "'reduce' integrates every element once and sums interface rows over NCCL send/recv")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -198,7 +201,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pyfem_gpu_testflight_b200 as pf
-    from pyfem_gpu_testflight_b200.partition import structured_slab
+    from pyfem_gpu_testflight_b200.partition import slab_node_ranges, structured_slab
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
@@ -213,13 +216,21 @@ def main():
         nx = n_side + 1
         ny_el = (n_side // 2 if args.workload == "c3" else n_side) * (world if scaling == "weak" else 1)
         part = structured_slab(nx, ny_el + 1, None, rank, world)
+        ranges = slab_node_ranges(nx, ny_el + 1, None, world)
         ndims = 2
     else:
         nz_el = n_side * (world if scaling == "weak" else 1)
         part = structured_slab(n_side + 1, n_side + 1, nz_el + 1, rank, world)
+        ranges = slab_node_ranges(n_side + 1, n_side + 1, nz_el + 1, world)
         ndims = 3
-    mesh = pf.DeviceMesh(part.X, part.conn, m, device=dev, own_range=part.own_range, node_gid=part.node_gid,
-                         ncols_nodes=part.nnodes_global)
+    reducer = None
+    if args.halo == "reduce" and world > 1 and physics in ("elasticity", "poisson", "nlpoisson"):
+        from pyfem_gpu_testflight_b200.halo import ReduceAssembler
+        reducer = ReduceAssembler(part, m, ranges, device=dev)
+        mesh = reducer.mesh
+    else:
+        mesh = pf.DeviceMesh(part.X, part.conn, m, device=dev, own_range=part.own_range, node_gid=part.node_gid,
+                             ncols_nodes=part.nnodes_global)
     torch.cuda.synchronize()
     setup_s = time.perf_counter() - t_setup
     own_nodes = part.own_range[1] - part.own_range[0]
@@ -235,7 +246,14 @@ def main():
     xdv = np.ones(10) / 10.0
 
     def step(rho=1.0, p=0.0):
-        if physics == "elasticity":
+        if reducer is not None:
+            if physics == "elasticity":
+                reducer.assemble_elasticity(rho, p, out=vals, mode=args.mode)
+            elif physics == "poisson":
+                reducer.assemble_poisson(rho, p, out=vals, mode=args.mode)
+            else:
+                reducer.assemble_nlpoisson(xdv, u, mode=args.mode)
+        elif physics == "elasticity":
             mesh.assemble_elasticity(rho, p, out=vals, mode=args.mode)
         elif physics == "poisson":
             mesh.assemble_poisson(rho, p, out=vals, mode=args.mode)
@@ -333,7 +351,9 @@ def main():
         "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
                    "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
                    "csr_nnz_rank0": mesh.nnz, "scatter": "gather" if (args.mode != "atomic" and mesh.nchunks) else "atomic",
-                   "partition": f"row slabs x{world}, ghost-element layer, no data-path collective",
+                   "partition": (f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
+                                 f"send/recv + indexed add" if reducer is not None else
+                                 f"row slabs x{world}, ghost-element layer, no data-path collective"),
                    "l2": "outputs (4.8 GB/step for c2) and inputs exceed the 126 MB L2; no flush needed",
                    "rho": "constant 1.0, p=0 (device-resident headline); e2e uses a host nodal rho field, p=5",
                    "setup_s_once_per_mesh": round(setup_s, 3), "halo_recompute_factor": round(mesh.chunk_elems / max(1, mesh.nelems), 4),
@@ -342,7 +362,9 @@ def main():
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                      "peak_source": peak_src},
         "clocks": clocks,
-        "gpu_launches": args.steps * 1,
+        # own kernels per step: the assembly kernel; the reduce variant adds one halo assembly per neighbour it
+        # sends to and one indexed add per neighbour it receives from (rank 0's count)
+        "gpu_launches": args.steps * (1 + (len(reducer.halo) + len(reducer.recv) if reducer is not None else 0)),
     }
     if e2e is not None:
         line["e2e"] = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}

@@ -101,6 +101,21 @@ PFG_API int pfg_mesh_destroy(pfg_mesh* mesh);
 PFG_API int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value);
 
 /*
+ * Multi-GPU, interface rows summed by a reduce (the north_star's "NCCL reduce over NVLink" variant; the
+ * default ghost-layer variant needs no exchange).  elem_skip_dev: (nelems,) uint8, non-zero for elements of
+ * this handle's mesh whose contributions arrive from another rank: they stay in the pattern but are not
+ * integrated.  NULL clears the mask.  Reference: none (the reference is single-process); the summation it
+ * completes is the duplicate-summing of coo->csr (pyfem.py:930-931) across partitions.
+ */
+PFG_API int pfg_mesh_set_element_mask(pfg_mesh* mesh, const uint8_t* elem_skip_dev, void* stream);
+
+/*
+ * vals[idx[i]] += src[i] for i < n, idx unique: adds a neighbour's interface-row contributions (received with
+ * NCCL into src_dev) into the owner's CSR values or rhs.  Part of the same cross-partition duplicate sum.
+ */
+PFG_API int pfg_add_indexed(double* vals_dev, const int64_t* idx_dev, const double* src_dev, int64_t n, void* stream);
+
+/*
  * CSR pattern of the owned rows, identical to K.indptr / K.indices of the reference's
  * ModelBase._assemble_jacobian (pyfem.py:920-931): sorted unique columns, explicit zeros kept.
  *   indptr_dev  (nrows + 1) entries, indices_dev (nnz) entries, each idx_bytes (4 or 8) wide.

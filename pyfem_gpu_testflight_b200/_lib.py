@@ -50,6 +50,8 @@ PROTOTYPES = {
     "pfg_poisson_rhs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_apply_dirichlet": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pfg_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pfg_mesh_set_element_mask": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pfg_add_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 _lib = None

@@ -128,6 +128,7 @@ template <class Op>
 __global__ void __launch_bounds__(128) k_assemble_atomic(MeshView mv, typename Op::Params prm, Outputs out) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (e >= mv.nelems) return;
+    if (mv.elem_skip != nullptr && mv.elem_skip[e]) return;  // integrated by another rank
     constexpr int NNE = Op::NNE;
     int nodes[NNE];
     if constexpr (NNE == 4) {
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(128) k_elasticity_hex8_atomic(MeshView mv, Ela
     const int lane8 = threadIdx.x & 7;
     const unsigned octet_mask = 0xffu << ((threadIdx.x & 31) & ~7);
     if (e >= mv.nelems) return;  // whole octets leave together
+    if (mv.elem_skip != nullptr && mv.elem_skip[e]) return;
     int nodes[8];
     const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e);
     const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e + 1);
@@ -673,6 +675,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 loc[0] = v.x & 0xFFFFu, loc[1] = v.x >> 16, loc[2] = v.y & 0xFFFFu, loc[3] = v.y >> 16;
                 loc[4] = v.z & 0xFFFFu, loc[5] = v.z >> 16, loc[6] = v.w & 0xFFFFu, loc[7] = v.w >> 16;
             }
+            if (loc[0] & 0x8000u) {  // masked element (another rank integrates it): its record contributes zeros
+                for (int i = 0; i < St::RAW; ++i) sink.rec[i] = 0.0;
+                continue;
+            }
             double xe[NNE][DIM], fe[NNE];
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
@@ -754,6 +760,11 @@ __global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv,
         nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
         const uint16_t my_dst = __ldg(mv.rec_dst + rr * 8 + lane8);
         HexSmemRowSink sink{rb + (int)my_dst * L::RB};
+        if (mv.elem_skip != nullptr && mv.elem_skip[__ldg(mv.rec_elem + rr)]) {  // integrated by another rank
+            if (my_dst != kNoDst)
+                for (int i = 0; i < 72; ++i) sink.row[i] = 0.0;
+            continue;
+        }
         elasticity_hex8_octet(mv, prm, nodes, stage + (threadIdx.x >> 3) * kHexStageDoubles, lane8, octet_mask,
                               my_dst != kNoDst, sink);
     }
@@ -862,6 +873,7 @@ static MeshView view_of(const MeshDev& d) {
     mv.conn = d.conn;
     mv.blk_ptr = d.blk_ptr;
     mv.rank = d.rank;
+    mv.elem_skip = d.elem_skip;
     mv.nelems = d.nelems;
     mv.chunks = d.chunks;
     mv.cnodes = d.cnodes;
@@ -1150,6 +1162,22 @@ extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev
     PFG_CUDA_TRY(cudaGetLastError());
     PFG_CUDA_TRY(cudaFreeAsync(is_fixed, st));
     PFG_CUDA_TRY(cudaFreeAsync(u0, st));
+    return PFG_OK;
+}
+
+__global__ void k_add_indexed(double* __restrict__ vals, const int64_t* __restrict__ idx, const double* __restrict__ src,
+                              int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) vals[idx[i]] += src[i];
+}
+
+extern "C" int pfg_add_indexed(double* vals_dev, const int64_t* idx_dev, const double* src_dev, int64_t n, void* stream) {
+    if (n < 0 || (n > 0 && (!vals_dev || !idx_dev || !src_dev))) {
+        set_error("pfg_add_indexed: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    if (n) k_add_indexed<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, idx_dev, src_dev, n);
+    PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
 }
 

@@ -82,6 +82,7 @@ struct MeshView {
     const int32_t* conn;
     const int64_t* blk_ptr;
     const uint8_t* rank;
+    const uint8_t* elem_skip;  // nullptr: every element is integrated
     int64_t nelems;
     // gather path
     const ChunkHdr* chunks;

@@ -154,6 +154,7 @@ struct MeshDev {
     double* X = nullptr;        // (nnodes, ndims)
     int32_t* conn = nullptr;    // (nelems, nne)
     int64_t* gid = nullptr;     // optional local->global node id
+    uint8_t* elem_skip = nullptr; // optional (nelems): elements kept in the pattern but not integrated here
 
     // node -> element incidences (all local nodes), sorted by (node, element, local index)
     int64_t* inc_ptr = nullptr;   // (nnodes+1)

@@ -1193,7 +1193,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
-                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local};
+                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }
@@ -1311,6 +1311,42 @@ extern "C" int pfg_mesh_create(pfg_mesh** out, int elem_type, int ndof_per_node,
     int64_t ncols = d.ncols_nodes * d.m;
     d.idx_bytes = (std::max(coo_nnz, ncols) <= 0x7fffffffll) ? 4 : 8;
     *out = mesh;
+    return PFG_OK;
+}
+
+// tile plan: the skip flag of a record rides in the top bit of its first corner's window index
+__global__ void k_mask_records(const int32_t* __restrict__ rec_elem, const uint8_t* __restrict__ skip, int64_t nrecs,
+                               int nne, uint16_t* __restrict__ rec_local) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nrecs) return;
+    uint16_t v = rec_local[r * nne] & 0x7FFFu;
+    if (skip && skip[rec_elem[r]]) v |= 0x8000u;
+    rec_local[r * nne] = v;
+}
+
+extern "C" int pfg_mesh_set_element_mask(pfg_mesh* mesh, const uint8_t* elem_skip_dev, void* stream) {
+    if (!mesh) {
+        set_error("pfg_mesh_set_element_mask: mesh is NULL");
+        return PFG_ERR_INVALID;
+    }
+    MeshDev& d = mesh->d;
+    PFG_CUDA_TRY(cudaSetDevice(d.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.tile_dir && d.max_chunk_win > 0x7FFF) {
+        set_error("node windows of %d entries leave no room for the record skip flag", d.max_chunk_win);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    if (elem_skip_dev) {
+        if (!d.elem_skip) PFG_CUDA_TRY(cudaMalloc(&d.elem_skip, std::max<int64_t>(d.nelems, 1)));
+        PFG_CUDA_TRY(cudaMemcpyAsync(d.elem_skip, elem_skip_dev, d.nelems, cudaMemcpyDeviceToDevice, st));
+    } else if (d.elem_skip) {
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        cudaFree(d.elem_skip);
+        d.elem_skip = nullptr;
+    }
+    if (d.tile_dir && d.nrecs)
+        k_mask_records<<<grid_for(d.nrecs), kThreads, 0, st>>>(d.rec_elem, d.elem_skip, d.nrecs, d.nne, d.rec_local);
+    PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
 }
 

@@ -226,6 +226,29 @@ class DeviceMesh:
             _lib.check(self._lib.pfg_spmv(self._handle, _ptr(vals), _ptr(x), _ptr(out), self._stream()))
         return out
 
+    # ---- multi-GPU reduce variant (halo.py) ---------------------------------------------------------
+    def set_element_mask(self, skip):
+        """Elements with skip != 0 stay in the pattern but are not integrated by this handle (another rank ships
+        their contributions, halo.ReduceAssembler).  None clears the mask."""
+        torch = _torch()
+        t = None
+        if skip is not None:
+            t = torch.as_tensor(np.asarray(skip, dtype=np.uint8)).to(self.device).contiguous()
+            if t.numel() != self.nelems:
+                raise ValueError(f"element mask must have {self.nelems} entries")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_mesh_set_element_mask(self._handle, _ptr(t), self._stream()))
+
+    def add_indexed(self, vals, idx, src):
+        """vals[idx] += src on the device (idx unique): a neighbour's interface-row contributions."""
+        torch = _torch()
+        n = int(idx.numel())
+        if src.numel() != n:
+            raise ValueError("idx and src differ in length")
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_add_indexed(_ptr(vals), _ptr(idx), _ptr(src), n, self._stream()))
+        return vals
+
     # ---- host views -------------------------------------------------------------------------------
     def to_scipy(self, vals, copy_pattern=True, out=None):
         """scipy.sparse.csr_matrix on the host from device values (one D2H copy of nnz doubles).

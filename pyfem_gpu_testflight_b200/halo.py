@@ -1,0 +1,207 @@
+"""Interface rows summed by a reduce over NCCL -- the north_star's partitioning variant.
+
+Default multi-GPU assembly (partition.py) integrates the one ghost layer of elements on both neighbours and needs no
+exchange.  Here every element is integrated on exactly ONE rank (the owner of its lowest-numbered node); a CSR row
+of an interface node then receives partial sums from several ranks, and the non-owners ship theirs to the owner:
+
+    setup (once per mesh)   rank r builds, per neighbour q, a thin "halo" handle over its own elements that touch
+                            q-owned nodes, whose rows are exactly those nodes; it sends the halo pattern to q, and q
+                            matches it against its own rows -> an index map into its CSR values;
+    every assembly          r assembles its slab with the ghost elements masked out (pfg_mesh_set_element_mask) and its
+                            halo handles; halo values travel with ncclSend/ncclRecv (torch.distributed P2P over
+                            NVLink); q adds them at the mapped slots (pfg_add_indexed).  The cross-partition sum
+                            completes the duplicate summation of the reference's coo->csr (pyfem.py:930-931).
+
+The planning below is numpy and runs anywhere (gloo test on CPU); `ReduceAssembler` is the device part.
+"""
+import numpy as np
+
+from .partition import LocalMesh
+
+
+def owner_of_nodes(node_gid, ranges):
+    """Owner rank of every global node id, for contiguous ownership ranges [(b0,e0), (b1,e1), ...]."""
+    starts = np.array([b for b, _ in ranges], dtype=np.int64)
+    return np.searchsorted(starts, np.asarray(node_gid), side="right") - 1
+
+
+class HaloSend:
+    """One neighbour's share: my own elements that touch nodes owned by rank `dest`, as a self-contained mesh whose
+    owned rows are exactly those nodes."""
+
+    def __init__(self, dest, X, conn, own_range, node_gid, local_nodes, elem_local):
+        self.dest = dest
+        self.X, self.conn, self.own_range, self.node_gid = X, conn, own_range, node_gid
+        self.local_nodes = local_nodes  # index of the halo mesh's nodes in the rank's local numbering (nodal fields)
+        self.elem_local = elem_local    # index of the halo mesh's elements in the rank's local element list
+
+
+class HaloPlan:
+    """Which local elements this rank integrates, and what it owes to / expects from its neighbours."""
+
+    def __init__(self, part: LocalMesh, ranges):
+        self.part, self.ranges = part, list(ranges)
+        rank = part.rank
+        conn_gid = part.node_gid[part.conn]
+        elem_owner = owner_of_nodes(conn_gid.min(axis=1), ranges)
+        self.mine = elem_owner == rank
+        self.skip_mask = (~self.mine).astype(np.uint8)           # ghost elements: in the pattern, not integrated
+        self.recv_from = sorted(set(int(q) for q in np.unique(elem_owner[~self.mine])))
+        node_owner = owner_of_nodes(conn_gid, ranges)             # (nelems, nne)
+        self.sends = []
+        for q in sorted(set(int(v) for v in np.unique(node_owner[self.mine])) - {rank}):
+            sel = np.nonzero(self.mine & (node_owner == q).any(axis=1))[0]
+            sub = part.conn[sel]
+            local_nodes = np.unique(sub)
+            conn_h = np.searchsorted(local_nodes, sub).astype(np.int64)
+            gid_h = part.node_gid[local_nodes]
+            b, e = ranges[q]
+            lb, le = np.searchsorted(gid_h, [b, e])
+            self.sends.append(HaloSend(q, np.ascontiguousarray(part.X[local_nodes]), conn_h, (int(lb), int(le)),
+                                       gid_h.astype(np.int64), local_nodes, sel))
+
+
+def match_rows(own_row_gid0, m, indptr, indices, row_gids, h_indptr, h_indices):
+    """Slots of a neighbour's halo entries inside the owner's CSR values.
+
+    own_row_gid0: global id of the owner's first node; indptr / indices: the owner's slab pattern (global columns);
+    row_gids: global node ids of the halo rows; h_indptr / h_indices: the halo pattern (m dof rows per node, global
+    columns).  Every halo entry must exist in the owner's row (the owner's pattern holds the ghost elements)."""
+    indptr = np.asarray(indptr, dtype=np.int64)
+    h_indptr = np.asarray(h_indptr, dtype=np.int64)
+    out = np.empty(int(h_indptr[-1]), dtype=np.int64)
+    dof_rows = (np.repeat(np.asarray(row_gids, dtype=np.int64) - own_row_gid0, m) * m +
+                np.tile(np.arange(m, dtype=np.int64), len(row_gids)))
+    for i, r in enumerate(dof_rows):
+        seg = np.asarray(indices[indptr[r]:indptr[r + 1]], dtype=np.int64)
+        want = np.asarray(h_indices[h_indptr[i]:h_indptr[i + 1]], dtype=np.int64)
+        pos = np.searchsorted(seg, want)
+        if pos.size and (pos.max() >= seg.size or not np.array_equal(seg[pos], want)):
+            raise ValueError("halo pattern is not contained in the owner's rows")
+        out[h_indptr[i]:h_indptr[i + 1]] = indptr[r] + pos
+    return out
+
+
+class ReduceAssembler:
+    """Device side: the rank's slab handle with masked ghost elements + one halo handle per neighbour, and the
+    exchange.  Methods mirror DeviceMesh.assemble_*; nodal fields are given in the rank's local numbering."""
+
+    def __init__(self, part: LocalMesh, ndof_per_node, ranges, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        from .engine import DeviceMesh
+        self.torch, self.dist, self.group = torch, dist, group
+        self.part, self.m = part, int(ndof_per_node)
+        self.plan = HaloPlan(part, ranges)
+        self.mesh = DeviceMesh(part.X, part.conn, self.m, device=device, own_range=part.own_range,
+                               node_gid=part.node_gid, ncols_nodes=part.nnodes_global)
+        self.device = self.mesh.device
+        self.mesh.set_element_mask(self.plan.skip_mask)
+        self.halo = [(s, DeviceMesh(s.X, s.conn, self.m, device=self.device, own_range=s.own_range, node_gid=s.node_gid,
+                                    ncols_nodes=part.nnodes_global),
+                      torch.as_tensor(s.local_nodes, device=self.device)) for s in self.plan.sends]
+        self._exchange_patterns()
+
+    # ---- setup: halo patterns travel to the owners, owners build their index maps --------------------------------
+    def _p2p(self, ops):
+        if ops:
+            for req in self.dist.batch_isend_irecv(ops):
+                req.wait()
+
+    def _exchange_patterns(self):
+        torch, dist = self.torch, self.dist
+        rank, size = self.part.rank, self.part.size
+        # sizes first (tiny, one all_gather), then the pattern arrays point to point
+        mine = torch.zeros((size, 2), dtype=torch.int64, device=self.device)
+        for s, hm, _ in self.halo:
+            mine[s.dest, 0], mine[s.dest, 1] = hm.nrows // self.m, hm.nnz
+        table = [torch.zeros_like(mine) for _ in range(size)]
+        dist.all_gather(table, mine, group=self.group)
+        ops, send_keep, recv_bufs = [], [], {}
+        for s, hm, _ in self.halo:
+            rows = torch.as_tensor(s.node_gid[s.own_range[0]:s.own_range[1]], device=self.device)
+            indptr, indices = hm.pattern(idx_bytes=8)
+            for t in (rows, indptr, indices):
+                send_keep.append(t)
+                ops.append(dist.P2POp(dist.isend, t, s.dest, group=self.group))
+        for q in range(size):
+            nrows, nnz = int(table[q][rank, 0]), int(table[q][rank, 1])
+            if q == rank or nrows == 0:
+                continue
+            bufs = (torch.empty(nrows, dtype=torch.int64, device=self.device),
+                    torch.empty(nrows * self.m + 1, dtype=torch.int64, device=self.device),
+                    torch.empty(nnz, dtype=torch.int64, device=self.device))
+            recv_bufs[q] = bufs
+            for t in bufs:
+                ops.append(dist.P2POp(dist.irecv, t, q, group=self.group))
+        self._p2p(ops)
+        torch.cuda.synchronize(self.device)
+        # owner side: slots of every received entry, and of every received vector row
+        self.recv = []
+        if recv_bufs:
+            indptr, indices = self.mesh.pattern()
+            ip = indptr.cpu().numpy()
+            gid0 = int(self.part.node_gid[self.part.own_range[0]])
+        for q, (rows, h_indptr, h_indices) in sorted(recv_bufs.items()):
+            rows_np = rows.cpu().numpy()
+            dof_rows = (np.repeat(rows_np - gid0, self.m) * self.m + np.tile(np.arange(self.m), len(rows_np)))
+            # fetch only the owner's interface rows from the device pattern
+            lo, hi = ip[dof_rows], ip[dof_rows + 1]
+            lens = (hi - lo).astype(np.int64)
+            flat = np.repeat(lo.astype(np.int64) - np.concatenate(([0], np.cumsum(lens)[:-1])), lens) + np.arange(int(lens.sum()))
+            seg = indices[torch.as_tensor(flat, device=self.device)].cpu().numpy()
+            sub_indptr = np.concatenate(([0], np.cumsum(lens)))
+            rel = match_rows(0, 1, sub_indptr, seg, np.arange(len(dof_rows)), h_indptr.cpu().numpy(), h_indices.cpu().numpy())
+            slots = flat[rel]
+            self.recv.append((q, torch.as_tensor(slots, device=self.device),
+                              torch.as_tensor(dof_rows.astype(np.int64), device=self.device),
+                              torch.empty(len(slots), dtype=torch.float64, device=self.device),
+                              torch.empty(len(dof_rows), dtype=torch.float64, device=self.device)))
+
+    # ---- every assembly ---------------------------------------------------------------------------------------------
+    def _reduce(self, main_vals, halo_vals, main_vec=None, halo_vecs=None):
+        dist = self.dist
+        ops = []
+        for i, (s, _, _) in enumerate(self.halo):
+            if halo_vals is not None:
+                ops.append(dist.P2POp(dist.isend, halo_vals[i], s.dest, group=self.group))
+            if halo_vecs is not None:
+                ops.append(dist.P2POp(dist.isend, halo_vecs[i], s.dest, group=self.group))
+        for q, _, _, vbuf, rbuf in self.recv:
+            if halo_vals is not None:
+                ops.append(dist.P2POp(dist.irecv, vbuf, q, group=self.group))
+            if halo_vecs is not None:
+                ops.append(dist.P2POp(dist.irecv, rbuf, q, group=self.group))
+        self._p2p(ops)
+        for q, slots, rows, vbuf, rbuf in self.recv:
+            if halo_vals is not None:
+                self.mesh.add_indexed(main_vals, slots, vbuf)
+            if halo_vecs is not None:
+                self.mesh.add_indexed(main_vec, rows, rbuf)
+
+    def _field(self, f, local_nodes):
+        if f is None or not hasattr(f, "__len__"):
+            return f
+        return self.torch.as_tensor(f, device=self.device)[local_nodes]
+
+    def assemble_elasticity(self, rho=1.0, p=0.0, E=10.0, nu=0.3, out=None, mode="auto"):
+        vals = self.mesh.assemble_elasticity(rho, p, E, nu, out=out, mode=mode)
+        hv = [hm.assemble_elasticity(self._field(rho, ln), p, E, nu, mode=mode) for _, hm, ln in self.halo]
+        self._reduce(vals, hv)
+        return vals
+
+    def assemble_poisson(self, rho=1.0, p=0.0, out=None, mode="auto"):
+        vals = self.mesh.assemble_poisson(rho, p, out=out, mode=mode)
+        hv = [hm.assemble_poisson(self._field(rho, ln), p, mode=mode) for _, hm, ln in self.halo]
+        self._reduce(vals, hv)
+        return vals
+
+    def assemble_nlpoisson(self, xdv, u, mode="auto"):
+        K, res = self.mesh.assemble_nlpoisson(xdv, u, mode=mode)
+        hk, hr = [], []
+        for _, hm, ln in self.halo:
+            k, r = hm.assemble_nlpoisson(xdv, self._field(u, ln), mode=mode)
+            hk.append(k)
+            hr.append(r)
+        self._reduce(K, hk, res, hr)
+        return K, res

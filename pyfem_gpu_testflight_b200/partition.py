@@ -102,6 +102,14 @@ def structured_slab(nnodes_x, nnodes_y, nnodes_z, rank, size, Lx=None, Ly=None, 
     return LocalMesh(X, conn, own, node_gid, nslow * plane, elem_gid, rank, size)
 
 
+def slab_node_ranges(nnodes_x, nnodes_y, nnodes_z, size):
+    """Global node-id ranges owned by the ranks of structured_slab(...): whole node layers along the slab axis."""
+    three_d = nnodes_z is not None
+    nslow = nnodes_z if three_d else nnodes_y
+    plane = nnodes_x * nnodes_y if three_d else nnodes_x
+    return [(b * plane, e * plane) for b, e in split_range(nslow, size)]
+
+
 def concat_slabs(slabs, ncols):
     """Row-wise concatenation of per-rank CSR slabs (indptr, indices, data) into the global matrix."""
     from scipy import sparse
