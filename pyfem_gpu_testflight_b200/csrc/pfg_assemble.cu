@@ -484,13 +484,15 @@ PFG_DEV void tile_phase_b_items(const TileHdr& h, const unsigned char* __restric
 template <class Op, int THREADS>
 PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict__ blob,
                                const uint16_t* __restrict__ codes, const double* __restrict__ stage,
-                               double* __restrict__ image) {
+                               double* __restrict__ image, int rot) {
     using St = TileStage<Op>;
     static_assert(Op::M == 2 && Op::NMAT == 1, "row format is for one matrix of 2x2 blocks");
     const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
     const unsigned char* __restrict__ stage_b = reinterpret_cast<const unsigned char*>(stage);
     const int n_nodes = (int)h.n_nodes, gmax = (int)h.gmax;
-    for (int p = threadIdx.x; p < n_nodes; p += THREADS) {
+    // a chunk has fewer nodes than the CTA has threads, so one warp idles through this phase; `rot` moves that
+    // warp around from chunk to chunk so that no scheduler (warp id mod 4) is systematically under-used
+    for (int p = (int)((threadIdx.x + 32u * (unsigned)rot) % (unsigned)THREADS); p < n_nodes; p += THREADS) {
         const TileNode tn = nodes[p];
         const int row_bytes = (int)tn.code_off * 16;  // k neighbours: 2k doubles per dof row
         const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(codes) + p;  // [group][node]
@@ -710,7 +712,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         mbar_wait(&bars[0], i & 1);
         if constexpr (ROWS) {
             const TileHdr h = *reinterpret_cast<const TileHdr*>(blob_s);
-            tile_phase_b_rows<Op, THREADS>(h, blob_s, codes_s, stage, image);
+            tile_phase_b_rows<Op, THREADS>(h, blob_s, codes_s, stage, image, (i + (int)blockIdx.x) & 3);
             // runs of consecutive node ids leave as TMA bulk stores, spread over the warps' leading lanes;
             // the run entry is read before the barrier so that the blob may be overwritten right after it
             // (a chunk has at most 128 runs: checked when the plan is built)

@@ -359,23 +359,59 @@ __global__ void k_inc_keys(const uint32_t* __restrict__ slot_node, const uint32_
 
 template <int NNE>
 __global__ void k_fill_records(const uint64_t* __restrict__ rec_keys, int64_t nrecs, const int32_t* __restrict__ conn,
-                               int32_t* __restrict__ rec_nodes, uint16_t* __restrict__ rec_dst,
-                               int32_t* __restrict__ rec_elem, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
+                               const uint32_t* __restrict__ rec_pos, int32_t* __restrict__ rec_nodes,
+                               uint16_t* __restrict__ rec_dst, int32_t* __restrict__ rec_elem,
+                               ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= nrecs) return;
     uint64_t key = rec_keys[r];
     uint32_t c = (uint32_t)(key >> 32);
     int64_t e = (int64_t)(key & 0xffffffffull);
-    rec_elem[r] = (int32_t)e;
+    const int64_t at = rec_pos ? (int64_t)rec_pos[r] : r;  // position inside the chunk's record range (tile plan)
+    rec_elem[at] = (int32_t)e;
 #pragma unroll
     for (int a = 0; a < NNE; ++a) {
-        rec_nodes[r * NNE + a] = conn[e * NNE + a];
-        rec_dst[r * NNE + a] = kNoDst;
+        rec_nodes[at * NNE + a] = conn[e * NNE + a];
+        rec_dst[at * NNE + a] = kNoDst;
     }
     bool first = (r == 0) || ((uint32_t)(rec_keys[r - 1] >> 32) != c);
     bool last = (r == nrecs - 1) || ((uint32_t)(rec_keys[r + 1] >> 32) != c);
     if (first) chunks[c].rec_begin = r;
     if (last) chunks[c].n_recs = (uint32_t)(r + 1);  // end index (fits: checked on host), fixed up below
+}
+
+// tile plan: records of a chunk are ordered by the chunk position of their first corner node (records whose first
+// corner belongs to another chunk come last).  Consecutive chunk nodes then read consecutive records in phase B --
+// on a regular mesh every contribution slot of a quarter-warp hits eight consecutive records, which the record
+// stride maps to distinct banks.  Any order is correct; this one is a bank-conflict heuristic.
+__global__ void k_slot_of_node(const uint32_t* __restrict__ slot_node, int64_t nslots, uint32_t* __restrict__ slot_of) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p < nslots) slot_of[slot_node[p]] = (uint32_t)p;
+}
+
+template <int NNE>
+__global__ void k_rec_order_keys(const uint64_t* __restrict__ rec_keys, int64_t nrecs, const int32_t* __restrict__ conn,
+                                 const uint32_t* __restrict__ group, const uint32_t* __restrict__ slot_of,
+                                 const ChunkHdr* __restrict__ chunks, int64_t own_begin, int64_t own_end,
+                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nrecs) return;
+    const uint64_t key = rec_keys[r];
+    const uint32_t c = (uint32_t)(key >> 32);
+    const int64_t e = (int64_t)(key & 0xffffffffull);
+    const int64_t n0 = conn[e * NNE];
+    uint64_t k2 = 0xFFFF;
+    if (n0 >= own_begin && n0 < own_end && group[n0 - own_begin] == c) {
+        const uint64_t pos = (uint64_t)slot_of[n0 - own_begin] - chunks[c].node_begin;
+        k2 = pos < 0xFFFF ? pos : 0xFFFE;
+    }
+    keys[r] = ((uint64_t)c << 16) | k2;
+    vals[r] = (uint32_t)r;
+}
+
+__global__ void k_invert_perm(const uint32_t* __restrict__ perm, int64_t n, uint32_t* __restrict__ inv) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j < n) inv[perm[j]] = (uint32_t)j;
 }
 
 __global__ void k_chunk_rec_finish(int64_t nchunks, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
@@ -580,6 +616,7 @@ struct TileFillArgs {
     const ChunkHdr* chunks;
     const TileDir* dir;
     const uint64_t* rec_keys;
+    const uint32_t* rec_pos;
     const int64_t *sb_excl, *nc_excl, *kk_excl;
     const uint32_t *run_flag, *run_id;
     int64_t own_begin, nslots;
@@ -699,7 +736,7 @@ __global__ void k_tile_fill(TileFillArgs A) {
             int64_t mid = (lo + hi) >> 1;
             if (A.rec_keys[mid] < key) lo = mid + 1; else hi = mid;
         }
-        const uint32_t rloc = (uint32_t)(lo - h.rec_begin);
+        const uint32_t rloc = (uint32_t)((int64_t)A.rec_pos[lo] - h.rec_begin);
         const uint32_t a = ia % NNE;
         const uint8_t* rk = A.rank + (int64_t)ia * NNE;
 #pragma unroll
@@ -1007,8 +1044,29 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t) + 64));  // bulk copies may over-read
     PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t) + 32));
     PFG_CUDA_TRY(cudaMalloc(&d.rec_elem, d.nrecs * sizeof(int32_t)));
-    k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, d.rec_nodes, d.rec_dst,
-                                                               d.rec_elem, d.chunks, maxima.p);
+    DBuf<uint32_t> rec_pos;  // tile plan: position of the i-th (chunk, element) key inside the record arrays
+    if (tile) {
+        DBuf<uint32_t> slot_of, perm_in, perm;
+        DBuf<uint64_t> okeys, okeys_sorted;
+        PFG_CUDA_TRY(slot_of.alloc(nown));
+        PFG_CUDA_TRY(perm_in.alloc(d.nrecs));
+        PFG_CUDA_TRY(perm.alloc(d.nrecs));
+        PFG_CUDA_TRY(okeys.alloc(d.nrecs));
+        PFG_CUDA_TRY(okeys_sorted.alloc(d.nrecs));
+        PFG_CUDA_TRY(rec_pos.alloc(d.nrecs));
+        k_slot_of_node<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, nown, slot_of.p);
+        k_rec_order_keys<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, group.p, slot_of.p,
+                                                                     d.chunks, d.own_begin, d.own_end, okeys.p,
+                                                                     perm_in.p);
+        PFG_CUB(scratch, st,
+                cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint64_t*)okeys.p,
+                                                okeys_sorted.p, (const uint32_t*)perm_in.p, perm.p, d.nrecs, 0,
+                                                16 + bits_for((uint64_t)d.nchunks), st));
+        k_invert_perm<<<grid_for(d.nrecs), kThreads, 0, st>>>(perm.p, d.nrecs, rec_pos.p);
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, rec_pos.p, d.rec_nodes,
+                                                               d.rec_dst, d.rec_elem, d.chunks, maxima.p);
     k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
     if (tile) {
         // ---- tile plan: blob (header, node table, format tables) and contribution codes per chunk
@@ -1120,7 +1178,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         TileFillArgs fa;
         fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
         fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr, fa.nbr = d.nbr;
-        fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p;
+        fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p, fa.rec_pos = rec_pos.p;
         fa.sb_excl = sb_excl.p, fa.nc_excl = nc_excl.p, fa.kk_excl = kk_excl.p;
         fa.run_flag = run_flag.p, fa.run_id = run_id.p;
         fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m, fa.rows = rows;
