@@ -350,7 +350,8 @@ def main():
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
                    "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
-                   "csr_nnz_rank0": mesh.nnz, "scatter": "gather" if (args.mode != "atomic" and mesh.nchunks) else "atomic",
+                   "csr_nnz_rank0": mesh.nnz, "scatter": ("atomic" if (args.mode == "atomic" or not mesh.nchunks or (args.mode == "auto" and m == 3))
+                                                             else "gather"),
                    "partition": (f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
                                  f"send/recv + indexed add" if reducer is not None else
                                  f"row slabs x{world}, ghost-element layer, no data-path collective"),

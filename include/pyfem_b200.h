@@ -53,7 +53,8 @@ typedef enum pfg_elem {
 } pfg_elem;
 
 typedef enum pfg_mode {
-    PFG_MODE_AUTO = 0,   /* gather when the mesh has a gather plan, else atomic */
+    PFG_MODE_AUTO = 0,   /* the faster strategy for the operator: gather when the mesh has a gather plan (atomic for
+                            hex8 3-D elasticity, whose gather kernel is slower), else atomic */
     PFG_MODE_ATOMIC = 1, /* element-per-thread, slot-indexed red.global.add.f64 scatter */
     PFG_MODE_GATHER = 2  /* owner-computes: element matrices staged in shared memory, every CSR value
                             summed in a fixed order and written exactly once (no atomics, deterministic) */

@@ -246,6 +246,23 @@ __global__ void k_coord_keys(const double* __restrict__ X, int ndims, int axis, 
     vals[r] = (uint32_t)r;
 }
 
+// which coordinate changes between consecutive node ids (counts[axis]), to find the direction node ids run along
+__global__ void k_id_direction(const double* __restrict__ X, int ndims, int64_t own_begin, int64_t nown,
+                               unsigned long long* __restrict__ counts) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r + 1 >= nown) return;
+    int changed = 0, axis = -1;
+    for (int l = 0; l < ndims; ++l)
+        if (X[(own_begin + r) * ndims + l] != X[(own_begin + r + 1) * ndims + l]) ++changed, axis = l;
+    if (changed == 1) atomicAdd(&counts[axis], 1ull);
+}
+
+__global__ void k_count_distinct(const uint64_t* __restrict__ sorted_keys, int64_t n, unsigned long long* __restrict__ count) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n) return;
+    if (r == 0 || sorted_keys[r] != sorted_keys[r - 1]) atomicAdd(count, 1ull);
+}
+
 __global__ void k_gather_u32(const uint32_t* __restrict__ table, const uint32_t* __restrict__ idx, int64_t n,
                              uint32_t* __restrict__ out) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -359,15 +376,14 @@ __global__ void k_inc_keys(const uint32_t* __restrict__ slot_node, const uint32_
 
 template <int NNE>
 __global__ void k_fill_records(const uint64_t* __restrict__ rec_keys, int64_t nrecs, const int32_t* __restrict__ conn,
-                               const uint32_t* __restrict__ rec_pos, int32_t* __restrict__ rec_nodes,
-                               uint16_t* __restrict__ rec_dst, int32_t* __restrict__ rec_elem,
-                               ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
+                               int32_t* __restrict__ rec_nodes, uint16_t* __restrict__ rec_dst,
+                               int32_t* __restrict__ rec_elem, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= nrecs) return;
     uint64_t key = rec_keys[r];
     uint32_t c = (uint32_t)(key >> 32);
     int64_t e = (int64_t)(key & 0xffffffffull);
-    const int64_t at = rec_pos ? (int64_t)rec_pos[r] : r;  // position inside the chunk's record range (tile plan)
+    const int64_t at = r;
     rec_elem[at] = (int32_t)e;
 #pragma unroll
     for (int a = 0; a < NNE; ++a) {
@@ -378,40 +394,6 @@ __global__ void k_fill_records(const uint64_t* __restrict__ rec_keys, int64_t nr
     bool last = (r == nrecs - 1) || ((uint32_t)(rec_keys[r + 1] >> 32) != c);
     if (first) chunks[c].rec_begin = r;
     if (last) chunks[c].n_recs = (uint32_t)(r + 1);  // end index (fits: checked on host), fixed up below
-}
-
-// tile plan: records of a chunk are ordered by the chunk position of their first corner node (records whose first
-// corner belongs to another chunk come last).  Consecutive chunk nodes then read consecutive records in phase B --
-// on a regular mesh every contribution slot of a quarter-warp hits eight consecutive records, which the record
-// stride maps to distinct banks.  Any order is correct; this one is a bank-conflict heuristic.
-__global__ void k_slot_of_node(const uint32_t* __restrict__ slot_node, int64_t nslots, uint32_t* __restrict__ slot_of) {
-    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (p < nslots) slot_of[slot_node[p]] = (uint32_t)p;
-}
-
-template <int NNE>
-__global__ void k_rec_order_keys(const uint64_t* __restrict__ rec_keys, int64_t nrecs, const int32_t* __restrict__ conn,
-                                 const uint32_t* __restrict__ group, const uint32_t* __restrict__ slot_of,
-                                 const ChunkHdr* __restrict__ chunks, int64_t own_begin, int64_t own_end,
-                                 uint64_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= nrecs) return;
-    const uint64_t key = rec_keys[r];
-    const uint32_t c = (uint32_t)(key >> 32);
-    const int64_t e = (int64_t)(key & 0xffffffffull);
-    const int64_t n0 = conn[e * NNE];
-    uint64_t k2 = 0xFFFF;
-    if (n0 >= own_begin && n0 < own_end && group[n0 - own_begin] == c) {
-        const uint64_t pos = (uint64_t)slot_of[n0 - own_begin] - chunks[c].node_begin;
-        k2 = pos < 0xFFFF ? pos : 0xFFFE;
-    }
-    keys[r] = ((uint64_t)c << 16) | k2;
-    vals[r] = (uint32_t)r;
-}
-
-__global__ void k_invert_perm(const uint32_t* __restrict__ perm, int64_t n, uint32_t* __restrict__ inv) {
-    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (j < n) inv[perm[j]] = (uint32_t)j;
 }
 
 __global__ void k_chunk_rec_finish(int64_t nchunks, ChunkHdr* __restrict__ chunks, int* __restrict__ maxima) {
@@ -616,7 +598,6 @@ struct TileFillArgs {
     const ChunkHdr* chunks;
     const TileDir* dir;
     const uint64_t* rec_keys;
-    const uint32_t* rec_pos;
     const int64_t *sb_excl, *nc_excl, *kk_excl;
     const uint32_t *run_flag, *run_id;
     int64_t own_begin, nslots;
@@ -736,7 +717,7 @@ __global__ void k_tile_fill(TileFillArgs A) {
             int64_t mid = (lo + hi) >> 1;
             if (A.rec_keys[mid] < key) lo = mid + 1; else hi = mid;
         }
-        const uint32_t rloc = (uint32_t)((int64_t)A.rec_pos[lo] - h.rec_begin);
+        const uint32_t rloc = (uint32_t)(lo - h.rec_begin);
         const uint32_t a = ia % NNE;
         const uint8_t* rk = A.rank + (int64_t)ia * NNE;
 #pragma unroll
@@ -896,7 +877,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
             const double recs_per_node = std::pow((side + 1.0) / side, (double)d.ndims);
             const double per_node = recs_per_node * (42 * 8 + NNE * 2 + 20) + 4.0 * 8 * std::max(1, d.max_k) +
                                     2.0 * NNE * std::max(1, d.max_valence) + 16;
-            const int64_t c_smem = (int64_t)(env_int("PFG_TILE_SMEM_BYTES", 75 * 1024) * 0.86 / per_node);
+            const int64_t c_smem = (int64_t)(env_int("PFG_TILE_SMEM_BYTES", 75 * 1024) * 0.89 / per_node);
             C = std::min(C, c_smem);
         }
     } else {
@@ -932,18 +913,55 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(gstart.alloc(nown));
         PFG_CUDA_TRY(vstart.alloc(nown));
         double avg_group = (double)nown;
+        // Row format on lattice-like 2-D meshes: make the chunk rows (nodes that are consecutive in id) a whole number
+        // of quarter-warps wide.  Phase B maps consecutive lanes to consecutive chunk nodes; with rows of 8 (or 16)
+        // nodes a quarter-warp never straddles a row, so each of its gather loads hits eight consecutive element
+        // records -- bank-conflict free by the record stride.  Detected from the data (the direction ids run along
+        // and how many nodes share a coordinate); any other mesh keeps the plain count-based tiling.
+        int axis_order[3] = {0, 1, 2};
+        int64_t level0_target = 0;
+        const int tile_width = env_int("PFG_TILE_WIDTH", 8);
+        if (tile && d.m == 2 && d.ndims == 2 && tile_width > 0 && nown > 64) {
+            DBuf<unsigned long long> cnt;
+            PFG_CUDA_TRY(cnt.alloc(4));
+            PFG_CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(unsigned long long), st));
+            k_id_direction<<<grid_for(nown), kThreads, 0, st>>>(d.X, d.ndims, d.own_begin, nown, cnt.p);
+            unsigned long long h_cnt[4] = {0, 0, 0, 0};
+            PFG_CUDA_TRY(cudaMemcpyAsync(h_cnt, cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+            PFG_CUDA_TRY(cudaStreamSynchronize(st));
+            const int fast = (h_cnt[1] > h_cnt[0]) ? 1 : 0;
+            if ((double)h_cnt[fast] >= 0.8 * (double)(nown - 1)) {
+                k_coord_keys<<<grid_for(nown), kThreads, 0, st>>>(d.X, d.ndims, fast, d.own_begin, nown, ckeys.p, ord0.p);
+                PFG_CUB(scratch, st,
+                        cub::DeviceRadixSort::SortKeys(d_temp_storage, temp_storage_bytes, (const uint64_t*)ckeys.p,
+                                                       ckeys2.p, nown, 0, 64, st));
+                k_count_distinct<<<grid_for(nown), kThreads, 0, st>>>(ckeys2.p, nown, cnt.p + 2);
+                PFG_CUDA_TRY(cudaMemcpyAsync(h_cnt, cnt.p, sizeof(h_cnt), cudaMemcpyDeviceToHost, st));
+                PFG_CUDA_TRY(cudaStreamSynchronize(st));
+                const double run = (double)nown / (double)std::max<unsigned long long>(1, h_cnt[2]);  // nodes per coordinate value
+                if (run >= 8.0 && (double)h_cnt[2] >= 2.0 * tile_width) {
+                    axis_order[0] = fast;
+                    axis_order[1] = 1 - fast;
+                    level0_target = (int64_t)std::llround(run * tile_width);
+                    if (C > 2 * tile_width) C -= C % tile_width;  // whole rows
+                }
+            }
+        }
         for (int level = 0; level < d.ndims; ++level) {
             int remaining = d.ndims - level;
+            const int axis = axis_order[level];
             int64_t target;
             if (remaining == 1) {
                 target = C;
+            } else if (level == 0 && level0_target > 0) {
+                target = level0_target;
             } else {
                 double splits = std::ceil(std::pow(std::max(1.0, avg_group / (double)C), 1.0 / remaining) - 1e-9);
                 target = (int64_t)std::ceil(avg_group / std::max(1.0, splits));
             }
             target = std::max<int64_t>(1, target);
-            // order (group, coord[level], id): stable sort by coord, then stable sort by group
-            k_coord_keys<<<grid_for(nown), kThreads, 0, st>>>(d.X, d.ndims, level, d.own_begin, nown, ckeys.p, ord0.p);
+            // order (group, coord[axis], id): stable sort by coord, then stable sort by group
+            k_coord_keys<<<grid_for(nown), kThreads, 0, st>>>(d.X, d.ndims, axis, d.own_begin, nown, ckeys.p, ord0.p);
             PFG_CUB(scratch, st,
                     cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint64_t*)ckeys.p,
                                                     ckeys2.p, (const uint32_t*)ord0.p, ord1.p, nown, 0, 64, st));
@@ -952,7 +970,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                     cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint32_t*)gtmp.p,
                                                     gsorted.p, (const uint32_t*)ord1.p, ord2.p, nown, 0,
                                                     bits_for((uint64_t)ngroups), st));
-            k_mark_starts<<<grid_for(nown), kThreads, 0, st>>>(gsorted.p, ord2.p, d.X, d.ndims, level, d.own_begin,
+            k_mark_starts<<<grid_for(nown), kThreads, 0, st>>>(gsorted.p, ord2.p, d.X, d.ndims, axis, d.own_begin,
                                                               nown, gstart.p, vstart.p);
             PFG_CUB(scratch, st,
                     cub::DeviceScan::InclusiveScan(d_temp_storage, temp_storage_bytes, gstart.p, gstart.p,
@@ -1044,29 +1062,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     PFG_CUDA_TRY(cudaMalloc(&d.rec_nodes, d.nrecs * NNE * sizeof(int32_t) + 64));  // bulk copies may over-read
     PFG_CUDA_TRY(cudaMalloc(&d.rec_dst, d.nrecs * NNE * sizeof(uint16_t) + 32));
     PFG_CUDA_TRY(cudaMalloc(&d.rec_elem, d.nrecs * sizeof(int32_t)));
-    DBuf<uint32_t> rec_pos;  // tile plan: position of the i-th (chunk, element) key inside the record arrays
-    if (tile) {
-        DBuf<uint32_t> slot_of, perm_in, perm;
-        DBuf<uint64_t> okeys, okeys_sorted;
-        PFG_CUDA_TRY(slot_of.alloc(nown));
-        PFG_CUDA_TRY(perm_in.alloc(d.nrecs));
-        PFG_CUDA_TRY(perm.alloc(d.nrecs));
-        PFG_CUDA_TRY(okeys.alloc(d.nrecs));
-        PFG_CUDA_TRY(okeys_sorted.alloc(d.nrecs));
-        PFG_CUDA_TRY(rec_pos.alloc(d.nrecs));
-        k_slot_of_node<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, nown, slot_of.p);
-        k_rec_order_keys<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, group.p, slot_of.p,
-                                                                     d.chunks, d.own_begin, d.own_end, okeys.p,
-                                                                     perm_in.p);
-        PFG_CUB(scratch, st,
-                cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint64_t*)okeys.p,
-                                                okeys_sorted.p, (const uint32_t*)perm_in.p, perm.p, d.nrecs, 0,
-                                                16 + bits_for((uint64_t)d.nchunks), st));
-        k_invert_perm<<<grid_for(d.nrecs), kThreads, 0, st>>>(perm.p, d.nrecs, rec_pos.p);
-        PFG_CUDA_TRY(cudaStreamSynchronize(st));
-    }
-    k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, rec_pos.p, d.rec_nodes,
-                                                               d.rec_dst, d.rec_elem, d.chunks, maxima.p);
+    k_fill_records<NNE><<<grid_for(d.nrecs), kThreads, 0, st>>>(rec_keys.p, d.nrecs, d.conn, d.rec_nodes, d.rec_dst,
+                                                               d.rec_elem, d.chunks, maxima.p);
     k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
     if (tile) {
         // ---- tile plan: blob (header, node table, format tables) and contribution codes per chunk
@@ -1178,7 +1175,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         TileFillArgs fa;
         fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
         fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr, fa.nbr = d.nbr;
-        fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p, fa.rec_pos = rec_pos.p;
+        fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p;
         fa.sb_excl = sb_excl.p, fa.nc_excl = nc_excl.p, fa.kk_excl = kk_excl.p;
         fa.run_flag = run_flag.p, fa.run_id = run_id.p;
         fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m, fa.rows = rows;
