@@ -741,6 +741,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
     if constexpr (ROWS) tma_store_wait_read();
 }
 
+static inline int align16(int x) { return (x + 15) & ~15; }
+
 struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
 
 template <int THREADS>
@@ -914,7 +916,6 @@ static int zero_outputs(const MeshDev& d, const Outputs& out, cudaStream_t st) {
     return PFG_OK;
 }
 
-static inline int align16(int x) { return (x + 15) & ~15; }
 
 template <class Op, int THREADS, int MINB>
 static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params& prm, const Outputs& out,
