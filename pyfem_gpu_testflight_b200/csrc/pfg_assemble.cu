@@ -15,6 +15,8 @@
 
 namespace pfg {
 
+static inline int align16(int x) { return (x + 15) & ~15; }
+
 // ---------------------------------------------------------------------------------------------
 // shared-memory row-block stride (doubles) per incidence; odd multiples of the access width keep
 // element-per-thread stores and plan-ordered loads spread over the banks
@@ -369,6 +371,7 @@ struct TileStage {
         L.sym = SYM ? 1 : 0;
         L.blk_units = BLK / UNIT_D;
         L.has_mat = Op::NMAT > 0 ? 1 : 0;
+        L.vec_units = Op::NVEC > 0 ? MATD / UNIT_D : -1;
         return L;
     }
 };
@@ -399,94 +402,23 @@ struct TileCfg {
     int off_loc;                  // window indices of the record corners (one stage)
     int off_x, off_field;         // coordinates / nodal field of the window nodes (one stage)
     int off_stage;                // element-record staging
-    int off_image;                // row format: image of the chunk's CSR values (TMA bulk-store source)
+    int off_image;                // image of the chunk's CSR values (TMA bulk-store source)
+    int image_stride;             // doubles between the images of an operator's matrices (Helmholtz: K and R)
     int nchunks;
 };
 
-// phase B, item format: one thread per (chunk node, neighbour) block sums the staged contributions in plan
-// order and writes the block's m x m CSR values once.
-// CP > 0: every block of the chunk has at most CP contributions; the loop is fully unrolled and slots past a
-// block's count read the all-zero record 0 (code 0), so a warp runs one branch-free instruction stream.
-template <class Op, int THREADS, int CP>
-PFG_DEV void tile_phase_b_items(const TileHdr& h, const unsigned char* __restrict__ blob,
-                                const uint16_t* __restrict__ codes, const double* __restrict__ stage,
-                                const Outputs& out) {
-    using St = TileStage<Op>;
-    constexpr int M = Op::M, BLK = M * M, NMAT = Op::NMAT;
-    const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
-    const int kpad = (int)h.kpad;
-    const int items = (int)h.n_nodes * kpad;
-    const float inv_kpad = 1.0f / (float)kpad;
-    double* vbase[NMAT];
-#pragma unroll
-    for (int mt = 0; mt < NMAT; ++mt) vbase[mt] = out.vals[mt] ? out.vals[mt] + h.gbase : nullptr;
-    for (int idx = threadIdx.x; idx < items; idx += THREADS) {
-        const int p = (int)(((float)idx + 0.5f) * inv_kpad);
-        const int t = idx - p * kpad;
-        const TileNode tn = nodes[p];
-        const uint8_t* __restrict__ pl = blob + tn.aux;
-        const int k = pl[0];
-        if (t >= k) continue;
-        const int s0 = pl[2 + t], cnt = (int)pl[3 + t] - s0;
-        const uint16_t* __restrict__ cp = codes + tn.code_off + s0;
-        double acc[NMAT][BLK];
-#pragma unroll
-        for (int mt = 0; mt < NMAT; ++mt)
-#pragma unroll
-            for (int i = 0; i < BLK; ++i) acc[mt][i] = 0.0;
-        auto add = [&](unsigned code) {
-            const double* __restrict__ q = stage + (code >> 2) * St::UNIT_D;
-#pragma unroll
-            for (int mt = 0; mt < NMAT; ++mt) {
-                const double* __restrict__ qm = q + mt * St::NB * BLK;
-                if constexpr (M == 2) {
-                    const double2 v0 = reinterpret_cast<const double2*>(qm)[0];
-                    const double2 v1 = reinterpret_cast<const double2*>(qm)[1];
-                    const bool tr = St::SYM && (code & 1u);
-                    acc[mt][0] += v0.x;
-                    acc[mt][1] += tr ? v1.x : v0.y;
-                    acc[mt][2] += tr ? v0.y : v1.x;
-                    acc[mt][3] += v1.y;
-                } else {
-                    acc[mt][0] += qm[0];
-                }
-            }
-        };
-        if constexpr (CP > 0) {
-            unsigned code[CP];
-#pragma unroll
-            for (int j = 0; j < CP; ++j) code[j] = cp[j];  // may read past the block's codes: stays in the padded buffer
-#pragma unroll
-            for (int j = 0; j < CP; ++j) add(j < cnt ? code[j] : 0u);
-        } else {
-#pragma unroll 1
-            for (int j = 0; j < cnt; ++j) add(cp[j]);
-        }
-#pragma unroll
-        for (int mt = 0; mt < NMAT; ++mt) {
-            if (vbase[mt] == nullptr) continue;
-            double* dst = vbase[mt] + (tn.gslot_rel + (unsigned)(M * t));
-            if constexpr (M == 2) {
-                __stcs(reinterpret_cast<double2*>(dst), make_double2(acc[mt][0], acc[mt][1]));
-                __stcs(reinterpret_cast<double2*>(dst + 2 * k), make_double2(acc[mt][2], acc[mt][3]));
-            } else {
-                __stcs(dst, acc[mt][0]);
-            }
-        }
-    }
-}
-
-// phase B, row format (2x2 blocks, one matrix): one thread per chunk node walks the node's codes in groups of
-// eight, sums each (node, neighbour) block in plan order and, at the block's end flag, drops its two rows into
-// the shared-memory image of the CSR values.  Neighbouring lanes read the same block of neighbouring records,
-// so on a regular mesh the gather runs at one bank-conflict-free wavefront per 128 bytes.
-// The running sums restart without a branch: acc = fma(acc, keep, v) with keep = 0 after an end flag.
+// phase B: one thread per chunk node walks the node's codes in groups of eight, sums each (node, neighbour) block in
+// plan order and, at the block's end flag, drops its rows into the shared-memory image of the CSR values.
+// Neighbouring lanes read the same block of neighbouring records, so on a regular mesh the gather runs at one
+// bank-conflict-free wavefront per 128 bytes.  The running sums restart without a branch: acc = fma(acc, keep, v)
+// with keep = 0 after an end flag.  Scalar handles then sum the node's vector entries (residual / right-hand side).
 template <class Op, int THREADS>
-PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict__ blob,
-                               const uint16_t* __restrict__ codes, const double* __restrict__ stage,
-                               double* __restrict__ image, int rot) {
+PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsigned char* __restrict__ blob,
+                                const uint16_t* __restrict__ codes, const double* __restrict__ stage,
+                                double* __restrict__ image, int image_stride, const Outputs& out, int rot) {
     using St = TileStage<Op>;
-    static_assert(Op::M == 2 && Op::NMAT == 1, "row format is for one matrix of 2x2 blocks");
+    constexpr int M = Op::M, NMAT = Op::NMAT;
+    static_assert(M == 1 || (M == 2 && NMAT == 1), "tile kernel: scalar operators or one matrix of 2x2 blocks");
     const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
     const unsigned char* __restrict__ stage_b = reinterpret_cast<const unsigned char*>(stage);
     const int n_nodes = (int)h.n_nodes, gmax = (int)h.gmax;
@@ -494,73 +426,97 @@ PFG_DEV void tile_phase_b_rows(const TileHdr& h, const unsigned char* __restrict
     // warp around from chunk to chunk so that no scheduler (warp id mod 4) is systematically under-used
     for (int p = (int)((threadIdx.x + 32u * (unsigned)rot) % (unsigned)THREADS); p < n_nodes; p += THREADS) {
         const TileNode tn = nodes[p];
-        const int row_bytes = (int)tn.code_off * 16;  // k neighbours: 2k doubles per dof row
         const uint4* __restrict__ cp = reinterpret_cast<const uint4*>(codes) + p;  // [group][node]
-        unsigned char* o = reinterpret_cast<unsigned char*>(image) + (size_t)tn.aux * 16;
-        double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, keep = 0.0;
-        auto add = [&](unsigned code) {  // code in the low 16 bits
-            const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code & 0xFFFCu) << 2));
-            const double2 v0 = q[0], v1 = q[1];
-            const bool tr = St::SYM && (code & 1u);
-            a00 = fma(a00, keep, v0.x);
-            a01 = fma(a01, keep, tr ? v1.x : v0.y);
-            a10 = fma(a10, keep, tr ? v0.y : v1.x);
-            a11 = fma(a11, keep, v1.y);
-            const bool end = (code & 2u) != 0;  // last contribution of this block
-            if (end) {
-                *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
-                *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
-                o += 16;
-            }
-            keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
-        };
+        if constexpr (NMAT > 0) {
+            if constexpr (M == 2) {
+                const int row_bytes = (int)tn.k * 16;  // k neighbours: 2k doubles per dof row
+                unsigned char* o = reinterpret_cast<unsigned char*>(image) + (size_t)tn.aux * 16;
+                double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, keep = 0.0;
+                auto add = [&](unsigned code) {  // code in the low 16 bits
+                    const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code & 0xFFFCu) << 2));
+                    const double2 v0 = q[0], v1 = q[1];
+                    const bool tr = St::SYM && (code & 1u);
+                    a00 = fma(a00, keep, v0.x);
+                    a01 = fma(a01, keep, tr ? v1.x : v0.y);
+                    a10 = fma(a10, keep, tr ? v0.y : v1.x);
+                    a11 = fma(a11, keep, v1.y);
+                    const bool end = (code & 2u) != 0;  // last contribution of this block
+                    if (end) {
+                        *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
+                        *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
+                        o += 16;
+                    }
+                    keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
+                };
 #pragma unroll 1
-        for (int g = 0; g < gmax; ++g) {
-            const uint4 c = cp[(size_t)g * n_nodes];
-            add(c.x & 0xFFFFu), add(c.x >> 16);
-            add(c.y & 0xFFFFu), add(c.y >> 16);
-            add(c.z & 0xFFFFu), add(c.z >> 16);
-            add(c.w & 0xFFFFu), add(c.w >> 16);
+                for (int g = 0; g < gmax; ++g) {
+                    const uint4 c = cp[(size_t)g * n_nodes];
+                    add(c.x & 0xFFFFu), add(c.x >> 16);
+                    add(c.y & 0xFFFFu), add(c.y >> 16);
+                    add(c.z & 0xFFFFu), add(c.z >> 16);
+                    add(c.w & 0xFFFFu), add(c.w >> 16);
+                }
+            } else {
+                double* o = image + tn.aux;
+                double acc[NMAT], keep = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < NMAT; ++mt) acc[mt] = 0.0;
+                auto add = [&](unsigned code) {
+                    const double* __restrict__ q = reinterpret_cast<const double*>(stage_b + ((code & 0xFFFCu) << 1));
+#pragma unroll
+                    for (int mt = 0; mt < NMAT; ++mt) acc[mt] = fma(acc[mt], keep, q[mt * St::NB]);
+                    const bool end = (code & 2u) != 0;
+                    if (end) {
+#pragma unroll
+                        for (int mt = 0; mt < NMAT; ++mt) o[mt * image_stride] = acc[mt];
+                        o += 1;
+                    }
+                    keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
+                };
+#pragma unroll 1
+                for (int g = 0; g < gmax; ++g) {
+                    const uint4 c = cp[(size_t)g * n_nodes];
+                    add(c.x & 0xFFFFu), add(c.x >> 16);
+                    add(c.y & 0xFFFFu), add(c.y >> 16);
+                    add(c.z & 0xFFFFu), add(c.z >> 16);
+                    add(c.w & 0xFFFFu), add(c.w >> 16);
+                }
+            }
+        }
+        if constexpr (Op::NVEC > 0) {
+            if (out.vec != nullptr) {  // the node's incidences, in element order; padding codes read the zero record
+                const uint2* __restrict__ vp = reinterpret_cast<const uint2*>(codes + (size_t)gmax * n_nodes * 8) + p;
+                const uint32_t* __restrict__ row = reinterpret_cast<const uint32_t*>(nodes + n_nodes);
+                double sum = 0.0;
+                for (int g = 0; g < (int)h.gvmax; ++g) {
+                    const uint2 c = vp[(size_t)g * n_nodes];
+                    sum += *reinterpret_cast<const double*>(stage_b + (((c.x & 0xFFFFu) & 0xFFFCu) << 1));
+                    sum += *reinterpret_cast<const double*>(stage_b + (((c.x >> 16) & 0xFFFCu) << 1));
+                    sum += *reinterpret_cast<const double*>(stage_b + (((c.y & 0xFFFFu) & 0xFFFCu) << 1));
+                    sum += *reinterpret_cast<const double*>(stage_b + (((c.y >> 16) & 0xFFFCu) << 1));
+                }
+                out.vec[row[p]] = sum;
+            }
         }
     }
 }
 
-template <class Op, int THREADS>
-PFG_DEV void tile_phase_b(const MeshView& mv, const unsigned char* __restrict__ blob,
-                          const uint16_t* __restrict__ codes, const double* __restrict__ stage, const Outputs& out) {
-    using St = TileStage<Op>;
-    constexpr int NNE = Op::NNE, BLK = Op::M * Op::M, NMAT = Op::NMAT;
-    const TileHdr h = *reinterpret_cast<const TileHdr*>(blob);
-    if constexpr (NMAT > 0) {
-        if (h.cpad <= 4) tile_phase_b_items<Op, THREADS, 4>(h, blob, codes, stage, out);
-        else tile_phase_b_items<Op, THREADS, 0>(h, blob, codes, stage, out);
-    }
-    if constexpr (Op::NVEC > 0) {
-        if (out.vec != nullptr) {
-            const TileNode* __restrict__ nodes = reinterpret_cast<const TileNode*>(blob + sizeof(TileHdr));
-            for (int p = threadIdx.x; p < (int)h.n_nodes; p += THREADS) {
-                const TileNode tn = nodes[p];
-                const uint8_t* __restrict__ pl = blob + tn.aux;
-                const int self_t = pl[1];
-                const int s0 = pl[2 + self_t], s1 = pl[3 + self_t];
-                const uint16_t* __restrict__ cp = codes + tn.code_off;
-                double sum = 0.0;
-                for (int s = s0; s < s1; ++s) {  // the diagonal block's contributions are the node's incidences
-                    const int off = (int)(cp[s] >> 2) * St::UNIT_D;  // doubles from the chunk's staging base
-                    const int r = off / St::S;                       // staged record (record 0 is the zero record)
-                    int a = off - r * St::S;  // vector-only operators address the entry directly
-                    if constexpr (NMAT > 0) {
-                        const int bi = a / BLK;
-                        a = 0;
-#pragma unroll
-                        for (int c = 1; c < NNE; ++c)
-                            if (bi == St::block_index(c, c)) a = c;
-                    }
-                    sum += stage[r * St::S + St::MATD + a];
-                }
-                out.vec[mv.cnode_id[h.node_begin + p] - mv.own_begin] = sum;
-            }
-        }
+// One run of consecutive node ids: image -> CSR values.  2x2 blocks: everything is 16-byte aligned, one TMA bulk
+// store.  Scalars: the run sits on the same 16-byte phase in the image as in the CSR values; its aligned middle part
+// leaves as a bulk store, a leading / trailing odd value by a plain store.
+template <int M>
+PFG_DEV void tile_store_run(double* __restrict__ vals, const double* __restrict__ image, const TileHdr& h, const TileRun& run) {
+    if constexpr (M == 2) {
+        tma_store_1d(vals + h.gbase + run.gslot_rel, image + (size_t)run.out_off * 2, (uint32_t)run.len * 16u);
+    } else {
+        double* g = vals + h.gbase + run.gslot_rel;
+        const double* s = image + run.out_off;
+        const int len = (int)run.len;
+        const int head = (int)((h.gbase + run.gslot_rel) & 1);
+        if (head) g[0] = s[0];
+        const int body = (len - head) & ~1;
+        if (body > 0) tma_store_1d(g + head, s + head, (uint32_t)body * 8u);
+        if ((len - head) & 1) g[len - 1] = s[len - 1];
     }
 }
 
@@ -582,7 +538,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
     extern __shared__ __align__(128) unsigned char smem[];
     using St = TileStage<Op>;
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
-    constexpr bool ROWS = (Op::M == 2);  // row format: handles with two dofs per node
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] window ids, [3] corner indices, [4] window data
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
@@ -697,7 +652,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
             if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + dir_s[i & 7].rec_begin + r);
             Op::run(prm, xe, fe, elem, sink);
         }
-        if constexpr (ROWS) tma_store_wait_read();  // the previous chunk's bulk stores have read the image
+        tma_store_wait_read();  // the previous chunk's bulk stores have read the image
         __syncthreads();
         // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
         if (threadIdx.x == 0) {
@@ -708,40 +663,36 @@ __global__ void __launch_bounds__(THREADS, MINB)
             mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
             gather_window(i + 1);
         }
-        // ---- phase B: plan-ordered sums, each CSR block written once
+        // ---- phase B: plan-ordered sums into the CSR image, each CSR value written once
         mbar_wait(&bars[0], i & 1);
-        if constexpr (ROWS) {
+        {
             const TileHdr h = *reinterpret_cast<const TileHdr*>(blob_s);
-            tile_phase_b_rows<Op, THREADS>(h, blob_s, codes_s, stage, image, (i + (int)blockIdx.x) & 3);
+            tile_phase_b_nodes<Op, THREADS>(mv, h, blob_s, codes_s, stage, image, cfg.image_stride, out,
+                                            (i + (int)blockIdx.x) & 3);
             // runs of consecutive node ids leave as TMA bulk stores, spread over the warps' leading lanes;
             // the run entry is read before the barrier so that the blob may be overwritten right after it
             // (a chunk has at most 128 runs: checked when the plan is built)
             constexpr int NW = THREADS / 32;
             const int my_run = (int)(threadIdx.x & 31) * NW + (int)(threadIdx.x >> 5);
             TileRun run;
-            run.len16 = 0;
-            if (my_run < (int)h.n_runs)
-                run = reinterpret_cast<const TileRun*>(blob_s + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes)[my_run];
+            run.len = 0;
+            if (Op::NMAT > 0 && my_run < (int)h.n_runs)
+                run = reinterpret_cast<const TileRun*>(blob_s + tile_blob_tables(h.n_nodes, Op::M))[my_run];
             fence_proxy_async();  // image writes (generic proxy) -> visible to the bulk-copy engine
             __syncthreads();
             if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
-            if (out.vals[0] != nullptr) {
-                if (run.len16)
-                    tma_store_1d(out.vals[0] + h.gbase + run.gslot_rel,
-                                 reinterpret_cast<const unsigned char*>(image) + (size_t)run.out_off16 * 16,
-                                 (uint32_t)run.len16 * 16u);
+            if constexpr (Op::NMAT > 0) {
+                if (run.len) {
+#pragma unroll
+                    for (int mt = 0; mt < Op::NMAT; ++mt)
+                        if (out.vals[mt] != nullptr) tile_store_run<Op::M>(out.vals[mt], image + (size_t)mt * cfg.image_stride, h, run);
+                }
                 tma_store_commit();
             }
-        } else {
-            tile_phase_b<Op, THREADS>(mv, blob_s, codes_s, stage, out);
-            __syncthreads();
-            if (threadIdx.x == 0 && i + 1 < nloc) issue_meta(i + 1);
         }
     }
-    if constexpr (ROWS) tma_store_wait_read();
+    tma_store_wait_read();
 }
-
-static inline int align16(int x) { return (x + 15) & ~15; }
 
 struct ElasticityHex8GatherOp : ElasticityHex8Tag {};
 
@@ -935,11 +886,12 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     cfg.off_stage = cfg.off_field + (Op::field(prm) ? align16(d.max_chunk_win * 8) : 0);
     cfg.nchunks = (int)d.nchunks;
     cfg.off_image = align16(cfg.off_stage + (d.max_chunk_recs + 1) * St::S * 8);
-    if ((Op::M == 2) != d.tile_rows) {
-        set_error("tile plan sub-format does not match the operator");
+    if ((Op::M == 2) != (d.m == 2)) {
+        set_error("tile plan was built for %d dofs per node, the operator has %d", d.m, Op::M);
         return PFG_ERR_INVALID;
     }
-    const size_t smem = (size_t)cfg.off_image + (Op::M == 2 ? (size_t)d.max_out_bytes : 0);
+    cfg.image_stride = align16(d.max_out_bytes) / 8;
+    const size_t smem = (size_t)cfg.off_image + (size_t)Op::NMAT * cfg.image_stride * 8;
     if (smem > 227 * 1024) {
         set_error("chunk staging of %zu bytes exceeds shared memory", smem);
         return PFG_ERR_UNSUPPORTED;
@@ -954,7 +906,7 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     static const bool debug = getenv("PFG_DEBUG") != nullptr;
     if (debug)
         fprintf(stderr, "[pfg] k_tile: %d threads, %zu B smem (stage %d, image %d, blob %d, codes %d, win %d, recs<=%d), %d CTA/SM, grid %u\n",
-                THREADS, smem, (d.max_chunk_recs + 1) * St::S * 8, Op::M == 2 ? d.max_out_bytes : 0, d.max_blob_bytes,
+                THREADS, smem, (d.max_chunk_recs + 1) * St::S * 8, Op::NMAT * cfg.image_stride * 8, d.max_blob_bytes,
                 d.max_code_bytes, d.max_chunk_win, d.max_chunk_recs, per_sm, grid);
     kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
     PFG_CUDA_TRY(cudaGetLastError());

@@ -78,19 +78,18 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 // blocks, 8 B for scalars) from the start of the chunk's staging area, whose record slot 0 is all zeros
 // (code 0 adds nothing); `end` marks the last contribution of a (node, neighbour) block.  Codes depend on
 // the staging layout of the operator (record stride, symmetric or full storage); they are kept in the
-// neutral form (end << 15 | record << 2*lb | a << lb | b, 0xFFFF = padding) beside the working copy, which
-// is re-encoded when an operator with another layout runs.
+// neutral form (end << 15 | vec << 14 | record << 2*lb | a << lb | b, 0xFFFF = padding) beside the working
+// copy, which is re-encoded when an operator with another layout runs.
 //
-// Two sub-formats, chosen by ndof_per_node when the mesh handle is built:
-//   item format (m == 1): one phase-B thread per (node, neighbour) block.  After the node table the blob
-//       holds, per node, uint8 k, uint8 self rank, uint8 start[k+1] (prefix of contribution counts);
-//       TileNode::aux = byte offset of that record, TileNode::code_off = index of the node's first code.
-//   row format (m == 2): one phase-B thread per node walks the node's codes, writes the node's two dof
-//       rows into a shared-memory image of the CSR values, and the image leaves through one TMA bulk
-//       store per run of consecutive node ids.  Codes are stored group-major, [group][node][8 codes],
-//       every node padded with code 0 to the chunk's TileHdr::gmax groups, so that a warp's 16-byte code
-//       loads are contiguous.  After the node table: TileRun[n_runs].
-//       TileNode::aux = offset of the node's rows in the image (16 B units), TileNode::code_off = k.
+// Blob: TileHdr | TileNode[n_nodes] | (scalar handles) uint32 row[n_nodes] = owned-row index of each node (vector
+// outputs), padded to 8 B | TileRun[n_runs].
+// Codes: group-major, [group][node][8 codes], every node padded with code 0 to the chunk's TileHdr::gmax groups, so
+// that a warp's 16-byte code loads are contiguous; scalar handles append [group][node][4] vector codes (the node's
+// incidences, for residual / right-hand-side outputs), padded to TileHdr::gvmax groups.
+// Phase B runs one thread per chunk node: it walks the node's codes, sums every (node, neighbour) block in plan order
+// and drops the node's dof rows into a shared-memory image of the CSR values; the image leaves through one TMA bulk
+// store per run of consecutive node ids (scalar runs: the 16-byte aligned middle part; a leading / trailing odd value
+// goes by a plain store).
 // ---------------------------------------------------------------------------------------------
 struct __align__(16) TileDir {  // 16 bytes; entry nchunks is a sentinel, so every length is a difference of neighbours
     uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
@@ -102,26 +101,30 @@ struct __align__(16) TileDir {  // 16 bytes; entry nchunks is a sentinel, so eve
 struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
     int64_t gbase;         // CSR value slot of the chunk's first node (node slots are relative to it)
     uint32_t rec_begin;
-    uint32_t node_begin;   // first chunk-ordered node slot (row ids of the vector output: cnode_id)
+    uint32_t pad0_;
     uint16_t n_nodes, n_recs;
-    uint16_t kpad;         // max neighbour count over the chunk's nodes
-    uint16_t cpad;         // max contributions to one block over the chunk
-    uint16_t n_runs;       // row format: runs of consecutive node ids
-    uint16_t gmax;         // row format: code groups (8 codes) per node, padded to the chunk maximum
+    uint16_t gmax;         // matrix code groups (8 codes) per node, padded to the chunk maximum
+    uint16_t gvmax;        // vector code groups (4 codes) per node (scalar handles)
+    uint16_t n_runs;       // runs of consecutive node ids
+    uint16_t pad_;
     uint32_t pad2_;
 };
 
 struct __align__(8) TileNode {  // 8 bytes
     uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileHdr::gbase
-    uint16_t aux;          // item format: byte offset of the node's start record; row format: image offset / 16
-    uint16_t code_off;     // item format: first code index; row format: neighbour count k
+    uint16_t aux;          // offset of the node's rows in the chunk's CSR image, in units (16 B for m = 2, 8 B for m = 1)
+    uint16_t k;            // neighbour count: a dof row holds m * k values
 };
 
-struct __align__(8) TileRun {  // 8 bytes: one bulk store, image -> CSR values
+struct __align__(8) TileRun {  // 8 bytes: one run of consecutive node ids, image -> CSR values
     uint32_t gslot_rel;    // first value slot, relative to TileHdr::gbase
-    uint16_t out_off16;    // image offset / 16
-    uint16_t len16;        // bytes / 16
+    uint16_t out_off;      // image offset, in units
+    uint16_t len;          // length, in units
 };
+
+__host__ __device__ inline int64_t tile_blob_tables(int64_t n_nodes, int m) {  // offset of the run table in a blob
+    return (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * n_nodes + (m == 1 ? ((4 * n_nodes + 7) / 8) * 8 : 0);
+}
 
 struct TileLayout {  // how an operator stages one record; decides the code encoding
     int nne = 0;       // nodes per element
@@ -129,10 +132,11 @@ struct TileLayout {  // how an operator stages one record; decides the code enco
     int rec_units = 0; // record stride in code units
     int sym = 0;       // upper-triangle storage
     int blk_units = 0; // units per node-pair block
-    int has_mat = 0;   // 0: vector-only operator, codes address the vector entry of node a
+    int has_mat = 0;   // 0: vector-only operator
+    int vec_units = -1;// offset of the vector entries inside a record, in code units (-1: the operator has none)
     bool operator==(const TileLayout& o) const {
         return nne == o.nne && unit_shift == o.unit_shift && rec_units == o.rec_units && sym == o.sym &&
-               blk_units == o.blk_units && has_mat == o.has_mat;
+               blk_units == o.blk_units && has_mat == o.has_mat && vec_units == o.vec_units;
     }
 };
 
@@ -187,7 +191,6 @@ struct MeshDev {
     int max_chunk_win = 0;
     int64_t tile_blob_bytes = 0, tile_ncodes = 0;
     int max_blob_bytes = 0, max_code_bytes = 0, max_out_bytes = 0;
-    bool tile_rows = false;            // row sub-format (m == 2)
     TileLayout tile_layout;            // encoding of tile_codes (nne == 0: not encoded yet)
     int tile_threads = 128;            // CTA size of the tile kernels = target element records per chunk
 

@@ -483,19 +483,17 @@ __global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64
 
 
 // ---- tile plan (second format) -----------------------------------------------------------------
-__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk,
-                                  const uint32_t* __restrict__ slot_chunk, int nne, int rows, int64_t nslots,
-                                  uint32_t* __restrict__ start_bytes, uint32_t* __restrict__ ncodes,
-                                  int* __restrict__ chunk_gmax) {
+// per node: code groups (8 codes) of the matrix blocks and (scalar handles) groups of 4 vector codes
+__global__ void k_tile_node_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ slot_chunk, int nne,
+                                  int64_t nslots, int* __restrict__ chunk_gmax, int* __restrict__ chunk_gvmax) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (p >= nslots) return;
     const uint32_t n = valence[p] * nne;
-    start_bytes[p] = rows ? 0 : kk[p] + 3;  // item format: k, self rank, start[k+1]
-    ncodes[p] = rows ? 0 : n;               // row format: codes are group-major per chunk (gmax * n_nodes groups)
-    if (rows) atomicMax(&chunk_gmax[slot_chunk[p]], (int)((n + 7) / 8));
+    atomicMax(&chunk_gmax[slot_chunk[p]], (int)((n + 7) / 8));
+    atomicMax(&chunk_gvmax[slot_chunk[p]], (int)((valence[p] + 3) / 4));
 }
 
-// row format: a run starts where the chunk starts or the node ids stop being consecutive
+// a run starts where the chunk starts or the node ids stop being consecutive
 __global__ void k_tile_run_flags(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
                                  int64_t nslots, uint32_t* __restrict__ flag) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -504,27 +502,17 @@ __global__ void k_tile_run_flags(const uint32_t* __restrict__ slot_node, const u
 }
 
 __global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__ chunks,
-                                   const int64_t* __restrict__ sb_excl, const int64_t* __restrict__ nc_excl,
-                                   const int64_t* __restrict__ kk_excl, const uint32_t* __restrict__ run_id,
-                                   const int* __restrict__ chunk_gmax, int rows, int m,
-                                   uint32_t* __restrict__ blob_len16, uint32_t* __restrict__ code_len16,
-                                   int* __restrict__ maxima) {
+                                   const uint32_t* __restrict__ run_id, const int* __restrict__ chunk_gmax,
+                                   const int* __restrict__ chunk_gvmax, int m, uint32_t* __restrict__ blob_len16,
+                                   uint32_t* __restrict__ code_len16, int* __restrict__ maxima) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
     const ChunkHdr h = chunks[c];
     const int64_t p0 = h.node_begin, p1 = p0 + h.n_nodes;
-    int64_t blob = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
-    int64_t codes;
-    if (rows) {
-        const int64_t nruns = (int64_t)run_id[p1 - 1] - run_id[p0] + 1;
-        blob += (int64_t)sizeof(TileRun) * nruns;
-        const int64_t out_bytes = (kk_excl[p1] - kk_excl[p0]) * m * m * 8;
-        atomicMax(&maxima[7], (int)min((int64_t)INT_MAX, out_bytes));
-        codes = 16 * (int64_t)chunk_gmax[c] * h.n_nodes;  // group-major: [group][node] 8 codes
-    } else {
-        blob += sb_excl[p1] - sb_excl[p0];
-        codes = 2 * (nc_excl[p1] - nc_excl[p0]);
-    }
+    const int64_t nruns = (int64_t)run_id[p1 - 1] - run_id[p0] + 1;
+    const int64_t blob = tile_blob_tables(h.n_nodes, m) + (int64_t)sizeof(TileRun) * nruns;
+    // group-major codes: [group][node] 8 matrix codes, then (scalar handles) [group][node] 4 vector codes
+    const int64_t codes = 16 * (int64_t)chunk_gmax[c] * h.n_nodes + (m == 1 ? 8 * (int64_t)chunk_gvmax[c] * h.n_nodes : 0);
     blob_len16[c] = (uint32_t)((blob + 15) / 16);
     code_len16[c] = (uint32_t)((codes + 15) / 16);
     atomicMax(&maxima[5], (int)min((int64_t)INT_MAX, (blob + 15) / 16 * 16));
@@ -594,21 +582,21 @@ struct TileFillArgs {
     const uint32_t* inc_list;
     const uint8_t* rank;
     const int64_t* blk_ptr;
-    const int32_t* nbr;
     const ChunkHdr* chunks;
     const TileDir* dir;
     const uint64_t* rec_keys;
-    const int64_t *sb_excl, *nc_excl, *kk_excl;
     const uint32_t *run_flag, *run_id;
     int64_t own_begin, nslots;
-    int m, rows;
+    int m;
     uint8_t* blob_pool;
     uint16_t* codes_neutral;
     int32_t* cnode_id;
-    int *chunk_cpad, *err;
-    const int* chunk_gmax;
+    int* err;
+    const int *chunk_gmax, *chunk_gvmax;
+    int* maxima;
 };
 
+// neutral code: end << 15 | vec << 14 | record << 2*LB | a << LB | b; 0xFFFF = padding
 template <int NNE>
 __global__ void k_tile_fill(TileFillArgs A) {
     constexpr int LB = (NNE == 4) ? 2 : 3;
@@ -624,23 +612,12 @@ __global__ void k_tile_fill(TileFillArgs A) {
     uint8_t* blob = A.blob_pool + (size_t)td.blob_off16 * 16;
     const int k = (int)(A.blk_ptr[r + 1] - A.blk_ptr[r]);
     const int64_t s0 = A.inc_ptr[node], s1 = A.inc_ptr[node + 1];
-    const int64_t code_off = A.nc_excl[p] - A.nc_excl[h.node_begin];
     const int64_t grel = (A.blk_ptr[r] - A.blk_ptr[r_first]) * A.m * A.m;
-    const int64_t tables = (int64_t)sizeof(TileHdr) + (int64_t)sizeof(TileNode) * h.n_nodes;
-    const int64_t nruns = A.rows ? (int64_t)A.run_id[p_end - 1] - A.run_id[h.node_begin] + 1 : 0;
-    int64_t aux, code_index;
-    bool bad = grel < 0 || grel > 0xFFFFFFFFll || h.n_recs >= (0x7FFFu >> (2 * LB));
-    if (A.rows) {
-        aux = (A.kk_excl[p] - A.kk_excl[h.node_begin]) * A.m * A.m * 8 / 16;  // image offset of the node's rows
-        code_index = k;  // row format keeps the neighbour count here; codes are addressed [group][node]
-        bad = bad || A.chunk_gmax[c] > 0xFFFF || nruns > 128;
-    } else {
-        aux = tables + (A.sb_excl[p] - A.sb_excl[h.node_begin]);
-        code_index = code_off;
-        bad = bad || aux + k + 3 > 0xFFFF;
-    }
-    bad = bad || aux > 0xFFFF || code_index > 0xFFFF;
-    if (bad) {
+    const int64_t nruns = (int64_t)A.run_id[p_end - 1] - A.run_id[h.node_begin] + 1;
+    const int64_t pl = p - h.node_begin;
+    const int gmax = A.chunk_gmax[c], gvmax = A.chunk_gvmax[c];
+    if (grel < 0 || grel > 0xFFFFFFFFll || h.n_recs >= (0x3FFFu >> (2 * LB)) || gmax > 0xFFFF || gvmax > 0xFFFF ||
+        nruns > 128 || k > 0xFFFF) {
         atomicExch(A.err, 1);
         return;
     }
@@ -648,21 +625,21 @@ __global__ void k_tile_fill(TileFillArgs A) {
         TileHdr th;
         th.gbase = A.blk_ptr[r_first] * A.m * A.m;
         th.rec_begin = (uint32_t)h.rec_begin;
-        th.node_begin = h.node_begin;
+        th.pad0_ = 0;
         th.n_nodes = (uint16_t)h.n_nodes;
         th.n_recs = (uint16_t)h.n_recs;
-        th.kpad = (uint16_t)h.kpad;
-        th.cpad = 0;  // filled by k_tile_cpad
+        th.gmax = (uint16_t)gmax;
+        th.gvmax = (uint16_t)gvmax;
         th.n_runs = (uint16_t)nruns;
-        th.gmax = (uint16_t)(A.rows ? A.chunk_gmax[c] : 0);
+        th.pad_ = 0;
         th.pad2_ = 0;
         *reinterpret_cast<TileHdr*>(blob) = th;
     }
-    TileNode tn;
-    tn.gslot_rel = (uint32_t)grel;
-    tn.aux = (uint16_t)aux;
-    tn.code_off = (uint16_t)code_index;
-    reinterpret_cast<TileNode*>(blob + sizeof(TileHdr))[p - h.node_begin] = tn;
+    TileNode* tn = reinterpret_cast<TileNode*>(blob + sizeof(TileHdr)) + pl;
+    tn->gslot_rel = (uint32_t)grel;  // aux (image offset) is filled by k_tile_image_layout
+    tn->k = (uint16_t)k;
+    if (A.m == 1)
+        reinterpret_cast<uint32_t*>(blob + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes)[pl] = (uint32_t)r;
     // counting sort of the valence*NNE contributions by neighbour rank
     uint8_t cnt[kMaxRowBlocks + 1];
     for (int t = 0; t <= k; ++t) cnt[t] = 0;
@@ -671,45 +648,15 @@ __global__ void k_tile_fill(TileFillArgs A) {
 #pragma unroll
         for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
     }
-    int cmax = 0;
-    for (int t = 0; t < k; ++t) cmax = max(cmax, (int)cnt[t + 1]);
-    atomicMax(&A.chunk_cpad[c], cmax);
     for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
-    if (A.rows) {
-        if (A.run_flag[p]) {  // this node starts a run: find its length
-            int64_t len16 = 0, q = p;
-            do {
-                const int64_t rq = A.slot_node[q];
-                len16 += (A.blk_ptr[rq + 1] - A.blk_ptr[rq]) * A.m * A.m * 8 / 16;
-                ++q;
-            } while (q < p_end && !A.run_flag[q]);
-            if (len16 > 0xFFFF) atomicExch(A.err, 1);
-            TileRun run;
-            run.gslot_rel = (uint32_t)grel;
-            run.out_off16 = (uint16_t)aux;
-            run.len16 = (uint16_t)len16;
-            TileRun* runs = reinterpret_cast<TileRun*>(blob + tables);
-            runs[A.run_id[p] - A.run_id[h.node_begin]] = run;
-        }
-    } else {
-        // rank of the node in its own (sorted) neighbour list
-        int64_t lo = A.blk_ptr[r], hi = A.blk_ptr[r + 1];
-        const int64_t lo0 = lo;
-        while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if (A.nbr[mid] < (int32_t)node) lo = mid + 1; else hi = mid;
-        }
-        uint8_t* pl = blob + aux;
-        pl[0] = (uint8_t)k;
-        pl[1] = (uint8_t)(lo - lo0);
-        for (int t = 0; t <= k; ++t) pl[2 + t] = cnt[t];
-    }
-    // neutral codes in block order; the last contribution of each block carries the end flag
-    uint16_t* codes = A.codes_neutral + (size_t)td.code_off16 * 8 + (A.rows ? 0 : code_off);
-    const int64_t pl = p - h.node_begin;  // row format: code s of this node sits at [s / 8][node][s % 8]
+    // matrix codes in block order, group-major: code s of this node sits at [s / 8][node][s % 8]; the last
+    // contribution of each block carries the end flag.  Vector codes (scalar handles): [j / 4][node][j % 4].
+    uint16_t* codes = A.codes_neutral + (size_t)td.code_off16 * 8;
+    uint16_t* vcodes = codes + (size_t)gmax * h.n_nodes * 8;
     uint8_t end_at[kMaxRowBlocks + 1];  // last code index of block t = start of block t+1 minus one
     for (int t = 0; t < k; ++t) end_at[t] = (uint8_t)(cnt[t + 1] - 1);
-    for (int64_t s = s0; s < s1; ++s) {
+    int j = 0;
+    for (int64_t s = s0; s < s1; ++s, ++j) {
         const uint32_t ia = A.inc_list[s];
         const uint64_t key = ((uint64_t)c << 32) | (uint64_t)(ia / NNE);
         int64_t lo = h.rec_begin, hi = h.rec_begin + h.n_recs;
@@ -725,18 +672,55 @@ __global__ void k_tile_fill(TileFillArgs A) {
             const int t = rk[b];
             const int pos = cnt[t]++;
             const uint32_t end = (pos == end_at[t]) ? 0x8000u : 0u;
-            const int64_t at = A.rows ? (((int64_t)(pos >> 3) * h.n_nodes + pl) * 8 + (pos & 7)) : pos;
-            codes[at] = (uint16_t)(end | (rloc << (2 * LB)) | (a << LB) | b);
+            codes[((int64_t)(pos >> 3) * h.n_nodes + pl) * 8 + (pos & 7)] = (uint16_t)(end | (rloc << (2 * LB)) | (a << LB) | b);
+        }
+        if (A.m == 1) {
+            const uint32_t end = (s + 1 == s1) ? 0x8000u : 0u;
+            vcodes[((int64_t)(j >> 2) * h.n_nodes + pl) * 4 + (j & 3)] = (uint16_t)(end | 0x4000u | (rloc << (2 * LB)) | (a << LB) | a);
         }
     }
     A.cnode_id[p] = (int32_t)node;
 }
 
-__global__ void k_tile_cpad(int64_t nchunks, const TileDir* __restrict__ dir, const int* __restrict__ chunk_cpad,
-                            uint8_t* __restrict__ blob_pool) {
+// one thread per chunk: place the nodes' rows in the chunk's CSR image and list the runs of consecutive node ids.
+// Units are 16 bytes (2 dofs per node) or 8 bytes (scalar); a scalar run starts on the same 16-byte phase in the
+// image as in the CSR values, so that its aligned middle part can leave as one bulk store.
+__global__ void k_tile_image_layout(int64_t nchunks, const ChunkHdr* __restrict__ chunks, const TileDir* __restrict__ dir,
+                                    const uint32_t* __restrict__ slot_node, const int64_t* __restrict__ blk_ptr,
+                                    const uint32_t* __restrict__ run_flag, int m, uint8_t* __restrict__ blob_pool,
+                                    int* __restrict__ maxima, int* __restrict__ err) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c >= nchunks) return;
-    reinterpret_cast<TileHdr*>(blob_pool + (size_t)dir[c].blob_off16 * 16)->cpad = (uint16_t)chunk_cpad[c];
+    const ChunkHdr h = chunks[c];
+    uint8_t* blob = blob_pool + (size_t)dir[c].blob_off16 * 16;
+    TileNode* nodes = reinterpret_cast<TileNode*>(blob + sizeof(TileHdr));
+    TileRun* runs = reinterpret_cast<TileRun*>(blob + tile_blob_tables(h.n_nodes, m));
+    const int64_t gbase = reinterpret_cast<const TileHdr*>(blob)->gbase;
+    const int unit_doubles = (m == 2) ? 2 : 1;
+    int64_t off = 0;  // image offset in units
+    int nrun = -1;
+    int64_t run_start = 0;
+    for (int64_t q = 0; q < (int64_t)h.n_nodes; ++q) {
+        const int64_t p = h.node_begin + q;
+        const int64_t rq = slot_node[p];
+        const int64_t len = (blk_ptr[rq + 1] - blk_ptr[rq]) * m * m / unit_doubles;
+        if (run_flag[p]) {
+            if (nrun >= 0) runs[nrun].len = (uint16_t)(off - run_start);
+            if (unit_doubles == 1 && (((gbase + nodes[q].gslot_rel) ^ off) & 1)) ++off;  // same 16-byte phase
+            ++nrun;
+            run_start = off;
+            runs[nrun].gslot_rel = nodes[q].gslot_rel;
+            runs[nrun].out_off = (uint16_t)off;
+        }
+        nodes[q].aux = (uint16_t)off;
+        off += len;
+        if (off > 0xFFFF) {
+            atomicExch(err, 1);
+            return;
+        }
+    }
+    if (nrun >= 0) runs[nrun].len = (uint16_t)(off - run_start);
+    atomicMax(&maxima[7], (int)((off + 1) * unit_doubles * 8));
 }
 
 // neutral codes -> staging offsets of one operator layout (record slot 0 is the zero record; padding -> 0)
@@ -744,8 +728,10 @@ __host__ __device__ inline uint32_t tile_encode(const TileLayout& L, uint32_t ne
     if (neutral == 0xFFFFu) return 0;
     const int lb = (L.nne == 4) ? 2 : 3;
     const uint32_t end = (neutral >> 15) << 1;
-    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = ((neutral & 0x7FFFu) >> (2 * lb)) + 1;
-    if (!L.has_mat) return ((r * L.rec_units + a) << 2) | end;
+    const bool vec = (neutral >> 14) & 1u;
+    const uint32_t b = neutral & (L.nne - 1), a = (neutral >> lb) & (L.nne - 1), r = ((neutral & 0x3FFFu) >> (2 * lb)) + 1;
+    if (vec) return L.vec_units >= 0 ? (((r * L.rec_units + L.vec_units + a) << 2) | end) : 0;
+    if (!L.has_mat) return 0;
     if (!L.sym) return ((r * L.rec_units + (a * L.nne + b) * L.blk_units) << 2) | end;
     const uint32_t lo = a < b ? a : b, hi = a < b ? b : a;
     const uint32_t tri = lo * (2 * L.nne - 1 - lo) / 2 + hi;
@@ -921,7 +907,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         int axis_order[3] = {0, 1, 2};
         int64_t level0_target = 0;
         const int tile_width = env_int("PFG_TILE_WIDTH", 8);
-        if (tile && d.m == 2 && d.ndims == 2 && tile_width > 0 && nown > 64) {
+        if (tile && d.ndims == 2 && tile_width > 0 && nown > 64) {
             DBuf<unsigned long long> cnt;
             PFG_CUDA_TRY(cnt.alloc(4));
             PFG_CUDA_TRY(cudaMemsetAsync(cnt.p, 0, 4 * sizeof(unsigned long long), st));
@@ -1066,11 +1052,9 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                                                                d.rec_elem, d.chunks, maxima.p);
     k_chunk_rec_finish<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, maxima.p);
     if (tile) {
-        // ---- tile plan: blob (header, node table, format tables) and contribution codes per chunk
+        // ---- tile plan: node windows, then blob (header, node table, runs) and contribution codes per chunk
         cudaFree(d.rec_dst);
         d.rec_dst = nullptr;
-        const int rows = (d.m == 2) ? 1 : 0;
-        d.tile_rows = rows != 0;
         DBuf<uint32_t> win_begin;
         DBuf<int> terr;
         PFG_CUDA_TRY(terr.alloc(1));
@@ -1109,43 +1093,30 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
             PFG_CUDA_TRY(cudaStreamSynchronize(st));
             PFG_CUDA_TRY(cudaGetLastError());
         }
-        DBuf<uint32_t> sbytes, ncodes, blob_len16, code_len16, run_flag, run_id;
-        DBuf<int64_t> sb_excl, nc_excl, kk_excl, blob_off, code_off;
-        DBuf<int> chunk_cpad, chunk_gmax;
-        PFG_CUDA_TRY(chunk_cpad.alloc(d.nchunks));
+        DBuf<uint32_t> blob_len16, code_len16, run_flag, run_id;
+        DBuf<int64_t> blob_off, code_off;
+        DBuf<int> chunk_gmax, chunk_gvmax;
         PFG_CUDA_TRY(chunk_gmax.alloc(d.nchunks));
-        PFG_CUDA_TRY(cudaMemsetAsync(chunk_cpad.p, 0, d.nchunks * sizeof(int), st));
+        PFG_CUDA_TRY(chunk_gvmax.alloc(d.nchunks));
         PFG_CUDA_TRY(cudaMemsetAsync(chunk_gmax.p, 0, d.nchunks * sizeof(int), st));
-        PFG_CUDA_TRY(sbytes.alloc(nown + 1));
-        PFG_CUDA_TRY(ncodes.alloc(nown + 1));
+        PFG_CUDA_TRY(cudaMemsetAsync(chunk_gvmax.p, 0, d.nchunks * sizeof(int), st));
         PFG_CUDA_TRY(run_flag.alloc(nown + 1));
         PFG_CUDA_TRY(run_id.alloc(nown + 1));
-        PFG_CUDA_TRY(sb_excl.alloc(nown + 1));
-        PFG_CUDA_TRY(nc_excl.alloc(nown + 1));
-        PFG_CUDA_TRY(kk_excl.alloc(nown + 1));
         PFG_CUDA_TRY(blob_len16.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(code_len16.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(blob_off.alloc(d.nchunks + 1));
         PFG_CUDA_TRY(code_off.alloc(d.nchunks + 1));
-        PFG_CUDA_TRY(cudaMemsetAsync(sbytes.p, 0, (nown + 1) * sizeof(uint32_t), st));
-        PFG_CUDA_TRY(cudaMemsetAsync(ncodes.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(run_flag.p, 0, (nown + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(blob_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
         PFG_CUDA_TRY(cudaMemsetAsync(code_len16.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
-        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, kk.p, slot_chunk.p, NNE, rows, nown, sbytes.p,
-                                                               ncodes.p, chunk_gmax.p);
+        k_tile_node_sizes<<<grid_for(nown), kThreads, 0, st>>>(valence.p, slot_chunk.p, NNE, nown, chunk_gmax.p,
+                                                               chunk_gvmax.p);
         k_tile_run_flags<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, nown, run_flag.p);
         PFG_CUB(scratch, st,
-                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, sbytes.p, sb_excl.p, nown + 1, st));
-        PFG_CUB(scratch, st,
-                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, ncodes.p, nc_excl.p, nown + 1, st));
-        PFG_CUB(scratch, st,
-                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, kk.p, kk_excl.p, nown + 1, st));
-        PFG_CUB(scratch, st,
                 cub::DeviceScan::InclusiveSum(d_temp_storage, temp_storage_bytes, run_flag.p, run_id.p, nown + 1, st));
-        k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, sb_excl.p, nc_excl.p, kk_excl.p,
-                                                                     run_id.p, chunk_gmax.p, rows, d.m, blob_len16.p,
-                                                                     code_len16.p, maxima.p);
+        k_tile_chunk_sizes<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, run_id.p, chunk_gmax.p,
+                                                                     chunk_gvmax.p, d.m, blob_len16.p, code_len16.p,
+                                                                     maxima.p);
         PFG_CUB(scratch, st,
                 cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, blob_len16.p, blob_off.p,
                                               d.nchunks + 1, st));
@@ -1174,15 +1145,16 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                                                                  win_begin.p, d.nrecs, d.nwin, d.tile_dir);
         TileFillArgs fa;
         fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
-        fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr, fa.nbr = d.nbr;
+        fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr;
         fa.chunks = d.chunks, fa.dir = d.tile_dir, fa.rec_keys = rec_keys.p;
-        fa.sb_excl = sb_excl.p, fa.nc_excl = nc_excl.p, fa.kk_excl = kk_excl.p;
         fa.run_flag = run_flag.p, fa.run_id = run_id.p;
-        fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m, fa.rows = rows;
+        fa.own_begin = d.own_begin, fa.nslots = nown, fa.m = d.m;
         fa.blob_pool = d.tile_blob, fa.codes_neutral = d.tile_codes_neutral, fa.cnode_id = d.cnode_id;
-        fa.chunk_cpad = chunk_cpad.p, fa.err = terr.p, fa.chunk_gmax = chunk_gmax.p;
+        fa.err = terr.p, fa.chunk_gmax = chunk_gmax.p, fa.chunk_gvmax = chunk_gvmax.p, fa.maxima = maxima.p;
         k_tile_fill<NNE><<<grid_for(nown, 128), 128, 0, st>>>(fa);
-        k_tile_cpad<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.tile_dir, chunk_cpad.p, d.tile_blob);
+        k_tile_image_layout<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, d.tile_dir, slot_node.p,
+                                                                      d.blk_ptr, run_flag.p, d.m, d.tile_blob, maxima.p,
+                                                                      terr.p);
         int h_terr = 0, h_max[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
