@@ -922,7 +922,6 @@ static int launch(const MeshDev& d, const typename Op::Params& prm, const Output
         const unsigned grid = (unsigned)((d.nelems + 127) / 128);
         k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
-        if (d.tile_threads == 256) return launch_tile<Op, 256, 1>(const_cast<MeshDev&>(d), mv, prm, out, st);
         return launch_tile<Op, 128, MINB>(const_cast<MeshDev&>(d), mv, prm, out, st);
     }
     PFG_CUDA_TRY(cudaGetLastError());

@@ -849,7 +849,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     if (d.max_valence > kMaxValence || d.max_k > kMaxRowBlocks) return PFG_OK;  // atomic path only
 
     // ---- chunk size
-    d.tile_threads = (env_int("PFG_TILE_THREADS", 128) >= 256) ? 256 : 128;
+    d.tile_threads = 128;
     const bool tile = (d.m != 3);  // tile plan for the one-thread-per-element physics, first format for hex8 elasticity
     int64_t C;
     if (tile) {
