@@ -143,6 +143,7 @@ def cpu_sample_side(physics, nne, budget_s):
 
 def run_reference(args, desc, physics, nne):
     budget = max(0.5, min(15.0, 150.0 / max(1, args.steps + args.warmup)))
+    budget = float(os.environ.get("PFG_BENCH_CPU_BUDGET_S", budget))  # tests shrink the sample
     side = cpu_sample_side(physics, nne, budget)
     for _ in range(args.warmup):
         oracle_step(physics, nne, side)
