@@ -57,4 +57,4 @@ for mode in modes:
             ts.append(e0.elapsed_time(e1))
         ts = np.array(ts)
         print(f"{phys} n={n} mode={mode} rho={'field' if use_rho else 'const'}: best {ts.min():.3f} ms median {np.median(ts):.3f} ms "
-              f"-> {E/ts.min()/1e6:.1f} M elem/s (best), checksum {float(vals.sum()):.6e}", flush=True)
+              f"-> {E/ts.min()/1e6:.2f} G elem/s (best), checksum {float(vals.sum()):.6e}", flush=True)
