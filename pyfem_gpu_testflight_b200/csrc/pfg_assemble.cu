@@ -897,11 +897,19 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
         return PFG_ERR_UNSUPPORTED;
     }
     auto kern = k_tile<Op, THREADS, MINB>;
-    PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-    int per_sm = 1;
-    PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, smem));
-    per_sm = std::max(1, per_sm);
+    // attribute / occupancy queries cost more than a small assembly: repeat them only when the configuration changes
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_device = -1, cached_per_sm = 1;
+    if (cached_smem != smem || cached_device != d.device) {
+        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        int q = 1;
+        PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));
+        cached_per_sm = std::max(1, q);
+        cached_smem = smem;
+        cached_device = d.device;
+    }
+    const int per_sm = cached_per_sm;
     const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
     static const bool debug = getenv("PFG_DEBUG") != nullptr;
     if (debug)
