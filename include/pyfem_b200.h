@@ -167,6 +167,34 @@ PFG_API int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream);
 PFG_API int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs_dev, int mode, void* stream);
 
 /*
+ * The scatter on its own, for caller-supplied element matrices / vectors -- the slot the reference's A2DWrapper uses
+ * (pyfem.py:2255-2277: a native plugin fills the element Jacobians, pyfem assembles them):
+ *   pfg_scatter_matrix  ModelBase._assemble_jacobian(Ke_mat) (pyfem.py:920-931); Ke_dev is (nelems, D, D) row-major
+ *                       with D = nnodes_per_elem * ndof_per_node in the interleaved (node, axis) dof order of
+ *                       utils.create_dof (utils.py:293-296); duplicates summed, explicit zeros kept.
+ *   pfg_scatter_vector  ModelBase._assemble_rhs(rhs_e, rhs) (pyfem.py:860-875) for scalar handles; fe_dev is
+ *                       (nelems, nnodes_per_elem).
+ */
+PFG_API int pfg_scatter_matrix(pfg_mesh* mesh, const double* Ke_dev, double* vals_dev, int mode, void* stream);
+PFG_API int pfg_scatter_vector(pfg_mesh* mesh, const double* fe_dev, double* rhs_dev, int mode, void* stream);
+
+/*
+ * Element matrices / vectors without the scatter: the outputs of the reference's _compute_element_jacobian and
+ * _compute_element_rhs methods (Ke_mat (nelems, D, D), rhs_e (nelems, nnodes_per_elem)) for callers that read them
+ * (examples/SciTech2023/performance/performance_test.py:52).
+ *   physics      PFG_PHYS_POISSON     pyfem.py:1188-1217   params {p}              field = rho
+ *                PFG_PHYS_ELASTICITY  pyfem.py:2029-2068   params {p, E, nu}       field = rho
+ *                PFG_PHYS_HELMHOLTZ   pyfem.py:2138-2177   params {r0}             Ke_dev = Ke, Ke2_dev = Re
+ *                PFG_PHYS_NLPOISSON   pyfem.py:1541-1610, 1474-1539   params = xdv (nparams of them), field = u;
+ *                                     Ke_dev = Jacobian, fe_dev = residual
+ *   field_dev    nodal field or NULL for the constant field_const; params_host is a HOST array.
+ */
+typedef enum pfg_physics { PFG_PHYS_POISSON = 1, PFG_PHYS_ELASTICITY = 2, PFG_PHYS_HELMHOLTZ = 3, PFG_PHYS_NLPOISSON = 4 } pfg_physics;
+PFG_API int pfg_element_matrices(pfg_mesh* mesh, int physics, const double* field_dev, double field_const,
+                                 const double* params_host, int nparams, double* Ke_dev, double* Ke2_dev,
+                                 double* fe_dev, void* stream);
+
+/*
  * ModelBase.apply_dirichlet_bcs (pyfem.py:780-835) on the device CSR, keeping the pattern
  * (no eliminate_zeros): rows of fixed dofs zeroed, columns too when enforce_symmetric != 0,
  * unit diagonal, rhs[fixed] = vals (0 when fixed_vals_dev is NULL) and, in the symmetric

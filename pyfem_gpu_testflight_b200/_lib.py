@@ -28,6 +28,8 @@ MODES = {"auto": MODE_AUTO, "atomic": MODE_ATOMIC, "gather": MODE_GATHER}
 INFO_NNZ, INFO_NROWS, INFO_NCOLS, INFO_IDX_BYTES, INFO_NCHUNKS, INFO_CHUNK_ELEMS, INFO_PLAN_BYTES, \
     INFO_DEVICE_BYTES, INFO_MAX_ROW_BLOCKS, INFO_MAX_VALENCE = range(10)
 
+PHYS_POISSON, PHYS_ELASTICITY, PHYS_HELMHOLTZ, PHYS_NLPOISSON = 1, 2, 3, 4
+
 CREATE_NO_GATHER_PLAN = 1
 CREATE_NO_REORDER = 2
 
@@ -50,6 +52,10 @@ PROTOTYPES = {
     "pfg_poisson_rhs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_apply_dirichlet": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pfg_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pfg_scatter_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pfg_scatter_vector": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "pfg_element_matrices": (c_int, [c_void_p, c_int, c_void_p, c_double, POINTER(c_double), c_int, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
     "pfg_mesh_set_element_mask": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pfg_add_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }

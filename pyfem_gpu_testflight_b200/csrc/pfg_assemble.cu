@@ -149,9 +149,51 @@ __global__ void __launch_bounds__(128) k_assemble_atomic(MeshView mv, typename O
     Op::run(prm, xe, fe, e, sink);
 }
 
+// element matrices only (no scatter): one thread per element
+template <class Op>
+__global__ void __launch_bounds__(128) k_element_matrices(MeshView mv, typename Op::Params prm, double* Ke0, double* Ke1,
+                                                          double* fe) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= mv.nelems) return;
+    constexpr int NNE = Op::NNE;
+    int nodes[NNE];
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
+    GlobalSink<Op> sink{{Ke0, Ke1}, fe, e};
+    double xe[NNE][Elem<NNE>::DIM], fld[NNE];
+    load_coords<NNE>(mv.X, nodes, xe);
+    load_field<NNE>(Op::field(prm), nodes, fld);
+    Op::run(prm, xe, fld, e, sink);
+}
+
+struct HexGlobalRowSink {  // octet kernel: this thread's 3 x 24 row block of the element matrix
+    double* row;  // Ke + e*576 + lane8*3*24
+    PFG_DEV void block(int, int, int b, const double* blk) const {
+#pragma unroll
+        for (int al = 0; al < 3; ++al)
+#pragma unroll
+            for (int be = 0; be < 3; ++be) row[al * 24 + b * 3 + be] = blk[al * 3 + be];
+    }
+};
+
 struct ElasticityHex8Tag {  // layout / sink traits of the octet kernel
     static constexpr int NNE = 8, M = 3, NMAT = 1, NVEC = 0;
 };
+
+__global__ void __launch_bounds__(128) k_elasticity_hex8_matrices(MeshView mv, ElasticityHex8Params prm, double* Ke) {
+    __shared__ double stage[16 * kHexStageDoubles];
+    const int64_t e = blockIdx.x * 16ll + (threadIdx.x >> 3);
+    const int lane8 = threadIdx.x & 7;
+    const unsigned octet_mask = 0xffu << ((threadIdx.x & 31) & ~7);
+    if (e >= mv.nelems) return;
+    int nodes[8];
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e);
+    const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e + 1);
+    nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+    nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+    HexGlobalRowSink sink{Ke + e * 576 + lane8 * 72};
+    elasticity_hex8_octet(mv, prm, nodes, stage + (threadIdx.x >> 3) * kHexStageDoubles, lane8, octet_mask, true, sink);
+}
 
 __global__ void __launch_bounds__(128) k_elasticity_hex8_atomic(MeshView mv, ElasticityHex8Params prm, Outputs out) {
     __shared__ double stage[16 * kHexStageDoubles];
@@ -930,7 +972,12 @@ static int launch(const MeshDev& d, const typename Op::Params& prm, const Output
         const unsigned grid = (unsigned)((d.nelems + 127) / 128);
         k_assemble_atomic<Op><<<grid, 128, 0, st>>>(mv, prm, out);
     } else {
-        return launch_tile<Op, 128, MINB>(const_cast<MeshDev&>(d), mv, prm, out, st);
+        if constexpr (Op::M <= 2) {
+            return launch_tile<Op, 128, MINB>(const_cast<MeshDev&>(d), mv, prm, out, st);
+        } else {
+            set_error("no tile kernel for %d dofs per node", Op::M);
+            return PFG_ERR_UNSUPPORTED;
+        }
     }
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
@@ -1128,6 +1175,112 @@ extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev
     PFG_CUDA_TRY(cudaFreeAsync(is_fixed, st));
     PFG_CUDA_TRY(cudaFreeAsync(u0, st));
     return PFG_OK;
+}
+
+template <class Op>
+static int launch_elements(const MeshDev& d, const typename Op::Params& prm, double* Ke0, double* Ke1, double* fe,
+                           cudaStream_t st) {
+    const MeshView mv = view_of(d);
+    k_element_matrices<Op><<<(unsigned)((d.nelems + 127) / 128), 128, 0, st>>>(mv, prm, Ke0, Ke1, fe);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+extern "C" int pfg_element_matrices(pfg_mesh* mesh, int physics, const double* field_dev, double field_const,
+                                    const double* params_host, int nparams, double* Ke_dev, double* Ke2_dev,
+                                    double* fe_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    cudaStream_t st = (cudaStream_t)stream;
+    auto par = [&](int i, double dflt) { return (params_host && i < nparams) ? params_host[i] : dflt; };
+    switch (physics) {
+        case PFG_PHYS_POISSON: {
+            if (d.m != 1 || !Ke_dev) break;
+            if (d.nne == 4) {
+                PoissonOp<4>::Params prm{material_of(field_dev, field_const, par(0, 0.0))};
+                return launch_elements<PoissonOp<4>>(d, prm, Ke_dev, nullptr, nullptr, st);
+            }
+            PoissonOp<8>::Params prm{material_of(field_dev, field_const, par(0, 0.0))};
+            return launch_elements<PoissonOp<8>>(d, prm, Ke_dev, nullptr, nullptr, st);
+        }
+        case PFG_PHYS_ELASTICITY: {
+            if (d.m != d.ndims || !Ke_dev) break;
+            const double p = par(0, 0.0), E = par(1, 10.0), nu = par(2, 0.3);
+            if (d.nne == 4) {
+                const double f = E / (1.0 - nu * nu);
+                ElasticityQuad4Op::Params prm{material_of(field_dev, field_const, p), f, f * nu, f * 0.5 * (1.0 - nu)};
+                return launch_elements<ElasticityQuad4Op>(d, prm, Ke_dev, nullptr, nullptr, st);
+            }
+            const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+            ElasticityHex8Params prm{material_of(field_dev, field_const, p), f * (1.0 - nu), f * nu, f * (0.5 - nu)};
+            k_elasticity_hex8_matrices<<<(unsigned)((d.nelems + 15) / 16), 128, 0, st>>>(view_of(d), prm, Ke_dev);
+            PFG_CUDA_TRY(cudaGetLastError());
+            return PFG_OK;
+        }
+        case PFG_PHYS_HELMHOLTZ: {
+            if (d.m != 1 || (!Ke_dev && !Ke2_dev)) break;
+            const double r0 = par(0, 0.0);
+            if (d.nne == 4) {
+                HelmholtzOp<4>::Params prm{r0 * r0};
+                return launch_elements<HelmholtzOp<4>>(d, prm, Ke_dev, Ke2_dev, nullptr, st);
+            }
+            HelmholtzOp<8>::Params prm{r0 * r0};
+            return launch_elements<HelmholtzOp<8>>(d, prm, Ke_dev, Ke2_dev, nullptr, st);
+        }
+        case PFG_PHYS_NLPOISSON: {
+            if (d.m != 1 || d.nne != 4 || !field_dev || nparams < 1 || nparams > kMaxXdv || (!Ke_dev && !fe_dev)) break;
+            NlPoissonQuad4Op::Params prm;
+            prm.u = field_dev;
+            prm.nxdv = nparams;
+            double binom = 1.0;
+            for (int k = 0; k < kMaxXdv; ++k) {
+                prm.coef[k] = (k < nparams) ? params_host[k] * binom : 0.0;
+                if (k < nparams - 1) binom = binom * (double)(nparams - 1 - k) / (double)(k + 1);
+            }
+            return launch_elements<NlPoissonQuad4Op>(d, prm, Ke_dev, nullptr, fe_dev, st);
+        }
+        default:
+            set_error("pfg_element_matrices: unknown physics %d", physics);
+            return PFG_ERR_INVALID;
+    }
+    set_error("pfg_element_matrices: physics %d does not fit this mesh handle or an output is missing", physics);
+    return PFG_ERR_INVALID;
+}
+
+extern "C" int pfg_scatter_matrix(pfg_mesh* mesh, const double* Ke_dev, double* vals_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!Ke_dev || !vals_dev) {
+        set_error("pfg_scatter_matrix: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    cudaStream_t st = (cudaStream_t)stream;
+    Outputs out{{vals_dev, nullptr}, nullptr};
+    if (d.nne == 4 && d.m == 1) return launch<ScatterMatOp<4, 1>, 128, 4>(d, {Ke_dev}, out, gather, st);
+    if (d.nne == 4 && d.m == 2) return launch<ScatterMatOp<4, 2>, 128, 2>(d, {Ke_dev}, out, gather, st);
+    if (d.nne == 8 && d.m == 1) return launch<ScatterMatOp<8, 1>, 128, 2>(d, {Ke_dev}, out, gather, st);
+    // hex8 with three dofs per node: slot-indexed atomic scatter (no tile plan for 24 x 24 element matrices)
+    if (mode == PFG_MODE_GATHER) {
+        set_error("pfg_scatter_matrix: hex8 elasticity handles scatter supplied matrices with atomics only");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    return launch<ScatterMatOp<8, 3>, 128, 1>(d, {Ke_dev}, out, false, st);
+}
+
+extern "C" int pfg_scatter_vector(pfg_mesh* mesh, const double* fe_dev, double* rhs_dev, int mode, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || !fe_dev || !rhs_dev) {
+        set_error("pfg_scatter_vector: needs ndof_per_node == 1, element vectors and an output");
+        return PFG_ERR_INVALID;
+    }
+    bool gather;
+    PFG_TRY(resolve_mode(d, mode, &gather));
+    Outputs out{{nullptr, nullptr}, rhs_dev};
+    if (d.nne == 4) return launch<ScatterVecOp<4>, 128, 4>(d, {fe_dev}, out, gather, (cudaStream_t)stream);
+    return launch<ScatterVecOp<8>, 128, 4>(d, {fe_dev}, out, gather, (cudaStream_t)stream);
 }
 
 __global__ void k_add_indexed(double* __restrict__ vals, const int64_t* __restrict__ idx, const double* __restrict__ src,

@@ -517,6 +517,76 @@ struct PoissonRhsOp {  // LinearPoisson._compute_element_rhs (pyfem.py:1137-1173
 };
 
 // ---------------------------------------------------------------------------------------------
+// Caller-supplied element matrices / vectors: the scatter of ModelBase._assemble_jacobian (pyfem.py:920-931) and
+// ModelBase._assemble_rhs (pyfem.py:860-875) on their own -- the slot the reference's A2DWrapper uses
+// (pyfem.py:2255-2277: a native plugin fills the element Jacobians, pyfem scatters them).
+// ---------------------------------------------------------------------------------------------
+template <int NNE_, int M_>
+struct ScatterMatOp {
+    static constexpr int NNE = NNE_, M = M_, NMAT = 1, NVEC = 0, D = NNE_ * M_;
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr bool NEEDS_ELEM = true, SYM = false;  // nothing is assumed about the supplied matrices
+    struct Params {
+        const double* Ke;  // (nelems, D, D) row-major
+    };
+    __host__ __device__ __forceinline__ static const double* field(const Params&) { return nullptr; }
+    template <class Sink>
+    PFG_DEV static void run(const Params& prm, const double (&)[NNE][DIM], const double (&)[NNE], int64_t elem,
+                            Sink& sink) {
+        const double* __restrict__ K = prm.Ke + elem * (int64_t)(D * D);
+#pragma unroll
+        for (int a = 0; a < NNE; ++a)
+#pragma unroll
+            for (int b = 0; b < NNE; ++b) {
+                double blk[M * M];
+#pragma unroll
+                for (int al = 0; al < M; ++al)
+#pragma unroll
+                    for (int be = 0; be < M; ++be) blk[al * M + be] = __ldg(K + (a * M + al) * D + b * M + be);
+                sink.block(0, a, b, blk);
+            }
+    }
+};
+
+template <int NNE_>
+struct ScatterVecOp {  // rhs[conn[e, a]] += fe[e, a]
+    static constexpr int NNE = NNE_, M = 1, NMAT = 0, NVEC = 1;
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr bool NEEDS_ELEM = true, SYM = false;
+    struct Params {
+        const double* fe;  // (nelems, NNE)
+    };
+    __host__ __device__ __forceinline__ static const double* field(const Params&) { return nullptr; }
+    template <class Sink>
+    PFG_DEV static void run(const Params& prm, const double (&)[NNE][DIM], const double (&)[NNE], int64_t elem,
+                            Sink& sink) {
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) sink.vec(a, __ldg(prm.fe + elem * NNE + a));
+    }
+};
+
+// Element matrices / vectors to global memory, (nelems, D, D) and (nelems, NNE): the reference's
+// _compute_element_jacobian / _compute_element_rhs outputs (Ke_mat, rhs_e) for callers that want them.
+template <class Op>
+struct GlobalSink {
+    static constexpr int NNE = Op::NNE, M = Op::M, D = NNE * M;
+    double* Ke[2];  // per matrix (may be null)
+    double* fe;     // (may be null)
+    int64_t e;
+    PFG_DEV void block(int mat, int a, int b, const double* blk) const {
+        if (Ke[mat] == nullptr) return;
+        double* dst = Ke[mat] + e * (int64_t)(D * D) + (a * M) * D + b * M;
+#pragma unroll
+        for (int al = 0; al < M; ++al)
+#pragma unroll
+            for (int be = 0; be < M; ++be) dst[al * D + be] = blk[al * M + be];
+    }
+    PFG_DEV void vec(int a, double v) const {
+        if (fe != nullptr) fe[e * NNE + a] = v;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
 // hex8 3-D elasticity: 8 threads per element.  Thread t first acts as quadrature point t (geometry
 // into shared staging), then as local row node t (3 x 24 row block from 72 accumulators).
 // LinearElasticity._compute_element_jacobian, 3-D branch (pyfem.py:2000-2011, 2017-2026, 1752-1757).

@@ -226,6 +226,52 @@ class DeviceMesh:
             _lib.check(self._lib.pfg_spmv(self._handle, _ptr(vals), _ptr(x), _ptr(out), self._stream()))
         return out
 
+    # ---- the scatter on its own, and element matrices without the scatter ------------------------------
+    @property
+    def ndof_per_elem(self):
+        return self.nnodes_per_elem * self.ndof_per_node
+
+    def scatter_matrix(self, Ke, out=None, mode="auto"):
+        """ModelBase._assemble_jacobian(Ke_mat) (pyfem.py:920-931) for caller-supplied element matrices
+        (nelems, D, D): CSR values on the device."""
+        torch = _torch()
+        D = self.ndof_per_elem
+        Ke = self._dev_f64(Ke, self.nelems * D * D, "element matrices")
+        out = self.new_values() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_scatter_matrix(self._handle, _ptr(Ke), _ptr(out), _lib.MODES[mode], self._stream()))
+        return out
+
+    def scatter_vector(self, fe, out=None, mode="auto"):
+        """ModelBase._assemble_rhs(rhs_e, rhs) (pyfem.py:860-875) for scalar handles: fe is (nelems, nnodes_per_elem)."""
+        torch = _torch()
+        fe = self._dev_f64(fe, self.nelems * self.nnodes_per_elem, "element vectors")
+        out = self.new_vector() if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_scatter_vector(self._handle, _ptr(fe), _ptr(out), _lib.MODES[mode], self._stream()))
+        return out
+
+    def element_matrices(self, physics, field=None, field_const=1.0, params=(), want_Ke=True, want_Ke2=False,
+                         want_fe=False):
+        """Element matrices / vectors without the scatter (the reference's Ke_mat, Re, rhs_e): device tensors
+        (nelems, D, D) and (nelems, nnodes_per_elem).  physics: "poisson" params (p,), "elasticity" params (p, E, nu),
+        "helmholtz" params (r0,) [Ke2 = Re], "nlpoisson" params = xdv, field = u [fe = residual]."""
+        torch = _torch()
+        code = {"poisson": _lib.PHYS_POISSON, "elasticity": _lib.PHYS_ELASTICITY, "helmholtz": _lib.PHYS_HELMHOLTZ,
+                "nlpoisson": _lib.PHYS_NLPOISSON}[physics]
+        D = self.ndof_per_elem
+        f = None if field is None else self._dev_f64(field, self.nnodes, "nodal field")
+        par = np.ascontiguousarray(np.asarray(params, dtype=np.float64).reshape(-1))
+        mk = lambda shape: torch.empty(shape, dtype=torch.float64, device=self.device)
+        Ke = mk((self.nelems, D, D)) if want_Ke else None
+        Ke2 = mk((self.nelems, D, D)) if want_Ke2 else None
+        fe = mk((self.nelems, self.nnodes_per_elem)) if want_fe else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_element_matrices(
+                self._handle, code, _ptr(f), float(field_const), par.ctypes.data_as(ctypes.POINTER(c_double)),
+                int(par.size), _ptr(Ke), _ptr(Ke2), _ptr(fe), self._stream()))
+        return Ke, Ke2, fe
+
     # ---- multi-GPU reduce variant (halo.py) ---------------------------------------------------------
     def set_element_mask(self, skip):
         """Elements with skip != 0 stay in the pattern but are not integrated by this handle (another rank ships

@@ -88,6 +88,33 @@ class ModelBase:
     def compute_jacobian(self):
         raise NotImplementedError
 
+    # ---- the reference's internal two-step interface (element matrices, then scatter) ---------------------
+    @property
+    def Ke_mat(self):
+        """(nelems, D, D) element-matrix buffer of the reference (pyfem.py:721), allocated on first use: the fused
+        path never needs it, but scripts such as performance_test.py:52 and plugin back-ends in the style of
+        A2DWrapper (pyfem.py:2255-2277) fill it and hand it to _assemble_jacobian."""
+        if getattr(self, "_Ke_mat", None) is None:
+            D = self.nnodes_per_elem * self.ndof_per_node
+            self._Ke_mat = np.zeros((self.nelems, D, D))
+        return self._Ke_mat
+
+    def _assemble_jacobian(self, Ke_mat):
+        """Scatter caller-supplied element matrices into the global CSR (pyfem.py:920-931)."""
+        return self._to_scipy(self.mesh.scatter_matrix(Ke_mat, mode=self.scatter))
+
+    def _assemble_rhs(self, rhs_e, rhs):
+        """rhs[conn] += rhs_e, after zeroing rhs (pyfem.py:860-875); scalar models."""
+        rhs[:] = self.mesh.scatter_vector(rhs_e, mode=self.scatter).cpu().numpy()
+        return rhs
+
+    def _element_matrices(self, physics, out, **kw):
+        Ke, _, _ = self.mesh.element_matrices(physics, **kw)
+        if out is not None:
+            out[...] = Ke.cpu().numpy()
+            return out
+        return Ke
+
     # ---- helpers -------------------------------------------------------------------------------------
     def _to_scipy(self, vals):
         return self.mesh.to_scipy(vals)
@@ -147,6 +174,11 @@ class LinearPoisson(ModelBase):
 
     def compute_jacobian(self, rho=1.0):
         return self._to_scipy(self.compute_jacobian_device(rho))
+
+    def _compute_element_jacobian(self, Ke_mat, rho=1.0):
+        """Element matrices only (pyfem.py:1188-1217); the reference reads rho from the last material update."""
+        rho_t, rho_c = self.mesh._rho(rho)
+        return self._element_matrices("poisson", Ke_mat, field=rho_t, field_const=rho_c, params=(self.p,))
 
     def _source_at_quads(self):
         """g(x_q): the user callable runs on a CUDA tensor of quadrature coordinates; callables that need
@@ -215,6 +247,12 @@ class LinearElasticity(ModelBase):
     def compute_jacobian_device(self, rho=1.0, out=None):
         _check_real(rho)
         return self.mesh.assemble_elasticity(rho, self.p, self.E, self.nu, out=out, mode=self.scatter)
+
+    def _compute_element_jacobian(self, Ke_mat, rho=1.0):
+        """Element matrices only (pyfem.py:2029-2068)."""
+        rho_t, rho_c = self.mesh._rho(rho)
+        return self._element_matrices("elasticity", Ke_mat, field=rho_t, field_const=rho_c,
+                                      params=(self.p, self.E, self.nu))
 
     def compute_jacobian(self, rho=1.0):
         return self._to_scipy(self.compute_jacobian_device(rho))
