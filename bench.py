@@ -26,6 +26,11 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv:
+    # the CPU arm may use every host thread numpy / BLAS can use: torchrun pins OMP_NUM_THREADS=1 for its ranks
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np  # noqa: E402
 
 METRIC = "assembled elements/sec (fp64 Ke + CSR scatter)"
