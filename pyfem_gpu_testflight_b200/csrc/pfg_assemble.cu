@@ -474,29 +474,33 @@ PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsi
                 const int row_bytes = (int)tn.k * 16;  // k neighbours: 2k doubles per dof row
                 unsigned char* o = reinterpret_cast<unsigned char*>(image) + (size_t)tn.aux * 16;
                 double a00 = 0.0, a01 = 0.0, a10 = 0.0, a11 = 0.0, keep = 0.0;
-                auto add = [&](unsigned code) {  // code in the low 16 bits
-                    const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code & 0xFFFCu) << 2));
-                    const double2 v0 = q[0], v1 = q[1];
-                    const bool tr = St::SYM && (code & 1u);
-                    a00 = fma(a00, keep, v0.x);
-                    a01 = fma(a01, keep, tr ? v1.x : v0.y);
-                    a10 = fma(a10, keep, tr ? v0.y : v1.x);
-                    a11 = fma(a11, keep, v1.y);
-                    const bool end = (code & 2u) != 0;  // last contribution of this block
-                    if (end) {
-                        *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
-                        *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
-                        o += 16;
-                    }
-                    keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
-                };
 #pragma unroll 1
                 for (int g = 0; g < gmax; ++g) {
                     const uint4 c = cp[(size_t)g * n_nodes];
-                    add(c.x & 0xFFFFu), add(c.x >> 16);
-                    add(c.y & 0xFFFFu), add(c.y >> 16);
-                    add(c.z & 0xFFFFu), add(c.z >> 16);
-                    add(c.w & 0xFFFFu), add(c.w >> 16);
+                    const unsigned code[8] = {c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16,
+                                              c.z & 0xFFFFu, c.z >> 16, c.w & 0xFFFFu, c.w >> 16};
+                    // all sixteen loads of the group are issued before the dependent sums start
+                    double2 v0[8], v1[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double2* __restrict__ q = reinterpret_cast<const double2*>(stage_b + ((code[j] & 0xFFFCu) << 2));
+                        v0[j] = q[0], v1[j] = q[1];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const bool tr = St::SYM && (code[j] & 1u);
+                        a00 = fma(a00, keep, v0[j].x);
+                        a01 = fma(a01, keep, tr ? v1[j].x : v0[j].y);
+                        a10 = fma(a10, keep, tr ? v0[j].y : v1[j].x);
+                        a11 = fma(a11, keep, v1[j].y);
+                        const bool end = (code[j] & 2u) != 0;  // last contribution of this block
+                        if (end) {
+                            *reinterpret_cast<double2*>(o) = make_double2(a00, a01);
+                            *reinterpret_cast<double2*>(o + row_bytes) = make_double2(a10, a11);
+                            o += 16;
+                        }
+                        keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
+                    }
                 }
             } else {
                 double* o = image + tn.aux;
