@@ -207,6 +207,7 @@ def main():
     import torch
     import torch.distributed as dist
     import pyfem_gpu_testflight_b200 as pf
+    from pyfem_gpu_testflight_b200 import _lib
     from pyfem_gpu_testflight_b200.partition import slab_node_ranges, structured_slab
 
     if not torch.cuda.is_available():
@@ -350,14 +351,19 @@ def main():
             traffic = json.load(open(tpath)).get(f"{args.workload}:{'gather' if mesh.nchunks else 'atomic'}")
         except Exception:
             traffic = None
+    hex_rows = m == 3 and args.mode != "atomic" and mesh.info(_lib.INFO_HEX_ROWS) == 1
+    if args.mode == "atomic" or not mesh.nchunks or (m == 3 and not hex_rows and args.mode == "auto"):
+        scatter_name = "atomic"
+    else:
+        scatter_name = "gather (geometry pass + chunk-row pass, no atomics)" if hex_rows else "gather"
+    own_kernels_per_step = 2 if hex_rows else 1
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
                    "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
-                   "csr_nnz_rank0": mesh.nnz, "scatter": ("atomic" if (args.mode == "atomic" or not mesh.nchunks or (args.mode == "auto" and m == 3))
-                                                             else "gather"),
+                   "csr_nnz_rank0": mesh.nnz, "scatter": scatter_name,
                    "partition": (f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
                                  f"send/recv + indexed add" if reducer is not None else
                                  f"row slabs x{world}, ghost-element layer, no data-path collective"),
@@ -371,7 +377,7 @@ def main():
         "clocks": clocks,
         # own kernels per step: the assembly kernel; the reduce variant adds one halo assembly per neighbour it
         # sends to and one indexed add per neighbour it receives from (rank 0's count)
-        "gpu_launches": args.steps * (1 + (len(reducer.halo) + len(reducer.recv) if reducer is not None else 0)),
+        "gpu_launches": args.steps * (own_kernels_per_step + (len(reducer.halo) + len(reducer.recv) if reducer is not None else 0)),
     }
     if e2e is not None:
         line["e2e"] = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}

@@ -70,7 +70,8 @@ typedef enum pfg_info {
     PFG_INFO_PLAN_BYTES = 6, /* device bytes of plan metadata read per assembly */
     PFG_INFO_DEVICE_BYTES = 7,/* device bytes held by the handle */
     PFG_INFO_MAX_ROW_BLOCKS = 8, /* largest number of neighbour nodes of any owned node */
-    PFG_INFO_MAX_VALENCE = 9     /* largest number of elements around any node */
+    PFG_INFO_MAX_VALENCE = 9,    /* largest number of elements around any node */
+    PFG_INFO_HEX_ROWS = 10       /* 1: hex8 elasticity runs the owner-computes geometry + chunk-row passes in AUTO / GATHER mode */
 } pfg_info;
 
 PFG_API int pfg_abi_version(void);

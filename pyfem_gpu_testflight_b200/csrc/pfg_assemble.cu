@@ -368,6 +368,9 @@ PFG_DEV void cp_async_16(void* smem_dst, const void* gmem_src) {
 PFG_DEV void cp_async_8(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+PFG_DEV void cp_async_4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 PFG_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 PFG_DEV void cp_async_wait() {
@@ -507,25 +510,30 @@ PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsi
                 double acc[NMAT], keep = 0.0;
 #pragma unroll
                 for (int mt = 0; mt < NMAT; ++mt) acc[mt] = 0.0;
-                auto add = [&](unsigned code) {
-                    const double* __restrict__ q = reinterpret_cast<const double*>(stage_b + ((code & 0xFFFCu) << 1));
-#pragma unroll
-                    for (int mt = 0; mt < NMAT; ++mt) acc[mt] = fma(acc[mt], keep, q[mt * St::NB]);
-                    const bool end = (code & 2u) != 0;
-                    if (end) {
-#pragma unroll
-                        for (int mt = 0; mt < NMAT; ++mt) o[mt * image_stride] = acc[mt];
-                        o += 1;
-                    }
-                    keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
-                };
 #pragma unroll 1
                 for (int g = 0; g < gmax; ++g) {
                     const uint4 c = cp[(size_t)g * n_nodes];
-                    add(c.x & 0xFFFFu), add(c.x >> 16);
-                    add(c.y & 0xFFFFu), add(c.y >> 16);
-                    add(c.z & 0xFFFFu), add(c.z >> 16);
-                    add(c.w & 0xFFFFu), add(c.w >> 16);
+                    const unsigned code[8] = {c.x & 0xFFFFu, c.x >> 16, c.y & 0xFFFFu, c.y >> 16,
+                                              c.z & 0xFFFFu, c.z >> 16, c.w & 0xFFFFu, c.w >> 16};
+                    double v[8][NMAT];  // the group's loads are issued before the dependent sums start
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const double* __restrict__ q = reinterpret_cast<const double*>(stage_b + ((code[j] & 0xFFFCu) << 1));
+#pragma unroll
+                        for (int mt = 0; mt < NMAT; ++mt) v[j][mt] = q[mt * St::NB];
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                        for (int mt = 0; mt < NMAT; ++mt) acc[mt] = fma(acc[mt], keep, v[j][mt]);
+                        const bool end = (code[j] & 2u) != 0;
+                        if (end) {
+#pragma unroll
+                            for (int mt = 0; mt < NMAT; ++mt) o[mt * image_stride] = acc[mt];
+                            o += 1;
+                        }
+                        keep = __hiloint2double(end ? 0 : 0x3FF00000, 0);
+                    }
                 }
             }
         }
@@ -772,6 +780,198 @@ __global__ void __launch_bounds__(THREADS) k_elasticity_hex8_gather(MeshView mv,
     __syncthreads();
     sm.wait_metadata();
     gather_phase_b<ElasticityHex8GatherOp>(mv, h, sm.nodes, sm.plan, sm.rb, nullptr, out);
+}
+
+// ---- hex8 3-D elasticity, owner-computes: geometry pass + node-row pass -----------------------------------
+// Pass 1: one lane per (element, quadrature point) -> hex_geo[(e*8 + q)*10 ..] (adjugate of J and s_q).
+__global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHex8Params prm, double* __restrict__ geo) {
+    const int64_t t = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t e = t >> 3;
+    if (e >= mv.nelems) return;
+    int nodes[8];
+    const int4 v0 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e);
+    const int4 v1 = __ldg(reinterpret_cast<const int4*>(mv.conn) + 2 * e + 1);
+    nodes[0] = v0.x, nodes[1] = v0.y, nodes[2] = v0.z, nodes[3] = v0.w;
+    nodes[4] = v1.x, nodes[5] = v1.y, nodes[6] = v1.z, nodes[7] = v1.w;
+    const bool skip = mv.elem_skip != nullptr && mv.elem_skip[e];
+    hex8_geometry_point(mv, prm.mat, nodes, (int)(t & 7), skip, geo + t * kHexGeoDoubles);
+}
+
+// Pass 2: persistent CTAs over contiguous ranges of row chunks (first-format plan: ~28 nodes and the element
+// records touching them).  A producer warp brings the records' geometry into a two-stage shared-memory ring by
+// TMA bulk copies (640 B each, full / empty mbarriers); seven consumer warps free-run over the chunks.  Eight
+// lanes serve a chunk node, one per incident element (a node of this path has at most eight).  A lane forms its
+// element's 3 x 24 row block for the node and adds the 3 x 3 blocks into the warp's shared-memory image of its
+// four nodes' CSR rows at the slots the rank map gives; the lanes of a node take the same local column index at
+// the same time, which puts them on different neighbours (checked when the mesh handle is built:
+// MeshDev::hex_rows_ok).  Each node's rows leave as one contiguous run of the CSR values.  Node and incidence
+// tables of the next chunk are fetched while the current one is computed.  No atomics, no zero-fill of the
+// output, every CSR value written once, bitwise reproducible.
+#ifndef PFG_HEX_NB
+#define PFG_HEX_NB 4  // column nodes per pass over the quadrature points: two passes with 36 running sums each
+#endif                // (no spills, 3.98 ms for 128^3 hex) beat one pass with 72 (4.16 ms)
+constexpr int kHexRowsThreads = 256, kHexRowWarps = kHexRowsThreads / 32 - 1;
+constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
+constexpr int kHexGeoStride = 8 * kHexGeoDoubles + 2;  // doubles per staged record: 656 B keeps 16-byte reads of
+                                                       // consecutive records on different banks
+
+PFG_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+template <int B0, int NB>
+PFG_DEV void hex8_rows_part(const ElasticityHex8Params& prm, const double* __restrict__ geo_e, double sx8, double sy8,
+                            double sz8, bool active, double* __restrict__ rows, int k3, uint2 ranks) {
+    double P[NB][3][3];
+    if (active) hex8_row_products<B0, NB>(geo_e, sx8, sy8, sz8, P);
+#pragma unroll
+    for (int bb = 0; bb < NB; ++bb) {
+        if (active) {
+            double blk[9];
+            hex8_apply_c0(prm, P[bb], blk);
+            const unsigned rk = (B0 + bb < 4) ? ranks.x : ranks.y;  // four 8-bit ranks per word
+            double* dst = rows + 3 * (int)((rk >> (8 * ((B0 + bb) & 3))) & 0xFFu);
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) dst[i * k3 + j] += blk[i * 3 + j];
+        }
+        __syncwarp();  // the next column index may land on a block another lane of the node has just updated
+    }
+}
+
+struct HexRowsCfg {
+    int off_geo, geo_stage_bytes;  // two geometry stages
+    int off_image, image_stride;   // per consumer warp: four nodes x image_stride doubles (9 * max neighbours)
+    int off_meta;                  // per consumer thread 2 x 32 B of node / incidence tables, per warp 2 x 8 B
+    int nchunks;
+};
+
+struct HexLaneMeta {  // what a lane needs for its (node, incident element) pair
+    int64_t gslot;    // first CSR value of the node
+    int k9;           // 9 * neighbours of the node (0: no node)
+    int ra;           // record * 8 + local node, 0xFFFF: no incidence
+    uint2 ranks;      // rank[(e*8 + a)*8 + 0..7]
+};
+
+__global__ void __launch_bounds__(kHexRowsThreads, 1)
+    k_hex8_chunk_rows(MeshView mv, ElasticityHex8Params prm, const double* __restrict__ geo,
+                      const uint32_t* __restrict__ inc_rec8, const uint2* __restrict__ inc_ranks8,
+                      double* __restrict__ vals, HexRowsCfg cfg) {
+    extern __shared__ __align__(128) unsigned char hex_smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hex_smem);  // [0..1] stage full, [2..3] stage empty
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
+    const int nloc = (int)((int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x - c_begin);
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
+        mbar_init(&bars[2], kHexRowWarps), mbar_init(&bars[3], kHexRowWarps);
+    }
+    __syncthreads();
+    if (warp == kHexRowWarps) {
+        // ---- producer warp: geometry of chunk i's records -> stage i & 1
+        for (int i = 0; i < nloc; ++i) {
+            const int s = i & 1, f = i >> 1;
+            const ChunkHdr h = mv.chunks[c_begin + i];
+            const int e_lo = ((int)h.n_recs > lane) ? __ldg(mv.rec_elem + h.rec_begin + lane) : 0;
+            mbar_wait(&bars[2 + s], (f & 1) ^ 1);  // consumers have left the stage's previous chunk
+            if (lane == 0) mbar_expect_tx(&bars[s], h.n_recs * (uint32_t)kHexGeoBytes);
+            __syncwarp();
+            unsigned char* stage = hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes;
+            for (int r = lane; r < (int)h.n_recs; r += 32) {
+                const int e = (r < 32) ? e_lo : __ldg(mv.rec_elem + h.rec_begin + r);
+                tma_load_1d(stage + (size_t)r * (kHexGeoStride * 8), geo + (size_t)e * (8 * kHexGeoDoubles),
+                            (uint32_t)kHexGeoBytes, &bars[s]);
+            }
+        }
+        return;
+    }
+    // ---- consumer warps
+    const int j = lane & 7;
+    const int64_t nown = mv.own_end - mv.own_begin;
+    double* image = reinterpret_cast<double*>(hex_smem + cfg.off_image) + (size_t)warp * 4 * cfg.image_stride;
+    double* rows = image + (size_t)(lane >> 3) * cfg.image_stride;
+    // Node / incidence tables travel one chunk ahead by cp.async into a per-thread slot (two buffers), the next
+    // chunk's (node_begin, n_nodes) into a per-warp slot: no register is held across a chunk's arithmetic.
+    unsigned char* meta_s = hex_smem + cfg.off_meta + (size_t)threadIdx.x * 64;
+    unsigned char* hd_s = hex_smem + cfg.off_meta + (size_t)kHexRowWarps * 32 * 64 + (size_t)warp * 16;
+    auto issue_meta = [&](int64_t first_slot, int i_chunk) {  // tables of local chunk i_chunk, whose nodes start at first_slot
+        const int buf = i_chunk & 1;
+        const int64_t slot = min(first_slot + warp * 4 + (lane >> 3), nown - 1);  // past the chunk: loaded, not used
+        cp_async_16(meta_s + buf * 32, mv.cnodes + slot);
+        cp_async_8(meta_s + buf * 32 + 16, inc_ranks8 + slot * 8 + j);
+        cp_async_4(meta_s + buf * 32 + 24, inc_rec8 + slot * 8 + j);
+        if (lane == 0 && i_chunk < nloc) cp_async_8(hd_s + buf * 8, mv.chunks + c_begin + i_chunk);
+        cp_async_commit();
+    };
+    auto read_meta = [&](uint2 hd, int buf) -> HexLaneMeta {
+        HexLaneMeta m;
+        m.gslot = 0, m.k9 = 0, m.ra = 0xFFFF, m.ranks = make_uint2(0u, 0u);
+        if (warp * 4 + (lane >> 3) < (int)hd.y) {
+            const ChunkNode cn = *reinterpret_cast<const ChunkNode*>(meta_s + buf * 32);
+            m.gslot = cn.gslot;
+            m.k9 = (int)cn.k * 9;
+            m.ranks = *reinterpret_cast<const uint2*>(meta_s + buf * 32 + 16);
+            m.ra = (int)*reinterpret_cast<const uint32_t*>(meta_s + buf * 32 + 24);
+        }
+        return m;
+    };
+    auto load_meta = [&](uint2 hd, int p0) -> HexLaneMeta {  // direct loads: second round of a large chunk
+        HexLaneMeta m;
+        m.gslot = 0, m.k9 = 0, m.ra = 0xFFFF, m.ranks = make_uint2(0u, 0u);
+        const int p = p0 + (lane >> 3);
+        if (p < (int)hd.y) {
+            const size_t slot = (size_t)hd.x + p;
+            const ChunkNode cn = mv.cnodes[slot];
+            m.gslot = cn.gslot;
+            m.k9 = (int)cn.k * 9;
+            m.ra = (int)__ldg(inc_rec8 + slot * 8 + j);
+            m.ranks = __ldg(inc_ranks8 + slot * 8 + j);
+        }
+        return m;
+    };
+    if (nloc > 0) issue_meta((int64_t)__ldg(&mv.chunks[c_begin].node_begin), 0);
+    for (int i = 0; i < nloc; ++i) {
+        const int s = i & 1, f = i >> 1;
+        cp_async_wait<0>();
+        __syncwarp();
+        const uint2 hd = *reinterpret_cast<const uint2*>(hd_s + s * 8);  // (node_begin, n_nodes)
+        HexLaneMeta meta = read_meta(hd, s);
+        issue_meta((int64_t)hd.x + hd.y, i + 1);
+        const double* geo_s = reinterpret_cast<const double*>(hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes);
+        bool waited = false;
+        for (int p0 = warp * 4; p0 < (int)hd.y; p0 += kHexRowWarps * 4) {
+            if (p0 != warp * 4) meta = load_meta(hd, p0);
+            for (int t = lane; t < 4 * cfg.image_stride; t += 32) image[t] = 0.0;
+            const bool active = meta.ra != 0xFFFF;
+            const int a = meta.ra & 7;
+            const double sx8 = ((a & 3) == 1 || (a & 3) == 2) ? 0.125 : -0.125;  // local coordinate signs / 8
+            const double sy8 = ((a & 3) >= 2) ? 0.125 : -0.125, sz8 = (a >= 4) ? 0.125 : -0.125;
+            const double* geo_e = geo_s + (size_t)(active ? (meta.ra >> 3) : 0) * kHexGeoStride;
+            if (!waited) mbar_wait(&bars[s], f & 1);  // the chunk's geometry has landed
+            waited = true;
+            __syncwarp();
+#if PFG_HEX_NB == 8
+            hex8_rows_part<0, 8>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
+#else
+            hex8_rows_part<0, 4>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
+            hex8_rows_part<4, 4>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
+#endif
+            // the warp's four nodes, one after the other: 256 contiguous bytes per store instruction
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+                const int64_t g = __shfl_sync(0xffffffffu, meta.gslot, q4 * 8);
+                const int n = __shfl_sync(0xffffffffu, meta.k9, q4 * 8);
+                const double* __restrict__ src = image + (size_t)q4 * cfg.image_stride;
+                for (int t = lane; t < n; t += 32) __stcs(vals + g + t, src[t]);
+            }
+            __syncwarp();  // the image is zeroed again by the next round
+        }
+        if (!waited) mbar_wait(&bars[s], f & 1);  // keep the ring in step even without a node in this chunk
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[2 + s]);
+    }
+    cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1066,8 +1266,46 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
     const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
     ElasticityHex8Params prm{material_of(rho_dev, rho_const, p), f * (1.0 - nu), f * nu, f * (0.5 - nu)};
     const MeshView mv = view_of(d);
-    // measured on B200 (128^3 hex): the slot-indexed atomic scatter (6.4 ms) beats the first-format gather kernel
-    // (9.1 ms; 2.3x halo recompute of its small 3-D chunks), so AUTO means atomic here until that kernel is rebuilt
+    const bool rows_ok = d.hex_rows_ok == 1 && d.nchunks > 0 && d.inc_rec8 && getenv("PFG_HEX_ROWS") == nullptr;
+    if (mode != PFG_MODE_ATOMIC && rows_ok) {
+        // owner-computes: geometry pass into the handle's scratch, then the chunk-row pass
+        MeshDev& dm = const_cast<MeshDev&>(d);
+        if (!dm.hex_geo) {
+            PFG_CUDA_TRY(cudaMalloc(&dm.hex_geo, (size_t)d.nelems * 8 * kHexGeoDoubles * sizeof(double)));
+            dm.device_bytes += d.nelems * 8 * kHexGeoDoubles * (int64_t)sizeof(double);
+        }
+        HexRowsCfg cfg;
+        cfg.image_stride = 9 * d.max_k;
+        cfg.nchunks = (int)d.nchunks;
+        cfg.off_geo = 128;
+        cfg.geo_stage_bytes = align16(d.max_chunk_recs * kHexGeoStride * 8);
+        cfg.off_image = cfg.off_geo + 2 * cfg.geo_stage_bytes;
+        cfg.off_meta = cfg.off_image + kHexRowWarps * 4 * cfg.image_stride * 8;
+        const size_t smem = (size_t)cfg.off_meta + (size_t)kHexRowWarps * (32 * 64 + 16);
+        if (smem > 227 * 1024) {
+            set_error("chunk staging of %zu bytes exceeds shared memory", smem);
+            return PFG_ERR_UNSUPPORTED;
+        }
+        static thread_local size_t cached_smem = 0;
+        if (cached_smem != smem) {
+            PFG_CUDA_TRY(cudaFuncSetAttribute(k_hex8_chunk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PFG_CUDA_TRY(cudaFuncSetAttribute(k_hex8_chunk_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            cached_smem = smem;
+        }
+        const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, d.sm_count);
+        static const bool debug = getenv("PFG_DEBUG") != nullptr;
+        if (debug)
+            fprintf(stderr, "[pfg] k_hex8_chunk_rows: %zu B smem (records<=%d, nodes<=%d), %lld chunks, grid %u\n", smem,
+                    d.max_chunk_recs, d.max_chunk_nodes, (long long)d.nchunks, grid);
+        k_hex8_geometry<<<(unsigned)((d.nelems * 8 + 255) / 256), 256, 0, st>>>(mv, prm, dm.hex_geo);
+        k_hex8_chunk_rows<<<grid, kHexRowsThreads, smem, st>>>(mv, prm, dm.hex_geo, d.inc_rec8,
+                                                               reinterpret_cast<const uint2*>(d.inc_ranks8), vals_dev, cfg);
+        PFG_CUDA_TRY(cudaGetLastError());
+        return PFG_OK;
+    }
+    // meshes the chunk-row pass does not cover (a node with more than eight elements or 48 neighbours, or two
+    // elements of a node that reach one neighbour through the same local index): the slot-indexed atomic scatter
+    // (measured on B200, 128^3 hex: 6.4 ms) beats the first-format gather kernel (9.1 ms), so AUTO means atomic
     if (mode == PFG_MODE_AUTO) gather = false;
     if (!gather) {
         PFG_TRY(zero_outputs(d, out, st));

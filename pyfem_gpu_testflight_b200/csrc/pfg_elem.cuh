@@ -711,4 +711,119 @@ PFG_DEV void elasticity_hex8_octet(const MeshView& mv, const ElasticityHex8Param
     __syncwarp(octet_mask);  // staging may be reused by the caller's next element
 }
 
+// ---------------------------------------------------------------------------------------------
+// hex8 3-D elasticity, owner-computes form (no atomics): a geometry pass stores the adjugate of J and the
+// quadrature weight s_q = c_q / det(J_q) per (element, quadrature point) -- 10 doubles -- and a row pass gives
+// every (node, incident element) pair one lane that forms the node's 3 x 24 row block of that element and adds
+// it into a shared-memory image of the node's CSR rows (pfg_assemble.cu: k_hex8_geometry, k_hex8_chunk_rows).
+// Same math as elasticity_hex8_octet above.
+// ---------------------------------------------------------------------------------------------
+constexpr int kHexGeoDoubles = 10;  // per (element, quadrature point): A[3][3] = det(J) inv(J), then s_q
+
+// lane = (element, quadrature point `q`): nodes are the element's eight corners
+PFG_DEV void hex8_geometry_point(const MeshView& mv, const Material& mat, const int (&nodes)[8], int q, bool skip,
+                                 double* __restrict__ out) {
+    double xe[8][3];
+    load_coords<8>(mv.X, nodes, xe);
+    const double qx = (q & 4) ? PFG_G : -PFG_G, qy = (q & 2) ? PFG_G : -PFG_G, qz = (q & 1) ? PFG_G : -PFG_G;
+    const double fx[2] = {1.0 - qx, 1.0 + qx}, fy[2] = {1.0 - qy, 1.0 + qy}, fz[2] = {1.0 - qz, 1.0 + qz};
+    double J[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) J[j][k] = 0.0;
+    double rq = 0.0;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        constexpr double e8 = 0.125;
+        const int ix = Elem<8>::sgn(a, 0) > 0 ? 1 : 0, iy = Elem<8>::sgn(a, 1) > 0 ? 1 : 0, iz = Elem<8>::sgn(a, 2) > 0 ? 1 : 0;
+        const double dn0 = (Elem<8>::sgn(a, 0) * e8) * (fy[iy] * fz[iz]);
+        const double dn1 = (Elem<8>::sgn(a, 1) * e8) * (fx[ix] * fz[iz]);
+        const double dn2 = (Elem<8>::sgn(a, 2) * e8) * (fx[ix] * fy[iy]);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            J[j][0] = fma(dn0, xe[a][j], J[j][0]);
+            J[j][1] = fma(dn1, xe[a][j], J[j][1]);
+            J[j][2] = fma(dn2, xe[a][j], J[j][2]);
+        }
+        if (mat.rho != nullptr) rq = fma(e8 * fx[ix] * (fy[iy] * fz[iz]), __ldg(mat.rho + nodes[a]), rq);
+    }
+    double A[3][3];
+    A[0][0] = J[1][1] * J[2][2] - J[1][2] * J[2][1];
+    A[0][1] = -(J[0][1] * J[2][2] - J[0][2] * J[2][1]);
+    A[0][2] = J[0][1] * J[1][2] - J[0][2] * J[1][1];
+    A[1][0] = -(J[1][0] * J[2][2] - J[1][2] * J[2][0]);
+    A[1][1] = J[0][0] * J[2][2] - J[0][2] * J[2][0];
+    A[1][2] = -(J[0][0] * J[1][2] - J[0][2] * J[1][0]);
+    A[2][0] = J[1][0] * J[2][1] - J[1][1] * J[2][0];
+    A[2][1] = -(J[0][0] * J[2][1] - J[0][1] * J[2][0]);
+    A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
+    const double det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
+    double cq;
+    if (mat.rho == nullptr) cq = mat.rho_const / (1.0 + mat.p * (1.0 - mat.rho_const));
+    else cq = rq * fast_rcp(fma(mat.p, 1.0 - rq, 1.0));
+    const double s = skip ? 0.0 : cq * fast_rcp(det);  // a masked element (another rank integrates it) adds zeros
+    double2* o = reinterpret_cast<double2*>(out);
+    o[0] = make_double2(A[0][0], A[0][1]);
+    o[1] = make_double2(A[0][2], A[1][0]);
+    o[2] = make_double2(A[1][1], A[1][2]);
+    o[3] = make_double2(A[2][0], A[2][1]);
+    o[4] = make_double2(A[2][2], s);
+}
+
+// lane = (row node, incident element): the row node's local coordinate signs (/ 8) are run-time values, the NB
+// column nodes B0 .. B0+NB-1 are compile time.  P[b][i][j] = sum_q s_q G_a,i G_b,j.
+// `geo_e` points at the element's 8 x 10 doubles in shared memory.
+template <int B0, int NB>
+PFG_DEV void hex8_row_products(const double* __restrict__ geo_e, double sx8, double sy8, double sz8,
+                               double (&P)[NB][3][3]) {
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) P[b][i][j] = 0.0;
+    for_each_q<8>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        const double2* g = reinterpret_cast<const double2*>(geo_e + Q * kHexGeoDoubles);
+        const double2 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4];
+        const double A[3][3] = {{g0.x, g0.y, g1.x}, {g1.y, g2.x, g2.y}, {g3.x, g3.y, g4.x}};
+        const double s = g4.y;
+        // row node: basis derivatives at run time (s?8 = local coordinate sign / 8: 1 + sign * q = fma(s?8, 8 q, 1))
+        const double ax = fma(sx8, 8.0 * Elem<8>::qp(Q, 0), 1.0), ay = fma(sy8, 8.0 * Elem<8>::qp(Q, 1), 1.0),
+                     az = fma(sz8, 8.0 * Elem<8>::qp(Q, 2), 1.0);
+        const double d0 = sx8 * (ay * az), d1 = sy8 * (ax * az), d2 = sz8 * (ax * ay);
+        double h[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) h[l] = s * (d0 * A[0][l] + d1 * A[1][l] + d2 * A[2][l]);
+#pragma unroll
+        for (int bb = 0; bb < NB; ++bb) {
+            double gb[3];
+#pragma unroll
+            for (int l = 0; l < 3; ++l)
+                gb[l] = Elem<8>::dN(Q, B0 + bb, 0) * A[0][l] + Elem<8>::dN(Q, B0 + bb, 1) * A[1][l] +
+                        Elem<8>::dN(Q, B0 + bb, 2) * A[2][l];
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) P[bb][i][j] = fma(h[i], gb[j], P[bb][i][j]);
+        }
+    });
+}
+
+// C0 applied to one summed product block (pyfem.py:1752-1757, 2017-2026)
+PFG_DEV void hex8_apply_c0(const ElasticityHex8Params& prm, const double (&P)[3][3], double (&blk)[9]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            if (i == j) {
+                const int l1 = (i + 1) % 3, l2 = (i + 2) % 3;
+                blk[i * 3 + j] = fma(prm.c11, P[i][i], prm.c44 * (P[l1][l1] + P[l2][l2]));
+            } else {
+                blk[i * 3 + j] = fma(prm.c12, P[i][j], prm.c44 * P[j][i]);
+            }
+        }
+}
+
 }  // namespace pfg

@@ -194,6 +194,12 @@ struct MeshDev {
     TileLayout tile_layout;            // encoding of tile_codes (nne == 0: not encoded yet)
     int tile_threads = 128;            // CTA size of the tile kernels = target element records per chunk
 
+    // hex8 3-D elasticity, owner-computes passes (k_hex8_geometry / k_hex8_chunk_rows)
+    int hex_rows_ok = 0;               // 1: every owned node has <= 8 elements, <= 48 neighbours and conflict-free rounds
+    double* hex_geo = nullptr;         // scratch (nelems, 8, 10), allocated by the first assembly that needs it
+    uint32_t* inc_rec8 = nullptr;      // (nown, 8) chunk-ordered node slot x incidence -> record * 8 + local node, 0xFFFF: none
+    uint64_t* inc_ranks8 = nullptr;    // (nown, 8) the incidence's eight ranks, rank[(e*8 + a)*8 + 0..7]
+
     int64_t device_bytes = 0;
     int sm_count = 148;
     int device = 0;

@@ -429,6 +429,36 @@ __global__ void k_fill_dst(const uint32_t* __restrict__ slot_node, const uint32_
     }
 }
 
+// hex8 chunk-row pass: per chunk-ordered node slot and incidence, the element's record inside the chunk, the node's
+// local index in it and the eight ranks of the element's nodes in the node's row (one load each in k_hex8_chunk_rows)
+__global__ void k_fill_inc8(const uint32_t* __restrict__ slot_node, const uint32_t* __restrict__ slot_chunk,
+                            const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
+                            const ChunkHdr* __restrict__ chunks, const uint64_t* __restrict__ rec_keys,
+                            const uint8_t* __restrict__ rank, int64_t own_begin, int64_t nslots,
+                            uint32_t* __restrict__ inc_rec8, uint64_t* __restrict__ inc_ranks8) {
+    int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (p >= nslots) return;
+    const uint32_t c = slot_chunk[p];
+    const ChunkHdr h = chunks[c];
+    const int64_t node = own_begin + slot_node[p];
+    int j = 0;
+    for (int64_t s = inc_ptr[node]; s < inc_ptr[node + 1] && j < 8; ++s, ++j) {
+        const uint32_t ia = inc_list[s];
+        const uint64_t key = ((uint64_t)c << 32) | (uint64_t)(ia / 8);
+        int64_t lo = h.rec_begin, hi = h.rec_begin + h.n_recs;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (rec_keys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        inc_rec8[p * 8 + j] = (uint32_t)((lo - h.rec_begin) * 8 + (ia % 8));
+        inc_ranks8[p * 8 + j] = *reinterpret_cast<const uint64_t*>(rank + (size_t)ia * 8);
+    }
+    for (; j < 8; ++j) {
+        inc_rec8[p * 8 + j] = 0xFFFF;
+        inc_ranks8[p * 8 + j] = 0;
+    }
+}
+
 __global__ void k_plan_sizes(const uint32_t* __restrict__ valence, const uint32_t* __restrict__ kk, int nne,
                              int64_t nslots, uint32_t* __restrict__ words) {
     int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
@@ -829,6 +859,31 @@ static int build_pattern(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     return PFG_OK;
 }
 
+// hex8 chunk-row pass (k_hex8_chunk_rows): the lanes of a node add the block of local column index b at the same
+// time, so for every owned node and every b the incident elements must reach pairwise different neighbours.
+// True for any mesh in which two elements sharing a node do not hold it and a common second node at the same
+// local positions; flags the first violation.
+__global__ void k_hex_round_check(const int64_t* __restrict__ inc_ptr, const uint32_t* __restrict__ inc_list,
+                                  const uint8_t* __restrict__ rank, int64_t own_begin, int64_t nown,
+                                  int* __restrict__ bad) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int64_t i0 = inc_ptr[own_begin + r], i1 = inc_ptr[own_begin + r + 1];
+    if (i1 - i0 > 8) {
+        atomicExch(bad, 1);
+        return;
+    }
+    for (int b = 0; b < 8; ++b) {
+        int seen[8];
+        for (int64_t i = i0; i < i1; ++i) {
+            const int t = rank[(size_t)inc_list[i] * 8 + b];
+            for (int64_t q = i0; q < i; ++q)
+                if (seen[q - i0] == t) atomicExch(bad, 1);
+            seen[i - i0] = t;
+        }
+    }
+}
+
 static int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -870,6 +925,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         int budget = env_int("PFG_CHUNK_SMEM_BYTES", 160 * 1024);
         int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
         C = budget / per_node * 4 / 5;  // tie-aware cuts may overshoot the target by up to 1/4
+        // chunk-row pass of hex8 elasticity (k_hex8_chunk_rows): seven consumer warps x four nodes per round
+        if (d.hex_rows_ok) C = env_int("PFG_HEX_CHUNK_NODES", 27);
     }
     C = env_int("PFG_CHUNK_NODES", (int)C);
     C = std::max<int64_t>(4, std::min<int64_t>(C, 1024));
@@ -1188,6 +1245,14 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     }
     k_fill_dst<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,
                                                         d.chunks, rec_keys.p, d.own_begin, nown, d.rec_dst);
+    if (NNE == 8 && d.hex_rows_ok) {
+        PFG_CUDA_TRY(cudaMalloc(&d.inc_rec8, nown * 8 * sizeof(uint32_t)));
+        PFG_CUDA_TRY(cudaMalloc(&d.inc_ranks8, nown * 8 * sizeof(uint64_t)));
+        k_fill_inc8<<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, d.chunks,
+                                                         rec_keys.p, d.rank, d.own_begin, nown, d.inc_rec8,
+                                                         d.inc_ranks8);
+        d.device_bytes += nown * 8 * (int64_t)(sizeof(uint32_t) + sizeof(uint64_t));
+    }
 
     // ---- per-node plans
     d.plan_bytes = h_plan_words * 4;
@@ -1220,7 +1285,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
-                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip};
+                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip, d.hex_geo, d.inc_rec8, d.inc_ranks8};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }
@@ -1253,6 +1318,17 @@ static int create_impl(MeshDev& d, const double* X_dev, const int64_t* conn_dev,
         return PFG_ERR_MESH;
     }
     PFG_TRY(build_pattern<NNE>(d, st, scratch));
+    if (NNE == 8 && d.m == 3 && d.max_valence <= 8 && d.max_k <= 48 && d.own_end > d.own_begin) {
+        DBuf<int> bad;
+        PFG_CUDA_TRY(bad.alloc(1));
+        PFG_CUDA_TRY(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+        const int64_t nown = d.own_end - d.own_begin;
+        k_hex_round_check<<<grid_for(nown), kThreads, 0, st>>>(d.inc_ptr, d.inc_list, d.rank, d.own_begin, nown, bad.p);
+        int h_bad = 1;
+        PFG_CUDA_TRY(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        d.hex_rows_ok = h_bad ? 0 : 1;
+    }
     if (!(d.flags & PFG_CREATE_NO_GATHER_PLAN)) PFG_TRY(build_gather_plan<NNE>(d, st, scratch));
     PFG_CUDA_TRY(cudaStreamSynchronize(st));
     PFG_CUDA_TRY(cudaGetLastError());
@@ -1408,6 +1484,7 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_DEVICE_BYTES: *value = d.device_bytes; break;
         case PFG_INFO_MAX_ROW_BLOCKS: *value = d.max_k; break;
         case PFG_INFO_MAX_VALENCE: *value = d.max_valence; break;
+        case PFG_INFO_HEX_ROWS: *value = (d.hex_rows_ok == 1 && d.nchunks > 0 && d.inc_rec8) ? 1 : 0; break;
         default:
             set_error("pfg_mesh_get: unknown query %d", what);
             return PFG_ERR_INVALID;
