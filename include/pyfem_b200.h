@@ -206,6 +206,22 @@ PFG_API int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, c
                         int64_t nfixed, int enforce_symmetric, double* vals_dev, double* rhs_dev, void* stream);
 
 /*
+ * _compute_K_dv_sens(rho, phi, psi): d(phi^T K(rho) psi) / d rho at the nodes, the kernel behind compliance_grad
+ * (LinearPoisson pyfem.py:1239-1276 with :1220-1236 and :1304-1329; LinearElasticity pyfem.py:1872-1920).  Fused:
+ * no (nelems, D, D, nnodes_per_elem) derivative tensor is formed -- per quadrature point the scalar
+ * ramp'(rho_q) detJ w (grad phi . grad psi   or   strain(phi)^T C0 strain(psi)) is spread with N[q, o] and added to
+ * the element's nodes (np.add.at, pyfem.py:1272-1275).
+ *   physics      PFG_PHYS_POISSON (handle with 1 dof per node, params {})  or
+ *                PFG_PHYS_ELASTICITY (handle with ndims dofs per node, params_host = {E, nu})
+ *   rho_dev      nodal density or NULL for the constant rho_const; p is the RAMP parameter
+ *   phi_dev, psi_dev   dof vectors (nnodes * ndof_per_node,), local node numbering
+ *   out_dev      one entry per owned node; zeroed here, then accumulated with atomic adds
+ */
+PFG_API int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
+                          const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
+                          double* out_dev, void* stream);
+
+/*
  * y = A x on the device CSR of the owned rows (Helmholtz.compute_rhs = R.dot(x), pyfem.py:2117-2120).
  */
 PFG_API int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream);

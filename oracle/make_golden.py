@@ -115,6 +115,18 @@ def main():
             np.savez_compressed(os.path.join(OUT, f"nlpoisson_{mname}.npz"), X=Xn, conn=conn, xdv=xdv,
                                 u=u, res=res, **csr_fields(K))
 
+        # ---- sensitivities d(phi^T K psi)/d rho (drawn after everything above: earlier files keep their inputs)
+        d = X.shape[1]
+        phi, psi = rng.random(nn), rng.random(nn)
+        m = ref.LinearPoisson(X, conn, [0], None, quadrature, basis, test_gfunc, p=3.0)
+        g_poisson = m._compute_K_dv_sens(rho, phi, psi).copy()
+        phi_v, psi_v = rng.random(nn * d) - 0.5, rng.random(nn * d) - 0.5
+        m = ref.LinearElasticity(X, conn, [0], None, {0: [0.0] * d}, quadrature, basis, E=7.5, nu=0.22, p=5.0)
+        g_elast = m._compute_K_dv_sens(rho, phi_v, psi_v).copy()
+        np.savez_compressed(os.path.join(OUT, f"sens_{mname}.npz"), X=X, conn=conn, rho=rho, phi=phi, psi=psi,
+                            p_poisson=3.0, g_poisson=g_poisson, phi_v=phi_v, psi_v=psi_v, p_elast=5.0, E=7.5,
+                            nu=0.22, g_elast=g_elast)
+
     print("wrote", len(os.listdir(OUT)), "files to", OUT)
 
 

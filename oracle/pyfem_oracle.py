@@ -156,6 +156,12 @@ def ramp(rho, conn, N, p, nnodes):
     return rho_q / (1.0 + p * (1.0 - rho_q))
 
 
+def ramp_deriv(rho, conn, N, p):
+    """d/d rho_q of the RAMP factor, (1 + p) / (1 + p (1 - rho_q))^2 (pyfem.py:1319-1325)."""
+    rho_q = to_quad(N, np.asarray(rho)[conn])
+    return (1.0 + p) / (1.0 + p * (1.0 - rho_q)) ** 2
+
+
 # --------------------------------------------------------------------------
 # Element matrices / vectors
 # --------------------------------------------------------------------------
@@ -331,6 +337,41 @@ def assemble_nlpoisson(X, conn, xdv, u):
     K = scatter_matrix(nlpoisson_Ke(X, conn, xdv, u), conn)
     res = scatter_vector(nlpoisson_res_e(X, conn, xdv, u), conn, X.shape[0], 4)
     return K, res
+
+
+# --------------------------------------------------------------------------
+# Sensitivities d(phi^T K psi) / d rho  (the step after assembly in the topology-optimisation loop)
+# --------------------------------------------------------------------------
+def _scatter_nodal(inner, conn, nnodes):
+    """np.add.at over the element's local nodes (pyfem.py:1272-1275, 1916-1919)."""
+    out = np.zeros(nnodes)
+    for i in range(conn.shape[1]):
+        np.add.at(out, conn[:, i], inner[:, i])
+    return out
+
+
+def poisson_K_dv_sens(X, conn, rho, p, phi, psi):
+    """LinearPoisson._compute_K_dv_sens (pyfem.py:1239-1276): Ke_deriv by the einsum of :1220-1230 with
+    kappa_q_deriv = N[q,o] ramp'(rho_q) (:1325-1328), inner product :1234-1236, nodal scatter :1272-1275."""
+    _, w, N, dN = tables_for(conn.shape[1])
+    _, _, detJ, Ngrad = geometry(X, conn, dN)
+    dk = np.einsum("ql,iq->iql", N, ramp_deriv(rho, conn, N, p))
+    Ke_deriv = np.einsum("iqo,iq,q,iqjl,iqkl->ijko", dk, detJ, w, Ngrad, Ngrad, optimize=True)
+    inner = np.einsum("ij,ik,ijko->io", np.asarray(phi)[conn], np.asarray(psi)[conn], Ke_deriv)
+    return _scatter_nodal(inner, conn, X.shape[0])
+
+
+def elasticity_K_dv_sens(X, conn, rho, p, phi, psi, E=10.0, nu=0.3):
+    """LinearElasticity._compute_K_dv_sens (pyfem.py:1872-1920): einsum :1900-1909, inner product :1912-1914."""
+    _, w, N, dN = tables_for(conn.shape[1])
+    _, _, detJ, Ngrad = geometry(X, conn, dN)
+    B = strain_displacement(Ngrad)
+    C0 = elasticity_C0(X.shape[1], E, nu)
+    dC = np.einsum("ql,iq->iql", N, ramp_deriv(rho, conn, N, p))
+    Ke_deriv = np.einsum("iq,q,iqnj,iqo,nm,iqmk->ijko", detJ, w, B, dC, C0, B, optimize=True)
+    cd = conn_to_dof(conn, X.shape[1])
+    inner = np.einsum("ij,ik,ijko->io", np.asarray(phi)[cd], np.asarray(psi)[cd], Ke_deriv)
+    return _scatter_nodal(inner, conn, X.shape[0])
 
 
 def elasticity_point_loads(ndof, ndims, nodal_force):

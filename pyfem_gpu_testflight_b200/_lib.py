@@ -56,6 +56,8 @@ PROTOTYPES = {
     "pfg_scatter_vector": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_element_matrices": (c_int, [c_void_p, c_int, c_void_p, c_double, POINTER(c_double), c_int, c_void_p, c_void_p,
                                      c_void_p, c_void_p]),
+    "pfg_k_dv_sens": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, POINTER(c_double), c_int, c_void_p,
+                              c_void_p, c_void_p, c_void_p]),
     "pfg_mesh_set_element_mask": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pfg_add_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
 }

@@ -999,6 +999,84 @@ __global__ void k_quad_points(MeshView mv, double* __restrict__ Xq) {  // utils.
     });
 }
 
+// d(phi^T K psi) / d rho at the nodes, one thread per element (pyfem.py:1239-1276, 1872-1920 fused: the reference's
+// (nelems, D, D, nnodes_per_elem) derivative tensor is never formed).  M = 1: Poisson, M = DIM: elasticity.
+struct SensParams {
+    Material mat;
+    const double* phi;
+    const double* psi;
+    double c11, c12, c33;  // elasticity: C0 diagonal, off-diagonal and shear entries
+};
+
+template <int NNE, int M>
+__global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, double* __restrict__ out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= mv.nelems) return;
+    if (mv.elem_skip != nullptr && mv.elem_skip[e]) return;  // integrated by another rank
+    constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    int nodes[NNE];
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
+    double xe[NNE][DIM], re[NNE], ue[NNE][M], ve[NNE][M], inner[NNE];
+    load_coords<NNE>(mv.X, nodes, xe);
+    load_field<NNE>(prm.mat.rho, nodes, re);
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) {
+#pragma unroll
+        for (int c = 0; c < M; ++c) {
+            ue[a][c] = __ldg(prm.phi + (int64_t)nodes[a] * M + c);
+            ve[a][c] = __ldg(prm.psi + (int64_t)nodes[a] * M + c);
+        }
+        inner[a] = 0.0;
+    }
+    GeoCtx<NNE> geo(xe);
+    for_each_q<NQ>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        double det, G[NNE][DIM];  // G = det * grad N
+        geo.template at<Q>(xe, det, G);
+        const double rq = (prm.mat.rho != nullptr) ? interp<NNE, Q>(re) : prm.mat.rho_const;
+        const double den = fma(prm.mat.p, 1.0 - rq, 1.0);
+        const double dr = (1.0 + prm.mat.p) / (den * den);  // ramp'(rho_q), pyfem.py:1325
+        double gu[M][DIM], gv[M][DIM];                      // det * gradients of the two fields
+#pragma unroll
+        for (int c = 0; c < M; ++c)
+#pragma unroll
+            for (int l = 0; l < DIM; ++l) {
+                double su = 0.0, sv = 0.0;
+#pragma unroll
+                for (int a = 0; a < NNE; ++a) {
+                    su = fma(G[a][l], ue[a][c], su);
+                    sv = fma(G[a][l], ve[a][c], sv);
+                }
+                gu[c][l] = su, gv[c][l] = sv;
+            }
+        double energy;
+        if constexpr (M == 1) {
+            energy = 0.0;
+#pragma unroll
+            for (int l = 0; l < DIM; ++l) energy = fma(gu[0][l], gv[0][l], energy);
+        } else if constexpr (DIM == 2) {  // strains [ex, ey, gxy] (pyfem.py:1988-1998)
+            const double gxu = gu[0][1] + gu[1][0], gxv = gv[0][1] + gv[1][0];
+            energy = prm.c11 * (gu[0][0] * gv[0][0] + gu[1][1] * gv[1][1]) +
+                     prm.c12 * (gu[0][0] * gv[1][1] + gu[1][1] * gv[0][0]) + prm.c33 * gxu * gxv;
+        } else {  // [ex, ey, ez, gxy, gyz, gxz] (pyfem.py:2000-2011)
+            const double su = gu[0][0] + gu[1][1] + gu[2][2], sv = gv[0][0] + gv[1][1] + gv[2][2];
+            double diag = 0.0;
+#pragma unroll
+            for (int l = 0; l < 3; ++l) diag = fma(gu[l][l], gv[l][l], diag);
+            const double sh = (gu[0][1] + gu[1][0]) * (gv[0][1] + gv[1][0]) + (gu[1][2] + gu[2][1]) * (gv[1][2] + gv[2][1]) +
+                              (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
+            energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
+        }
+        const double t = dr * energy / det;  // (gu / det) . (gv / det) * det * w, w = 1
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
+    });
+#pragma unroll
+    for (int a = 0; a < NNE; ++a)
+        if (nodes[a] >= mv.own_begin && nodes[a] < mv.own_end) atomicAdd(out + (nodes[a] - mv.own_begin), inner[a]);
+}
+
 // Dirichlet rows/columns on the device CSR, pattern kept (pyfem.py:780-835 minus eliminate_zeros).
 __global__ void k_mark_fixed(const int64_t* __restrict__ fixed, const double* __restrict__ fixed_vals, int64_t nfixed,
                              int64_t ncols, uint8_t* __restrict__ is_fixed, double* __restrict__ u0) {
@@ -1487,6 +1565,44 @@ extern "C" int pfg_element_matrices(pfg_mesh* mesh, int physics, const double* f
     }
     set_error("pfg_element_matrices: physics %d does not fit this mesh handle or an output is missing", physics);
     return PFG_ERR_INVALID;
+}
+
+extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
+                             const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
+                             double* out_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!phi_dev || !psi_dev || !out_dev) {
+        set_error("pfg_k_dv_sens: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    if ((physics == PFG_PHYS_POISSON && d.m != 1) || (physics == PFG_PHYS_ELASTICITY && d.m != d.ndims) ||
+        (physics != PFG_PHYS_POISSON && physics != PFG_PHYS_ELASTICITY)) {
+        set_error("pfg_k_dv_sens: physics %d does not fit a handle with %d dofs per node", physics, d.m);
+        return PFG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SensParams prm{material_of(rho_dev, rho_const, p), phi_dev, psi_dev, 0.0, 0.0, 0.0};
+    if (physics == PFG_PHYS_ELASTICITY) {
+        const double E = (params_host && nparams > 0) ? params_host[0] : 10.0;
+        const double nu = (params_host && nparams > 1) ? params_host[1] : 0.3;
+        if (d.ndims == 2) {  // plane stress (pyfem.py:1746-1750)
+            const double f = E / (1.0 - nu * nu);
+            prm.c11 = f, prm.c12 = f * nu, prm.c33 = f * 0.5 * (1.0 - nu);
+        } else {  // pyfem.py:1752-1757
+            const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+            prm.c11 = f * (1.0 - nu), prm.c12 = f * nu, prm.c33 = f * (0.5 - nu);
+        }
+    }
+    PFG_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (d.own_end - d.own_begin) * sizeof(double), st));
+    const MeshView mv = view_of(d);
+    const unsigned grid = (unsigned)((d.nelems + 127) / 128);
+    if (d.nne == 4 && d.m == 1) k_dv_sens<4, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    else if (d.nne == 4) k_dv_sens<4, 2><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    else if (d.m == 1) k_dv_sens<8, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    else k_dv_sens<8, 3><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
 }
 
 extern "C" int pfg_scatter_matrix(pfg_mesh* mesh, const double* Ke_dev, double* vals_dev, int mode, void* stream) {

@@ -272,6 +272,23 @@ class DeviceMesh:
                 int(par.size), _ptr(Ke), _ptr(Ke2), _ptr(fe), self._stream()))
         return Ke, Ke2, fe
 
+    def k_dv_sens(self, physics, rho, p, phi, psi, E=10.0, nu=0.3, out=None):
+        """d(phi^T K(rho) psi)/d rho at the owned nodes (the reference's _compute_K_dv_sens, pyfem.py:1239-1276 and
+        1872-1920), fused on the device.  physics: "poisson" (scalar handle) or "elasticity"."""
+        torch = _torch()
+        code = {"poisson": _lib.PHYS_POISSON, "elasticity": _lib.PHYS_ELASTICITY}[physics]
+        rho_t, rho_c = self._rho(rho)
+        ndof = self.nnodes * self.ndof_per_node
+        phi_t, psi_t = self._dev_f64(phi, ndof, "phi"), self._dev_f64(psi, ndof, "psi")
+        par = np.ascontiguousarray(np.asarray((E, nu), dtype=np.float64))
+        if out is None:
+            out = torch.empty(self.nrows // self.ndof_per_node, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_k_dv_sens(self._handle, code, _ptr(rho_t), rho_c, float(p),
+                                               par.ctypes.data_as(ctypes.POINTER(c_double)), 2, _ptr(phi_t),
+                                               _ptr(psi_t), _ptr(out), self._stream()))
+        return out
+
     # ---- multi-GPU reduce variant (halo.py) ---------------------------------------------------------
     def set_element_mask(self, skip):
         """Elements with skip != 0 stay in the pattern but are not integrated by this handle (another rank ships

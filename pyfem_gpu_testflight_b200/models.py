@@ -153,13 +153,39 @@ class ModelBase:
         return K, rhs
 
 
+class _DensityFunctions:
+    """compliance / volume and their gradients (LinearPoisson pyfem.py:1033-1123, LinearElasticity :1796-1870).
+    The solves stay on the host, as in the reference; iterative solvers need pyamg, which this image lacks."""
+
+    def _solve_compliance_system(self, rho, solver):
+        assert solver == "direct" or solver == "cg" or solver == "gmres"
+        if solver != "direct":
+            raise NotImplementedError("cg / gmres use a pyamg preconditioner (pyfem.py:1059-1060); use solver='direct'")
+        from scipy.sparse.linalg import spsolve
+        K = self.compute_jacobian(rho)
+        rhs = self.compute_rhs()
+        K, rhs = self.apply_dirichlet_bcs(K, rhs, enforce_symmetric_K=True)
+        return K, rhs, spsolve(K.tocsc(), rhs)
+
+    def volume(self, rho):
+        return np.asarray(rho).sum() / self.nnodes
+
+    def volume_grad(self, rho):
+        return np.ones(self.nnodes) / self.nnodes
+
+    def _k_dv_sens(self, physics, rho, phi, psi, **kw):
+        _check_real(rho)
+        rho = np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho
+        return self.mesh.k_dv_sens(physics, rho, self.p, phi, psi, **kw).cpu().numpy()
+
+
 def _check_real(rho):
     if np.iscomplexobj(rho):
         raise NotImplementedError("complex rho (complex-step verification, pyfem.py:1019-1020) has no device "
                                   "path and this engine has no CPU fallback")
 
 
-class LinearPoisson(ModelBase):
+class LinearPoisson(_DensityFunctions, ModelBase):
     """-k lap(u) = g with RAMP-penalised conductivity (pyfem.py:934-1329)."""
 
     def __init__(self, X, conn, dof_fixed, dof_fixed_vals, quadrature, basis, gfunc, kappa0=1.0, p=0.0, **kw):
@@ -199,6 +225,27 @@ class LinearPoisson(ModelBase):
         return self._vec_to_host(self.compute_rhs_device(), self.rhs)
 
 
+    def _compute_K_dv_sens(self, rho, phi, psi):
+        """d(phi^T K psi)/d rho (pyfem.py:1239-1276)."""
+        return self._k_dv_sens("poisson", rho, phi, psi)
+
+    def compliance(self, rho, solver="cg", weighted=True):
+        """Thermal compliance and the solution (pyfem.py:1033-1073)."""
+        _, rhs, u = self._solve_compliance_system(rho, solver)
+        return (rhs.dot(u) if weighted else np.sum(u) / len(u)), u
+
+    def compliance_grad(self, rho, u, weighted=True):
+        """pyfem.py:1075-1101."""
+        if weighted:
+            psi = u
+        else:
+            from scipy.sparse.linalg import spsolve
+            K = self.compute_jacobian(rho)
+            K, rhs = self.apply_dirichlet_bcs(K, np.ones(len(u)), enforce_symmetric_K=True)
+            psi = spsolve(K.tocsc(), rhs) / len(u)
+        return -self._compute_K_dv_sens(rho, psi, u)
+
+
 class NonlinearPoisson2D(ModelBase):
     """-div(h(x)(1+u^2) grad u) = g on quad4 meshes (pyfem.py:1332-1664)."""
 
@@ -221,7 +268,7 @@ class NonlinearPoisson2D(ModelBase):
         return self._vec_to_host(res, self.rhs)
 
 
-class LinearElasticity(ModelBase):
+class LinearElasticity(_DensityFunctions, ModelBase):
     """Linear elasticity, plane stress in 2-D (pyfem.py:1667-2068)."""
 
     def __init__(self, X, conn, dof_fixed, dof_fixed_vals, nodal_force, quadrature, basis, E=10.0, nu=0.3, p=0.0,
@@ -256,6 +303,20 @@ class LinearElasticity(ModelBase):
 
     def compute_jacobian(self, rho=1.0):
         return self._to_scipy(self.compute_jacobian_device(rho))
+
+
+    def _compute_K_dv_sens(self, rho, phi, psi):
+        """d(phi^T K psi)/d rho (pyfem.py:1872-1920)."""
+        return self._k_dv_sens("elasticity", rho, phi, psi, E=self.E, nu=self.nu)
+
+    def compliance(self, rho, solver="cg"):
+        """Compliance and the solution (pyfem.py:1796-1833)."""
+        _, rhs, u = self._solve_compliance_system(rho, solver)
+        return rhs.dot(u), u
+
+    def compliance_grad(self, rho, u):
+        """pyfem.py:1835-1847."""
+        return -self._compute_K_dv_sens(rho, u, u)
 
 
 class Helmholtz(ModelBase):

@@ -45,6 +45,16 @@ def test_nlpoisson(path):
     assert_values_close(res, g["res"], ORACLE_TOL, "residual")
 
 
+@pytest.mark.parametrize("path", golden_files("sens"))
+def test_sensitivities(path):
+    g = np.load(path)
+    d = orc.poisson_K_dv_sens(g["X"], g["conn"], g["rho"], float(g["p_poisson"]), g["phi"], g["psi"])
+    assert_values_close(d, g["g_poisson"], ORACLE_TOL, "poisson dK/drho")
+    d = orc.elasticity_K_dv_sens(g["X"], g["conn"], g["rho"], float(g["p_elast"]), g["phi_v"], g["psi_v"],
+                                 float(g["E"]), float(g["nu"]))
+    assert_values_close(d, g["g_elast"], ORACLE_TOL, "elasticity dK/drho")
+
+
 def test_structured_mesh_matches_closed_form_nnz():
     # nnz = m^2 * prod(3 nn_k - 2)
     X, conn = orc.structured_mesh(9, 7)
