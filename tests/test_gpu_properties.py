@@ -221,3 +221,63 @@ def test_full_size_nlpoisson_properties(pf):
     fd = (rp - rm) / (2 * eps)
     Kv = mesh.spmv(K, v)
     assert float((fd - Kv).abs().max()) <= 1e-6 * float(Kv.abs().max())
+
+
+# ---- irregular hex meshes: the owner-computes chunk-row pass of hex8 elasticity and its fall-backs ------------------
+def _hex_jittered(nx, ny, nz, seed):
+    X, conn = orc.structured_mesh(nx, ny, nz)
+    h = 1.0 / (max(nx, ny, nz) - 1)
+    return X + np.random.default_rng(seed).uniform(-0.15 * h, 0.15 * h, size=X.shape), conn
+
+
+def _rotate_local_numbering(conn, seed):
+    """Renumber a random half of the elements by a quarter turn about the local zeta axis (still right-handed): two
+    elements around a node may then hold it and a common neighbour at the same local positions, which the chunk-row
+    pass does not cover (MeshDev::hex_rows_ok) -- AUTO must fall back to the atomic scatter, GATHER to the
+    first-format gather kernel."""
+    conn = conn.copy()
+    pick = np.random.default_rng(seed).random(conn.shape[0]) < 0.5
+    conn[pick] = conn[pick][:, [1, 2, 3, 0, 5, 6, 7, 4]]
+    return conn
+
+
+def extruded_three_patch_mesh(n, nz, seed=0):
+    """The 'Y' block quad mesh extruded in z: the centre column has six elements per node instead of eight."""
+    X2, quads = three_patch_mesh(n, seed=seed)
+    nn2 = X2.shape[0]
+    X = np.vstack([np.column_stack([X2, np.full(nn2, k / nz)]) for k in range(nz + 1)])
+    conn = np.vstack([np.hstack([quads + k * nn2, quads + (k + 1) * nn2]) for k in range(nz)])
+    X[:, 2] += np.random.default_rng(seed + 1).uniform(-0.1, 0.1, size=X.shape[0]) / nz
+    return X, conn.astype(np.int64)
+
+
+@pytest.mark.parametrize("mode", ["auto", "atomic", "gather"])
+@pytest.mark.parametrize("case", ["rotated", "extruded_y", "lattice"])
+def test_hex_elasticity_irregular_meshes(pf, mode, case):
+    from pyfem_gpu_testflight_b200 import _lib
+    if case == "rotated":
+        X, conn = _hex_jittered(9, 8, 7, seed=3)
+        conn = _rotate_local_numbering(conn, seed=4)
+    elif case == "extruded_y":
+        X, conn = extruded_three_patch_mesh(5, 4, seed=2)
+    else:
+        X, conn = _hex_jittered(12, 7, 9, seed=5)
+    rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+    Kr = orc.assemble_elasticity(X, conn, rho, 4.0, 6.0, 0.25)
+    q = pf.QuadratureBlock3D()
+    m = pf.LinearElasticity(X, conn, [0], None, {0: [0.0, 0.0, 0.0]}, q, pf.BasisBlock3D(q), E=6.0, nu=0.25, p=4.0,
+                            scatter=mode)
+    assert_csr_matches(m.compute_jacobian(rho), Kr.indptr, Kr.indices, Kr.data)
+    if case == "lattice":
+        assert m.mesh.info(_lib.INFO_HEX_ROWS) == 1  # the chunk-row pass is what ran for auto / gather
+
+
+def test_hex_chunk_rows_bitwise_reproducible(pf):
+    X, conn = _hex_jittered(11, 10, 9, seed=7)
+    mesh = pf.DeviceMesh(X, conn, 3)
+    rho = 0.2 + 0.8 * np.random.default_rng(1).random(X.shape[0])
+    v1 = mesh.assemble_elasticity(rho, 3.0, mode="gather").cpu().numpy()
+    v2 = mesh.assemble_elasticity(rho, 3.0, mode="gather").cpu().numpy()
+    va = mesh.assemble_elasticity(rho, 3.0, mode="atomic").cpu().numpy()
+    assert np.array_equal(v1, v2)
+    assert_values_close(v1, va, 1e-13)
