@@ -305,16 +305,27 @@ def main():
     e2e = None
     h2d = d2h = 0
     # (skipped when the CSR values alone exceed 8 GB: the full 256^3 hex case would pin > 60 GB of host memory)
-    if args.e2e_steps > 0 and physics in ("elasticity", "poisson") and mesh.nnz * 8 <= 8e9:
+    if args.e2e_steps > 0 and reducer is None and mesh.nnz * 8 <= 8e9:
         rho_host = torch.from_numpy(0.1 + 0.9 * np.random.default_rng(0).random(mesh.nnodes)).pin_memory()
         data_host = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory()
         data_np = data_host.numpy()
+        data2_np = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory().numpy() if physics == "helmholtz" else None
+        res_host = torch.empty(mesh.nrows, dtype=torch.float64).pin_memory() if physics == "nlpoisson" else None
 
         def e2e_step():
-            # the public call path of LinearElasticity.compute_jacobian(rho): host rho in, host scipy CSR out
-            v = (mesh.assemble_elasticity if physics == "elasticity" else mesh.assemble_poisson)(
-                rho_host, 5.0, out=vals, mode=args.mode)
-            return mesh.to_scipy(v, copy_pattern=False, out=data_np)
+            # the public call path of model.compute_jacobian(...): host nodal field in, host scipy CSR (and vector) out
+            if physics in ("elasticity", "poisson"):
+                v = (mesh.assemble_elasticity if physics == "elasticity" else mesh.assemble_poisson)(
+                    rho_host, 5.0, out=vals, mode=args.mode)
+                return mesh.to_scipy(v, copy_pattern=False, out=data_np)
+            if physics == "helmholtz":  # Helmholtz.__init__: K and R, no nodal input
+                mesh.assemble_helmholtz(0.05, out_K=vals, out_R=vals2, mode=args.mode)
+                return (mesh.to_scipy(vals, copy_pattern=False, out=data_np),
+                        mesh.to_scipy(vals2, copy_pattern=False, out=data2_np))
+            # one Newton re-assembly: host iterate u in, Jacobian and residual out
+            mesh.assemble_nlpoisson(xdv, rho_host, out_K=vals, out_res=res, mode=args.mode)
+            res_host.copy_(res)
+            return mesh.to_scipy(vals, copy_pattern=False, out=data_np)
 
         mesh.pattern_host()  # pattern fetched once per mesh
         e2e_step()
@@ -328,7 +339,8 @@ def main():
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e = total_elems_global / float(t.item())
-        h2d, d2h = mesh.nnodes * 8, mesh.nnz * 8
+        h2d = 0 if physics == "helmholtz" else mesh.nnodes * 8
+        d2h = mesh.nnz * 8 * (2 if physics == "helmholtz" else 1) + (mesh.nrows * 8 if physics == "nlpoisson" else 0)
         del K
 
     if rank != 0:

@@ -1297,7 +1297,7 @@ extern "C" int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, doubl
     Outputs out{{vals_dev, nullptr}, nullptr};
     if (d.nne == 4) {
         PoissonOp<4>::Params prm{material_of(rho_dev, rho_const, p)};
-        return launch<PoissonOp<4>, 128, 4>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<PoissonOp<4>, 128, 6>(d, prm, out, gather, (cudaStream_t)stream);
     }
     PoissonOp<8>::Params prm{material_of(rho_dev, rho_const, p)};
     return launch<PoissonOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
@@ -1316,7 +1316,7 @@ extern "C" int pfg_assemble_helmholtz(pfg_mesh* mesh, double r0, double* K_vals_
     Outputs out{{K_vals_dev, R_vals_dev}, nullptr};
     if (d.nne == 4) {
         HelmholtzOp<4>::Params prm{r0 * r0};
-        return launch<HelmholtzOp<4>, 128, 4>(d, prm, out, gather, (cudaStream_t)stream);
+        return launch<HelmholtzOp<4>, 128, 5>(d, prm, out, gather, (cudaStream_t)stream);
     }
     HelmholtzOp<8>::Params prm{r0 * r0};
     return launch<HelmholtzOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
