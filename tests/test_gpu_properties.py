@@ -281,3 +281,17 @@ def test_hex_chunk_rows_bitwise_reproducible(pf):
     va = mesh.assemble_elasticity(rho, 3.0, mode="atomic").cpu().numpy()
     assert np.array_equal(v1, v2)
     assert_values_close(v1, va, 1e-13)
+
+
+def test_hex_chunk_rows_large_chunks_second_round(pf, monkeypatch):
+    """Chunks with more nodes than the consumer warps take in one round (7 warps x 4 nodes): the second round reads
+    its node / incidence tables directly instead of from the prefetch slots."""
+    from pyfem_gpu_testflight_b200 import _lib
+    monkeypatch.setenv("PFG_HEX_CHUNK_NODES", "45")
+    X, conn = _hex_jittered(10, 9, 8, seed=11)
+    rho = 0.05 + 0.95 * np.random.default_rng(3).random(X.shape[0])
+    mesh = pf.DeviceMesh(X, conn, 3)
+    assert mesh.info(_lib.INFO_HEX_ROWS) == 1
+    Kr = orc.assemble_elasticity(X, conn, rho, 2.0)
+    v = mesh.assemble_elasticity(rho, 2.0, mode="gather").cpu().numpy()
+    assert_values_close(v, Kr.data, VAL_TOL)
