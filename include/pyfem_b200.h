@@ -53,8 +53,8 @@ typedef enum pfg_elem {
 } pfg_elem;
 
 typedef enum pfg_mode {
-    PFG_MODE_AUTO = 0,   /* the faster strategy for the operator: gather when the mesh has a gather plan (atomic for
-                            hex8 3-D elasticity, whose gather kernel is slower), else atomic */
+    PFG_MODE_AUTO = 0,   /* the faster strategy for the operator: owner-computes (gather) when the mesh has a plan
+                            for it, else atomic */
     PFG_MODE_ATOMIC = 1, /* element-per-thread, slot-indexed red.global.add.f64 scatter */
     PFG_MODE_GATHER = 2  /* owner-computes: element matrices staged in shared memory, every CSR value
                             summed in a fixed order and written exactly once (no atomics, deterministic) */
@@ -136,6 +136,9 @@ PFG_API int pfg_assemble_poisson(pfg_mesh* mesh, const double* rho_dev, double r
 /*
  * LinearElasticity.compute_jacobian(rho) (pyfem.py:1770-1795): plane stress for QUAD4
  * (ndof_per_node 2), 3-D for HEX8 (ndof_per_node 3); C0 from E, nu as pyfem.py:1746-1757.
+ * HEX8: PFG_MODE_AUTO / PFG_MODE_GATHER run the owner-computes geometry + chunk-row passes when the mesh
+ * allows (PFG_INFO_HEX_ROWS == 1; the first call allocates nelems * 640 B of scratch inside the handle),
+ * otherwise AUTO is the atomic scatter and GATHER the staged-row-block kernel.
  */
 PFG_API int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, double rho_const, double p, double E,
                             double nu, double* vals_dev, int mode, void* stream);
