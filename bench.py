@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="elements per side (default: the workload's named size)")
     ap.add_argument("--mode", default="auto", choices=["auto", "gather", "atomic"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--halo", default="ghost", choices=["ghost", "reduce"],
+    ap.add_argument("--halo", default="ghost", choices=["ghost", "reduce", "p2p"],
                     help="N > 1: 'ghost' integrates the ghost element layer on both neighbours (no exchange); "
                          "'reduce' integrates every element once and sums interface rows over NCCL send/recv")
     ap.add_argument("--e2e-steps", type=int, default=3)
@@ -231,9 +231,9 @@ def main():
         ranges = slab_node_ranges(n_side + 1, n_side + 1, nz_el + 1, world)
         ndims = 3
     reducer = None
-    if args.halo == "reduce" and world > 1 and physics in ("elasticity", "poisson", "nlpoisson"):
+    if args.halo in ("reduce", "p2p") and world > 1 and physics in ("elasticity", "poisson", "nlpoisson"):
         from pyfem_gpu_testflight_b200.halo import ReduceAssembler
-        reducer = ReduceAssembler(part, m, ranges, device=dev)
+        reducer = ReduceAssembler(part, m, ranges, device=dev, transport="p2p" if args.halo == "p2p" else "nccl")
         mesh = reducer.mesh
     else:
         mesh = pf.DeviceMesh(part.X, part.conn, m, device=dev, own_range=part.own_range, node_gid=part.node_gid,
@@ -394,8 +394,11 @@ def main():
         "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
                    "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
                    "csr_nnz_rank0": mesh.nnz, "scatter": scatter_name,
-                   "partition": (f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
-                                 f"send/recv + indexed add" if reducer is not None else
+                   "partition": ((f"row slabs x{world}, every element integrated once, halo handles assemble straight into "
+                                  f"the owners' symmetric-memory inboxes over NVLink (fused compute + transfer), "
+                                  f"indexed add" if args.halo == "p2p" else
+                                  f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
+                                  f"send/recv + indexed add") if reducer is not None else
                                  f"row slabs x{world}, ghost-element layer, no data-path collective"),
                    "l2": "outputs (4.8 GB/step for c2) and inputs exceed the 126 MB L2; no flush needed",
                    "rho": "constant 1.0, p=0 (device-resident headline); e2e uses a host nodal rho field, p=5",

@@ -12,6 +12,13 @@ of an interface node then receives partial sums from several ranks, and the non-
                             NVLink); q adds them at the mapped slots (pfg_add_indexed).  The cross-partition sum
                             completes the duplicate summation of the reference's coo->csr (pyfem.py:930-931).
 
+Transport "p2p" fuses the halo assembly with its transfer: every rank keeps an inbox in symmetric memory
+(torch.distributed._symmetric_memory, NVLink peer mappings), and a sender's halo handle assembles STRAIGHT INTO the
+owner's inbox -- the tile kernel's TMA bulk stores (or the atomic kernel's red.global) target the peer's HBM through
+NVLink / NVSwitch, chunk by chunk as they complete; no staging copy, no send/recv launch.  A device-side barrier on the
+symmetric-memory signal pads orders "all halo kernels done" before the owners' indexed adds, a second one frees the
+inboxes for the next assembly.
+
 The planning below is numpy and runs anywhere (gloo test on CPU); `ReduceAssembler` is the device part.
 """
 import numpy as np
@@ -86,11 +93,13 @@ class ReduceAssembler:
     """Device side: the rank's slab handle with masked ghost elements + one halo handle per neighbour, and the
     exchange.  Methods mirror DeviceMesh.assemble_*; nodal fields are given in the rank's local numbering."""
 
-    def __init__(self, part: LocalMesh, ndof_per_node, ranges, device=None, group=None):
+    def __init__(self, part: LocalMesh, ndof_per_node, ranges, device=None, group=None, transport="nccl"):
         import torch
         import torch.distributed as dist
         from .engine import DeviceMesh
-        self.torch, self.dist, self.group = torch, dist, group
+        if transport not in ("nccl", "p2p"):
+            raise ValueError(f"unknown halo transport {transport!r}")
+        self.torch, self.dist, self.group, self.transport = torch, dist, group, transport
         self.part, self.m = part, int(ndof_per_node)
         self.plan = HaloPlan(part, ranges)
         self.mesh = DeviceMesh(part.X, part.conn, self.m, device=device, own_range=part.own_range,
@@ -101,6 +110,36 @@ class ReduceAssembler:
                                     ncols_nodes=part.nnodes_global),
                       torch.as_tensor(s.local_nodes, device=self.device)) for s in self.plan.sends]
         self._exchange_patterns()
+        if transport == "p2p":
+            self._setup_p2p()
+
+    # ---- p2p transport: inboxes in symmetric memory -----------------------------------------------------------------
+    def _setup_p2p(self):
+        import torch.distributed._symmetric_memory as symm_mem
+        torch, rank, size, m = self.torch, self.part.rank, self.part.size, self.m
+        T = self._send_table  # T[q, d] = (node rows, nnz) that rank q sends to rank d
+
+        def block(q, d):  # doubles q writes into d's inbox: CSR values, then one vector entry per dof row
+            return int(T[q, d, 1]) + int(T[q, d, 0]) * m
+
+        def offset(q, d):
+            return sum(block(qq, d) for qq in range(q) if qq != d)
+
+        n = max(1, max(sum(block(q, d) for q in range(size) if q != d) for d in range(size)))
+        self.inbox = symm_mem.empty(n, dtype=torch.float64, device=self.device)  # same size on every rank
+        self.symm = symm_mem.rendezvous(self.inbox, self.group if self.group is not None else self.dist.group.WORLD)
+        self.peer_out = []
+        for s, hm, _ in self.halo:
+            off = offset(rank, s.dest)
+            self.peer_out.append((self.symm.get_buffer(s.dest, (hm.nnz,), torch.float64, off),
+                                  self.symm.get_buffer(s.dest, (hm.nrows,), torch.float64, off + hm.nnz)))
+        recv = []
+        for q, slots, rows, _, _ in self.recv:
+            off = offset(q, rank)
+            recv.append((q, slots, rows, self.inbox[off:off + len(slots)],
+                         self.inbox[off + len(slots):off + len(slots) + len(rows)]))
+        self.recv = recv
+        self.symm.barrier()
 
     # ---- setup: halo patterns travel to the owners, owners build their index maps --------------------------------
     def _p2p(self, ops):
@@ -117,6 +156,7 @@ class ReduceAssembler:
             mine[s.dest, 0], mine[s.dest, 1] = hm.nrows // self.m, hm.nnz
         table = [torch.zeros_like(mine) for _ in range(size)]
         dist.all_gather(table, mine, group=self.group)
+        self._send_table = torch.stack(table).cpu().numpy()
         ops, send_keep, recv_bufs = [], [], {}
         for s, hm, _ in self.halo:
             rows = torch.as_tensor(s.node_gid[s.own_range[0]:s.own_range[1]], device=self.device)
@@ -159,8 +199,24 @@ class ReduceAssembler:
                               torch.empty(len(dof_rows), dtype=torch.float64, device=self.device)))
 
     # ---- every assembly ---------------------------------------------------------------------------------------------
+    def _halo_out(self, i):
+        """(values, vector) outputs of halo handle i: the owner's inbox for the p2p transport, else fresh tensors."""
+        return self.peer_out[i] if self.transport == "p2p" else (None, None)
+
+    def _before_halo(self):
+        if self.transport == "p2p":
+            self.symm.barrier()  # every owner has consumed the previous assembly's inbox contents
+
     def _reduce(self, main_vals, halo_vals, main_vec=None, halo_vecs=None):
         dist = self.dist
+        if self.transport == "p2p":
+            self.symm.barrier()  # every rank's halo kernels have written their peers' inboxes
+            for q, slots, rows, vbuf, rbuf in self.recv:
+                if halo_vals is not None:
+                    self.mesh.add_indexed(main_vals, slots, vbuf)
+                if halo_vecs is not None:
+                    self.mesh.add_indexed(main_vec, rows, rbuf)
+            return
         ops = []
         for i, (s, _, _) in enumerate(self.halo):
             if halo_vals is not None:
@@ -185,23 +241,29 @@ class ReduceAssembler:
         return self.torch.as_tensor(f, device=self.device)[local_nodes]
 
     def assemble_elasticity(self, rho=1.0, p=0.0, E=10.0, nu=0.3, out=None, mode="auto"):
-        vals = self.mesh.assemble_elasticity(rho, p, E, nu, out=out, mode=mode)
-        hv = [hm.assemble_elasticity(self._field(rho, ln), p, E, nu, mode=mode) for _, hm, ln in self.halo]
+        self._before_halo()
+        hv = [hm.assemble_elasticity(self._field(rho, ln), p, E, nu, out=self._halo_out(i)[0], mode=mode)
+              for i, (_, hm, ln) in enumerate(self.halo)]
+        vals = self.mesh.assemble_elasticity(rho, p, E, nu, out=out, mode=mode)  # overlaps the halo stores' flight
         self._reduce(vals, hv)
         return vals
 
     def assemble_poisson(self, rho=1.0, p=0.0, out=None, mode="auto"):
+        self._before_halo()
+        hv = [hm.assemble_poisson(self._field(rho, ln), p, out=self._halo_out(i)[0], mode=mode)
+              for i, (_, hm, ln) in enumerate(self.halo)]
         vals = self.mesh.assemble_poisson(rho, p, out=out, mode=mode)
-        hv = [hm.assemble_poisson(self._field(rho, ln), p, mode=mode) for _, hm, ln in self.halo]
         self._reduce(vals, hv)
         return vals
 
     def assemble_nlpoisson(self, xdv, u, mode="auto"):
-        K, res = self.mesh.assemble_nlpoisson(xdv, u, mode=mode)
+        self._before_halo()
         hk, hr = [], []
-        for _, hm, ln in self.halo:
-            k, r = hm.assemble_nlpoisson(xdv, self._field(u, ln), mode=mode)
+        for i, (_, hm, ln) in enumerate(self.halo):
+            ok, orr = self._halo_out(i)
+            k, r = hm.assemble_nlpoisson(xdv, self._field(u, ln), out_K=ok, out_res=orr, mode=mode)
             hk.append(k)
             hr.append(r)
+        K, res = self.mesh.assemble_nlpoisson(xdv, u, mode=mode)
         self._reduce(K, hk, res, hr)
         return K, res
