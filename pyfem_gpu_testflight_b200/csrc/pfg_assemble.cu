@@ -1344,7 +1344,7 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
     const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
     ElasticityHex8Params prm{material_of(rho_dev, rho_const, p), f * (1.0 - nu), f * nu, f * (0.5 - nu)};
     const MeshView mv = view_of(d);
-    const bool rows_ok = d.hex_rows_ok == 1 && d.nchunks > 0 && d.inc_rec8 && getenv("PFG_HEX_ROWS") == nullptr;
+    const bool rows_ok = d.hex_rows_ok == 1 && d.nchunks > 0 && d.inc_rec8;
     if (mode != PFG_MODE_ATOMIC && rows_ok) {
         // owner-computes: geometry pass into the handle's scratch, then the chunk-row pass
         MeshDev& dm = const_cast<MeshDev&>(d);

@@ -482,24 +482,26 @@ __global__ void k_fill_plans(const uint32_t* __restrict__ slot_node, const int64
     int k = (int)(blk_ptr[r + 1] - blk_ptr[r]);
     int64_t s0 = inc_ptr[node], s1 = inc_ptr[node + 1];
     int val = (int)(s1 - s0);
-    uint8_t* rec = pool + plan_off[p] * 4;
-    uint8_t* start = rec;
-    uint8_t* src = rec + k + 1;
-    // counting sort of the valence*NNE contributions by neighbour rank
-    uint8_t cnt[kMaxRowBlocks + 1];
-    for (int t = 0; t <= k; ++t) cnt[t] = 0;
-    for (int64_t s = s0; s < s1; ++s) {
-        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+    if (pool != nullptr) {  // (no plan records for handles served by the hex8 chunk-row pass: node table only)
+        uint8_t* rec = pool + plan_off[p] * 4;
+        uint8_t* start = rec;
+        uint8_t* src = rec + k + 1;
+        // counting sort of the valence*NNE contributions by neighbour rank
+        uint8_t cnt[kMaxRowBlocks + 1];
+        for (int t = 0; t <= k; ++t) cnt[t] = 0;
+        for (int64_t s = s0; s < s1; ++s) {
+            const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
 #pragma unroll
-        for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
-    }
-    for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
-    for (int t = 0; t <= k; ++t) start[t] = cnt[t];
-    int j = 0;
-    for (int64_t s = s0; s < s1; ++s, ++j) {
-        const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
+            for (int b = 0; b < NNE; ++b) cnt[rk[b] + 1]++;
+        }
+        for (int t = 0; t < k; ++t) cnt[t + 1] += cnt[t];
+        for (int t = 0; t <= k; ++t) start[t] = cnt[t];
+        int j = 0;
+        for (int64_t s = s0; s < s1; ++s, ++j) {
+            const uint8_t* rk = rank + (int64_t)inc_list[s] * NNE;
 #pragma unroll
-        for (int b = 0; b < NNE; ++b) src[cnt[rk[b]]++] = (uint8_t)((j << 3) | b);
+            for (int b = 0; b < NNE; ++b) src[cnt[rk[b]]++] = (uint8_t)((j << 3) | b);
+        }
     }
     ChunkNode cn;
     cn.gslot = blk_ptr[r] * m * m;
@@ -1254,11 +1256,14 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         d.device_bytes += nown * 8 * (int64_t)(sizeof(uint32_t) + sizeof(uint64_t));
     }
 
-    // ---- per-node plans
-    d.plan_bytes = h_plan_words * 4;
-    // +32 bytes: a chunk's plan is fetched with 16-byte aligned bulk copies that may over-read either end
-    PFG_CUDA_TRY(cudaMalloc(&d.plan_pool, d.plan_bytes + 32));
-    PFG_CUDA_TRY(cudaMemsetAsync(d.plan_pool, 0, d.plan_bytes + 32, st));
+    // ---- per-node plans (the hex8 chunk-row pass needs the node table only: no plan pool, no record corner tables)
+    const bool rows_only = (NNE == 8 && d.hex_rows_ok);
+    d.plan_bytes = rows_only ? 0 : h_plan_words * 4;
+    if (!rows_only) {
+        // +32 bytes: a chunk's plan is fetched with 16-byte aligned bulk copies that may over-read either end
+        PFG_CUDA_TRY(cudaMalloc(&d.plan_pool, d.plan_bytes + 32));
+        PFG_CUDA_TRY(cudaMemsetAsync(d.plan_pool, 0, d.plan_bytes + 32, st));
+    }
     PFG_CUDA_TRY(cudaMalloc(&d.cnodes, nown * sizeof(ChunkNode)));
     PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
     k_fill_plans<NNE><<<grid_for(nown, 128), 128, 0, st>>>(slot_node.p, d.inc_ptr, d.inc_list, d.rank, d.blk_ptr,
@@ -1276,6 +1281,14 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
     if (d.max_chunk_inc > 0xFFFE) {
         set_error("chunk with %d incidences exceeds the 16-bit slot range", d.max_chunk_inc);
         return PFG_ERR_UNSUPPORTED;
+    }
+    if (rows_only) {
+        cudaFree(d.rec_nodes);
+        cudaFree(d.rec_dst);
+        d.rec_nodes = nullptr;
+        d.rec_dst = nullptr;
+        d.device_bytes += d.nchunks * sizeof(ChunkHdr) + nown * (sizeof(ChunkNode) + 4) + d.nrecs * 4;
+        return PFG_OK;
     }
     d.device_bytes += d.nchunks * sizeof(ChunkHdr) + nown * (sizeof(ChunkNode) + 4) + d.nrecs * (NNE * 6 + 4) +
                       d.plan_bytes;
@@ -1476,6 +1489,9 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_PLAN_BYTES:
             if (d.tile_dir)
                 *value = (int64_t)(d.nchunks * sizeof(TileDir) + d.nrecs * (d.nne * 2) + d.nwin * 4 + d.plan_bytes);
+            else if (d.inc_rec8)  // hex8 chunk-row pass: chunk headers, node table, incidence tables, record elements
+                *value = (int64_t)(d.nchunks * sizeof(ChunkHdr) +
+                                   (d.own_end - d.own_begin) * (sizeof(ChunkNode) + 8 * (4 + 8)) + d.nrecs * 4);
             else
                 *value = d.nchunks ? (int64_t)(d.nchunks * sizeof(ChunkHdr) + (d.own_end - d.own_begin) * sizeof(ChunkNode) +
                                                d.nrecs * (d.nne * 6) + d.plan_bytes)

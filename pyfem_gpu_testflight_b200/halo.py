@@ -89,6 +89,19 @@ def match_rows(own_row_gid0, m, indptr, indices, row_gids, h_indptr, h_indices):
     return out
 
 
+def inbox_layout(send_table, m):
+    """Layout of the symmetric-memory inboxes of the p2p transport.  send_table[q, d] = (node rows, nnz) that rank q
+    sends to rank d.  Rank q's block in d's inbox holds its nnz CSR values, then one vector entry per dof row; blocks
+    follow each other in sender order.  Returns (doubles per inbox -- the same on every rank, symmetric allocations
+    must agree -- and offset[q][d] of q's block inside d's inbox)."""
+    T = np.asarray(send_table)
+    size = T.shape[0]
+    block = [[0 if q == d else int(T[q, d, 1]) + int(T[q, d, 0]) * m for d in range(size)] for q in range(size)]
+    offset = [[sum(block[qq][d] for qq in range(q)) for d in range(size)] for q in range(size)]
+    n = max(1, max(sum(block[q][d] for q in range(size)) for d in range(size)))
+    return n, offset
+
+
 class ReduceAssembler:
     """Device side: the rank's slab handle with masked ghost elements + one halo handle per neighbour, and the
     exchange.  Methods mirror DeviceMesh.assemble_*; nodal fields are given in the rank's local numbering."""
@@ -117,15 +130,11 @@ class ReduceAssembler:
     def _setup_p2p(self):
         import torch.distributed._symmetric_memory as symm_mem
         torch, rank, size, m = self.torch, self.part.rank, self.part.size, self.m
-        T = self._send_table  # T[q, d] = (node rows, nnz) that rank q sends to rank d
-
-        def block(q, d):  # doubles q writes into d's inbox: CSR values, then one vector entry per dof row
-            return int(T[q, d, 1]) + int(T[q, d, 0]) * m
+        n, off_table = inbox_layout(self._send_table, m)
 
         def offset(q, d):
-            return sum(block(qq, d) for qq in range(q) if qq != d)
+            return off_table[q][d]
 
-        n = max(1, max(sum(block(q, d) for q in range(size) if q != d) for d in range(size)))
         self.inbox = symm_mem.empty(n, dtype=torch.float64, device=self.device)  # same size on every rank
         self.symm = symm_mem.rendezvous(self.inbox, self.group if self.group is not None else self.dist.group.WORLD)
         self.peer_out = []
