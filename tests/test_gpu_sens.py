@@ -86,3 +86,29 @@ def test_compliance_gradient_matches_finite_difference(pf):
     cm, _ = mp.compliance(rho - h * pert, solver="direct")
     fd = (cp - cm) / (2 * h)
     assert abs(fd - grad.dot(pert)) <= 1e-6 * abs(fd)
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_sensitivities_on_row_slabs(pf, three_d):
+    """Multi-GPU decomposition with the ranks emulated one after another: each rank's handle (element block + ghost
+    layer, owned node range) yields the owned nodes' sensitivities; concatenated they are the global vector."""
+    from pyfem_gpu_testflight_b200.partition import partition_mesh
+    if three_d:
+        X, conn = orc.structured_mesh(8, 7, 12)
+        X = jitter(X, (8, 7, 12), seed=9)
+    else:
+        X, conn = orc.structured_mesh(37, 45)
+        X = jitter(X, (37, 45), seed=9)
+    nn, d = X.shape
+    rng = np.random.default_rng(4)
+    rho = 0.05 + 0.95 * rng.random(nn)
+    phi, psi = rng.random(nn * d) - 0.5, rng.random(nn * d) - 0.5
+    ref = orc.elasticity_K_dv_sens(X, conn, rho, 3.0, phi, psi, 8.0, 0.31)
+    out = []
+    for r in range(3):
+        part = partition_mesh(X, conn, r, 3)
+        mesh = pf.DeviceMesh(part.X, part.conn, d, own_range=part.own_range, node_gid=part.node_gid,
+                             ncols_nodes=part.nnodes_global)
+        dof = (part.node_gid[:, None] * d + np.arange(d)[None, :]).ravel()
+        out.append(mesh.k_dv_sens("elasticity", rho[part.node_gid], 3.0, phi[dof], psi[dof], E=8.0, nu=0.31).cpu().numpy())
+    assert_values_close(np.concatenate(out), ref, VAL_TOL)
