@@ -810,10 +810,11 @@ __global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHe
 #ifndef PFG_HEX_NB
 #define PFG_HEX_NB 4  // column nodes per pass over the quadrature points: two passes with 36 running sums each
 #endif                // (no spills, 3.98 ms for 128^3 hex) beat one pass with 72 (4.16 ms)
-constexpr int kHexRowsThreads = 256, kHexRowWarps = kHexRowsThreads / 32 - 1;
+constexpr int kHexRowsThreads = (kHexRowWarps + 1) * 32;
 constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
-constexpr int kHexGeoStride = 8 * kHexGeoDoubles + 2;  // doubles per staged record: 656 B keeps 16-byte reads of
+constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
                                                        // consecutive records on different banks
+static_assert(kHexGeoRecordBytes == (8 * kHexGeoDoubles + 2) * 8, "hex8 geometry record layout");
 
 PFG_DEV void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -1352,18 +1353,15 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
             PFG_CUDA_TRY(cudaMalloc(&dm.hex_geo, (size_t)d.nelems * 8 * kHexGeoDoubles * sizeof(double)));
             dm.device_bytes += d.nelems * 8 * kHexGeoDoubles * (int64_t)sizeof(double);
         }
+        const HexRowsSmem L = hex_rows_smem(d.max_chunk_recs, d.max_k);  // fits: checked when the plan was built
         HexRowsCfg cfg;
-        cfg.image_stride = 9 * d.max_k;
+        cfg.image_stride = L.image_stride;
         cfg.nchunks = (int)d.nchunks;
-        cfg.off_geo = 128;
-        cfg.geo_stage_bytes = align16(d.max_chunk_recs * kHexGeoStride * 8);
-        cfg.off_image = cfg.off_geo + 2 * cfg.geo_stage_bytes;
-        cfg.off_meta = cfg.off_image + kHexRowWarps * 4 * cfg.image_stride * 8;
-        const size_t smem = (size_t)cfg.off_meta + (size_t)kHexRowWarps * (32 * 64 + 16);
-        if (smem > 227 * 1024) {
-            set_error("chunk staging of %zu bytes exceeds shared memory", smem);
-            return PFG_ERR_UNSUPPORTED;
-        }
+        cfg.off_geo = L.off_geo;
+        cfg.geo_stage_bytes = L.geo_stage_bytes;
+        cfg.off_image = L.off_image;
+        cfg.off_meta = L.off_meta;
+        const size_t smem = L.total;
         static thread_local size_t cached_smem = 0;
         if (cached_smem != smem) {
             PFG_CUDA_TRY(cudaFuncSetAttribute(k_hex8_chunk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1385,6 +1383,10 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
     // elements of a node that reach one neighbour through the same local index): the slot-indexed atomic scatter
     // (measured on B200, 128^3 hex: 6.4 ms) beats the first-format gather kernel (9.1 ms), so AUTO means atomic
     if (mode == PFG_MODE_AUTO) gather = false;
+    if (gather && d.plan_pool == nullptr) {
+        set_error("this hex8 handle has no plan for the staged-row-block gather kernel");
+        return PFG_ERR_UNSUPPORTED;
+    }
     if (!gather) {
         PFG_TRY(zero_outputs(d, out, st));
         const unsigned grid = (unsigned)((d.nelems + 15) / 16);

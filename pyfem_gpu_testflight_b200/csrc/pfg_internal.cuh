@@ -140,6 +140,26 @@ struct TileLayout {  // how an operator stages one record; decides the code enco
     }
 };
 
+// hex8 chunk-row pass (k_hex8_chunk_rows): shared-memory layout shared by the plan builder (does a mesh fit?) and
+// the launch
+constexpr int kHexRowWarps = 7;                     // consumer warps, four chunk nodes each (+ one producer warp)
+constexpr int kHexGeoRecordBytes = (8 * 10 + 2) * 8; // staged geometry of one element record: 640 B + 16 B bank shift
+struct HexRowsSmem {
+    int off_geo, geo_stage_bytes, off_image, image_stride, off_meta;
+    size_t total;
+};
+inline HexRowsSmem hex_rows_smem(int max_chunk_recs, int max_k) {
+    HexRowsSmem L;
+    L.image_stride = 9 * max_k;  // doubles per chunk node in a warp's image
+    L.off_geo = 128;
+    L.geo_stage_bytes = (max_chunk_recs * kHexGeoRecordBytes + 15) & ~15;
+    L.off_image = L.off_geo + 2 * L.geo_stage_bytes;
+    L.off_meta = L.off_image + kHexRowWarps * 4 * L.image_stride * 8;
+    L.total = (size_t)L.off_meta + (size_t)kHexRowWarps * (32 * 64 + 16);
+    return L;
+}
+constexpr size_t kMaxDynamicSmem = 227 * 1024;
+
 constexpr int kMaxValence = 31;      // 5-bit ordinal; start[] must fit uint8 (31*8 = 248)
 constexpr int kMaxRowBlocks = 255;   // rank fits uint8
 constexpr uint16_t kNoDst = 0xFFFF;

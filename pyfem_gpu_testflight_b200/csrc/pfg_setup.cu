@@ -1287,6 +1287,14 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         cudaFree(d.rec_dst);
         d.rec_nodes = nullptr;
         d.rec_dst = nullptr;
+        if (hex_rows_smem(d.max_chunk_recs, d.max_k).total > kMaxDynamicSmem) {
+            // chunks with too many element records for the geometry ring (very irregular meshes): atomic scatter only
+            cudaFree(d.inc_rec8);
+            cudaFree(d.inc_ranks8);
+            d.inc_rec8 = nullptr;
+            d.inc_ranks8 = nullptr;
+            d.hex_rows_ok = 0;
+        }
         d.device_bytes += d.nchunks * sizeof(ChunkHdr) + nown * (sizeof(ChunkNode) + 4) + d.nrecs * 4;
         return PFG_OK;
     }

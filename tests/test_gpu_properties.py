@@ -295,3 +295,17 @@ def test_hex_chunk_rows_large_chunks_second_round(pf, monkeypatch):
     Kr = orc.assemble_elasticity(X, conn, rho, 2.0)
     v = mesh.assemble_elasticity(rho, 2.0, mode="gather").cpu().numpy()
     assert_values_close(v, Kr.data, VAL_TOL)
+
+
+def test_hex_chunk_rows_fall_back_when_chunks_exceed_shared_memory(pf, monkeypatch):
+    """Chunks whose element records do not fit the geometry ring: the handle drops the chunk-row pass when it is
+    built; AUTO assembles with the atomic scatter, GATHER says so."""
+    from pyfem_gpu_testflight_b200 import _lib
+    monkeypatch.setenv("PFG_HEX_CHUNK_NODES", "150")
+    X, conn = _hex_jittered(11, 10, 9, seed=13)
+    mesh = pf.DeviceMesh(X, conn, 3)
+    assert mesh.info(_lib.INFO_HEX_ROWS) == 0
+    Kr = orc.assemble_elasticity(X, conn, 1.0, 0.0)
+    assert_values_close(mesh.assemble_elasticity(mode="auto").cpu().numpy(), Kr.data, VAL_TOL)
+    with pytest.raises(NotImplementedError):
+        mesh.assemble_elasticity(mode="gather")
