@@ -444,8 +444,9 @@ struct TileCfg {
     int off_dir;                  // ring of 8 TileDir entries
     int off_blob, off_codes;      // chunk blob / codes buffers (one stage each)
     int off_win, win_stride;      // node-window ids, two stages
-    int off_loc;                  // window indices of the record corners (one stage)
-    int off_x, off_field;         // coordinates / nodal field of the window nodes (one stage)
+    int off_loc, loc_stride;      // window indices of the record corners (DEEP: two stages, loc_stride apart)
+    int off_x, off_field;         // coordinates / nodal field of the window nodes (DEEP: two stages)
+    int x_stride, field_stride;
     int off_stage;                // element-record staging
     int off_image;                // image of the chunk's CSR values (TMA bulk-store source)
     int image_stride;             // doubles between the images of an operator's matrices (Helmholtz: K and R)
@@ -586,9 +587,18 @@ PFG_DEV void cp_async_mbar_arrive(uint64_t* bar) {  // the mbarrier sees this th
 // register scoreboards: TMA bulk copies bring the directory-addressed blob + codes (one ahead), the corner
 // indices (one ahead) and the window's node ids (two ahead); cp.async gathers the window's coordinates one
 // chunk ahead and reports to an mbarrier.
+// Operators with `static constexpr bool DEEP_PREFETCH = true` double-buffer the window coordinates / field and the
+// corner indices and fetch them a whole chunk ahead (costs 3-4 KB of shared memory: pays for the register-limited
+// nonlinear Poisson kernel, 1.99 -> 1.90 ms, not where it would cost a CTA per SM).
+template <class Op, class = void>
+struct op_deep_prefetch : std::false_type {};
+template <class Op>
+struct op_deep_prefetch<Op, std::enable_if_t<Op::DEEP_PREFETCH>> : std::true_type {};
+
 template <class Op, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB)
     k_tile(MeshView mv, typename Op::Params prm, Outputs out, TileCfg cfg) {
+    constexpr bool DEEP = op_deep_prefetch<Op>::value;
     extern __shared__ __align__(128) unsigned char smem[];
     using St = TileStage<Op>;
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
@@ -601,9 +611,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
     TileDir* dir_s = reinterpret_cast<TileDir*>(smem + cfg.off_dir);
     unsigned char* blob_s = smem + cfg.off_blob;
     uint16_t* codes_s = reinterpret_cast<uint16_t*>(smem + cfg.off_codes);
-    unsigned char* loc_s = smem + cfg.off_loc;
-    double* xs = reinterpret_cast<double*>(smem + cfg.off_x);
-    double* fs = reinterpret_cast<double*>(smem + cfg.off_field);
+    auto loc_stage = [&](int j) -> unsigned char* { return smem + cfg.off_loc + (DEEP ? (j & 1) * cfg.loc_stride : 0); };
+    auto x_stage = [&](int j) -> double* {
+        return reinterpret_cast<double*>(smem + cfg.off_x + (DEEP ? (j & 1) * cfg.x_stride : 0));
+    };
+    auto f_stage = [&](int j) -> double* {
+        return reinterpret_cast<double*>(smem + cfg.off_field + (DEEP ? (j & 1) * cfg.field_stride : 0));
+    };
     double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
     double* image = reinterpret_cast<double*>(smem + cfg.off_image);
     const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;  // entries 0..nloc (nloc = next CTA's first / sentinel)
@@ -624,7 +638,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const size_t lo = (size_t)dir_s[j & 7].rec_begin * NNE * 2, lo16 = lo & ~(size_t)15;
         const uint32_t bytes = (uint32_t)(((lo + (size_t)n_recs_of(j) * NNE * 2 + 15) & ~(size_t)15) - lo16);
         mbar_expect_tx(&bars[3], bytes);
-        if (bytes) tma_load_1d(loc_s, reinterpret_cast<const unsigned char*>(mv.rec_local) + lo16, bytes, &bars[3]);
+        if (bytes) tma_load_1d(loc_stage(j), reinterpret_cast<const unsigned char*>(mv.rec_local) + lo16, bytes, &bars[3]);
     };
     auto issue_meta = [&](int j) {
         const TileDir t = dir_s[j & 7], t1 = dir_s[(j + 1) & 7];
@@ -638,6 +652,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
         const uint32_t* __restrict__ win =
             reinterpret_cast<const uint32_t*>(win_stage(j) + (((size_t)dir_s[j & 7].win_begin * 4) & 15));
         const int n_win = n_win_of(j);
+        double* xs = x_stage(j);
+        double* fs = f_stage(j);
         for (int t = threadIdx.x; t < n_win; t += THREADS) {
             const size_t node = win[t];
             double* dst = xs + (size_t)t * DIM;
@@ -672,9 +688,23 @@ __global__ void __launch_bounds__(THREADS, MINB)
         if (threadIdx.x == 0 && i + 5 <= nloc) cp_async_16(&dir_s[(i + 5) & 7], &dir_g[i + 5]);  // rides on the next arrive
         mbar_wait(&bars[4], i & 1);  // the window's coordinates have landed (all threads' copies)
         mbar_wait(&bars[3], i & 1);  // and so have the corner indices
+        // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
+        auto prefetch_next = [&]() {
+            if (threadIdx.x == 0) {
+                if (i + 2 < nloc) issue_win(i + 2);
+                if (i + 1 < nloc) issue_loc(i + 1);
+            }
+            if (i + 1 < nloc) {
+                mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
+                gather_window(i + 1);
+            }
+        };
+        if constexpr (DEEP) prefetch_next();  // into the other stage: phases A and B of this chunk to land
         // ---- phase A: one thread per element record -> staged element matrices
         const int n_recs = n_recs_of(i);
-        const unsigned char* loc_i = loc_s + (((size_t)dir_s[i & 7].rec_begin * NNE * 2) & 15);
+        const unsigned char* loc_i = loc_stage(i) + (((size_t)dir_s[i & 7].rec_begin * NNE * 2) & 15);
+        const double* xs = x_stage(i);
+        const double* fs = f_stage(i);
         for (int r = threadIdx.x; r < n_recs; r += THREADS) {
             TileSink<Op> sink{stage + (size_t)(r + 1) * St::S};  // slot 0 is the all-zero record
             unsigned loc[NNE];
@@ -708,15 +738,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         tma_store_wait_read();  // the previous chunk's bulk stores have read the image
         __syncthreads();
-        // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
-        if (threadIdx.x == 0) {
-            if (i + 2 < nloc) issue_win(i + 2);
-            if (i + 1 < nloc) issue_loc(i + 1);
-        }
-        if (i + 1 < nloc) {
-            mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
-            gather_window(i + 1);
-        }
+        if constexpr (!DEEP) prefetch_next();  // single stage: free once phase A of this chunk has read it
         // ---- phase B: plan-ordered sums into the CSR image, each CSR value written once
         mbar_wait(&bars[0], i & 1);
         {
@@ -1205,10 +1227,14 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
     cfg.off_codes = cfg.off_blob + align16(d.max_blob_bytes);
     cfg.off_win = cfg.off_codes + align16(d.max_code_bytes) + 16;  // slack: phase B may read a few codes past the end
     cfg.win_stride = align16(d.max_chunk_win * 4) + 16;            // copies start at the enclosing 16-byte boundary
+    constexpr int NST = op_deep_prefetch<Op>::value ? 2 : 1;  // stages of the corner-index / window-data buffers
     cfg.off_loc = cfg.off_win + 2 * cfg.win_stride;
-    cfg.off_x = cfg.off_loc + align16(d.max_chunk_recs * NNE * 2) + 16;
-    cfg.off_field = cfg.off_x + align16(d.max_chunk_win * DIM * 8);
-    cfg.off_stage = cfg.off_field + (Op::field(prm) ? align16(d.max_chunk_win * 8) : 0);
+    cfg.loc_stride = align16(d.max_chunk_recs * NNE * 2) + 16;
+    cfg.off_x = cfg.off_loc + NST * cfg.loc_stride;
+    cfg.x_stride = align16(d.max_chunk_win * DIM * 8);
+    cfg.off_field = cfg.off_x + NST * cfg.x_stride;
+    cfg.field_stride = Op::field(prm) ? align16(d.max_chunk_win * 8) : 0;
+    cfg.off_stage = cfg.off_field + NST * cfg.field_stride;
     cfg.nchunks = (int)d.nchunks;
     cfg.off_image = align16(cfg.off_stage + (d.max_chunk_recs + 1) * St::S * 8);
     if ((Op::M == 2) != (d.m == 2)) {

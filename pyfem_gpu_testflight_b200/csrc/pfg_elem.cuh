@@ -410,6 +410,7 @@ constexpr int kMaxXdv = 32;
 struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) + residual (pyfem.py:1474-1539)
     static constexpr int NNE = 4, M = 1, NMAT = 1, NVEC = 1, DIM = 2, NQ = 4;
     static constexpr bool NEEDS_ELEM = false, SYM = false;  // the Newton Jacobian is not symmetric
+    static constexpr bool DEEP_PREFETCH = true;             // register-limited (3 CTAs / SM): shared memory to spare
     struct Params {
         const double* u;
         int nxdv;
