@@ -1296,6 +1296,7 @@ static Material material_of(const double* rho_dev, double rho_const, double p) {
     Material m;
     m.rho = rho_dev;
     m.rho_const = rho_const;
+    m.c_const = rho_const / (1.0 + p * (1.0 - rho_const));
     m.p = p;
     return m;
 }

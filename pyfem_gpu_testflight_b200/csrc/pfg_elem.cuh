@@ -227,12 +227,13 @@ PFG_DEV double interp(const double (&f)[NNE]) {  // node -> quadrature point (ut
 struct Material {
     const double* rho;  // nodal field or nullptr
     double rho_const, p;
+    double c_const;  // RAMP factor of the constant field, rho_const / (1 + p (1 - rho_const)), formed once on the host
 };
 
 template <int NNE>
 PFG_DEV void material_at_quads(const Material& mat, const double (&re)[NNE], double (&cq)[Elem<NNE>::NQ]) {
     if (mat.rho == nullptr) {
-        const double c = mat.rho_const / (1.0 + mat.p * (1.0 - mat.rho_const));  // uniform: once per thread
+        const double c = mat.c_const;  // uniform field
 #pragma unroll
         for (int q = 0; q < Elem<NNE>::NQ; ++q) cq[q] = c;
         return;
@@ -649,7 +650,7 @@ PFG_DEV void elasticity_hex8_octet(const MeshView& mv, const ElasticityHex8Param
 #pragma unroll
             for (int l = 0; l < 3; ++l) G[a][l] = dn[a][0] * A[0][l] + dn[a][1] * A[1][l] + dn[a][2] * A[2][l];
         if (prm.mat.rho == nullptr) {
-            cq = prm.mat.rho_const / (1.0 + prm.mat.p * (1.0 - prm.mat.rho_const));
+            cq = prm.mat.c_const;
         } else {
             double rq = 0.0;
 #pragma unroll
@@ -761,7 +762,7 @@ PFG_DEV void hex8_geometry_point(const MeshView& mv, const Material& mat, const 
     A[2][2] = J[0][0] * J[1][1] - J[0][1] * J[1][0];
     const double det = J[0][0] * A[0][0] + J[0][1] * A[1][0] + J[0][2] * A[2][0];
     double cq;
-    if (mat.rho == nullptr) cq = mat.rho_const / (1.0 + mat.p * (1.0 - mat.rho_const));
+    if (mat.rho == nullptr) cq = mat.c_const;
     else cq = rq * fast_rcp(fma(mat.p, 1.0 - rq, 1.0));
     const double s = skip ? 0.0 : cq * fast_rcp(det);  // a masked element (another rank integrates it) adds zeros
     double2* o = reinterpret_cast<double2*>(out);
