@@ -44,7 +44,8 @@ typedef enum pfg_status {
     PFG_ERR_CUDA = -2,        /* CUDA runtime failure (reference: RuntimeError) */
     PFG_ERR_UNSUPPORTED = -3, /* element / physics combination not implemented on the device */
     PFG_ERR_MESH = -4,        /* conn.min() != 0 or conn.max() != nnodes-1 (reference asserts, pyfem.py:680-681) */
-    PFG_ERR_NOMEM = -5
+    PFG_ERR_NOMEM = -5,
+    PFG_ERR_NOCONV = -6       /* pfg_cg: max_iter reached before the tolerance (reference: RuntimeError "cg failed") */
 } pfg_status;
 
 typedef enum pfg_elem {
@@ -226,8 +227,34 @@ PFG_API int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, do
 
 /*
  * y = A x on the device CSR of the owned rows (Helmholtz.compute_rhs = R.dot(x), pyfem.py:2117-2120).
+ * x is indexed by global column (ncols entries), y has one entry per owned dof row.
  */
 PFG_API int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream);
+
+/*
+ * y = A^T x (Helmholtz.apply_gradient = RT.dot(Ksolve.solve(g)), pyfem.py:2109-2115), without forming the
+ * transpose: entry (c, r) is read from row c at the rank of r among c's columns.  Needs a handle that owns every
+ * row (PFG_ERR_UNSUPPORTED for a rank's slab).
+ */
+PFG_API int pfg_spmv_t(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream);
+
+/*
+ * Jacobi-preconditioned conjugate gradients on the device CSR: the GPU stand-in for
+ * Assembler._solve_linear_system(K, rhs, method="cg") (pyfem.py:2403-2423) and for the solves inside compliance
+ * (pyfem.py:1050-1068, 1814-1828), so that a solve never copies K to the host.  The reference preconditions with
+ * pyamg smoothed aggregation; the stopping rule is scipy's: |b - A x| <= max(rtol |b|, atol).
+ *   vals_dev    CSR values (after pfg_apply_dirichlet); symmetric positive definite
+ *   b_dev       right-hand side (nrows)
+ *   x_dev       in: initial guess unless x_is_zero != 0 (then zero-filled here); out: the solution
+ *   check_every iterations between two convergence checks (each check is one device->host copy of the partial sums
+ *               of |r|^2; <= 0: 16).  Dot products are summed in a fixed order: results are reproducible.
+ *   iters_out, resid_out   (host, may be NULL) iterations done and the final |r|
+ * Returns PFG_OK, or PFG_ERR_NOCONV when max_iter was reached first (x_dev holds the last iterate).  Needs a handle
+ * that owns every row.
+ */
+PFG_API int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, int x_is_zero,
+                   double rtol, double atol, int max_iter, int check_every, int* iters_out, double* resid_out,
+                   void* stream);
 
 #ifdef __cplusplus
 }

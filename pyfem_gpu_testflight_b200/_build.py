@@ -1,8 +1,11 @@
 """Build the in-tree CUDA library (libpyfem_b200.so) for sm_100a with nvcc.
 
 The .so is git-ignored but travels to the GPU box with the gpurun snapshot, so it is built here
-(nvcc cross-compiles without a GPU) and only rebuilt when a source is newer than the library.
+(nvcc cross-compiles without a GPU) and only rebuilt when the sources' content hash differs from the one stamped
+beside the library (libpyfem_b200.so.srchash).
 """
+import fcntl
+import hashlib
 import os
 import shutil
 import subprocess
@@ -12,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libpyfem_b200.so")
-SOURCES = ["pfg_setup.cu", "pfg_assemble.cu"]
+SOURCES = ["pfg_setup.cu", "pfg_assemble.cu", "pfg_solve.cu"]
 HEADERS = ["pfg_internal.cuh", "pfg_elem.cuh"]
 NVCC_FLAGS = [
     "-std=c++20", "-O3", "-lineinfo",
@@ -30,21 +33,46 @@ def _nvcc():
     raise RuntimeError("nvcc not found; cannot build libpyfem_b200.so")
 
 
+STAMP_PATH = LIB_PATH + ".srchash"
+
+
+def _deps():
+    return [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "pyfem_b200.h")]
+
+
+def _source_hash():
+    """Content hash of every source the library is built from (+ the flags): file times do not survive the copy to
+    the GPU box, contents do."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for d in _deps():
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale():
-    if not os.path.isfile(LIB_PATH):
+    if not os.path.isfile(LIB_PATH) or not os.path.isfile(STAMP_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.join(INCLUDE, "pyfem_b200.h"), __file__]
-    return any(os.path.getmtime(d) > t for d in deps)
+    with open(STAMP_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 def build(force=False, verbose=False):
-    """Compile every .cu for sm_100a and link libpyfem_b200.so next to this file."""
+    """Compile every .cu for sm_100a and link libpyfem_b200.so next to this file (no-op when the library matches the
+    sources).  Serialised across processes: several ranks may import the package at once."""
     if not force and not _stale():
         return LIB_PATH
-    nvcc = _nvcc()
     objdir = os.path.join(PKG_DIR, "build")
     os.makedirs(objdir, exist_ok=True)
+    with open(os.path.join(objdir, ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not _stale():  # another process built it while this one waited
+            return LIB_PATH
+        return _build_locked(objdir, verbose)
+
+
+def _build_locked(objdir, verbose):
+    nvcc = _nvcc()
     procs = []
     objs = []
     for src in SOURCES:
@@ -60,11 +88,15 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [nvcc, "-shared", "-o", LIB_PATH, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp = LIB_PATH + ".tmp"
+    link = [nvcc, "-shared", "-o", tmp, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
     res = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout)
         raise RuntimeError("link failed: " + " ".join(link))
+    os.replace(tmp, LIB_PATH)
+    with open(STAMP_PATH, "w") as f:
+        f.write(_source_hash() + "\n")
     return LIB_PATH
 
 

@@ -16,6 +16,7 @@ PFG_ERR_CUDA = -2
 PFG_ERR_UNSUPPORTED = -3
 PFG_ERR_MESH = -4
 PFG_ERR_NOMEM = -5
+PFG_ERR_NOCONV = -6
 
 PFG_QUAD4 = 4
 PFG_HEX8 = 8
@@ -52,6 +53,9 @@ PROTOTYPES = {
     "pfg_poisson_rhs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_apply_dirichlet": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),
     "pfg_spmv": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pfg_spmv_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pfg_cg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_int,
+                       POINTER(c_int), POINTER(c_double), c_void_p]),
     "pfg_scatter_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_scatter_vector": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_element_matrices": (c_int, [c_void_p, c_int, c_void_p, c_double, POINTER(c_double), c_int, c_void_p, c_void_p,
@@ -75,8 +79,13 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if not os.path.isfile(path) or (os.environ.get("PFG_REBUILD") == "1"):
-        _build.build()
+    # build() returns at once unless a source / header is newer than the library (or the library is missing); where
+    # there is no compiler (a box that received the prebuilt .so) a present library is loaded as it is
+    try:
+        _build.build(force=os.environ.get("PFG_REBUILD") == "1")
+    except RuntimeError:
+        if not os.path.isfile(path):
+            raise
     lib = ctypes.CDLL(path)
     for name, (restype, argtypes) in PROTOTYPES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported

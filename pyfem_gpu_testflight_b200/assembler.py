@@ -1,8 +1,9 @@
 """Assembler: the callers of the assembly path (pyfem.py:2286-2423) -- linear solve and Newton loop.
 
-The solver itself is outside the hot path: the assembled scipy CSR goes to
-scipy's direct solver, or to cg / gmres (preconditioned with pyamg smoothed aggregation when pyamg is
-installed, as in the reference, else unpreconditioned).
+By default the assembled scipy CSR goes to scipy's direct solver, or to cg / gmres (preconditioned with pyamg
+smoothed aggregation when pyamg is installed, as in the reference, else unpreconditioned).  `solve(method="cg",
+device=True)` is the GPU consumer of SURVEY.md section 8f #4: boundary conditions and conjugate gradients run on
+the device CSR, so the matrix never crosses PCIe.
 """
 import numpy as np
 from scipy.sparse.linalg import cg, gmres, spsolve
@@ -12,9 +13,16 @@ class Assembler:
     def __init__(self, model):
         self.model = model
 
-    def solve(self, method="gmres"):
-        """Static analysis (pyfem.py:2299-2317)."""
+    def solve(self, method="gmres", device=False):
+        """Static analysis (pyfem.py:2299-2317).  device=True (with method="cg"): assembly, Dirichlet conditions and
+        a Jacobi-preconditioned CG all run on the device CSR -- K is never copied to the host (SURVEY 8f #4)."""
         assert method in ("direct", "cg", "gmres")
+        if device:
+            if method != "cg":
+                raise NotImplementedError("the device solve is conjugate gradients: use method='cg'")
+            vals = self.model.compute_jacobian_device()
+            u, _, self.last_iterations = self.model.solve_device(vals, self.model.compute_rhs())
+            return u.cpu().numpy()
         K = self.model.compute_jacobian()
         rhs = self.model.compute_rhs()
         K, rhs = self.model.apply_dirichlet_bcs(K, rhs, enforce_symmetric_K=True)

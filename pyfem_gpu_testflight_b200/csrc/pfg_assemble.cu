@@ -1100,70 +1100,6 @@ __global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, do
         if (nodes[a] >= mv.own_begin && nodes[a] < mv.own_end) atomicAdd(out + (nodes[a] - mv.own_begin), inner[a]);
 }
 
-// Dirichlet rows/columns on the device CSR, pattern kept (pyfem.py:780-835 minus eliminate_zeros).
-__global__ void k_mark_fixed(const int64_t* __restrict__ fixed, const double* __restrict__ fixed_vals, int64_t nfixed,
-                             int64_t ncols, uint8_t* __restrict__ is_fixed, double* __restrict__ u0) {
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (i >= nfixed) return;
-    int64_t dof = fixed[i];
-    if (dof < 0 || dof >= ncols) return;
-    is_fixed[dof] = 1;
-    u0[dof] = fixed_vals ? fixed_vals[i] : 0.0;
-}
-
-__global__ void k_apply_dirichlet(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
-                                  const int64_t* __restrict__ gid, int64_t own_begin, int64_t nown, int m,
-                                  const uint8_t* __restrict__ is_fixed, const double* __restrict__ u0, int symmetric,
-                                  int have_vals, double* __restrict__ vals, double* __restrict__ rhs) {
-    // one thread per owned dof row
-    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= nown * m) return;
-    int64_t r = row / m;
-    int alpha = (int)(row - r * m);
-    int64_t node = own_begin + r;
-    int64_t grow = (gid ? gid[node] : node) * m + alpha;
-    int64_t p0 = blk_ptr[r], k = blk_ptr[r + 1] - p0;
-    double* v = vals + p0 * m * m + alpha * k * m;
-    const bool row_fixed = is_fixed[grow];
-    double corr = 0.0;
-    for (int64_t t = 0; t < k; ++t) {
-        int64_t cnode = nbr[p0 + t];
-        int64_t gcol0 = (gid ? gid[cnode] : cnode) * m;
-        for (int beta = 0; beta < m; ++beta) {
-            int64_t gcol = gcol0 + beta;
-            double& x = v[t * m + beta];
-            if (row_fixed) {
-                x = (gcol == grow) ? 1.0 : 0.0;
-            } else if (symmetric && is_fixed[gcol]) {
-                if (have_vals) corr = fma(x, u0[gcol], corr);
-                x = 0.0;
-            }
-        }
-    }
-    if (rhs) {
-        if (row_fixed) rhs[row] = u0[grow];
-        else if (symmetric && have_vals) rhs[row] -= corr;
-    }
-}
-
-__global__ void k_spmv(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
-                       const int64_t* __restrict__ gid, int64_t nown, int m, const double* __restrict__ vals,
-                       const double* __restrict__ x, double* __restrict__ y) {
-    int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (row >= nown * m) return;
-    int64_t r = row / m;
-    int alpha = (int)(row - r * m);
-    int64_t p0 = blk_ptr[r], k = blk_ptr[r + 1] - p0;
-    const double* v = vals + p0 * m * m + alpha * k * m;
-    double s = 0.0;
-    for (int64_t t = 0; t < k; ++t) {
-        int64_t cnode = nbr[p0 + t];
-        int64_t gcol0 = (gid ? gid[cnode] : cnode) * m;
-        for (int beta = 0; beta < m; ++beta) s = fma(v[t * m + beta], x[gcol0 + beta], s);
-    }
-    y[row] = s;
-}
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1241,6 +1177,13 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
         set_error("tile plan was built for %d dofs per node, the operator has %d", d.m, Op::M);
         return PFG_ERR_INVALID;
     }
+    // the image leaves through cp.async.bulk stores whose global addresses are formed from 16-byte aligned slots:
+    // a values buffer that is itself misaligned (a tensor view at an odd offset, a packed inbox block) would fault
+    for (int mt = 0; mt < 2; ++mt)
+        if (Op::NMAT > mt && out.vals[mt] != nullptr && (reinterpret_cast<uintptr_t>(out.vals[mt]) & 15) != 0) {
+            set_error("CSR values buffer %p is not 16-byte aligned (bulk stores need it)", (void*)out.vals[mt]);
+            return PFG_ERR_INVALID;
+        }
     cfg.image_stride = align16(d.max_out_bytes) / 8;
     const size_t smem = (size_t)cfg.off_image + (size_t)Op::NMAT * cfg.image_stride * 8;
     if (smem > 227 * 1024) {
@@ -1390,10 +1333,12 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         cfg.off_meta = L.off_meta;
         const size_t smem = L.total;
         static thread_local size_t cached_smem = 0;
-        if (cached_smem != smem) {
+        static thread_local int cached_device = -1;  // function attributes are per device
+        if (cached_smem != smem || cached_device != d.device) {
             PFG_CUDA_TRY(cudaFuncSetAttribute(k_hex8_chunk_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             PFG_CUDA_TRY(cudaFuncSetAttribute(k_hex8_chunk_rows, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
             cached_smem = smem;
+            cached_device = d.device;
         }
         const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, d.sm_count);
         static const bool debug = getenv("PFG_DEBUG") != nullptr;
@@ -1493,37 +1438,6 @@ extern "C" int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs
     }
     PoissonRhsOp<8>::Params prm{gq_dev};
     return launch<PoissonRhsOp<8>, 128, 2>(d, prm, out, gather, (cudaStream_t)stream);
-}
-
-extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, const double* fixed_vals_dev,
-                                   int64_t nfixed, int enforce_symmetric, double* vals_dev, double* rhs_dev,
-                                   void* stream) {
-    PFG_CHECK_MESH(mesh);
-    const MeshDev& d = mesh->d;
-    if (!vals_dev || nfixed < 0 || (nfixed > 0 && !fixed_dofs_dev)) {
-        set_error("pfg_apply_dirichlet: invalid argument");
-        return PFG_ERR_INVALID;
-    }
-    cudaStream_t st = (cudaStream_t)stream;
-    const int64_t ncols = d.ncols_nodes * d.m;
-    uint8_t* is_fixed = nullptr;
-    double* u0 = nullptr;
-    PFG_CUDA_TRY(cudaMallocAsync(&is_fixed, ncols, st));
-    PFG_CUDA_TRY(cudaMallocAsync(&u0, ncols * sizeof(double), st));
-    PFG_CUDA_TRY(cudaMemsetAsync(is_fixed, 0, ncols, st));
-    PFG_CUDA_TRY(cudaMemsetAsync(u0, 0, ncols * sizeof(double), st));
-    if (nfixed)
-        k_mark_fixed<<<(unsigned)((nfixed + 255) / 256), 256, 0, st>>>(fixed_dofs_dev, fixed_vals_dev, nfixed, ncols,
-                                                                      is_fixed, u0);
-    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
-    if (nrows)
-        k_apply_dirichlet<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
-            d.blk_ptr, d.nbr, d.gid, d.own_begin, d.own_end - d.own_begin, d.m, is_fixed, u0, enforce_symmetric,
-            fixed_vals_dev != nullptr, vals_dev, rhs_dev);
-    PFG_CUDA_TRY(cudaGetLastError());
-    PFG_CUDA_TRY(cudaFreeAsync(is_fixed, st));
-    PFG_CUDA_TRY(cudaFreeAsync(u0, st));
-    return PFG_OK;
 }
 
 template <class Op>
@@ -1682,22 +1596,6 @@ extern "C" int pfg_add_indexed(double* vals_dev, const int64_t* idx_dev, const d
         return PFG_ERR_INVALID;
     }
     if (n) k_add_indexed<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(vals_dev, idx_dev, src_dev, n);
-    PFG_CUDA_TRY(cudaGetLastError());
-    return PFG_OK;
-}
-
-extern "C" int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream) {
-    PFG_CHECK_MESH(mesh);
-    const MeshDev& d = mesh->d;
-    if (!vals_dev || !x_dev || !y_dev) {
-        set_error("pfg_spmv: NULL argument");
-        return PFG_ERR_INVALID;
-    }
-    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
-    if (nrows)
-        k_spmv<<<(unsigned)((nrows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(d.blk_ptr, d.nbr, d.gid,
-                                                                                 d.own_end - d.own_begin, d.m, vals_dev,
-                                                                                 x_dev, y_dev);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
 }

@@ -220,6 +220,11 @@ struct MeshDev {
     uint32_t* inc_rec8 = nullptr;      // (nown, 8) chunk-ordered node slot x incidence -> record * 8 + local node, 0xFFFF: none
     uint64_t* inc_ranks8 = nullptr;    // (nown, 8) the incidence's eight ranks, rank[(e*8 + a)*8 + 0..7]
 
+    // scratch of the device consumers (pfg_solve.cu), allocated on first use
+    uint8_t* bc_fixed = nullptr;       // (ncols) flags of the fixed dofs
+    double* bc_u0 = nullptr;           // (ncols) prescribed values, defined at the fixed dofs
+    double* cg_work = nullptr;         // r, z, p, Ap, 1/diag and the dot-product partial sums
+
     int64_t device_bytes = 0;
     int sm_count = 148;
     int device = 0;

@@ -1306,7 +1306,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
 static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
-                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip, d.hex_geo, d.inc_rec8, d.inc_ranks8};
+                    d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip, d.hex_geo, d.inc_rec8, d.inc_ranks8,
+                    d.bc_fixed, d.bc_u0, d.cg_work};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }

@@ -1,0 +1,419 @@
+// GPU consumers of the device CSR: the steps that follow the assembly in every
+// caller of the reference, kept in HBM so that a solve never copies the matrix to the host.
+//
+//   pfg_apply_dirichlet   ModelBase.apply_dirichlet_bcs (pyfem.py:780-835), pattern kept
+//   pfg_spmv / pfg_spmv_t R.dot(x) (pyfem.py:2117-2120) and RT.dot(x) (pyfem.py:2109-2115)
+//   pfg_cg                Jacobi-preconditioned conjugate gradients on the device CSR: the device stand-in for
+//                         Assembler._solve_linear_system(method="cg") (pyfem.py:2403-2423) and the solves inside
+//                         compliance (pyfem.py:1050-1068, 1814-1828)
+//
+// The CSR values are addressed through the node-level pattern of the handle (blk_ptr / nbr): the m dof rows of a
+// node are consecutive, each holding k blocks of m values (pfg_internal.cuh).
+#include <algorithm>
+#include <cmath>
+#include <vector>
+
+#include "pfg_internal.cuh"
+
+namespace pfg {
+
+constexpr int kRowLanes = 8;        // lanes that share one dof row in the SpMV kernels
+constexpr int kVecThreads = 256;    // CTA size of the vector kernels
+constexpr int kMaxPartials = 2048;  // upper bound of CTAs (= partial sums per dot product) of the CG kernels
+
+__device__ __forceinline__ double group_sum(double v) {  // sum over the kRowLanes lanes of a row group
+#pragma unroll
+    for (int o = kRowLanes / 2; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// y = A x: kRowLanes lanes per dof row stride over its k*m values (a warp reads 32 / kRowLanes consecutive rows, i.e.
+// one contiguous piece of the values array); x is gathered through the node-level column list.
+__global__ void __launch_bounds__(256) k_spmv_rows(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                                   const int64_t* __restrict__ gid, int64_t nown, int m,
+                                                   const double* __restrict__ vals, const double* __restrict__ x,
+                                                   double* __restrict__ y, const double* __restrict__ dot_with,
+                                                   double* __restrict__ partial) {
+    const int sub = threadIdx.x & (kRowLanes - 1);
+    const int64_t nrows = nown * m;
+    constexpr int RPB = 256 / kRowLanes;  // rows per CTA and step
+    double dot = 0.0;                     // this row group's share of <dot_with, y>
+    for (int64_t row = blockIdx.x * (int64_t)RPB + threadIdx.x / kRowLanes; row < nrows; row += (int64_t)gridDim.x * RPB) {
+        const int64_t r = row / m;
+        const int alpha = (int)(row - r * m);
+        const int64_t p0 = blk_ptr[r];
+        const int k = (int)(blk_ptr[r + 1] - p0);
+        const double* __restrict__ v = vals + p0 * m * m + (int64_t)alpha * k * m;
+        double s = 0.0;
+        for (int j = sub; j < k * m; j += kRowLanes) {
+            const int t = j / m, beta = j - t * m;
+            const int64_t cnode = nbr[p0 + t];
+            s = fma(v[j], x[(gid ? gid[cnode] : cnode) * m + beta], s);
+        }
+        s = group_sum(s);
+        if (sub == 0) {
+            y[row] = s;
+            if (dot_with != nullptr) dot = fma(s, dot_with[row], dot);
+        }
+    }
+    if (partial != nullptr) {  // fused dot product <dot_with, y> (CG: p . A p): one partial sum per CTA, fixed order
+        __shared__ double red[RPB];
+        if (sub == 0) red[threadIdx.x / kRowLanes] = dot;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int i = 0; i < RPB; ++i) t += red[i];
+            partial[blockIdx.x] = t;
+        }
+    }
+}
+
+// y = A^T x for a handle that owns every row: entry (c, r) of A sits in row c at the rank of r in c's sorted column
+// list (the node-level pattern is symmetric: c is a neighbour of r exactly when r is a neighbour of c).
+__global__ void __launch_bounds__(256) k_spmv_t_rows(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                                     int64_t nown, int m, const double* __restrict__ vals,
+                                                     const double* __restrict__ x, double* __restrict__ y) {
+    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kRowLanes;
+    const int sub = threadIdx.x & (kRowLanes - 1);
+    const int64_t nrows = nown * m;
+    double s = 0.0;
+    if (row < nrows) {
+        const int64_t r = row / m;
+        const int alpha = (int)(row - r * m);
+        const int64_t p0 = blk_ptr[r];
+        const int k = (int)(blk_ptr[r + 1] - p0);
+        for (int t = sub; t < k; t += kRowLanes) {
+            const int64_t c = nbr[p0 + t];
+            const int64_t q0 = blk_ptr[c];
+            const int kc = (int)(blk_ptr[c + 1] - q0);
+            int lo = 0, hi = kc;  // rank of r among c's neighbours
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (nbr[q0 + mid] < r) lo = mid + 1; else hi = mid;
+            }
+            const double* __restrict__ v = vals + q0 * m * m + (int64_t)lo * m + alpha;
+            for (int beta = 0; beta < m; ++beta) s = fma(v[(int64_t)beta * kc * m], x[c * m + beta], s);
+        }
+    }
+    s = group_sum(s);
+    if (row < nrows && sub == 0) y[row] = s;
+}
+
+// 1 / diag(A) of the owned rows (Jacobi preconditioner); a zero diagonal maps to 1
+__global__ void k_inv_diag(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr, int64_t own_begin,
+                           int64_t nown, int m, const double* __restrict__ vals, double* __restrict__ dinv) {
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nown * m) return;
+    const int64_t r = row / m;
+    const int alpha = (int)(row - r * m);
+    const int64_t p0 = blk_ptr[r];
+    const int k = (int)(blk_ptr[r + 1] - p0);
+    const int32_t self = (int32_t)(own_begin + r);
+    int lo = 0, hi = k;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (nbr[p0 + mid] < self) lo = mid + 1; else hi = mid;
+    }
+    const double d = vals[p0 * m * m + (int64_t)alpha * k * m + (int64_t)lo * m + alpha];
+    dinv[row] = (d != 0.0) ? 1.0 / d : 1.0;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* red) {  // fixed-order sum over the CTA, result in thread 0
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (threadIdx.x == 0)
+        for (int i = 0; i < kVecThreads / 32; ++i) t += red[i];
+    __syncthreads();
+    return t;
+}
+
+__device__ __forceinline__ double sum_partials(const double* __restrict__ partial, int n, double* red) {
+    double v = 0.0;  // every CTA re-sums the n partial sums of the previous kernel in the same order
+    for (int i = threadIdx.x; i < n; i += kVecThreads) v += partial[i];
+    __shared__ double bcast;
+    const double t = block_sum(v, red);
+    if (threadIdx.x == 0) bcast = t;
+    __syncthreads();
+    return bcast;
+}
+
+// r = b - A x0 is formed by the caller as r = b (x0 = 0) or through k_spmv_rows; this kernel starts the recurrences:
+// z = dinv r, p = z, partial sums of r.z and r.r
+__global__ void __launch_bounds__(kVecThreads) k_cg_init(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
+                                                         double* __restrict__ z, double* __restrict__ p,
+                                                         double* __restrict__ part_rz, double* __restrict__ part_rr) {
+    __shared__ double red[kVecThreads / 32];
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        const double ri = r[i], zi = dinv[i] * ri;
+        z[i] = zi, p[i] = zi;
+        rz = fma(ri, zi, rz), rr = fma(ri, ri, rr);
+    }
+    const double a = block_sum(rz, red), b = block_sum(rr, red);
+    if (threadIdx.x == 0) part_rz[blockIdx.x] = a, part_rr[blockIdx.x] = b;
+}
+
+// alpha = (r.z) / (p.Ap); x += alpha p; r -= alpha Ap; z = dinv r; partial sums of the new r.z and r.r
+__global__ void __launch_bounds__(kVecThreads) k_cg_update(int64_t n, int n_spmv_parts, int n_vec_parts,
+                                                           const double* __restrict__ part_pAp,
+                                                           const double* __restrict__ part_rz_old,
+                                                           const double* __restrict__ dinv, const double* __restrict__ p,
+                                                           const double* __restrict__ Ap, double* __restrict__ x,
+                                                           double* __restrict__ r, double* __restrict__ z,
+                                                           double* __restrict__ part_rz_new, double* __restrict__ part_rr) {
+    __shared__ double red[kVecThreads / 32];
+    const double pAp = sum_partials(part_pAp, n_spmv_parts, red);
+    const double rz_old = sum_partials(part_rz_old, n_vec_parts, red);
+    const double alpha = (pAp != 0.0) ? rz_old / pAp : 0.0;
+    double rz = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double ri = fma(-alpha, Ap[i], r[i]);
+        const double zi = dinv[i] * ri;
+        r[i] = ri, z[i] = zi;
+        rz = fma(ri, zi, rz), rr = fma(ri, ri, rr);
+    }
+    const double a = block_sum(rz, red), b = block_sum(rr, red);
+    if (threadIdx.x == 0) part_rz_new[blockIdx.x] = a, part_rr[blockIdx.x] = b;
+}
+
+// beta = (r.z)_new / (r.z)_old; p = z + beta p
+__global__ void __launch_bounds__(kVecThreads) k_cg_direction(int64_t n, int n_vec_parts, const double* __restrict__ part_rz_new,
+                                                              const double* __restrict__ part_rz_old,
+                                                              const double* __restrict__ z, double* __restrict__ p) {
+    __shared__ double red[kVecThreads / 32];
+    const double rz_new = sum_partials(part_rz_new, n_vec_parts, red);
+    const double rz_old = sum_partials(part_rz_old, n_vec_parts, red);
+    const double beta = (rz_old != 0.0) ? rz_new / rz_old : 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+        p[i] = fma(beta, p[i], z[i]);
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_residual(int64_t n, const double* __restrict__ b, const double* __restrict__ Ax,
+                                                          double* __restrict__ r) {
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+        r[i] = b[i] - Ax[i];
+}
+
+__global__ void __launch_bounds__(kVecThreads) k_norm2_partials(int64_t n, const double* __restrict__ v, double* __restrict__ part) {
+    __shared__ double red[kVecThreads / 32];
+    double s = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads)
+        s = fma(v[i], v[i], s);
+    const double a = block_sum(s, red);
+    if (threadIdx.x == 0) part[blockIdx.x] = a;
+}
+
+// ---- Dirichlet rows / columns on the device CSR, pattern kept (pyfem.py:780-835 minus eliminate_zeros) ----------
+__global__ void k_mark_fixed(const int64_t* __restrict__ fixed, const double* __restrict__ fixed_vals, int64_t nfixed,
+                             int64_t ncols, uint8_t* __restrict__ is_fixed, double* __restrict__ u0) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nfixed) return;
+    const int64_t dof = fixed[i];
+    if (dof < 0 || dof >= ncols) return;
+    is_fixed[dof] = 1;
+    u0[dof] = fixed_vals ? fixed_vals[i] : 0.0;  // u0 is read at fixed dofs only
+}
+
+__global__ void k_apply_dirichlet(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                  const int64_t* __restrict__ gid, int64_t own_begin, int64_t nown, int m,
+                                  const uint8_t* __restrict__ is_fixed, const double* __restrict__ u0, int symmetric,
+                                  int have_vals, double* __restrict__ vals, double* __restrict__ rhs) {
+    // one thread per owned dof row
+    const int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (row >= nown * m) return;
+    const int64_t r = row / m;
+    const int alpha = (int)(row - r * m);
+    const int64_t node = own_begin + r;
+    const int64_t grow = (gid ? gid[node] : node) * m + alpha;
+    const int64_t p0 = blk_ptr[r], k = blk_ptr[r + 1] - p0;
+    double* v = vals + p0 * m * m + alpha * k * m;
+    const bool row_fixed = is_fixed[grow];
+    double corr = 0.0;
+    for (int64_t t = 0; t < k; ++t) {
+        const int64_t cnode = nbr[p0 + t];
+        const int64_t gcol0 = (gid ? gid[cnode] : cnode) * m;
+        for (int beta = 0; beta < m; ++beta) {
+            const int64_t gcol = gcol0 + beta;
+            double& x = v[t * m + beta];
+            if (row_fixed) {
+                x = (gcol == grow) ? 1.0 : 0.0;
+            } else if (symmetric && is_fixed[gcol]) {
+                if (have_vals) corr = fma(x, u0[gcol], corr);
+                x = 0.0;
+            }
+        }
+    }
+    if (rhs) {
+        if (row_fixed) rhs[row] = u0[grow];
+        else if (symmetric && have_vals) rhs[row] -= corr;
+    }
+}
+
+static int ensure_solve_scratch(MeshDev& d, bool cg) {
+    const int64_t ncols = d.ncols_nodes * d.m;
+    if (!d.bc_fixed) {
+        PFG_CUDA_TRY(cudaMalloc(&d.bc_fixed, std::max<int64_t>(ncols, 1)));
+        PFG_CUDA_TRY(cudaMalloc(&d.bc_u0, std::max<int64_t>(ncols, 1) * sizeof(double)));
+        d.device_bytes += ncols * 9;
+    }
+    if (cg && !d.cg_work) {
+        const int64_t n = (d.own_end - d.own_begin) * d.m;
+        PFG_CUDA_TRY(cudaMalloc(&d.cg_work, (5 * std::max<int64_t>(n, 1) + 5 * kMaxPartials) * sizeof(double)));
+        d.device_bytes += (5 * n + 5 * kMaxPartials) * (int64_t)sizeof(double);
+    }
+    return PFG_OK;
+}
+
+}  // namespace pfg
+
+using namespace pfg;
+
+#define PFG_CHECK_MESH(mesh)                         \
+    if (!(mesh)) {                                   \
+        set_error("%s: mesh is NULL", __func__);     \
+        return PFG_ERR_INVALID;                      \
+    }                                                \
+    PFG_CUDA_TRY(cudaSetDevice((mesh)->d.device));
+
+extern "C" int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, const double* fixed_vals_dev,
+                                   int64_t nfixed, int enforce_symmetric, double* vals_dev, double* rhs_dev,
+                                   void* stream) {
+    PFG_CHECK_MESH(mesh);
+    MeshDev& d = mesh->d;
+    if (!vals_dev || nfixed < 0 || (nfixed > 0 && !fixed_dofs_dev)) {
+        set_error("pfg_apply_dirichlet: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t ncols = d.ncols_nodes * d.m;
+    PFG_TRY(ensure_solve_scratch(d, false));  // flags / values of the fixed dofs live in the handle
+    PFG_CUDA_TRY(cudaMemsetAsync(d.bc_fixed, 0, ncols, st));
+    if (nfixed)
+        k_mark_fixed<<<(unsigned)((nfixed + 255) / 256), 256, 0, st>>>(fixed_dofs_dev, fixed_vals_dev, nfixed, ncols,
+                                                                      d.bc_fixed, d.bc_u0);
+    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
+    if (nrows)
+        k_apply_dirichlet<<<(unsigned)((nrows + 127) / 128), 128, 0, st>>>(
+            d.blk_ptr, d.nbr, d.gid, d.own_begin, d.own_end - d.own_begin, d.m, d.bc_fixed, d.bc_u0, enforce_symmetric,
+            fixed_vals_dev != nullptr, vals_dev, rhs_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+static unsigned spmv_grid(int64_t nrows, int sm_count) {  // grid-stride kernel: at most eight CTAs per SM
+    const int64_t full = std::max<int64_t>(1, (nrows * kRowLanes + 255) / 256);
+    return (unsigned)std::min<int64_t>(full, std::min<int64_t>(kMaxPartials, (int64_t)sm_count * 8));
+}
+
+extern "C" int pfg_spmv(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!vals_dev || !x_dev || !y_dev) {
+        set_error("pfg_spmv: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    const int64_t nrows = (d.own_end - d.own_begin) * d.m;
+    if (nrows)
+        k_spmv_rows<<<spmv_grid(nrows, d.sm_count), 256, 0, (cudaStream_t)stream>>>(d.blk_ptr, d.nbr, d.gid, d.own_end - d.own_begin,
+                                                                       d.m, vals_dev, x_dev, y_dev, nullptr, nullptr);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+static int whole_matrix(const MeshDev& d, const char* who) {
+    if (d.own_begin != 0 || d.own_end != d.nnodes || d.gid != nullptr) {
+        set_error("%s: needs a handle that owns every row (a rank's row slab does not hold the transposed entries / the "
+                  "whole operator)", who);
+        return PFG_ERR_UNSUPPORTED;
+    }
+    return PFG_OK;
+}
+
+extern "C" int pfg_spmv_t(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (!vals_dev || !x_dev || !y_dev) {
+        set_error("pfg_spmv_t: NULL argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(whole_matrix(d, "pfg_spmv_t"));
+    const int64_t nrows = d.nnodes * d.m;
+    k_spmv_t_rows<<<(unsigned)((nrows * kRowLanes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d.blk_ptr, d.nbr, d.nnodes, d.m, vals_dev, x_dev,
+                                                                     y_dev);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+extern "C" int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, int x_is_zero,
+                      double rtol, double atol, int max_iter, int check_every, int* iters_out, double* resid_out,
+                      void* stream) {
+    PFG_CHECK_MESH(mesh);
+    MeshDev& d = mesh->d;
+    if (!vals_dev || !b_dev || !x_dev || max_iter < 0) {
+        set_error("pfg_cg: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(whole_matrix(d, "pfg_cg"));
+    PFG_TRY(ensure_solve_scratch(d, true));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = d.nnodes * d.m, nown = d.nnodes;
+    double* r = d.cg_work;
+    double *z = r + n, *p = z + n, *Ap = p + n, *dinv = Ap + n;
+    double* parts = dinv + n;  // [0] p.Ap (one per SpMV CTA, capped), [1..2] r.z ping-pong, [3] r.r, [4] |b|^2
+    const unsigned gs = spmv_grid(n, d.sm_count);  // persistent SpMV grid: one p.Ap partial per CTA
+    double* part_pAp = parts;
+    double* part_rz[2] = {parts + 1 * kMaxPartials, parts + 2 * kMaxPartials};
+    double* part_rr = parts + 3 * kMaxPartials;
+    double* part_bb = parts + 4 * kMaxPartials;
+    const int gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
+    const unsigned g256 = (unsigned)((n + 255) / 256);
+
+    k_inv_diag<<<g256, 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, nown, d.m, vals_dev, dinv);
+    if (x_is_zero) {
+        PFG_CUDA_TRY(cudaMemsetAsync(x_dev, 0, n * sizeof(double), st));
+        PFG_CUDA_TRY(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        k_spmv_rows<<<gs, 256, 0, st>>>(d.blk_ptr, d.nbr, nullptr, nown, d.m, vals_dev, x_dev, Ap, nullptr, nullptr);
+        k_residual<<<gv, kVecThreads, 0, st>>>(n, b_dev, Ap, r);
+    }
+    k_norm2_partials<<<gv, kVecThreads, 0, st>>>(n, b_dev, part_bb);
+    k_cg_init<<<gv, kVecThreads, 0, st>>>(n, dinv, r, z, p, part_rz[0], part_rr);
+    std::vector<double> h(kMaxPartials);
+    auto host_sum = [&](const double* dev, double* out) -> int {
+        PFG_CUDA_TRY(cudaMemcpyAsync(h.data(), dev, gv * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        double s = 0.0;
+        for (int i = 0; i < gv; ++i) s += h[i];
+        *out = s;
+        return PFG_OK;
+    };
+    double bb = 0.0, rr = 0.0;
+    PFG_TRY(host_sum(part_bb, &bb));
+    PFG_TRY(host_sum(part_rr, &rr));
+    const double target = std::max(rtol * std::sqrt(bb), atol);  // scipy's cg: |r| <= max(rtol |b|, atol)
+    int it = 0;
+    if (check_every <= 0) check_every = 16;
+    while (std::sqrt(rr) > target && it < max_iter) {
+        const int batch = std::min(check_every, max_iter - it);
+        for (int j = 0; j < batch; ++j, ++it) {
+            const int cur = it & 1;
+            k_spmv_rows<<<gs, 256, 0, st>>>(d.blk_ptr, d.nbr, nullptr, nown, d.m, vals_dev, p, Ap, p, part_pAp);
+            k_cg_update<<<gv, kVecThreads, 0, st>>>(n, (int)gs, gv, part_pAp, part_rz[cur], dinv, p, Ap, x_dev, r, z,
+                                                    part_rz[cur ^ 1], part_rr);
+            k_cg_direction<<<gv, kVecThreads, 0, st>>>(n, gv, part_rz[cur ^ 1], part_rz[cur], z, p);
+        }
+        PFG_CUDA_TRY(cudaGetLastError());
+        PFG_TRY(host_sum(part_rr, &rr));
+        if (!(rr == rr)) {
+            set_error("pfg_cg: the residual became NaN after %d iterations (matrix not positive definite?)", it);
+            return PFG_ERR_INVALID;
+        }
+    }
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = std::sqrt(rr);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return (std::sqrt(rr) <= target) ? PFG_OK : PFG_ERR_NOCONV;
+}

@@ -141,8 +141,8 @@ class DeviceMesh:
         """nodal density tensor or (None, scalar) -- scalar rho is a constant field (pyfem.py:1015-1016)."""
         if rho is None:
             return None, 1.0
-        if not hasattr(rho, "__len__") and not hasattr(rho, "shape"):
-            if isinstance(rho, complex):
+        if np.ndim(rho) == 0:  # Python / numpy scalars and 0-d arrays: the reference's `not hasattr(rho, "__len__")`
+            if np.iscomplexobj(rho):
                 raise NotImplementedError("complex rho (complex-step verification) has no device path")
             return None, float(rho)
         return self._dev_f64(rho, self.nnodes, "rho"), 0.0
@@ -225,6 +225,32 @@ class DeviceMesh:
         with torch.cuda.device(self.device):
             _lib.check(self._lib.pfg_spmv(self._handle, _ptr(vals), _ptr(x), _ptr(out), self._stream()))
         return out
+
+    def spmv_t(self, vals, x, out=None):
+        """y = A^T x without forming the transpose (Helmholtz.apply_gradient's RT.dot, pyfem.py:2114)."""
+        torch = _torch()
+        x = self._dev_f64(x, self.nrows, "x")
+        out = torch.empty(self.ncols, dtype=torch.float64, device=self.device) if out is None else out
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.pfg_spmv_t(self._handle, _ptr(vals), _ptr(x), _ptr(out), self._stream()))
+        return out
+
+    def cg(self, vals, b, x0=None, rtol=1e-8, atol=0.0, max_iter=None, check_every=16):
+        """Jacobi-preconditioned conjugate gradients on the device CSR (the matrix never leaves HBM): the device
+        stand-in for Assembler._solve_linear_system(method="cg") (pyfem.py:2403-2423).  Returns (x, iterations,
+        |r|); raises RuntimeError like the reference when max_iter is reached first."""
+        torch = _torch()
+        b = self._dev_f64(b, self.nrows, "b")
+        x = torch.empty_like(b) if x0 is None else self._dev_f64(x0, self.nrows, "x0").clone()
+        iters, resid = ctypes.c_int(0), c_double(0.0)
+        max_iter = 10 * self.nrows if max_iter is None else int(max_iter)  # scipy's default maxiter
+        with torch.cuda.device(self.device):
+            st = self._lib.pfg_cg(self._handle, _ptr(vals), _ptr(b), _ptr(x), 1 if x0 is None else 0, float(rtol),
+                                  float(atol), max_iter, int(check_every), byref(iters), byref(resid), self._stream())
+        if st == _lib.PFG_ERR_NOCONV:
+            raise RuntimeError(f"cg failed with code {iters.value}")  # scipy reports the iteration count as the code
+        _lib.check(st)
+        return x, int(iters.value), float(resid.value)
 
     # ---- the scatter on its own, and element matrices without the scatter ------------------------------
     @property

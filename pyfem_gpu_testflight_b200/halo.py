@@ -89,6 +89,10 @@ def match_rows(own_row_gid0, m, indptr, indices, row_gids, h_indptr, h_indices):
     return out
 
 
+def _even(n):
+    return n + (n & 1)
+
+
 def inbox_layout(send_table, m):
     """Layout of the symmetric-memory inboxes of the p2p transport.  send_table[q, d] = (node rows, nnz) that rank q
     sends to rank d.  Rank q's block in d's inbox holds its nnz CSR values, then one vector entry per dof row; blocks
@@ -96,7 +100,10 @@ def inbox_layout(send_table, m):
     must agree -- and offset[q][d] of q's block inside d's inbox)."""
     T = np.asarray(send_table)
     size = T.shape[0]
-    block = [[0 if q == d else int(T[q, d, 1]) + int(T[q, d, 0]) * m for d in range(size)] for q in range(size)]
+    # every block starts on a 16-byte boundary (an even number of doubles): the halo handles write their values with
+    # cp.async.bulk stores, which need 16-byte aligned global addresses
+    block = [[0 if q == d else _even(_even(int(T[q, d, 1])) + int(T[q, d, 0]) * m) for d in range(size)]
+             for q in range(size)]
     offset = [[sum(block[qq][d] for qq in range(q)) for d in range(size)] for q in range(size)]
     n = max(1, max(sum(block[q][d] for q in range(size)) for d in range(size)))
     return n, offset
@@ -141,12 +148,12 @@ class ReduceAssembler:
         for s, hm, _ in self.halo:
             off = offset(rank, s.dest)
             self.peer_out.append((self.symm.get_buffer(s.dest, (hm.nnz,), torch.float64, off),
-                                  self.symm.get_buffer(s.dest, (hm.nrows,), torch.float64, off + hm.nnz)))
+                                  self.symm.get_buffer(s.dest, (hm.nrows,), torch.float64, off + _even(hm.nnz))))
         recv = []
         for q, slots, rows, _, _ in self.recv:
             off = offset(q, rank)
-            recv.append((q, slots, rows, self.inbox[off:off + len(slots)],
-                         self.inbox[off + len(slots):off + len(slots) + len(rows)]))
+            v0 = off + _even(len(slots))
+            recv.append((q, slots, rows, self.inbox[off:off + len(slots)], self.inbox[v0:v0 + len(rows)]))
         self.recv = recv
         self.symm.barrier()
 
@@ -245,8 +252,8 @@ class ReduceAssembler:
                 self.mesh.add_indexed(main_vec, rows, rbuf)
 
     def _field(self, f, local_nodes):
-        if f is None or not hasattr(f, "__len__"):
-            return f
+        if f is None or np.ndim(f) == 0:  # scalars, numpy scalars and 0-d arrays / tensors are constant fields
+            return f if f is None else float(f)
         return self.torch.as_tensor(f, device=self.device)[local_nodes]
 
     def assemble_elasticity(self, rho=1.0, p=0.0, E=10.0, nu=0.3, out=None, mode="auto"):

@@ -123,6 +123,17 @@ class ModelBase:
         out[:] = vec.cpu().numpy()
         return out
 
+    def solve_device(self, vals, rhs, rtol=1e-8, atol=0.0, max_iter=None):
+        """Dirichlet conditions + conjugate gradients entirely in HBM: `vals` are the device
+        CSR values of compute_jacobian_device (edited in place, pattern kept), `rhs` a host or device vector.
+        Returns (u, rhs with the conditions applied, CG iterations), u and rhs as device tensors.  The matrix is
+        never copied to the host."""
+        torch = _torch()
+        rhs_d = torch.as_tensor(rhs).to(device=self.mesh.device, dtype=torch.float64).clone()
+        self.mesh.apply_dirichlet(vals, rhs_d, self.dof_fixed, self.dof_fixed_vals, enforce_symmetric=True)
+        u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
+        return u, rhs_d, iters
+
     def apply_dirichlet_bcs(self, K, rhs, enforce_symmetric_K=True):
         """Host-side Dirichlet conditions with the reference's semantics (pyfem.py:780-835): rows (and, if
         asked, columns) of fixed dofs zeroed, unit diagonal, explicit zeros eliminated, rhs updated.
@@ -155,17 +166,37 @@ class ModelBase:
 
 class _DensityFunctions:
     """compliance / volume and their gradients (LinearPoisson pyfem.py:1033-1123, LinearElasticity :1796-1870).
-    The solves stay on the host, as in the reference; iterative solvers need pyamg, which this image lacks."""
+    The solves stay on the host, as in the reference (the device CG of Assembler.solve(device=True) is the
+    GPU consumer of SURVEY 8f #4)."""
 
-    def _solve_compliance_system(self, rho, solver):
+    def _solve_compliance_system(self, rho, solver, device=False):
         assert solver == "direct" or solver == "cg" or solver == "gmres"
-        if solver != "direct":
-            raise NotImplementedError("cg / gmres use a pyamg preconditioner (pyfem.py:1059-1060); use solver='direct'")
-        from scipy.sparse.linalg import spsolve
+        if device:
+            # assembly, boundary conditions and the solve stay in HBM; only rhs and u cross PCIe
+            if solver != "cg":
+                raise NotImplementedError("the device solve is conjugate gradients: use solver='cg'")
+            rhs = self.compute_rhs()
+            u, rhs_d, _ = self.solve_device(self.compute_jacobian_device(rho), rhs)
+            rhs[:] = rhs_d.cpu().numpy()  # the persistent rhs is edited in place, as apply_dirichlet_bcs does
+            return None, rhs, u.cpu().numpy()
         K = self.compute_jacobian(rho)
         rhs = self.compute_rhs()
         K, rhs = self.apply_dirichlet_bcs(K, rhs, enforce_symmetric_K=True)
-        return K, rhs, spsolve(K.tocsc(), rhs)
+        if solver == "direct":
+            from scipy.sparse.linalg import spsolve
+            return K, rhs, spsolve(K.tocsc(), rhs)
+        # cg / gmres as in the reference (pyfem.py:1056-1068): pyamg smoothed aggregation as the preconditioner when
+        # pyamg is installed, unpreconditioned otherwise (same rule as Assembler._solve_linear_system)
+        from scipy.sparse.linalg import cg, gmres
+        try:
+            import pyamg
+            M = pyamg.smoothed_aggregation_solver(K).aspreconditioner()
+        except ImportError:
+            M = None
+        u, fail = (cg if solver == "cg" else gmres)(K, rhs, rtol=1e-8, atol=0.0, M=M)
+        if fail:
+            raise RuntimeError(f"{solver} failed with code {fail}")
+        return K, rhs, u
 
     def volume(self, rho):
         return np.asarray(rho).sum() / self.nnodes
@@ -229,9 +260,10 @@ class LinearPoisson(_DensityFunctions, ModelBase):
         """d(phi^T K psi)/d rho (pyfem.py:1239-1276)."""
         return self._k_dv_sens("poisson", rho, phi, psi)
 
-    def compliance(self, rho, solver="cg", weighted=True):
-        """Thermal compliance and the solution (pyfem.py:1033-1073)."""
-        _, rhs, u = self._solve_compliance_system(rho, solver)
+    def compliance(self, rho, solver="cg", weighted=True, device=False):
+        """Thermal compliance and the solution (pyfem.py:1033-1073).  device=True: Dirichlet conditions and a
+        Jacobi-preconditioned CG run on the device CSR (homogeneous or symmetric-eliminated conditions)."""
+        _, rhs, u = self._solve_compliance_system(rho, solver, device)
         return (rhs.dot(u) if weighted else np.sum(u) / len(u)), u
 
     def compliance_grad(self, rho, u, weighted=True):
@@ -309,9 +341,9 @@ class LinearElasticity(_DensityFunctions, ModelBase):
         """d(phi^T K psi)/d rho (pyfem.py:1872-1920)."""
         return self._k_dv_sens("elasticity", rho, phi, psi, E=self.E, nu=self.nu)
 
-    def compliance(self, rho, solver="cg"):
-        """Compliance and the solution (pyfem.py:1796-1833)."""
-        _, rhs, u = self._solve_compliance_system(rho, solver)
+    def compliance(self, rho, solver="cg", device=False):
+        """Compliance and the solution (pyfem.py:1796-1833); device=True keeps the system and the CG solve in HBM."""
+        _, rhs, u = self._solve_compliance_system(rho, solver, device)
         return rhs.dot(u), u
 
     def compliance_grad(self, rho, u):
@@ -357,6 +389,15 @@ class Helmholtz(ModelBase):
 
     def compute_rhs_device(self, x, out=None):
         return self.mesh.spmv(self.R_device, x, out=out)
+
+    def apply_device(self, x, rtol=1e-8):
+        """Filtered field K^-1 R x with R.x and the CG solve on the device (pyfem.py:2102-2107)."""
+        return self.mesh.cg(self.K_device, self.compute_rhs_device(x), rtol=rtol)[0]
+
+    def apply_gradient_device(self, gradrho, rtol=1e-8):
+        """R^T K^-1 g on the device (pyfem.py:2109-2115): CG solve, then the transposed product."""
+        y = self.mesh.cg(self.K_device, gradrho, rtol=rtol)[0]
+        return self.mesh.spmv_t(self.R_device, y)
 
     def compute_jacobian(self):
         return self.K
