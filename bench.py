@@ -1,18 +1,28 @@
 #!/usr/bin/env python
 """bench.py -- assembled elements/second of the FE assembly hot path (fp64 Ke + CSR scatter).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2] [--halo all] [--impl reference]
 
-One "step" = one assembly pass (element quadrature -> CSR values) over the workload's mesh with the mesh,
-pattern and gather plan already resident in HBM (built once per mesh, reported as setup_s).  Default
-workload: BASELINE.json configs[1], 2-D plane-stress elasticity on a 4096 x 4096 quad mesh (16.8 M
-elements, 604 M CSR values = 4.8 GB written per step -- far larger than the 126 MB L2, so no L2 flush
-is needed between iterations).  N > 1: one process per GPU (torchrun), weak scaling -- every rank owns a
-4096 x 4096 slab of a 4096 x (4096 N) mesh plus one ghost element layer; no data-path collective.
+One "step" = one assembly pass (element quadrature -> CSR values) over the workload's mesh with the mesh, pattern
+and gather plan already resident in HBM (built once per mesh, reported as setup_s).  Default workload:
+BASELINE.json configs[1], 2-D plane-stress elasticity on the 4096 x 4096 quad mesh (16.8 M elements, 604 M CSR
+values = 4.8 GB written per step -- far larger than the 126 MB L2, so no L2 flush is needed between iterations).
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's numpy /
-scipy assembly (oracle/pyfem_oracle.py; the reference is pure Python, so there is nothing to compile
-into oracle/_ref) on a bounded sample of the same workload.
+N > 1 (one process per GPU, torchrun): STRONG scaling -- the named mesh is split into N row slabs (element blocks
+in the generator's numbering, pyfem.py:2499-2502 / 2527-2534).  Every variant of the partitioned assembly is timed
+in the same run and reported in config.variants:
+    ghost        each rank also integrates the one ghost layer of elements touching its rows: no data-path collective
+    reduce_nccl  the north_star's variant: every element integrated once, interface rows summed on the owner after
+                 ncclSend / ncclRecv of the neighbours' contributions
+    reduce_p2p   the same sum, fused with the transfer: the sender's halo kernel stores straight into the owner's
+                 symmetric-memory inbox through NVLink
+`value` is the fastest variant (named in config.partition).  The line also carries config.c5 (hex8 256^3 strong-scaled
+over the same N), an in-run multi-rank parity check against the numpy oracle (config.parity_ok) and an end-to-end
+figure through the drop-in model API with host buffers (e2e).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference's numpy / scipy
+assembly (oracle/pyfem_oracle.py; the reference is pure Python -- nothing to compile into oracle/_ref, and its
+sources do not travel to the GPU box) on a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -36,13 +46,13 @@ import numpy as np  # noqa: E402
 METRIC = "assembled elements/sec (fp64 Ke + CSR scatter)"
 UNIT = "elements/s"
 
-# name -> (description, physics, nodes per elem, ndof per node, default elements per side, scaling at N>1)
+# name -> (description, physics, nodes per elem, ndof per node, default elements per side)
 WORKLOADS = {
-    "c1": ("2-D linear Poisson, quad 64x64", "poisson", 4, 1, 64, "weak"),
-    "c2": ("2-D plane-stress linear elasticity, quad 4096x4096 (16.8M elements)", "elasticity", 4, 2, 4096, "weak"),
-    "c3": ("Helmholtz filter K and R, quad 4096x2048 (8.4M elements)", "helmholtz", 4, 1, 4096, "weak"),
-    "c4": ("nonlinear Poisson Jacobian + residual, quad 4096x4096 (16.8M elements)", "nlpoisson", 4, 1, 4096, "weak"),
-    "c5": ("3-D hex8 linear elasticity, 256^3 elements partitioned across the ranks", "elasticity", 8, 3, 256, "strong"),
+    "c1": ("2-D linear Poisson, quad 64x64", "poisson", 4, 1, 64),
+    "c2": ("2-D plane-stress linear elasticity, quad 4096x4096 (16.8M elements)", "elasticity", 4, 2, 4096),
+    "c3": ("Helmholtz filter K and R, quad 4096x2048 (8.4M elements)", "helmholtz", 4, 1, 4096),
+    "c4": ("nonlinear Poisson Jacobian + residual, quad 4096x4096 (16.8M elements)", "nlpoisson", 4, 1, 4096),
+    "c5": ("3-D hex8 linear elasticity, 256^3 elements partitioned across the ranks", "elasticity", 8, 3, 256),
 }
 
 
@@ -52,6 +62,17 @@ def load_peaks():
         with open(path) as f:
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_profile_table(name):
+    path = os.path.join(ROOT, "profiles", name)
+    if os.path.isfile(path):
+        try:
+            with open(path) as f:
+                return json.load(f)
+        except Exception:
+            pass
+    return {}
 
 
 def algorithmic_bytes(nelems, nnodes, nne, ndims, nnz, n_value_arrays=1, nodal_fields=0, rhs_rows=0):
@@ -159,13 +180,16 @@ def run_reference(args, desc, physics, nne):
         wall += w
         cpu += c
     value = nel / wall
-    sample = (f"{side}^{2 if nne == 4 else 3} elements of the same structured mesh per step "
+    dim = 2 if nne == 4 else 3
+    sample = (f"{side}^{dim} elements of the same structured mesh per step "
               f"(numpy {np.__version__} einsum + scipy coo->csr, as the reference)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc, "host_cores_available": os.cpu_count()},
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc, "host_cores_available": os.cpu_count(), "cpu_sample_elements": side ** dim,
+                   "cpu_sample_note": "per-element rate of a bounded sample: the reference needs ~84 GB of host "
+                                      "memory for the named 16.8 M-element mesh (SURVEY H8)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": round(cpu / wall, 2), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -176,6 +200,234 @@ def run_reference(args, desc, physics, nne):
 # ---------------------------------------------------------------------------------------------------
 # device arm
 # ---------------------------------------------------------------------------------------------------
+class Ctx:
+    """Process-wide state of the device arm."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def min_over_ranks(self, x):
+        t = self.torch.tensor([float(x)], dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return float(t.item())
+
+
+def make_case(ctx, workload, n_side, scaling):
+    """This rank's slab of the ProblemCreator mesh of a workload (pyfem.py:2469-2535), generated directly."""
+    from pyfem_gpu_testflight_b200.partition import slab_node_ranges, structured_slab
+    desc, physics, nne, m, n_default = WORKLOADS[workload]
+    n_side = n_side or n_default
+    mult = ctx.world if scaling == "weak" else 1
+    if nne == 4:
+        ny_el = (n_side // 2 if workload == "c3" else n_side) * mult
+        dims = (n_side + 1, ny_el + 1, None)
+        total = n_side * ny_el
+    else:
+        nz_el = n_side * mult
+        dims = (n_side + 1, n_side + 1, nz_el + 1)
+        total = n_side * n_side * nz_el
+    part = structured_slab(*dims, ctx.rank, ctx.world)
+    ranges = slab_node_ranges(*dims, ctx.world)
+    return {"desc": desc, "physics": physics, "nne": nne, "m": m, "ndims": 2 if nne == 4 else 3, "n_side": n_side,
+            "part": part, "ranges": ranges, "total_elems": total, "workload": workload}
+
+
+def make_model(ctx, case, halo, mode):
+    """The drop-in physics model (the reference's constructor, pyfem.py:949-960 / 1357-1365 / 1683-1695 / 2085) as one
+    rank of the row-slab partition."""
+    import pyfem_gpu_testflight_b200 as pf
+    part, physics = case["part"], case["physics"]
+    q = pf.QuadratureBilinear2D() if case["nne"] == 4 else pf.QuadratureBlock3D()
+    b = pf.BasisBilinear2D(q) if case["nne"] == 4 else pf.BasisBlock3D(q)
+    kw = dict(partition=part, node_ranges=case["ranges"], halo=halo, device=ctx.dev, scatter=mode)
+    if physics == "elasticity":
+        return pf.LinearElasticity(part.X, part.conn, [], None, {}, q, b, **kw)
+    if physics == "poisson":
+        return pf.LinearPoisson(part.X, part.conn, [], None, q, b, lambda Xq: 1.0, **kw)
+    if physics == "helmholtz":
+        return pf.Helmholtz(0.05, part.X, part.conn, q, b, **kw)
+    return pf.NonlinearPoisson2D(part.X, part.conn, [], None, q, b, **kw)
+
+
+class Variant:
+    """One way of assembling the partitioned workload: model + preallocated outputs + the step closure."""
+
+    def __init__(self, ctx, case, halo, mode):
+        torch = ctx.torch
+        t0 = time.perf_counter()
+        self.halo, self.case = halo, case
+        self.model = make_model(ctx, case, halo, mode)
+        torch.cuda.synchronize()
+        self.setup_s = time.perf_counter() - t0
+        self.mesh = mesh = self.model.mesh
+        physics = case["physics"]
+        self.vals = mesh.new_values()
+        self.vals2 = mesh.new_values() if physics == "helmholtz" else None
+        self.res = mesh.new_vector() if physics == "nlpoisson" else None
+        self.u = torch.rand(mesh.nnodes, dtype=torch.float64, device=ctx.dev,
+                            generator=torch.Generator(ctx.dev).manual_seed(0)) if physics == "nlpoisson" else None
+        self.xdv = np.ones(10) / 10.0
+        red = self.model._reducer
+        hex_rows = case["m"] == 3 and mode != "atomic" and mesh.info(HEX_ROWS_INFO) == 1
+        self.own_kernels = 2 if hex_rows else 1  # hex8 elasticity: geometry pass + chunk-row pass
+        self.kernels_per_step = self.own_kernels + ((len(red.halo) * self.own_kernels + len(red.recv)) if red is not None else 0)
+        self.hex_rows = hex_rows
+
+    def step(self, rho=1.0, p=0.0):
+        physics, model = self.case["physics"], self.model
+        if physics in ("elasticity", "poisson"):
+            model.p = p
+            model.compute_jacobian_device(rho, out=self.vals)
+        elif physics == "helmholtz":
+            model._asm.assemble_helmholtz(0.05, out_K=self.vals, out_R=self.vals2, mode=model.scatter)
+        elif model._reducer is not None:
+            model._reducer.assemble_nlpoisson(self.xdv, self.u, mode=model.scatter)
+        else:
+            self.mesh.assemble_nlpoisson(self.xdv, self.u, out_K=self.vals, out_res=self.res, mode=model.scatter)
+
+    def close(self):
+        self.model = self.mesh = self.vals = self.vals2 = self.res = self.u = None
+
+
+HEX_ROWS_INFO = 10  # _lib.INFO_HEX_ROWS
+
+
+def time_variant(ctx, var, steps, warmup, sampler=None, sample=False):
+    """W warm-up steps, then K steps bracketed by barrier + synchronize; CUDA events on the launching stream; the
+    per-step events give the kernel's average launch duration for the roofline.  Returns (ms per step, max over
+    ranks; this rank's per-step list)."""
+    torch = ctx.torch
+    for _ in range(warmup):
+        var.step()
+    ctx.barrier()
+    if sample:  # every rank takes this branch; rank 0 owns the sampler
+        if sampler is not None:
+            sampler.start()
+        time.sleep(0.15)
+        ctx.barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for i in range(steps):
+        var.step()
+        ev[i + 1].record()
+    ctx.barrier()
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ctx.max_over_ranks(total_ms) / steps, per
+
+
+def variant_names(args, world, physics):
+    if world == 1:
+        return ["ghost"]
+    if args.halo == "all":
+        return ["ghost", "nccl", "p2p"]
+    return [{"reduce": "nccl"}.get(args.halo, args.halo)]
+
+
+def parity_check(ctx, halos):
+    """In-run parity of the partitioned assembly against the numpy oracle: every rank's slab rows (matrix, and the
+    nonlinear-Poisson residual) on a jittered 41 x 37 quad mesh and a 9 x 8 x 11 hex mesh, for every variant timed in
+    this run.  Pattern bit-exact (incl. dtype), values within 1e-12 of max|K| (BASELINE.json north_star)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyfem_oracle as orc
+    import pyfem_gpu_testflight_b200 as pf
+    from pyfem_gpu_testflight_b200.partition import partition_mesh, split_range
+    ok, worst, cases = True, 0.0, 0
+    for dims in ((41, 37, None), (9, 8, 11)):
+        X, conn = orc.structured_mesh(*dims)
+        X = X + np.random.default_rng(3).uniform(-0.004, 0.004, size=X.shape)
+        if dims[2] is None:
+            X = (X - X.min(axis=0)) / (X.max(axis=0) - X.min(axis=0))
+        plane = dims[0] if dims[2] is None else dims[0] * dims[1]
+        nslow = dims[1] if dims[2] is None else dims[2]
+        ranges = [(b * plane, e * plane) for b, e in split_range(nslow, ctx.world)]
+        part = partition_mesh(X, conn, ctx.rank, ctx.world, ranges)
+        gb, ge = part.owned_global_range
+        m = X.shape[1]
+        rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+        q = pf.QuadratureBilinear2D() if m == 2 else pf.QuadratureBlock3D()
+        b = pf.BasisBilinear2D(q) if m == 2 else pf.BasisBlock3D(q)
+        Kg = orc.assemble_elasticity(X, conn, rho, 3.0)
+        if m == 2:
+            xdv, u = np.ones(10) / 10.0, np.random.default_rng(5).random(X.shape[0]) - 0.4
+            Jg, rg = orc.assemble_nlpoisson(X, conn, xdv, u)
+        for halo in halos:
+            kw = dict(partition=part, node_ranges=ranges, halo=halo, device=ctx.dev)
+            model = pf.LinearElasticity(X, conn, [], None, {}, q, b, p=3.0, **kw)
+            for _ in range(2):  # twice: the p2p inboxes are reused
+                K = model.compute_jacobian(rho)
+                ref = Kg[gb * m: ge * m]
+                same = (K.indptr.dtype == Kg.indptr.dtype and np.array_equal(K.indptr, ref.indptr)
+                        and np.array_equal(K.indices, ref.indices))
+                err = float(np.max(np.abs(K.data - ref.data)) / np.max(np.abs(Kg.data)))
+                ok &= bool(same and err <= 1e-12)
+                worst, cases = max(worst, err), cases + 1
+            if m == 2:
+                nl = pf.NonlinearPoisson2D(X, conn, [], None, q, b, **kw)
+                J, r = nl.assemble_device(xdv, u)
+                errj = float(np.max(np.abs(J.cpu().numpy() - Jg[gb:ge].data)) / np.max(np.abs(Jg.data)))
+                errr = float(np.max(np.abs(r.cpu().numpy() - rg[gb:ge])) / np.max(np.abs(rg)))
+                ok &= bool(errj <= 1e-12 and errr <= 1e-12)
+                worst, cases = max(worst, errj, errr), cases + 2
+    ok = ctx.min_over_ranks(1.0 if ok else 0.0) == 1.0
+    return ok, ctx.max_over_ranks(worst), cases
+
+
+def run_c5_record(ctx, args, halos, peak):
+    """hex8 256^3 (BASELINE configs[4]) strong-scaled over the same N: ms per assembly for every variant."""
+    torch = ctx.torch
+    case = make_case(ctx, "c5", args.c5_n, "strong")
+    rec = {"workload": case["desc"] if args.c5_n is None else f"{case['desc']} [--c5-n {case['n_side']}]",
+           "elements_global": case["total_elems"], "variants": {}, "scaling": "strong"}
+    best = None
+    for halo in halos:
+        name = {"ghost": "ghost_ms", "nccl": "reduce_nccl_ms", "p2p": "reduce_p2p_ms"}[halo]
+        try:
+            var = Variant(ctx, case, halo, args.mode)
+            ms, per = time_variant(ctx, var, min(args.steps, 20), 3)
+            rec["variants"][name] = ms
+            if best is None or ms < best[0]:
+                nnz, nn, nel = var.mesh.nnz, var.mesh.nnodes, int(case["part"].conn.shape[0])
+                best = (ms, halo, algorithmic_bytes(nel, nn, 8, 3, nnz), statistics.mean(per), var.setup_s,
+                        "gather (geometry pass + chunk-row pass, no atomics)" if var.hex_rows else "atomic")
+            var.close()
+        except Exception as e:  # a variant that cannot run on this box is reported, not fatal
+            rec["variants"][name] = None
+            rec.setdefault("errors", {})[name] = f"{type(e).__name__}: {e}"[:300]
+        torch.cuda.empty_cache()
+    if best is not None:
+        ms, halo, alg, kernel_ms, setup_s, scatter = best
+        rec.update(ms_per_step=ms, value=case["total_elems"] / (ms * 1e-3), unit=UNIT, fastest=halo, scatter=scatter,
+                   setup_s_once_per_mesh=round(setup_s, 3),
+                   roofline={"bound": "hbm", "algorithmic_bytes_per_launch_rank0": alg,
+                             "achieved": alg / (kernel_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": alg / (kernel_ms * 1e-3) / 1e9 / peak, "kernel_ms": kernel_ms})
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -185,247 +437,229 @@ def main():
     ap.add_argument("--n", type=int, default=None, help="elements per side (default: the workload's named size)")
     ap.add_argument("--mode", default="auto", choices=["auto", "gather", "atomic"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--halo", default="ghost", choices=["ghost", "reduce", "p2p"],
-                    help="N > 1: 'ghost' integrates the ghost element layer on both neighbours (no exchange); "
-                         "'reduce' integrates every element once and sums interface rows over NCCL send/recv")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: split the named mesh over the ranks (default), or give every rank a mesh of the named size")
+    ap.add_argument("--halo", default="all", choices=["all", "ghost", "reduce", "nccl", "p2p"],
+                    help="N > 1: which variants of the partitioned assembly to time (default: all three)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--c5-n", type=int, default=None, help="elements per side of the config.c5 record (default 256)")
+    ap.add_argument("--quick", action="store_true",
+                    help="headline timing only: no parity check, e2e, c5 record, fp64 probe or CPU baseline (ncu runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c5", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
-    desc, physics, nne, m, n_default, scaling = WORKLOADS[args.workload]
-    n_side = args.n or n_default
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-
+    desc, physics, nne, m, n_default = WORKLOADS[args.workload]
     if args.impl == "reference":
-        if rank == 0:
+        if int(os.environ.get("RANK", "0")) == 0:
             run_reference(args, desc, physics, nne)
         return
 
-    import torch
-    import torch.distributed as dist
-    import pyfem_gpu_testflight_b200 as pf
+    ctx = Ctx(args)
+    torch, rank, world = ctx.torch, ctx.rank, ctx.world
     from pyfem_gpu_testflight_b200 import _lib
-    from pyfem_gpu_testflight_b200.partition import slab_node_ranges, structured_slab
+    peak, peak_src = load_peaks()
+    case = make_case(ctx, args.workload, args.n, args.scaling)
+    halos = variant_names(args, world, physics)
 
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    # ---- every variant of the partitioned assembly, device-resident (mesh / pattern / plan built once per mesh)
+    variants, errors, runs = {}, {}, {}
+    sampler = ClockSampler(ctx.local_rank) if rank == 0 else None
+    clocks = None
+    for halo in halos:
+        name = {"ghost": "ghost_ms", "nccl": "reduce_nccl_ms", "p2p": "reduce_p2p_ms"}[halo]
+        try:
+            var = Variant(ctx, case, halo, args.mode)
+            ms, per = time_variant(ctx, var, args.steps, args.warmup, sampler, sample=(halo == halos[0]))
+            if halo == halos[0] and sampler is not None:
+                clocks = sampler.stop()
+            variants[name] = ms
+            runs[halo] = (ms, per, var)
+        except Exception as e:
+            variants[name] = None
+            errors[name] = f"{type(e).__name__}: {e}"[:300]
+            if halo == "ghost":
+                raise
+    fastest = min(runs, key=lambda h: runs[h][0])
+    ms_per_step, per_launch_ms, var = runs[fastest]
+    mesh = var.mesh
+    total_elems = case["total_elems"]
+    value = total_elems / (ms_per_step * 1e-3)
+    checksum = float(var.vals.sum().item())
+    for h, (_, _, v) in runs.items():  # keep the ghost variant for the e2e leg (plus the fastest), free the rest
+        if h not in (fastest, "ghost"):
+            v.close()
+    ghost = runs["ghost"][2] if "ghost" in runs else var
+    torch.cuda.empty_cache()
 
-    # ---- mesh: this rank's slab (+ ghost layer) of the ProblemCreator mesh
-    t_setup = time.perf_counter()
-    if nne == 4:
-        nx = n_side + 1
-        ny_el = (n_side // 2 if args.workload == "c3" else n_side) * (world if scaling == "weak" else 1)
-        part = structured_slab(nx, ny_el + 1, None, rank, world)
-        ranges = slab_node_ranges(nx, ny_el + 1, None, world)
-        ndims = 2
-    else:
-        nz_el = n_side * (world if scaling == "weak" else 1)
-        part = structured_slab(n_side + 1, n_side + 1, nz_el + 1, rank, world)
-        ranges = slab_node_ranges(n_side + 1, n_side + 1, nz_el + 1, world)
-        ndims = 3
-    reducer = None
-    if args.halo in ("reduce", "p2p") and world > 1 and physics in ("elasticity", "poisson", "nlpoisson"):
-        from pyfem_gpu_testflight_b200.halo import ReduceAssembler
-        reducer = ReduceAssembler(part, m, ranges, device=dev, transport="p2p" if args.halo == "p2p" else "nccl")
-        mesh = reducer.mesh
-    else:
-        mesh = pf.DeviceMesh(part.X, part.conn, m, device=dev, own_range=part.own_range, node_gid=part.node_gid,
-                             ncols_nodes=part.nnodes_global)
-    torch.cuda.synchronize()
-    setup_s = time.perf_counter() - t_setup
-    own_nodes = part.own_range[1] - part.own_range[0]
-    # elements this rank is responsible for (its block, without the ghost layer)
-    total_elems_global = (n_side * (ny_el if nne == 4 else n_side * nz_el))
-    my_elems = total_elems_global // world  # slabs are balanced to within one element layer
-
-    vals = mesh.new_values()
-    vals2 = mesh.new_values() if physics == "helmholtz" else None
-    res = mesh.new_vector() if physics == "nlpoisson" else None
-    u = torch.rand(mesh.nnodes, dtype=torch.float64, device=dev, generator=torch.Generator(dev).manual_seed(0)) \
-        if physics == "nlpoisson" else None
-    xdv = np.ones(10) / 10.0
-
-    def step(rho=1.0, p=0.0):
-        if reducer is not None:
-            if physics == "elasticity":
-                reducer.assemble_elasticity(rho, p, out=vals, mode=args.mode)
-            elif physics == "poisson":
-                reducer.assemble_poisson(rho, p, out=vals, mode=args.mode)
-            else:
-                reducer.assemble_nlpoisson(xdv, u, mode=args.mode)
-        elif physics == "elasticity":
-            mesh.assemble_elasticity(rho, p, out=vals, mode=args.mode)
-        elif physics == "poisson":
-            mesh.assemble_poisson(rho, p, out=vals, mode=args.mode)
-        elif physics == "helmholtz":
-            mesh.assemble_helmholtz(0.05, out_K=vals, out_R=vals2, mode=args.mode)
-        else:
-            mesh.assemble_nlpoisson(xdv, u, out_K=vals, out_res=res, mode=args.mode)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        sampler.start()
-        time.sleep(0.15)
-    barrier()
-    # ---- timed region: K steps, CUDA events on the launching stream, one event pair per step as well
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
-    barrier()
-    total_ms = ev[0].elapsed_time(ev[-1])
-    per_launch_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-    ms_per_step = total_ms / args.steps
-    value = total_elems_global / (ms_per_step * 1e-3)
-    checksum = float(vals.sum().item())
-
-    # ---- the same assembly with a nodal density field and RAMP penalisation (p = 5, seeded random rho),
-    # device-resident like the headline; reported beside it, not instead of it
+    # ---- the same assembly with a nodal density field and RAMP penalisation (p = 5, seeded random rho)
     field_ms = None
-    if physics in ("elasticity", "poisson") and reducer is None:
-        rho_dev = 0.05 + 0.95 * torch.rand(mesh.nnodes, dtype=torch.float64, device=dev,
-                                           generator=torch.Generator(dev).manual_seed(0))
+    if physics in ("elasticity", "poisson") and not args.quick:
+        rho_dev = 0.05 + 0.95 * torch.rand(ghost.mesh.nnodes, dtype=torch.float64, device=ctx.dev,
+                                           generator=torch.Generator(ctx.dev).manual_seed(0))
         for _ in range(3):
-            step(rho_dev, 5.0)
+            ghost.step(rho_dev, 5.0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
-            step(rho_dev, 5.0)
+            ghost.step(rho_dev, 5.0)
         e1.record()
         torch.cuda.synchronize()
-        field_ms = e0.elapsed_time(e1) / 10
+        field_ms = ctx.max_over_ranks(e0.elapsed_time(e1) / 10)
         del rho_dev
 
-    # ---- end-to-end through the model API with HOST buffers (rank-local): H2D of the nodal field from
-    # pinned memory + assembly + D2H of the CSR values into a scipy matrix
+    # ---- end to end through the drop-in model API with HOST buffers: model.compute_jacobian(rho) takes the nodal
+    # field from pinned host memory and returns a host scipy CSR (values land in a pinned buffer of the handle's pool)
     e2e = None
     h2d = d2h = 0
-    # (skipped when the CSR values alone exceed 8 GB: the full 256^3 hex case would pin > 60 GB of host memory)
-    if args.e2e_steps > 0 and reducer is None and mesh.nnz * 8 <= 8e9:
-        rho_host = torch.from_numpy(0.1 + 0.9 * np.random.default_rng(0).random(mesh.nnodes)).pin_memory()
-        data_host = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory()
-        data_np = data_host.numpy()
-        data2_np = torch.empty(mesh.nnz, dtype=torch.float64).pin_memory().numpy() if physics == "helmholtz" else None
-        res_host = torch.empty(mesh.nrows, dtype=torch.float64).pin_memory() if physics == "nlpoisson" else None
+    e2e_path = None
+    if args.e2e_steps > 0 and not args.quick and ghost.mesh.nnz * 8 <= 8e9:
+        model, gm = ghost.model, ghost.mesh
+        rho_host = torch.from_numpy(0.1 + 0.9 * np.random.default_rng(0).random(gm.nnodes)).pin_memory().numpy()
+        if physics in ("elasticity", "poisson"):
+            model.p = 5.0
+            e2e_path = f"{type(model).__name__}.compute_jacobian(rho)"
 
-        def e2e_step():
-            # the public call path of model.compute_jacobian(...): host nodal field in, host scipy CSR (and vector) out
-            if physics in ("elasticity", "poisson"):
-                v = (mesh.assemble_elasticity if physics == "elasticity" else mesh.assemble_poisson)(
-                    rho_host, 5.0, out=vals, mode=args.mode)
-                return mesh.to_scipy(v, copy_pattern=False, out=data_np)
-            if physics == "helmholtz":  # Helmholtz.__init__: K and R, no nodal input
-                mesh.assemble_helmholtz(0.05, out_K=vals, out_R=vals2, mode=args.mode)
-                return (mesh.to_scipy(vals, copy_pattern=False, out=data_np),
-                        mesh.to_scipy(vals2, copy_pattern=False, out=data2_np))
-            # one Newton re-assembly: host iterate u in, Jacobian and residual out
-            mesh.assemble_nlpoisson(xdv, rho_host, out_K=vals, out_res=res, mode=args.mode)
-            res_host.copy_(res)
-            return mesh.to_scipy(vals, copy_pattern=False, out=data_np)
+            def e2e_step():
+                return model.compute_jacobian(rho_host)
+        elif physics == "helmholtz":  # Helmholtz.__init__ assembles K and R and hands both to the host
+            e2e_path = "Helmholtz: assemble K and R + host scipy matrices (as Helmholtz.__init__)"
 
-        mesh.pattern_host()  # pattern fetched once per mesh
-        e2e_step()
-        barrier()
+            def e2e_step():
+                model.K_device, model.R_device = model._asm.assemble_helmholtz(0.05, out_K=ghost.vals, out_R=ghost.vals2,
+                                                                               mode=model.scatter)
+                return model._to_scipy(model.R_device), model._to_scipy(model.K_device)
+        else:  # one Newton re-assembly: host iterate u in, Jacobian and residual out (pyfem.py:2339-2340)
+            e2e_path = "NonlinearPoisson2D.compute_jacobian(xdv, u) + compute_rhs(xdv, u)"
+
+            def e2e_step():
+                return model.compute_jacobian(ghost.xdv, rho_host), model.compute_rhs(ghost.xdv, rho_host)
+
+        K = e2e_step()  # first call: pattern fetched once per mesh, pinned buffers allocated
+        del K
+        K = e2e_step()
+        del K
+        ctx.barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             K = e2e_step()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.e2e_steps
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = total_elems_global / float(t.item())
-        h2d = 0 if physics == "helmholtz" else mesh.nnodes * 8
-        d2h = mesh.nnz * 8 * (2 if physics == "helmholtz" else 1) + (mesh.nrows * 8 if physics == "nlpoisson" else 0)
-        del K
+            del K
+        ctx.barrier()
+        e2e = total_elems / ctx.max_over_ranks((time.perf_counter() - t0) / args.e2e_steps)
+        h2d = 0 if physics == "helmholtz" else gm.nnodes * 8 * (2 if physics == "nlpoisson" else 1)
+        d2h = gm.nnz * 8 * (2 if physics == "helmholtz" else 1) + (gm.nrows * 8 if physics == "nlpoisson" else 0)
+        if hasattr(model, "p"):
+            model.p = 0.0
+
+    setup_s, plan_bytes, chunk_elems, nelems_local = var.setup_s, mesh.plan_bytes, mesh.chunk_elems, mesh.nelems
+    nnz0, nnodes0, nrows0, hex_rows, kernels_per_step = mesh.nnz, mesh.nnodes, mesh.nrows, var.hex_rows, var.kernels_per_step
+    gather_plan = bool(mesh.nchunks)
+    for _, _, v in runs.values():
+        v.close()
+    del var, ghost, mesh, runs
+    torch.cuda.empty_cache()
+
+    # ---- in-run multi-rank parity against the numpy oracle, for every variant that ran
+    parity = None
+    if not args.quick:
+        ran = [h for h in halos if variants[{"ghost": "ghost_ms", "nccl": "reduce_nccl_ms", "p2p": "reduce_p2p_ms"}[h]] is not None]
+        try:
+            ok, worst, ncases = parity_check(ctx, ran)
+            parity = {"ok": ok, "max_rel_err": worst, "cases_per_rank": ncases, "variants": ran,
+                      "meshes": "jittered quad 41x37 (elasticity, nonlinear Poisson K + residual), hex 9x8x11 (elasticity)"}
+        except Exception as e:
+            parity = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[4] beside the headline: hex8 256^3 over the same N
+    c5 = None
+    if not args.quick and not args.no_c5 and args.workload != "c5":
+        try:
+            c5 = run_c5_record(ctx, args, halos, peak)
+        except Exception as e:
+            c5 = {"error": f"{type(e).__name__}: {e}"[:300]}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
-            dist.destroy_process_group()
+            ctx.dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (the assembly kernel is the only kernel of a step)
-    peak, peak_src = load_peaks()
-    alg_bytes = algorithmic_bytes(part.conn.shape[0], mesh.nnodes, nne, ndims, mesh.nnz,
+    # ---- roofline of the dominant kernel (the assembly kernel is the only kernel of a ghost / single-GPU step)
+    ndims = case["ndims"]
+    alg_bytes = algorithmic_bytes(nelems_local, nnodes0, nne, ndims, nnz0,
                                   n_value_arrays=2 if physics == "helmholtz" else 1,
                                   nodal_fields=1 if physics == "nlpoisson" else 0,
-                                  rhs_rows=mesh.nrows if physics == "nlpoisson" else 0)
+                                  rhs_rows=nrows0 if physics == "nlpoisson" else 0)
     kernel_ms = statistics.mean(per_launch_ms)
     achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.isfile(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(f"{args.workload}:{'gather' if mesh.nchunks else 'atomic'}")
-        except Exception:
-            traffic = None
-    hex_rows = m == 3 and args.mode != "atomic" and mesh.info(_lib.INFO_HEX_ROWS) == 1
-    if args.mode == "atomic" or not mesh.nchunks or (m == 3 and not hex_rows and args.mode == "auto"):
+    key = f"{args.workload}:{'gather' if gather_plan else 'atomic'}"
+    traffic = load_profile_table("traffic.json").get(key) if world == 1 and args.n is None else None
+    if args.mode == "atomic" or not gather_plan or (m == 3 and not hex_rows and args.mode == "auto"):
         scatter_name = "atomic"
     else:
         scatter_name = "gather (geometry pass + chunk-row pass, no atomics)" if hex_rows else "gather"
-    own_kernels_per_step = 2 if hex_rows else 1
+    # second roof: FP64 FMA pipe.  Peak measured live (pfg_probe_fp64); the kernel's flop count per launch comes
+    # from ncu's sass op counters of the same workload (profiles/fp64_counts.json)
+    fp64 = None
+    if not args.quick:
+        import ctypes
+        tf, pms = ctypes.c_double(0.0), ctypes.c_double(0.0)
+        if _lib.load().pfg_probe_fp64(ctx.local_rank, 20000, ctypes.byref(tf), ctypes.byref(pms)) == 0:
+            counts = load_profile_table("fp64_counts.json").get(key) if world == 1 and args.n is None else None
+            fp64 = {"peak_tflops": tf.value, "peak_source": "pfg_probe_fp64 (DFMA-bound kernel, CUDA events, this run)",
+                    "flops_per_launch": counts, "achieved_tflops": None, "frac": None}
+            if counts:
+                fp64["achieved_tflops"] = counts / (kernel_ms * 1e-3) / 1e12
+                fp64["frac"] = fp64["achieved_tflops"] / tf.value
+    partition_text = {
+        "ghost": f"row slabs x{world}, ghost-element layer, no data-path collective",
+        "nccl": f"row slabs x{world}, every element integrated once, interface rows summed by NCCL send/recv + indexed add",
+        "p2p": f"row slabs x{world}, every element integrated once, halo kernels store straight into the owners' "
+               f"symmetric-memory inboxes over NVLink (fused compute + transfer), indexed add",
+    }[fastest]
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": desc if args.n is None else f"{desc} [--n {n_side}]",
-                   "elements_global": total_elems_global, "elements_per_rank_with_ghosts": int(part.conn.shape[0]),
-                   "csr_nnz_rank0": mesh.nnz, "scatter": scatter_name,
-                   "partition": ((f"row slabs x{world}, every element integrated once, halo handles assemble straight into "
-                                  f"the owners' symmetric-memory inboxes over NVLink (fused compute + transfer), "
-                                  f"indexed add" if args.halo == "p2p" else
-                                  f"row slabs x{world}, every element integrated once, interface rows summed by NCCL "
-                                  f"send/recv + indexed add") if reducer is not None else
-                                 f"row slabs x{world}, ghost-element layer, no data-path collective"),
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling if world > 1 else "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": desc if args.n is None else f"{desc} [--n {case['n_side']}]",
+                   "elements_global": total_elems, "elements_per_rank_with_ghosts": int(nelems_local),
+                   "csr_nnz_rank0": nnz0, "scatter": scatter_name,
+                   "partition": partition_text, "variants": variants, "fastest_variant": fastest,
+                   "variant_errors": errors or None,
+                   "parity_ok": None if parity is None else parity["ok"], "parity": parity,
+                   "c5": c5,
                    "l2": "outputs (4.8 GB/step for c2) and inputs exceed the 126 MB L2; no flush needed",
                    "rho": "constant 1.0, p=0 (device-resident headline); e2e uses a host nodal rho field, p=5",
                    "ms_per_step_rho_field_p5": field_ms,
-                   "setup_s_once_per_mesh": round(setup_s, 3), "halo_recompute_factor": round(mesh.chunk_elems / max(1, mesh.nelems), 4),
-                   "plan_bytes": mesh.plan_bytes, "checksum": checksum},
+                   "setup_s_once_per_mesh": round(setup_s, 3),
+                   "halo_recompute_factor": round(chunk_elems / max(1, nelems_local), 4),
+                   "plan_bytes": plan_bytes, "checksum": checksum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms,
                      "kernel_ms_best": min(per_launch_ms), "kernel_ms_median": statistics.median(per_launch_ms),
-                     "frac_of_nominal_8000_GBs": achieved / 8000.0,
-                     "peak_source": peak_src},
+                     "frac_of_nominal_8000_GBs": achieved / 8000.0, "peak_source": peak_src, "fp64": fp64},
         "clocks": clocks,
-        # own kernels per step: the assembly kernel; the reduce variant adds one halo assembly per neighbour it
-        # sends to and one indexed add per neighbour it receives from (rank 0's count)
-        "gpu_launches": args.steps * (own_kernels_per_step + (len(reducer.halo) + len(reducer.recv) if reducer is not None else 0)),
+        # own kernels per step of the headline variant: the assembly kernel(s); a reduce variant adds one halo
+        # assembly per neighbour it sends to and one indexed add per neighbour it receives from (rank 0's count)
+        "gpu_launches": args.steps * kernels_per_step,
     }
     if e2e is not None:
-        line["e2e"] = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
-    if world == 1 and not args.no_cpu_baseline:
+        line["e2e"] = {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "path": e2e_path}
+    if world == 1 and not args.no_cpu_baseline and not args.quick:
         side = cpu_sample_side(physics, nne, 12.0)
         n, w, c = oracle_step(physics, nne, side)
+        dim = 2 if nne == 4 else 3
         line["cpu_baseline"] = {"value": n / w, "unit": UNIT, "cores": round(c / w, 2), "kind": "port",
-                                "sample": f"one assembly of {side}^{2 if nne == 4 else 3} elements of the same mesh "
+                                "sample": f"one assembly of {side}^{dim} elements of the same mesh "
                                           f"family with the numpy/scipy oracle ({w:.1f} s)"}
+        line["config"]["cpu_sample_elements"] = side ** dim
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        ctx.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -256,6 +256,14 @@ PFG_API int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, 
                    double rtol, double atol, int max_iter, int check_every, int* iters_out, double* resid_out,
                    void* stream);
 
+/*
+ * Diagnostics for the bench's roofline: sustained FP64 FMA throughput of `device` in TFLOP/s (a DFMA-bound kernel,
+ * 8 CTAs of 256 threads per SM, 16 independent chains per thread, best of 4 timed launches with CUDA events).  The
+ * assembly kernels run their quadrature on the FP64 CUDA cores, so this is the second roof next to HBM bandwidth
+ * (SURVEY.md section 8d).  No reference counterpart.
+ */
+PFG_API int pfg_probe_fp64(int device, int iters, double* tflops_out, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

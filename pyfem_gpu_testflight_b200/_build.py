@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(os.path.dirname(PKG_DIR), "include")
 LIB_PATH = os.path.join(PKG_DIR, "libpyfem_b200.so")
-SOURCES = ["pfg_setup.cu", "pfg_assemble.cu", "pfg_solve.cu"]
+SOURCES = ["pfg_setup.cu", "pfg_assemble.cu", "pfg_solve.cu", "pfg_probe.cu"]
 HEADERS = ["pfg_internal.cuh", "pfg_elem.cuh"]
 NVCC_FLAGS = [
     "-std=c++20", "-O3", "-lineinfo",

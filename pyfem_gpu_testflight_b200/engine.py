@@ -23,16 +23,25 @@ def _ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else c_void_p(0)
 
 
+def index_bytes_rule(nelems, ndof_per_elem, ncols):
+    """scipy's index width for coo -> csr (scipy/sparse/_coo.py:59-61, 419; SURVEY trap T2): int32 iff
+    max(COO nnz = nelems * D^2, ncols) <= 2^31 - 1, else int64, for indptr AND indices.  For a rank's row slab the
+    rule is evaluated with the GLOBAL element count, so that concatenated slabs carry the dtype of the reference's
+    global matrix (256^3 hexes on 8 ranks: every slab is int64, as the global matrix is)."""
+    return 4 if max(int(nelems) * int(ndof_per_elem) ** 2, int(ncols)) <= 2 ** 31 - 1 else 8
+
+
 class DeviceMesh:
     """Device copies of the mesh, CSR pattern, element->slot map and gather plan (pfg_mesh_create).
 
     X (nnodes, ndims) float64; conn (nelems, nnodes_per_elem) integer; numpy arrays or torch tensors.
     own_range = (begin, end) node rows this handle assembles (default all); node_gid = strictly increasing
-    local->global node ids for the reported column indices (multi-GPU slabs).
+    local->global node ids for the reported column indices (multi-GPU slabs); nelems_global = element count of the
+    whole mesh when this handle is one rank's slab (index_bytes_rule).
     """
 
     def __init__(self, X, conn, ndof_per_node, device=None, own_range=None, node_gid=None, ncols_nodes=None,
-                 build_gather_plan=True, reorder=True):
+                 build_gather_plan=True, reorder=True, nelems_global=None):
         torch = _torch()
         self._lib = _lib.load()
         self._handle = None
@@ -65,12 +74,15 @@ class DeviceMesh:
         self.nnz = self.info(_lib.INFO_NNZ)
         self.nrows = self.info(_lib.INFO_NROWS)
         self.ncols = self.info(_lib.INFO_NCOLS)
-        self.idx_bytes = self.info(_lib.INFO_IDX_BYTES)
+        self.idx_bytes = self.info(_lib.INFO_IDX_BYTES)  # the rule applied to this handle's own element count
+        if nelems_global is not None:
+            self.idx_bytes = max(self.idx_bytes, index_bytes_rule(nelems_global, self.ndof_per_elem, self.ncols))
         self.nchunks = self.info(_lib.INFO_NCHUNKS)
         self.chunk_elems = self.info(_lib.INFO_CHUNK_ELEMS)
         self.plan_bytes = self.info(_lib.INFO_PLAN_BYTES)
         self._pattern = None
         self._pattern_host = None
+        self._host_pool = []  # pinned host buffers for to_scipy(reuse_host_buffers=True)
 
     # ---- plumbing -------------------------------------------------------------------------------
     def _stream(self):
@@ -134,6 +146,8 @@ class DeviceMesh:
         if self._pattern_host is None:
             indptr, indices = self.pattern()
             self._pattern_host = (indptr.cpu().numpy(), indices.cpu().numpy())
+            for a in self._pattern_host:  # shared with every matrix built by to_scipy(copy_pattern=False)
+                a.flags.writeable = False
         return self._pattern_host
 
     # ---- assembly -------------------------------------------------------------------------------
@@ -339,21 +353,42 @@ class DeviceMesh:
         return vals
 
     # ---- host views -------------------------------------------------------------------------------
-    def to_scipy(self, vals, copy_pattern=True, out=None):
+    def _pinned_values(self):
+        """A pinned host buffer of nnz doubles that no live matrix references: buffers handed out earlier are reused
+        as soon as the scipy matrix built on them is gone (reference counts), so a Newton loop alternates between
+        two buffers and never pays a fresh 4.8 GB allocation + page-fault pass per assembly."""
+        import sys
+        torch = _torch()
+        for arr in self._host_pool:
+            if sys.getrefcount(arr) <= 3:  # the pool's reference, the loop variable, getrefcount's argument
+                return arr
+        arr = torch.empty(self.nnz, dtype=torch.float64).pin_memory().numpy()
+        self._host_pool.append(arr)
+        if len(self._host_pool) > 4:  # matrices that stay alive keep their buffers; the pool forgets the oldest
+            self._host_pool.pop(0)
+        return arr
+
+    def to_scipy(self, vals, copy_pattern=True, out=None, reuse_host_buffers=False):
         """scipy.sparse.csr_matrix on the host from device values (one D2H copy of nnz doubles).
 
         copy_pattern=True hands out private copies of indptr / indices, so callers may edit the matrix in
-        place (apply_dirichlet_bcs runs eliminate_zeros on it) without touching the cached pattern.
-        `out` may be a float64 host array (e.g. the numpy view of a pinned torch tensor) to receive the values.
+        place without touching the cached pattern.  copy_pattern=False shares the cached arrays, marked read-only:
+        an in-place pattern edit (eliminate_zeros, sort_indices) then raises instead of corrupting the cache, and
+        ModelBase.apply_dirichlet_bcs copies them first (copy-on-write).
+        `out` may be a float64 host array (e.g. the numpy view of a pinned torch tensor) to receive the values;
+        reuse_host_buffers=True takes it from the handle's pool of pinned buffers instead.
         """
         torch = _torch()
         from scipy import sparse
         indptr, indices = self.pattern_host()
-        data = np.empty(self.nnz, dtype=np.float64) if out is None else out
+        if out is None:
+            out = self._pinned_values() if reuse_host_buffers else np.empty(self.nnz, dtype=np.float64)
+        data = out
         torch.from_numpy(data).copy_(vals)
         if copy_pattern:
             indptr, indices = indptr.copy(), indices.copy()
         K = sparse.csr_matrix((data, indices, indptr), shape=(self.nrows, self.ncols), copy=False)
         K.has_sorted_indices = True
         K.has_canonical_format = True
+        K._pfg_shared_pattern = not copy_pattern
         return K

@@ -113,7 +113,8 @@ class ReduceAssembler:
     """Device side: the rank's slab handle with masked ghost elements + one halo handle per neighbour, and the
     exchange.  Methods mirror DeviceMesh.assemble_*; nodal fields are given in the rank's local numbering."""
 
-    def __init__(self, part: LocalMesh, ndof_per_node, ranges, device=None, group=None, transport="nccl"):
+    def __init__(self, part: LocalMesh, ndof_per_node, ranges, device=None, group=None, transport="nccl",
+                 nelems_global=None):
         import torch
         import torch.distributed as dist
         from .engine import DeviceMesh
@@ -123,7 +124,8 @@ class ReduceAssembler:
         self.part, self.m = part, int(ndof_per_node)
         self.plan = HaloPlan(part, ranges)
         self.mesh = DeviceMesh(part.X, part.conn, self.m, device=device, own_range=part.own_range,
-                               node_gid=part.node_gid, ncols_nodes=part.nnodes_global)
+                               node_gid=part.node_gid, ncols_nodes=part.nnodes_global,
+                               nelems_global=nelems_global if nelems_global is not None else part.nelems_global)
         self.device = self.mesh.device
         self.mesh.set_element_mask(self.plan.skip_mask)
         self.halo = [(s, DeviceMesh(s.X, s.conn, self.m, device=self.device, own_range=s.own_range, node_gid=s.node_gid,
@@ -196,7 +198,7 @@ class ReduceAssembler:
         self.recv = []
         if recv_bufs:
             indptr, indices = self.mesh.pattern()
-            ip = indptr.cpu().numpy()
+            ip = indptr.cpu().numpy().astype(np.int64)
             gid0 = int(self.part.node_gid[self.part.own_range[0]])
         for q, (rows, h_indptr, h_indices) in sorted(recv_bufs.items()):
             rows_np = rows.cpu().numpy()
@@ -283,3 +285,20 @@ class ReduceAssembler:
         K, res = self.mesh.assemble_nlpoisson(xdv, u, mode=mode)
         self._reduce(K, hk, res, hr)
         return K, res
+
+    def assemble_helmholtz(self, r0, out_K=None, out_R=None, mode="auto"):
+        """K and R of the Helmholtz filter (pyfem.py:2084-2097): two value arrays per handle.  The halo handles keep
+        their outputs local and ship them with NCCL send/recv for either transport (an inbox holds one matrix)."""
+        hk, hr = [], []
+        for _, hm, _ in self.halo:
+            k, r = hm.assemble_helmholtz(r0, mode=mode)
+            hk.append(k)
+            hr.append(r)
+        K, R = self.mesh.assemble_helmholtz(r0, out_K=out_K, out_R=out_R, mode=mode)
+        transport, self.transport = self.transport, "nccl"
+        try:
+            self._reduce(K, hk)
+            self._reduce(R, hr)
+        finally:
+            self.transport = transport
+        return K, R

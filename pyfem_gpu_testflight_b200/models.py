@@ -18,7 +18,19 @@ class ModelBase:
     """Mesh arrays, dof maps, device handle and the scatter (pyfem.py:634-931)."""
 
     def __init__(self, ndof_per_node, X, conn, dof_fixed, dof_fixed_vals, quadrature: QuadratureBase,
-                 basis: BasisBase, device=None, scatter="auto"):
+                 basis: BasisBase, device=None, scatter="auto", group=None, partition=None, node_ranges=None,
+                 halo="ghost"):
+        """Reference arguments (pyfem.py:640-657) plus, keyword-only in practice:
+          device   torch device of the handle (default: the current CUDA device)
+          scatter  "auto" | "gather" | "atomic"
+          group    a torch.distributed process group: the model becomes ONE RANK of a row-slab partition of the
+                   (global) mesh passed in X / conn -- compute_jacobian returns the rank's row slab (scipy CSR,
+                   global columns, the reference's index dtype), gather() rebuilds the global matrix on rank 0
+          partition / node_ranges   a ready-made partition.LocalMesh (e.g. structured_slab) and every rank's global
+                   node range, instead of splitting X / conn here
+          halo     "ghost": ghost-element layer, no exchange | "nccl" / "p2p": every element integrated once,
+                   interface rows summed over NCCL send/recv or through NVLink peer stores (halo.py)
+        """
         self.ndof_per_node = int(ndof_per_node)
         self.X = np.array(X, dtype=float)
         self.conn = np.array(conn, dtype=int)
@@ -39,11 +51,59 @@ class ModelBase:
         self.ndof = self.nnodes * self.ndof_per_node
 
         # device: H2D of X / conn, the conn.min()/max() asserts of pyfem.py:680-681, CSR pattern, plans
-        self.mesh = DeviceMesh(self.X, self.conn, self.ndof_per_node, device=device)
+        self.slab = self._reducer = None
+        if group is not None or partition is not None:
+            self._init_slab(group, partition, node_ranges, halo, device)
+        else:
+            self.mesh = DeviceMesh(self.X, self.conn, self.ndof_per_node, device=device)
+        self._asm = self._reducer if self._reducer is not None else self.mesh
 
         # persistent right-hand side (pyfem.py:756; survey trap T7)
         self.rhs = np.zeros(self.ndof)
         self._dof = self._dof_each_node = self._conn_dof = self._dof_free = None
+
+    # ---- one rank of a row-slab partition --------------------------------------------------------------
+    def _init_slab(self, group, partition, node_ranges, halo, device):
+        from .partition import SlabContext
+        if halo not in ("ghost", "nccl", "p2p"):
+            raise ValueError(f"unknown halo variant {halo!r}")
+        if partition is not None and partition.nnodes_global != self.nnodes:
+            # X / conn may be the rank's local arrays when the global mesh was never built (bench.py at full size)
+            self.nnodes, self.ndof = partition.nnodes_global, partition.nnodes_global * self.ndof_per_node
+            self.nodes = np.arange(self.nnodes)
+        self.slab = SlabContext(self.X, self.conn, group=group, partition=partition, ranges=node_ranges)
+        part = self.slab.part
+        nel_global = int(part.nelems_global) if getattr(part, "nelems_global", None) else None
+        if self.slab.size == 1:  # a partition of one: the plain single-GPU handle
+            self.mesh = DeviceMesh(part.X, part.conn, self.ndof_per_node, device=device)
+        elif halo == "ghost":
+            self.mesh = DeviceMesh(part.X, part.conn, self.ndof_per_node, device=device, own_range=part.own_range,
+                                   node_gid=part.node_gid, ncols_nodes=part.nnodes_global, nelems_global=nel_global)
+        else:
+            from .halo import ReduceAssembler
+            self._reducer = ReduceAssembler(part, self.ndof_per_node, self.slab.ranges, device=device, group=group,
+                                            transport=halo, nelems_global=nel_global)
+            self.mesh = self._reducer.mesh
+        self._row0 = self.slab.owned_nodes[0] * self.ndof_per_node  # global dof of the slab's first row
+
+    def _local(self, f):
+        """Nodal field as the handle wants it: global -> this rank's local nodes in slab mode."""
+        return f if self.slab is None else self.slab.local_field(f)
+
+    def gather(self, K_slab, dst=0):
+        """Slab mode: the global CSR (the reference's matrix) on rank `dst`, None elsewhere."""
+        return K_slab if self.slab is None else self.slab.gather_matrix(K_slab, dst)
+
+    def gather_vector(self, v_owned, dst=0):
+        return v_owned if self.slab is None else self.slab.gather_vector(v_owned, dst)
+
+    def _owned(self, vec_global):
+        """The owned rows of a global dof vector (slab mode), the vector itself otherwise."""
+        if self.slab is None:
+            return vec_global
+        m = self.ndof_per_node
+        b, e = self.slab.owned_nodes
+        return vec_global[b * m: e * m]
 
     # ---- dof maps (utils.create_dof, utils.py:267-298), built on first use ---------------------------
     def _make_dof(self):
@@ -117,11 +177,13 @@ class ModelBase:
 
     # ---- helpers -------------------------------------------------------------------------------------
     def _to_scipy(self, vals):
-        return self.mesh.to_scipy(vals)
+        # values land in a pinned buffer of the handle's pool (reused once the previous matrix is gone); the cached
+        # indptr / indices are shared read-only and copied on write by apply_dirichlet_bcs
+        return self.mesh.to_scipy(vals, copy_pattern=False, reuse_host_buffers=True)
 
     def _vec_to_host(self, vec, out):
-        out[:] = vec.cpu().numpy()
-        return out
+        self._owned(out)[:] = vec.cpu().numpy()
+        return self._owned(out)
 
     def solve_device(self, vals, rhs, rtol=1e-8, atol=0.0, max_iter=None):
         """Dirichlet conditions + conjugate gradients entirely in HBM: `vals` are the device
@@ -139,28 +201,38 @@ class ModelBase:
         asked, columns) of fixed dofs zeroed, unit diagonal, explicit zeros eliminated, rhs updated.
         K and rhs are edited in place (Assembler.solve_nonlinear relies on that, pyfem.py:2343) and returned.
         """
-        fixed = self.dof_fixed
-        is_fixed = np.zeros(K.shape[0], dtype=bool)
-        is_fixed[fixed] = True
+        if getattr(K, "_pfg_shared_pattern", False):  # copy-on-write: eliminate_zeros below edits the pattern
+            K.indices, K.indptr = K.indices.copy(), K.indptr.copy()
+            K._pfg_shared_pattern = False
+        row0 = getattr(self, "_row0", 0) if getattr(self, "slab", None) is not None else 0  # slab: rows row0 ...
+        nrows = K.shape[0]
+        is_fixed = np.zeros(K.shape[1], dtype=bool)
+        is_fixed[self.dof_fixed] = True
+        row_fixed = is_fixed[row0: row0 + nrows]
+        free_rows = np.nonzero(~row_fixed)[0]
         Krb_u0 = None
-        if self.dof_fixed_vals is not None and enforce_symmetric_K:
+        u0 = None
+        if self.dof_fixed_vals is not None:
             u0 = np.zeros(K.shape[1])
-            u0[fixed] = self.dof_fixed_vals
-            Krb_u0 = (K @ u0)[self.dof_free] - 0.0  # only fixed columns carry non-zero u0
-        diag = K.diagonal()
-        row_of = np.repeat(np.arange(K.shape[0]), np.diff(K.indptr))
-        K.data[is_fixed[row_of]] = 0.0
+            u0[self.dof_fixed] = self.dof_fixed_vals
+            if enforce_symmetric_K:
+                Krb_u0 = (K @ u0)[free_rows] - 0.0  # only fixed columns carry non-zero u0
+        diag = K.diagonal(k=row0)
+        row_of = np.repeat(np.arange(nrows), np.diff(K.indptr))
+        K.data[row_fixed[row_of]] = 0.0
         if enforce_symmetric_K:
             K.data[is_fixed[K.indices]] = 0.0
-        diag[fixed] = 1.0
-        K.setdiag(diag)
+        diag[row_fixed] = 1.0
+        K.setdiag(diag, k=row0)
         K.eliminate_zeros()
+        if rhs.shape[0] != nrows:  # slab mode with the global persistent rhs: edit the owned rows
+            rhs = rhs[row0: row0 + nrows]
         if self.dof_fixed_vals is None:
-            rhs[fixed] = 0.0
+            rhs[row_fixed] = 0.0
         else:
-            rhs[fixed] = self.dof_fixed_vals[:]
+            rhs[row_fixed] = u0[row0: row0 + nrows][row_fixed]
             if enforce_symmetric_K:
-                rhs[self.dof_free] -= Krb_u0
+                rhs[free_rows] -= Krb_u0
         return K, rhs
 
 
@@ -206,6 +278,8 @@ class _DensityFunctions:
 
     def _k_dv_sens(self, physics, rho, phi, psi, **kw):
         _check_real(rho)
+        if self.slab is not None:
+            raise NotImplementedError("sensitivities of a slab-partitioned model are not implemented")
         rho = np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho
         return self.mesh.k_dv_sens(physics, rho, self.p, phi, psi, **kw).cpu().numpy()
 
@@ -227,7 +301,7 @@ class LinearPoisson(_DensityFunctions, ModelBase):
 
     def compute_jacobian_device(self, rho=1.0, out=None):
         _check_real(rho)
-        return self.mesh.assemble_poisson(rho, self.p, out=out, mode=self.scatter)
+        return self._asm.assemble_poisson(self._local(rho), self.p, out=out, mode=self.scatter)
 
     def compute_jacobian(self, rho=1.0):
         return self._to_scipy(self.compute_jacobian_device(rho))
@@ -250,7 +324,13 @@ class LinearPoisson(_DensityFunctions, ModelBase):
         return g.expand(Xq.shape[:-1]).contiguous() if g.dim() == 0 or g.shape != Xq.shape[:-1] else g.contiguous()
 
     def compute_rhs_device(self, out=None):
-        return self.mesh.poisson_rhs(self._source_at_quads(), out=out, mode=self.scatter)
+        if self._reducer is not None:  # the slab's ghost elements complete the owned rows: integrate them here too
+            self.mesh.set_element_mask(None)
+        try:
+            return self.mesh.poisson_rhs(self._source_at_quads(), out=out, mode=self.scatter)
+        finally:
+            if self._reducer is not None:
+                self.mesh.set_element_mask(self._reducer.plan.skip_mask)
 
     def compute_rhs(self):
         return self._vec_to_host(self.compute_rhs_device(), self.rhs)
@@ -288,7 +368,9 @@ class NonlinearPoisson2D(ModelBase):
 
     def assemble_device(self, xdv, u, want_K=True, want_res=True):
         """Jacobian values and residual from ONE pass over the elements (device tensors)."""
-        return self.mesh.assemble_nlpoisson(xdv, u, want_K=want_K, want_res=want_res, mode=self.scatter)
+        if self._reducer is not None:  # the reduce variant ships Jacobian and residual shares together
+            return self._reducer.assemble_nlpoisson(xdv, self._local(u), mode=self.scatter)
+        return self.mesh.assemble_nlpoisson(xdv, self._local(u), want_K=want_K, want_res=want_res, mode=self.scatter)
 
     def compute_jacobian(self, xdv, u):
         K, _ = self.assemble_device(xdv, u, want_K=True, want_res=False)
@@ -321,11 +403,11 @@ class LinearElasticity(_DensityFunctions, ModelBase):
         """Point loads assigned (not added) into the persistent rhs (pyfem.py:1760-1768)."""
         nodes = np.array(list(self.nodal_force.keys()), dtype=int)
         self.rhs[self.dof_each_node[nodes].flatten()] = np.array(list(self.nodal_force.values())).flatten()
-        return self.rhs
+        return self._owned(self.rhs)
 
     def compute_jacobian_device(self, rho=1.0, out=None):
         _check_real(rho)
-        return self.mesh.assemble_elasticity(rho, self.p, self.E, self.nu, out=out, mode=self.scatter)
+        return self._asm.assemble_elasticity(self._local(rho), self.p, self.E, self.nu, out=out, mode=self.scatter)
 
     def _compute_element_jacobian(self, Ke_mat, rho=1.0):
         """Element matrices only (pyfem.py:2029-2068)."""
@@ -357,7 +439,7 @@ class Helmholtz(ModelBase):
     def __init__(self, r0, X, conn, quadrature, basis, **kw):
         super().__init__(1, X, conn, [], None, quadrature, basis, **kw)
         self.r0 = r0
-        self.K_device, self.R_device = self.mesh.assemble_helmholtz(r0, mode=self.scatter)
+        self.K_device, self.R_device = self._asm.assemble_helmholtz(r0, mode=self.scatter)
         self.R = self._to_scipy(self.R_device)
         self.RT = self.R.transpose()
         self.K = self._to_scipy(self.K_device)
@@ -384,8 +466,8 @@ class Helmholtz(ModelBase):
         return self.RT.dot(self.Ksolve.solve(gradrho, tol=1e-8))
 
     def compute_rhs(self, x):
-        self.rhs[:] = self.R.dot(x)
-        return self.rhs
+        self._owned(self.rhs)[:] = self.R.dot(x)  # slab mode: x is the global field, the result the owned rows
+        return self._owned(self.rhs)
 
     def compute_rhs_device(self, x, out=None):
         return self.mesh.spmv(self.R_device, x, out=out)

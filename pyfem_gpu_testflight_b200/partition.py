@@ -25,7 +25,8 @@ def split_range(n, size):
 class LocalMesh:
     """One rank's piece: arrays to hand to DeviceMesh / the model constructors."""
 
-    def __init__(self, X, conn, own_range, node_gid, nnodes_global, elem_gid, rank, size):
+    def __init__(self, X, conn, own_range, node_gid, nnodes_global, elem_gid, rank, size, nelems_global=None):
+        self.nelems_global = nelems_global  # elements of the whole mesh (index-width rule of the global matrix)
         self.X = X
         self.conn = conn
         self.own_range = own_range          # (begin, end) in LOCAL node numbering
@@ -55,7 +56,7 @@ def partition_mesh(X, conn, rank, size, node_ranges=None):
     if le - lb != e - b:
         raise ValueError("an owned node is not referenced by any element")
     return LocalMesh(np.ascontiguousarray(X[node_gid]), conn_local.astype(np.int64), (int(lb), int(le)),
-                     node_gid.astype(np.int64), nnodes, elem_gid, rank, size)
+                     node_gid.astype(np.int64), nnodes, elem_gid, rank, size, nelems_global=int(conn.shape[0]))
 
 
 def structured_slab(nnodes_x, nnodes_y, nnodes_z, rank, size, Lx=None, Ly=None, Lz=None):
@@ -99,7 +100,8 @@ def structured_slab(nnodes_x, nnodes_y, nnodes_z, rank, size, Lx=None, Ly=None, 
     node_gid = np.arange(l0 * plane, (l1 + 1) * plane, dtype=np.int64)
     elem_gid = np.arange(e0 * elems_per_layer, e1 * elems_per_layer, dtype=np.int64)
     own = ((rb - l0) * plane, (re - l0) * plane)
-    return LocalMesh(X, conn, own, node_gid, nslow * plane, elem_gid, rank, size)
+    return LocalMesh(X, conn, own, node_gid, nslow * plane, elem_gid, rank, size,
+                     nelems_global=int(elems_per_layer) * (nslow - 1))
 
 
 def slab_node_ranges(nnodes_x, nnodes_y, nnodes_z, size):
@@ -134,3 +136,74 @@ def global_norm(local_owned_vec):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(s, op=dist.ReduceOp.SUM)
     return float(torch.sqrt(s).item())
+
+
+class SlabContext:
+    """What a physics model needs to run as ONE RANK of a row-slab partition (models.py, `group=` / `partition=`):
+    the rank's local mesh, the node ranges of all ranks, global <-> local nodal fields, and the gathers that rebuild
+    the reference's global CSR / vectors for parity checks.  Host logic only (numpy + torch.distributed): runs under
+    gloo on a CPU as well as under NCCL."""
+
+    def __init__(self, X, conn, group=None, partition=None, ranges=None, rank=None, size=None):
+        import torch.distributed as dist
+        self.group = group
+        if partition is not None:
+            rank, size = partition.rank, partition.size
+        elif rank is None or size is None:
+            if not (dist.is_available() and dist.is_initialized()):
+                raise RuntimeError("group= needs an initialised torch.distributed process group")
+            rank, size = dist.get_rank(group), dist.get_world_size(group)
+        self.rank, self.size = int(rank), int(size)
+        self.part = partition if partition is not None else partition_mesh(X, conn, self.rank, self.size,
+                                                                           node_ranges=ranges)
+        self.ranges = list(ranges) if ranges is not None else split_range(self.part.nnodes_global, self.size)
+        gb, ge = self.part.owned_global_range
+        if (gb, ge) != tuple(self.ranges[self.rank]):
+            raise ValueError(f"partition owns global nodes [{gb}, {ge}), the ranges say {self.ranges[self.rank]}")
+
+    @property
+    def owned_nodes(self):
+        """Global node range [begin, end) whose rows this rank assembles."""
+        return self.part.owned_global_range
+
+    def local_field(self, f):
+        """A nodal field given on the GLOBAL mesh (as the reference's callers pass it) -> the rank's local nodes;
+        scalars (constant fields) pass through."""
+        if f is None or np.ndim(f) == 0:
+            return f
+        f = np.asarray(f) if not hasattr(f, "device") else f
+        if f.shape[0] == len(self.part.node_gid):
+            return f  # already local (a single rank's local nodes are the global nodes)
+        if f.shape[0] == self.part.nnodes_global:
+            return f[self.part.node_gid] if not hasattr(f, "device") else f[_as_index(f, self.part.node_gid)]
+        raise ValueError(f"nodal field has {f.shape[0]} entries, expected {self.part.nnodes_global} (global) or "
+                         f"{len(self.part.node_gid)} (this rank's local nodes)")
+
+    def gather_matrix(self, K_slab, dst=0):
+        """Row-wise concatenation of every rank's slab (scipy CSR, global columns) on rank `dst`: the reference's
+        global matrix.  For checks and small problems -- the slabs travel as pickled host arrays."""
+        import torch.distributed as dist
+        mine = (np.asarray(K_slab.indptr), np.asarray(K_slab.indices), np.asarray(K_slab.data))
+        out = [None] * self.size if self.rank == dst else None
+        dist.gather_object(mine, out, dst=_global_rank(self.group, dst), group=self.group)
+        if self.rank != dst:
+            return None
+        K = concat_slabs(out, K_slab.shape[1])
+        idx = K_slab.indices.dtype  # every rank used the global index-width rule
+        return type(K)((K.data, K.indices.astype(idx), K.indptr.astype(idx)), shape=K.shape)
+
+    def gather_vector(self, v_owned, dst=0):
+        import torch.distributed as dist
+        out = [None] * self.size if self.rank == dst else None
+        dist.gather_object(np.asarray(v_owned), out, dst=_global_rank(self.group, dst), group=self.group)
+        return np.concatenate(out) if self.rank == dst else None
+
+
+def _global_rank(group, r):
+    import torch.distributed as dist
+    return r if group is None else dist.get_global_rank(group, r)
+
+
+def _as_index(like, idx):
+    import torch
+    return torch.as_tensor(idx, device=like.device)

@@ -221,3 +221,106 @@ def test_row_slabs_reproduce_global_matrix(pf, three_d, size):
     K = concat_slabs(slabs, Kg.shape[1])
     assert np.array_equal(K.indptr, Kg.indptr) and np.array_equal(K.indices, Kg.indices)
     assert_values_close(K.data, Kg.data, VAL_TOL)
+
+
+# ---- the model API as one rank of a row-slab partition (constructor keywords group= / partition=) ---------
+@pytest.mark.parametrize("three_d", [False, True])
+def test_model_slab_mode_matches_global_matrix(pf, three_d):
+    """LinearElasticity / LinearPoisson / Helmholtz / NonlinearPoisson2D built with partition= (ghost-layer variant,
+    ranks run one after another on this GPU): the row slabs, concatenated, are the oracle's global matrix -- pattern
+    bit-exact including the dtype, values to 1e-12 -- and the Dirichlet conditions act on a slab as on its rows."""
+    from pyfem_gpu_testflight_b200.partition import concat_slabs, partition_mesh, split_range
+    dims = (9, 8, 11) if three_d else (41, 37, None)
+    X, conn = orc.structured_mesh(*dims)
+    X = X + np.random.default_rng(3).uniform(-0.004, 0.004, size=X.shape)
+    if not three_d:
+        X = (X - X.min(axis=0)) / (X.max(axis=0) - X.min(axis=0))
+    size = 3
+    ranges = split_range(X.shape[0], size)
+    q = pf.QuadratureBlock3D() if three_d else pf.QuadratureBilinear2D()
+    basis = pf.BasisBlock3D(q) if three_d else pf.BasisBilinear2D(q)
+    rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+    m = X.shape[1]
+    fixed = np.arange(0, m * X.shape[0], 7)
+    Kg = orc.assemble_elasticity(X, conn, rho, 3.0)
+    Pg = orc.assemble_poisson(X, conn, rho, 3.0)
+    slabs_e, slabs_p, bc_rows = [], [], []
+    for r in range(size):
+        part = partition_mesh(X, conn, r, size)
+        me = pf.LinearElasticity(X, conn, fixed, None, {0: [0.0] * m}, q, basis, p=3.0, partition=part,
+                                 node_ranges=ranges)
+        K = me.compute_jacobian(rho)  # the GLOBAL nodal field, as a caller of the reference passes it
+        gb, ge = part.owned_global_range
+        assert K.shape == (m * (ge - gb), m * X.shape[0]) and K.indices.dtype == Kg.indices.dtype
+        slabs_e.append((K.indptr.copy(), K.indices.copy(), K.data.copy()))
+        Kb, rb = me.apply_dirichlet_bcs(K, me.compute_rhs(), enforce_symmetric_K=True)
+        bc_rows.append(Kb)
+        mp_ = pf.LinearPoisson(X, conn, [0], None, q, basis, gfunc, p=3.0, partition=part, node_ranges=ranges)
+        P = mp_.compute_jacobian(rho)
+        slabs_p.append((P.indptr.copy(), P.indices.copy(), P.data.copy()))
+        rhs = mp_.compute_rhs()
+        assert_values_close(rhs, orc.assemble_poisson_rhs(X, conn, gfunc)[gb:ge], VAL_TOL, "rhs slab")
+    K = concat_slabs(slabs_e, Kg.shape[1])
+    assert np.array_equal(K.indptr, Kg.indptr) and np.array_equal(K.indices, Kg.indices)
+    assert_values_close(K.data, Kg.data, VAL_TOL)
+    P = concat_slabs(slabs_p, Pg.shape[1])
+    assert np.array_equal(P.indptr, Pg.indptr) and np.array_equal(P.indices, Pg.indices)
+    assert_values_close(P.data, Pg.data, VAL_TOL)
+    # boundary conditions on slabs == boundary conditions on the global matrix, row range by row range
+    import scipy.sparse as sp
+    Kd = np.array(Kg.todense())
+    Kd[fixed, :] = 0.0
+    Kd[:, fixed] = 0.0
+    Kd[fixed, fixed] = 1.0
+    got = sp.vstack(bc_rows).toarray()
+    assert np.max(np.abs(got - Kd)) <= VAL_TOL * np.max(np.abs(Kd))
+    if not three_d:
+        xdv = np.ones(10) / 10.0
+        u = np.random.default_rng(5).random(X.shape[0]) - 0.4
+        Jg, rg = orc.assemble_nlpoisson(X, conn, xdv, u)
+        Hk, Hr = orc.assemble_helmholtz(X, conn, 0.05)
+        sj, sh = [], []
+        for r in range(size):
+            part = partition_mesh(X, conn, r, size)
+            gb, ge = part.owned_global_range
+            mn = pf.NonlinearPoisson2D(X, conn, [0], None, q, basis, partition=part, node_ranges=ranges)
+            J = mn.compute_jacobian(xdv, u)
+            sj.append((J.indptr.copy(), J.indices.copy(), J.data.copy()))
+            assert_values_close(mn.compute_rhs(xdv, u), rg[gb:ge], VAL_TOL, "residual slab")
+            mh = pf.Helmholtz(0.05, X, conn, q, basis, partition=part, node_ranges=ranges)
+            sh.append((mh.R.indptr.copy(), mh.R.indices.copy(), mh.R.data.copy()))
+            xfield = np.random.default_rng(9).random(X.shape[0])
+            assert_values_close(mh.compute_rhs(xfield), (Hr @ xfield)[gb:ge], 1e-13, "R x slab")
+        J = concat_slabs(sj, Jg.shape[1])
+        assert np.array_equal(J.indices, Jg.indices)
+        assert_values_close(J.data, Jg.data, VAL_TOL)
+        R = concat_slabs(sh, Hr.shape[1])
+        assert np.array_equal(R.indices, Hr.indices)
+        assert_values_close(R.data, Hr.data, VAL_TOL)
+
+
+def test_host_buffers_are_reused_but_never_aliased(pf):
+    """compute_jacobian lands in pinned host buffers of the handle's pool: a buffer is reused only once the matrix
+    built on it is gone, so two live matrices never share values; the cached pattern is shared read-only and copied
+    on write by apply_dirichlet_bcs."""
+    c = pf.ProblemCreator(25, 19)
+    conn, X, dof_fixed, force = c.create_linear_elasticity_problem()
+    q = pf.QuadratureBilinear2D()
+    model = pf.LinearElasticity(X, conn, dof_fixed, None, force, q, pf.BasisBilinear2D(q))
+    K1 = model.compute_jacobian(1.0)
+    K2 = model.compute_jacobian(2.0)
+    assert not np.shares_memory(K1.data, K2.data)
+    assert np.array_equal(2.0 * K1.data, K2.data)
+    addr = K1.data.__array_interface__["data"][0]
+    ref = K1.data.copy()
+    del K1
+    K3 = model.compute_jacobian(1.0)  # K1's buffer is free again
+    assert K3.data.__array_interface__["data"][0] == addr and np.array_equal(K3.data, ref)
+    assert np.shares_memory(K3.indices, K2.indices) and not K3.indices.flags.writeable
+    with pytest.raises(ValueError):
+        K3.eliminate_zeros()  # an in-place pattern edit on the shared arrays fails loudly
+    nnz = K2.nnz
+    model.apply_dirichlet_bcs(K3, model.compute_rhs())  # copy-on-write, then eliminate_zeros
+    assert K3.nnz < nnz and K2.nnz == nnz and K2.indices.flags.writeable is False
+    K4 = model.compute_jacobian(1.0)
+    assert K4.nnz == nnz and np.array_equal(K4.indices, K2.indices)

@@ -309,3 +309,157 @@ def test_hex_chunk_rows_fall_back_when_chunks_exceed_shared_memory(pf, monkeypat
     assert_values_close(mesh.assemble_elasticity(mode="auto").cpu().numpy(), Kr.data, VAL_TOL)
     with pytest.raises(NotImplementedError):
         mesh.assemble_elasticity(mode="gather")
+
+
+# ---- full-size properties for BASELINE configs[2] (Helmholtz 4096 x 2048) and configs[4] (hex8 256^3) ---------------
+def test_full_size_helmholtz_properties(pf):
+    """C3: closed-form nnz, bitwise repeatability, atomic-vs-gather agreement, sum(R) = area of the domain
+    (R_ij = int N_i N_j, a partition of unity), K - R = r0^2 * stiffness annihilates constants, symmetry."""
+    import torch
+    nx, ny = 4096, 2048
+    c = pf.ProblemCreator(nx + 1, ny + 1)
+    mesh = pf.DeviceMesh(c.X, c.conn, 1)
+    nn = (nx + 1) * (ny + 1)
+    assert mesh.nelems == nx * ny == 8388608
+    assert mesh.nnz == (3 * (nx + 1) - 2) * (3 * (ny + 1) - 2) == 75515905
+    assert mesh.idx_bytes == 4
+    r0 = 0.05
+    K, R = mesh.assemble_helmholtz(r0, mode="gather")
+    K2, R2 = mesh.assemble_helmholtz(r0, mode="gather")
+    assert torch.equal(K, K2) and torch.equal(R, R2)
+    del K2, R2
+    Ka, Ra = mesh.assemble_helmholtz(r0, mode="atomic")
+    assert float((Ka - K).abs().max()) <= 1e-13 * float(K.abs().max())
+    assert float((Ra - R).abs().max()) <= 1e-13 * float(R.abs().max())
+    del Ka, Ra
+    area = float(c.X[:, 0].max() * c.X[:, 1].max())
+    assert abs(float(R.sum()) - area) <= 1e-11 * area
+    ones = torch.ones(nn, dtype=torch.float64, device="cuda")
+    row_sums = mesh.spmv(R, ones)
+    assert abs(float(row_sums.sum()) - area) <= 1e-11 * area
+    # (K - R) 1 = r0^2 * (stiffness . 1) = 0
+    assert float((mesh.spmv(K, ones) - row_sums).abs().max()) <= 1e-12 * float(K.abs().max())
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    y = torch.rand(nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    a, b = float(x @ mesh.spmv(K, y)), float(y @ mesh.spmv(K, x))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b))
+    # R^T x through the transposed product equals R x for the symmetric R
+    assert float((mesh.spmv_t(R, x) - mesh.spmv(R, x)).abs().max()) <= 1e-13 * float(R.abs().max())
+
+
+def _lattice_row_columns(dims, node_ijk, m):
+    """Expected CSR columns of the m dof rows of a lattice node (sorted neighbour ids, interleaved dofs)."""
+    nbrs = []
+    for dk in (-1, 0, 1):
+        for dj in (-1, 0, 1):
+            for di in (-1, 0, 1):
+                p = [node_ijk[0] + di, node_ijk[1] + dj, node_ijk[2] + dk]
+                if all(0 <= p[a] < dims[a] for a in range(3)):
+                    nbrs.append(p[0] + dims[0] * (p[1] + dims[1] * p[2]))
+    nbrs = np.sort(np.array(nbrs, dtype=np.int64))
+    return (m * nbrs[:, None] + np.arange(m)[None, :]).ravel()
+
+
+def test_int64_index_pattern_hex(pf):
+    """SURVEY trap T2 at the size where it bites: 156^3 hexes with 3 dofs per node have 156^3 * 576 > 2^31 - 1 COO
+    entries, so scipy's coo -> csr (and this engine) switch indptr AND indices to int64.  k_write_indices<long> runs."""
+    import torch
+    n = 156
+    c = pf.ProblemCreator(n + 1, n + 1, n + 1)
+    mesh = pf.DeviceMesh(c.X, c.conn, 3)
+    assert mesh.nelems * 576 > 2 ** 31 - 1
+    assert mesh.idx_bytes == 8 and mesh.index_dtype == np.int64
+    assert mesh.nnz == 9 * (3 * (n + 1) - 2) ** 3
+    indptr, indices = mesh.pattern()
+    assert indptr.dtype == torch.int64 and indices.dtype == torch.int64
+    assert int(indptr[0]) == 0 and int(indptr[-1]) == mesh.nnz
+    dims = (n + 1, n + 1, n + 1)
+    for ijk in ((0, 0, 0), (1, 0, 0), (5, 7, 3), (n, n, n), (n, 3, 77)):
+        node = ijk[0] + dims[0] * (ijk[1] + dims[1] * ijk[2])
+        want = _lattice_row_columns(dims, ijk, 3)
+        for alpha in range(3):
+            a, b = int(indptr[3 * node + alpha]), int(indptr[3 * node + alpha + 1])
+            assert np.array_equal(indices[a:b].cpu().numpy(), want)
+    # values of a corner patch equal the oracle's rows on a small mesh with the same element size
+    K = mesh.assemble_elasticity(1.0, 0.0)
+    Xs, cs = orc.structured_mesh(6, 6, 6, Lx=5.0 / n * c.X[:, 0].max(), Ly=5.0 / n * c.X[:, 1].max(),
+                                 Lz=5.0 / n * c.X[:, 2].max())
+    Ks = orc.assemble_elasticity(Xs, cs)
+    for (i, j, k) in ((0, 0, 0), (2, 1, 3), (4, 4, 4)):
+        rs, rb = 3 * (i + 6 * (j + 6 * k)), 3 * (i + dims[0] * (j + dims[1] * k))
+        got = K[int(indptr[rb]):int(indptr[rb + 1])].cpu().numpy()
+        assert_values_close(got, Ks.data[Ks.indptr[rs]:Ks.indptr[rs + 1]], VAL_TOL, f"row of node ({i},{j},{k})")
+
+
+def test_slab_index_dtype_follows_global_rule(pf):
+    """A rank's slab reports the index dtype of the reference's GLOBAL matrix (engine.index_bytes_rule): small
+    slabs of a mesh whose global COO count exceeds 2^31 - 1 are int64, like the matrix they are rows of."""
+    from pyfem_gpu_testflight_b200.engine import index_bytes_rule
+    from pyfem_gpu_testflight_b200.partition import structured_slab
+    assert index_bytes_rule(16777216, 8, 33570818) == 4      # C2: COO nnz = 2^30
+    assert index_bytes_rule(16777216, 24, 50923779) == 8     # C5
+    assert index_bytes_rule(2097152, 24, 50923779) == 4      # one eighth of C5 judged by its own count
+    part = structured_slab(9, 8, 11, 1, 3)
+    local = pf.DeviceMesh(part.X, part.conn, 3, own_range=part.own_range, node_gid=part.node_gid,
+                          ncols_nodes=part.nnodes_global)
+    assert local.idx_bytes == 4 and local.pattern_host()[1].dtype == np.int32
+    as_c5 = pf.DeviceMesh(part.X, part.conn, 3, own_range=part.own_range, node_gid=part.node_gid,
+                          ncols_nodes=part.nnodes_global, nelems_global=16777216)
+    assert as_c5.idx_bytes == 8
+    ip, ix = as_c5.pattern_host()
+    assert ip.dtype == np.int64 and ix.dtype == np.int64
+    assert np.array_equal(ix, local.pattern_host()[1]) and np.array_equal(ip, local.pattern_host()[0])
+
+
+def test_full_size_hex_elasticity_properties(pf):
+    """C5 on one GPU (hex8 256^3, 4.09 G CSR values, int64 pattern): closed-form nnz, bitwise repeatability,
+    agreement with the atomic scatter, the six rigid-body modes (three translations, three rotations) in the null
+    space, symmetry, translation invariance of interior rows and oracle rows of a corner patch."""
+    import torch
+    n = 256
+    c = pf.ProblemCreator(n + 1, n + 1, n + 1)
+    mesh = pf.DeviceMesh(c.X, c.conn, 3)
+    nn = (n + 1) ** 3
+    assert mesh.nelems == n ** 3 == 16777216
+    assert mesh.nnz == 9 * (3 * (n + 1) - 2) ** 3 == 4092809481
+    assert mesh.idx_bytes == 8
+    K = mesh.assemble_elasticity(1.0, 0.0)
+    K2 = mesh.assemble_elasticity(1.0, 0.0)
+    assert torch.equal(K, K2)
+    scale = float(K.abs().max())
+    mesh.assemble_elasticity(1.0, 0.0, out=K2, mode="atomic")
+    K2 -= K
+    assert float(K2.abs().max()) <= 1e-13 * scale
+    del K2
+    X = torch.as_tensor(c.X, device="cuda")
+    for axis in range(3):  # translations
+        t = torch.zeros(3 * nn, dtype=torch.float64, device="cuda")
+        t[axis::3] = 1.0
+        assert float(mesh.spmv(K, t).abs().max()) <= 1e-12 * scale
+    for axis in range(3):  # infinitesimal rotations u = e_axis x (x - centre)
+        xc = X - 0.5
+        e = torch.zeros(3, dtype=torch.float64, device="cuda")
+        e[axis] = 1.0
+        u = torch.cross(e.expand_as(xc), xc, dim=1).reshape(-1).contiguous()
+        assert float(mesh.spmv(K, u).abs().max()) <= 1e-11 * scale
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(3 * nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    y = torch.rand(3 * nn, dtype=torch.float64, device="cuda", generator=g) - 0.5
+    a, b = float(x @ mesh.spmv(K, y)), float(y @ mesh.spmv(K, x))
+    assert abs(a - b) <= 1e-10 * max(abs(a), abs(b), scale)
+    d = n + 1
+    # interior rows: 3 x 81 values each, identical on the uniform mesh (the device pattern is not materialised
+    # on the host for 4 G entries: row offsets follow from the closed-form row lengths of interior planes)
+    indptr, _ = mesh.pattern()
+    rows = [3 * (i + d * (j + d * k)) for (i, j, k) in ((7, 9, 11), (128, 128, 128), (250, 3, 77))]
+    ref = K[int(indptr[rows[0]]):int(indptr[rows[0] + 3])]
+    assert ref.numel() == 3 * 81
+    for r in rows[1:]:
+        assert float((K[int(indptr[r]):int(indptr[r + 3])] - ref).abs().max()) <= 1e-12 * scale
+    Xs, cs = orc.structured_mesh(6, 6, 6, Lx=5.0 / n, Ly=5.0 / n, Lz=5.0 / n)
+    Ks = orc.assemble_elasticity(Xs, cs)
+    for (i, j, k) in ((0, 0, 0), (2, 1, 3), (4, 4, 4)):
+        rs, rb = 3 * (i + 6 * (j + 6 * k)), 3 * (i + d * (j + d * k))
+        got = K[int(indptr[rb]):int(indptr[rb + 1])].cpu().numpy()
+        assert_values_close(got, Ks.data[Ks.indptr[rs]:Ks.indptr[rs + 1]], VAL_TOL, f"row of node ({i},{j},{k})")

@@ -64,6 +64,22 @@ def _worker(rank, world, port, transport, out_dir):
             K, res = rs.assemble_nlpoisson(xdv, u[part.node_gid])
             ok &= slab_ok(K, Kg, 1)
             ok &= np.max(np.abs(res.cpu().numpy() - rg[gb:ge])) <= 1e-12 * np.max(np.abs(rg))
+    # the same through the model API: LinearElasticity(..., group=WORLD, halo=transport) is one rank of the partition,
+    # compute_jacobian returns its row slab and gather() rebuilds the reference's global matrix on rank 0
+    import pyfem_gpu_testflight_b200 as pf
+    X, conn = orc.structured_mesh(41, 37)
+    X = X + np.random.default_rng(3).uniform(-0.004, 0.004, size=X.shape)
+    rho = 0.05 + 0.95 * np.random.default_rng(0).random(X.shape[0])
+    q = pf.QuadratureBilinear2D()
+    for halo in ("ghost", transport):
+        model = pf.LinearElasticity(X, conn, [0, 1], None, {5: [0.0, -1.0]}, q, pf.BasisBilinear2D(q), p=3.0,
+                                    group=dist.group.WORLD, halo=halo)
+        Kall = model.gather(model.compute_jacobian(rho))
+        if rank == 0:
+            Kg = orc.assemble_elasticity(X, conn, rho, 3.0)
+            ok &= Kall.indices.dtype == Kg.indices.dtype and np.array_equal(Kall.indptr, Kg.indptr)
+            ok &= np.array_equal(Kall.indices, Kg.indices)
+            ok &= np.max(np.abs(Kall.data - Kg.data)) <= 1e-12 * np.max(np.abs(Kg.data))
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:

@@ -128,16 +128,18 @@ def test_halo_reduce_device_emulated_ranks(three_d, mode):
 
 
 def test_p2p_inbox_layout():
-    """Blocks of the symmetric-memory inboxes: disjoint, in sender order, one common size (CPU only)."""
-    from pyfem_gpu_testflight_b200.halo import inbox_layout
+    """Blocks of the symmetric-memory inboxes: disjoint, in sender order, one common size, every block (and its
+    vector part) on a 16-byte boundary even for odd nnz / row counts (the halo handles write with bulk stores)."""
+    from pyfem_gpu_testflight_b200.halo import _even, inbox_layout
     T = np.zeros((3, 3, 2), dtype=np.int64)  # [sender, dest] = (node rows, nnz)
-    T[0, 1], T[1, 0], T[1, 2], T[2, 1] = (5, 90), (5, 80), (7, 120), (7, 130)
-    m = 2
-    n, off = inbox_layout(T, m)
-    blk = lambda q, d: int(T[q, d, 1] + T[q, d, 0] * m)
-    for d in range(3):
-        spans = sorted((off[q][d], off[q][d] + blk(q, d)) for q in range(3) if q != d and blk(q, d))
-        assert spans[0][0] == 0
-        assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
-        assert spans[-1][1] <= n
-    assert n == max(blk(0, 1) + blk(2, 1), blk(1, 0), blk(1, 2))
+    T[0, 1], T[1, 0], T[1, 2], T[2, 1] = (5, 91), (5, 80), (7, 121), (7, 133)
+    for m in (1, 2, 3):
+        n, off = inbox_layout(T, m)
+        blk = lambda q, d: int(_even(_even(T[q, d, 1]) + T[q, d, 0] * m))
+        for d in range(3):
+            spans = sorted((off[q][d], off[q][d] + blk(q, d)) for q in range(3) if q != d and T[q, d, 1])
+            assert spans[0][0] == 0
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(a % 2 == 0 for a, _ in spans)
+            assert spans[-1][1] <= n
+        assert n == max(blk(0, 1) + blk(2, 1), blk(1, 0), blk(1, 2))

@@ -84,3 +84,53 @@ def test_structured_slab_equals_general_partition():
                 assert np.array_equal(a.conn, b.conn) and np.allclose(a.X, b.X)
                 assert a.own_range == b.own_range and np.array_equal(a.node_gid, b.node_gid)
                 assert np.array_equal(a.elem_gid, b.elem_gid)
+
+
+def _slab_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyfem_gpu_testflight_b200.partition import SlabContext
+    from scipy import sparse
+    X, conn = orc.structured_mesh(13, 10)
+    X = X + np.random.default_rng(3).uniform(-0.01, 0.01, size=X.shape)
+    ctx = SlabContext(X, conn, group=dist.group.WORLD)  # what ModelBase(..., group=...) builds
+    part = ctx.part
+    rho = 0.1 + np.random.default_rng(1).random(X.shape[0])
+    assert np.array_equal(ctx.local_field(rho), rho[part.node_gid]) and ctx.local_field(2.5) == 2.5
+    assert ctx.local_field(rho[part.node_gid]) is not None  # an already-local field passes
+    # the rank's slab, with the oracle standing in for the device handle
+    Kl = orc.assemble_poisson(part.X, part.conn, ctx.local_field(rho), 3.0)
+    lb, le = part.own_range
+    rows = Kl[lb:le]
+    slab = sparse.csr_matrix((rows.data, part.node_gid[rows.indices].astype(np.int32), rows.indptr),
+                             shape=(le - lb, X.shape[0]))
+    K = ctx.gather_matrix(slab)
+    gb, ge = ctx.owned_nodes
+    v = ctx.gather_vector(np.arange(gb, ge, dtype=float))
+    if rank == 0:
+        Kg = orc.assemble_poisson(X, conn, rho, 3.0)
+        ok = (K.indices.dtype == np.int32 and np.array_equal(K.indptr, Kg.indptr) and np.array_equal(K.indices, Kg.indices)
+              and np.max(np.abs(K.data - Kg.data)) <= 1e-13 * np.max(np.abs(Kg.data))
+              and np.array_equal(v, np.arange(X.shape[0], dtype=float)))
+        open(os.path.join(out_dir, "ok"), "w").write("1" if ok else "0")
+    else:
+        assert K is None and v is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_slab_context_world2(tmp_path):
+    """Host logic behind ModelBase(group=...): partition from the process group, global -> local fields, gathers."""
+    port = _free_port()
+    mp.spawn(_slab_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    assert open(tmp_path / "ok").read() == "1"
+
+
+def test_index_bytes_rule():
+    from pyfem_gpu_testflight_b200.engine import index_bytes_rule
+    assert index_bytes_rule(16777216, 8, 33570818) == 4        # C2: COO nnz = 2^30 <= 2^31 - 1
+    assert index_bytes_rule(16777216 * 2, 8, 2 * 33570818) == 8
+    assert index_bytes_rule(16777216, 24, 50923779) == 8       # C5
+    assert index_bytes_rule(10, 4, 2 ** 31) == 8               # many columns alone switch the width
