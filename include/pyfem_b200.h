@@ -68,11 +68,12 @@ typedef enum pfg_info {
     PFG_INFO_IDX_BYTES = 3,  /* 4 or 8: the index width scipy's coo->csr would pick (scipy _coo.py:59-61,419) */
     PFG_INFO_NCHUNKS = 4,    /* row chunks of the gather plan (0 = no plan) */
     PFG_INFO_CHUNK_ELEMS = 5,/* sum over chunks of elements touching the chunk (>= nelems: halo recompute) */
-    PFG_INFO_PLAN_BYTES = 6, /* device bytes of plan metadata read per assembly */
+    PFG_INFO_PLAN_BYTES = 6, /* device bytes of plan metadata read per assembly (chunk directory + distinct templates) */
     PFG_INFO_DEVICE_BYTES = 7,/* device bytes held by the handle */
     PFG_INFO_MAX_ROW_BLOCKS = 8, /* largest number of neighbour nodes of any owned node */
     PFG_INFO_MAX_VALENCE = 9,    /* largest number of elements around any node */
-    PFG_INFO_HEX_ROWS = 10       /* 1: hex8 elasticity runs the owner-computes geometry + chunk-row passes in AUTO / GATHER mode */
+    PFG_INFO_HEX_ROWS = 10,      /* 1: hex8 elasticity runs the owner-computes geometry + chunk-row passes in AUTO / GATHER mode */
+    PFG_INFO_TEMPLATES = 11      /* distinct chunk templates of the tile plan (== NCHUNKS when no two chunks share tables) */
 } pfg_info;
 
 PFG_API int pfg_abi_version(void);

@@ -27,7 +27,7 @@ MODE_GATHER = 2
 MODES = {"auto": MODE_AUTO, "atomic": MODE_ATOMIC, "gather": MODE_GATHER}
 
 INFO_NNZ, INFO_NROWS, INFO_NCOLS, INFO_IDX_BYTES, INFO_NCHUNKS, INFO_CHUNK_ELEMS, INFO_PLAN_BYTES, \
-    INFO_DEVICE_BYTES, INFO_MAX_ROW_BLOCKS, INFO_MAX_VALENCE, INFO_HEX_ROWS = range(11)
+    INFO_DEVICE_BYTES, INFO_MAX_ROW_BLOCKS, INFO_MAX_VALENCE, INFO_HEX_ROWS, INFO_TEMPLATES = range(12)
 
 PHYS_POISSON, PHYS_ELASTICITY, PHYS_HELMHOLTZ, PHYS_NLPOISSON = 1, 2, 3, 4
 

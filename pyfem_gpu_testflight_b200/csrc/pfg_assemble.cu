@@ -237,6 +237,9 @@ PFG_DEV void mbar_init(uint64_t* bar, uint32_t count) {
 PFG_DEV void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+PFG_DEV void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 PFG_DEV void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(smem_dst)),
@@ -461,7 +464,8 @@ struct TileCfg {
 template <class Op, int THREADS>
 PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsigned char* __restrict__ blob,
                                 const uint16_t* __restrict__ codes, const double* __restrict__ stage,
-                                double* __restrict__ image, int image_stride, const Outputs& out, int rot) {
+                                double* __restrict__ image, int image_stride, const Outputs& out, int rot,
+                                uint32_t row_base) {
     using St = TileStage<Op>;
     constexpr int M = Op::M, NMAT = Op::NMAT;
     static_assert(M == 1 || (M == 2 && NMAT == 1), "tile kernel: scalar operators or one matrix of 2x2 blocks");
@@ -550,7 +554,7 @@ PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsi
                     sum += *reinterpret_cast<const double*>(stage_b + (((c.y & 0xFFFFu) & 0xFFFCu) << 1));
                     sum += *reinterpret_cast<const double*>(stage_b + (((c.y >> 16) & 0xFFFCu) << 1));
                 }
-                out.vec[row[p]] = sum;
+                out.vec[row_base + row[p]] = sum;
             }
         }
     }
@@ -560,14 +564,14 @@ PFG_DEV void tile_phase_b_nodes(const MeshView& mv, const TileHdr& h, const unsi
 // store.  Scalars: the run sits on the same 16-byte phase in the image as in the CSR values; its aligned middle part
 // leaves as a bulk store, a leading / trailing odd value by a plain store.
 template <int M>
-PFG_DEV void tile_store_run(double* __restrict__ vals, const double* __restrict__ image, const TileHdr& h, const TileRun& run) {
+PFG_DEV void tile_store_run(double* __restrict__ vals, const double* __restrict__ image, int64_t gbase, const TileRun& run) {
     if constexpr (M == 2) {
-        tma_store_1d(vals + h.gbase + run.gslot_rel, image + (size_t)run.out_off * 2, (uint32_t)run.len * 16u);
+        tma_store_1d(vals + gbase + run.gslot_rel, image + (size_t)run.out_off * 2, (uint32_t)run.len * 16u);
     } else {
-        double* g = vals + h.gbase + run.gslot_rel;
+        double* g = vals + gbase + run.gslot_rel;
         const double* s = image + run.out_off;
         const int len = (int)run.len;
-        const int head = (int)((h.gbase + run.gslot_rel) & 1);
+        const int head = (int)((gbase + run.gslot_rel) & 1);
         if (head) g[0] = s[0];
         const int body = (len - head) & ~1;
         if (body > 0) tma_store_1d(g + head, s + head, (uint32_t)body * 8u);
@@ -602,7 +606,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
     extern __shared__ __align__(128) unsigned char smem[];
     using St = TileStage<Op>;
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] window ids, [3] corner indices, [4] window data
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] window ids, [3] (and [5]) corner indices, [4] window data
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
     const int nloc = (int)(c_end - c_begin);
@@ -620,29 +624,43 @@ __global__ void __launch_bounds__(THREADS, MINB)
     };
     double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
     double* image = reinterpret_cast<double*>(smem + cfg.off_image);
-    const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;  // entries 0..nloc (nloc = next CTA's first / sentinel)
+    const TileDir* __restrict__ dir_g = mv.tile_dir + c_begin;
 
-    auto n_recs_of = [&](int j) -> int { return (int)(dir_s[(j + 1) & 7].rec_begin - dir_s[j & 7].rec_begin); };
-    auto n_win_of = [&](int j) -> int { return (int)(dir_s[(j + 1) & 7].win_begin - dir_s[j & 7].win_begin); };
+    auto n_recs_of = [&](int j) -> int { return (int)dir_s[j & 7].n_recs; };
+    auto n_win_of = [&](int j) -> int { return (int)dir_s[j & 7].n_win; };
+    auto same_tmpl = [&](int j, int back) -> bool { return j >= back && dir_s[j & 7].tmpl == dir_s[(j - back) & 7].tmpl; };
     auto win_stage = [&](int j) -> unsigned char* { return smem + cfg.off_win + (j & 1) * cfg.win_stride; };
-    // thread 0: bulk copies.  Sources are only 4- or 8-byte aligned, so each copy starts at the enclosing 16-byte
-    // boundary and the readers skip the same number of bytes (the pools are padded at both ends).
-    auto issue_win = [&](int j) {
-        const size_t lo = (size_t)dir_s[j & 7].win_begin * 4, lo16 = lo & ~(size_t)15;
-        const uint32_t bytes = (uint32_t)(((lo + (size_t)n_win_of(j) * 4 + 15) & ~(size_t)15) - lo16);
+    // thread 0: bulk copies of chunk j's tables.  A table buffer still holds the tables of the chunk that used it last:
+    // when chunk j runs on the same TEMPLATE (pfg_internal.cuh) nothing is fetched and the barrier's phase is completed
+    // by a plain arrive -- on a lattice-like mesh a CTA loads its tables a handful of times per launch.
+    // Sources are only 4- or 8-byte aligned, so each copy starts at the enclosing 16-byte boundary and the readers
+    // skip the same number of bytes (the pools are padded at both ends).
+    auto issue_win = [&](int j) {  // two stages: the last user of stage j & 1 was chunk j - 2
         uint64_t* bar = &bars[1 + (j & 1)];
+        if (same_tmpl(j, 2)) return mbar_arrive(bar);
+        const size_t lo = (size_t)dir_s[j & 7].win_off * 4, lo16 = lo & ~(size_t)15;
+        const uint32_t bytes = (uint32_t)(((lo + (size_t)n_win_of(j) * 4 + 15) & ~(size_t)15) - lo16);
         mbar_expect_tx(bar, bytes);
         if (bytes) tma_load_1d(win_stage(j), reinterpret_cast<const unsigned char*>(mv.win_nodes) + lo16, bytes, bar);
     };
+    // DEEP: the corner indices of chunk i + 1 are issued at the top of iteration i, while slower threads may still be
+    // waiting for those of chunk i -- with one barrier an instantly completed phase (same template: plain arrive) could
+    // overtake such a waiter, so each of the two stages has its own barrier.  Single stage: one barrier, the issue
+    // comes after the __syncthreads that ends phase A.
+    auto loc_bar = [&](int j) -> uint64_t* { return &bars[(DEEP && (j & 1)) ? 5 : 3]; };
+    auto loc_parity = [&](int j) -> uint32_t { return (uint32_t)((DEEP ? (j >> 1) : j) & 1); };
     auto issue_loc = [&](int j) {
-        const size_t lo = (size_t)dir_s[j & 7].rec_begin * NNE * 2, lo16 = lo & ~(size_t)15;
+        uint64_t* bar = loc_bar(j);
+        if (same_tmpl(j, DEEP ? 2 : 1)) return mbar_arrive(bar);
+        const size_t lo = (size_t)dir_s[j & 7].loc_off * NNE * 2, lo16 = lo & ~(size_t)15;
         const uint32_t bytes = (uint32_t)(((lo + (size_t)n_recs_of(j) * NNE * 2 + 15) & ~(size_t)15) - lo16);
-        mbar_expect_tx(&bars[3], bytes);
-        if (bytes) tma_load_1d(loc_stage(j), reinterpret_cast<const unsigned char*>(mv.rec_local) + lo16, bytes, &bars[3]);
+        mbar_expect_tx(bar, bytes);
+        if (bytes) tma_load_1d(loc_stage(j), reinterpret_cast<const unsigned char*>(mv.rec_local) + lo16, bytes, bar);
     };
     auto issue_meta = [&](int j) {
-        const TileDir t = dir_s[j & 7], t1 = dir_s[(j + 1) & 7];
-        const uint32_t bb = (t1.blob_off16 - t.blob_off16) * 16u, cb = (t1.code_off16 - t.code_off16) * 16u;
+        if (same_tmpl(j, 1)) return mbar_arrive(&bars[0]);
+        const TileDir t = dir_s[j & 7];
+        const uint32_t bb = (uint32_t)t.blob_len16 * 16u, cb = (uint32_t)t.code_len16 * 16u;
         mbar_expect_tx(&bars[0], bb + cb);
         tma_load_1d(blob_s, mv.tile_blob + (size_t)t.blob_off16 * 16, bb, &bars[0]);
         if (cb) tma_load_1d(codes_s, reinterpret_cast<const unsigned char*>(mv.tile_codes) + (size_t)t.code_off16 * 16, cb, &bars[0]);
@@ -650,12 +668,13 @@ __global__ void __launch_bounds__(THREADS, MINB)
     // all threads: gather the coordinates (and nodal field) of chunk j's window nodes, one node per thread
     auto gather_window = [&](int j) {
         const uint32_t* __restrict__ win =
-            reinterpret_cast<const uint32_t*>(win_stage(j) + (((size_t)dir_s[j & 7].win_begin * 4) & 15));
+            reinterpret_cast<const uint32_t*>(win_stage(j) + (((size_t)dir_s[j & 7].win_off * 4) & 15));
         const int n_win = n_win_of(j);
+        const size_t node_base = dir_s[j & 7].node_base;
         double* xs = x_stage(j);
         double* fs = f_stage(j);
         for (int t = threadIdx.x; t < n_win; t += THREADS) {
-            const size_t node = win[t];
+            const size_t node = node_base + win[t];
             double* dst = xs + (size_t)t * DIM;
             if constexpr (DIM == 2) {
                 cp_async_16(dst, mv.X + node * 2);
@@ -668,13 +687,22 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         cp_async_mbar_arrive(&bars[4]);
     };
+    auto copy_dir_piece = [&](int j, int piece) {  // 16 bytes of directory entry j into the ring
+        cp_async_16(reinterpret_cast<unsigned char*>(&dir_s[j & 7]) + 16 * piece,
+                    reinterpret_cast<const unsigned char*>(&dir_g[j]) + 16 * piece);
+    };
 
     for (int i = threadIdx.x; i < St::S; i += THREADS) stage[i] = 0.0;  // record slot 0: zeros (code 0)
+    if (threadIdx.x < 15 && (int)threadIdx.x / 3 < nloc) {               // directory entries 0 .. 4
+        copy_dir_piece((int)threadIdx.x / 3, (int)threadIdx.x % 3);
+        cp_async_commit();
+        cp_async_wait<0>();
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         for (int s = 0; s < 4; ++s) mbar_init(&bars[s], 1);
         mbar_init(&bars[4], THREADS);
-        for (int j = 0; j <= 4 && j <= nloc; ++j) dir_s[j] = dir_g[j];
-        __threadfence_block();
+        mbar_init(&bars[5], 1);
         issue_win(0);
         if (nloc > 1) issue_win(1);
         issue_loc(0);
@@ -685,9 +713,14 @@ __global__ void __launch_bounds__(THREADS, MINB)
     gather_window(0);
 
     for (int i = 0; i < nloc; ++i) {
-        if (threadIdx.x == 0 && i + 5 <= nloc) cp_async_16(&dir_s[(i + 5) & 7], &dir_g[i + 5]);  // rides on the next arrive
+        // directory entry i + 5 rides on this thread's next arrive on bars[4]
+        if (threadIdx.x < 3 && i + 5 < nloc) copy_dir_piece(i + 5, (int)threadIdx.x);
+        const int n_recs = n_recs_of(i);
+        // skip flags of masked elements (halo.py's reduce variant): fetched before the waits, used in phase A
+        const uint8_t* __restrict__ skip_g = mv.rec_skip != nullptr ? mv.rec_skip + dir_s[i & 7].rec_begin : nullptr;
+        const unsigned skip_mine = (skip_g != nullptr && (int)threadIdx.x < n_recs) ? skip_g[threadIdx.x] : 0u;
         mbar_wait(&bars[4], i & 1);  // the window's coordinates have landed (all threads' copies)
-        mbar_wait(&bars[3], i & 1);  // and so have the corner indices
+        mbar_wait(loc_bar(i), loc_parity(i));  // and so have the corner indices
         // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
         auto prefetch_next = [&]() {
             if (threadIdx.x == 0) {
@@ -701,12 +734,16 @@ __global__ void __launch_bounds__(THREADS, MINB)
         };
         if constexpr (DEEP) prefetch_next();  // into the other stage: phases A and B of this chunk to land
         // ---- phase A: one thread per element record -> staged element matrices
-        const int n_recs = n_recs_of(i);
-        const unsigned char* loc_i = loc_stage(i) + (((size_t)dir_s[i & 7].rec_begin * NNE * 2) & 15);
+        const unsigned char* loc_i = loc_stage(i) + (((size_t)dir_s[i & 7].loc_off * NNE * 2) & 15);
         const double* xs = x_stage(i);
         const double* fs = f_stage(i);
         for (int r = threadIdx.x; r < n_recs; r += THREADS) {
             TileSink<Op> sink{stage + (size_t)(r + 1) * St::S};  // slot 0 is the all-zero record
+            if (skip_g != nullptr && (r == (int)threadIdx.x ? skip_mine : (unsigned)skip_g[r])) {
+                // masked element (another rank integrates it): its record contributes zeros
+                for (int i = 0; i < St::RAW; ++i) sink.rec[i] = 0.0;
+                continue;
+            }
             unsigned loc[NNE];
             if constexpr (NNE == 4) {
                 const uint2 v = reinterpret_cast<const uint2*>(loc_i)[r];
@@ -715,10 +752,6 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 const uint4 v = reinterpret_cast<const uint4*>(loc_i)[r];
                 loc[0] = v.x & 0xFFFFu, loc[1] = v.x >> 16, loc[2] = v.y & 0xFFFFu, loc[3] = v.y >> 16;
                 loc[4] = v.z & 0xFFFFu, loc[5] = v.z >> 16, loc[6] = v.w & 0xFFFFu, loc[7] = v.w >> 16;
-            }
-            if (loc[0] & 0x8000u) {  // masked element (another rank integrates it): its record contributes zeros
-                for (int i = 0; i < St::RAW; ++i) sink.rec[i] = 0.0;
-                continue;
             }
             double xe[NNE][DIM], fe[NNE];
 #pragma unroll
@@ -743,8 +776,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
         mbar_wait(&bars[0], i & 1);
         {
             const TileHdr h = *reinterpret_cast<const TileHdr*>(blob_s);
+            const int64_t gbase = dir_s[i & 7].gbase;
             tile_phase_b_nodes<Op, THREADS>(mv, h, blob_s, codes_s, stage, image, cfg.image_stride, out,
-                                            (i + (int)blockIdx.x) & 3);
+                                            (i + (int)blockIdx.x) & 3, dir_s[i & 7].row_base);
             // runs of consecutive node ids leave as TMA bulk stores, spread over the warps' leading lanes;
             // the run entry is read before the barrier so that the blob may be overwritten right after it
             // (a chunk has at most 128 runs: checked when the plan is built)
@@ -761,7 +795,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 if (run.len) {
 #pragma unroll
                     for (int mt = 0; mt < Op::NMAT; ++mt)
-                        if (out.vals[mt] != nullptr) tile_store_run<Op::M>(out.vals[mt], image + (size_t)mt * cfg.image_stride, h, run);
+                        if (out.vals[mt] != nullptr) tile_store_run<Op::M>(out.vals[mt], image + (size_t)mt * cfg.image_stride, gbase, run);
                 }
                 tma_store_commit();
             }
@@ -837,10 +871,6 @@ constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B
 constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
                                                        // consecutive records on different banks
 static_assert(kHexGeoRecordBytes == (8 * kHexGeoDoubles + 2) * 8, "hex8 geometry record layout");
-
-PFG_DEV void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 
 template <int B0, int NB>
 PFG_DEV void hex8_rows_part(const ElasticityHex8Params& prm, const double* __restrict__ geo_e, double sx8, double sy8,
@@ -1125,6 +1155,7 @@ static MeshView view_of(const MeshDev& d) {
     mv.tile_codes = d.tile_codes;
     mv.win_nodes = d.win_nodes;
     mv.rec_local = d.rec_local;
+    mv.rec_skip = d.rec_skip;
     mv.stage_nodes_bytes = d.max_chunk_nodes * (int)sizeof(ChunkNode);
     mv.stage_plan_bytes = ((d.max_chunk_plan_words * 4 + 15) / 16) * 16 + 32;
     return mv;

@@ -98,6 +98,7 @@ struct MeshView {
     const uint16_t* tile_codes;
     const uint32_t* win_nodes;
     const uint16_t* rec_local;
+    const uint8_t* rec_skip;  // per element record: 1 = masked (nullptr: no mask)
     // shared-memory staging sizes (bytes) for the gather kernels: chunk node table, chunk plan
     int stage_nodes_bytes, stage_plan_bytes;
 };

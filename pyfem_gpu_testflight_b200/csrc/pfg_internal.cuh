@@ -68,11 +68,11 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 // phase B reads each contribution at a shared-memory offset that is stored ready-made in the plan.
 //
 // Per chunk, three global arrays feed one CTA iteration:
-//   tile_dir[c]      16 B   where the chunk's blob / codes / records live
+//   tile_dir[c]      48 B   the chunk's bases and where its (template's) blob / codes / window / corner tables live
 //   blob             16 B aligned: TileHdr | TileNode[n_nodes] | format-specific tables (below)
 //   codes            16 B aligned: per node uint16 contribution codes, sorted by neighbour rank
-//   win_nodes        uint32 sorted unique node ids of the chunk's records (the "node window": coordinates and
-//                    nodal fields are gathered once per window node into shared memory)
+//   win_nodes        uint32 sorted unique node ids of the chunk's records, relative to TileDir::node_base (the "node
+//                    window": coordinates and nodal fields are gathered once per window node into shared memory)
 //   rec_local        (n_recs, nne) uint16 window index of every record corner
 // A code is (offset << 2) | end << 1 | transpose: offset in units of the staging block (16 B for 2x2
 // blocks, 8 B for scalars) from the start of the chunk's staging area, whose record slot 0 is all zeros
@@ -81,8 +81,8 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 // neutral form (end << 15 | vec << 14 | record << 2*lb | a << lb | b, 0xFFFF = padding) beside the working
 // copy, which is re-encoded when an operator with another layout runs.
 //
-// Blob: TileHdr | TileNode[n_nodes] | (scalar handles) uint32 row[n_nodes] = owned-row index of each node (vector
-// outputs), padded to 8 B | TileRun[n_runs].
+// Blob: TileHdr | TileNode[n_nodes] | (scalar handles) uint32 row[n_nodes] = owned-row index of each node relative to
+// TileDir::row_base (vector outputs), padded to 8 B | TileRun[n_runs].
 // Codes: group-major, [group][node][8 codes], every node padded with code 0 to the chunk's TileHdr::gmax groups, so
 // that a warp's 16-byte code loads are contiguous; scalar handles append [group][node][4] vector codes (the node's
 // incidences, for residual / right-hand-side outputs), padded to TileHdr::gvmax groups.
@@ -91,33 +91,44 @@ struct __align__(16) ChunkNode { // 16 bytes per owned node, chunk-ordered
 // store per run of consecutive node ids (scalar runs: the 16-byte aligned middle part; a leading / trailing odd value
 // goes by a plain store).
 // ---------------------------------------------------------------------------------------------
-struct __align__(16) TileDir {  // 16 bytes; entry nchunks is a sentinel, so every length is a difference of neighbours
-    uint32_t blob_off16;   // blob offset in the blob pool, 16-byte units
-    uint32_t code_off16;   // codes offset in the code pool, 16-byte units
-    uint32_t rec_begin;    // first record
-    uint32_t win_begin;    // first entry of the chunk's node window (sorted unique node ids of its records)
-};
-
-struct __align__(16) TileHdr {  // 32 bytes, first bytes of the blob
+// Chunk TEMPLATES.  Everything a chunk's tables hold is relative to per-chunk bases kept in its directory entry (CSR
+// slots relative to gbase, window node ids to node_base, owned-row indices to row_base, records and corner indices to
+// the chunk itself), so chunks with the same local topology -- on a lattice-like mesh all interior chunks -- have
+// byte-identical tables.  The plan builder hashes and compares them and points every chunk at the tables of the first
+// chunk with the same content (its template).  A CTA keeps the tables of the running template in shared memory and
+// reloads only when the template changes: on a structured mesh the 0.96 GB of plan reads per assembly of the 16.8 M
+// quad case shrink to the directory (48 B per chunk) plus a few KB of L2-resident templates.
+struct __align__(16) TileDir {  // 48 bytes
     int64_t gbase;         // CSR value slot of the chunk's first node (node slots are relative to it)
-    uint32_t rec_begin;
-    uint32_t pad0_;
+    uint32_t blob_off16;   // template blob in the blob pool, 16-byte units
+    uint32_t code_off16;   // template codes in the code pool, 16-byte units
+    uint32_t loc_off;      // first record of the template's corner-index table (rec_local), in records
+    uint32_t win_off;      // first entry of the template's node window (win_nodes)
+    uint32_t rec_begin;    // first record of THIS chunk (element ids for Op::NEEDS_ELEM, skip flags)
+    uint32_t node_base;    // the window holds node ids relative to this
+    uint32_t row_base;     // scalar handles: owned-row indices of the blob are relative to this
+    uint32_t tmpl;         // template id = id of the first chunk with the same tables
+    uint16_t blob_len16, code_len16;  // table lengths, 16-byte units
+    uint16_t n_recs, n_win;
+};
+static_assert(sizeof(TileDir) == 48, "TileDir layout");
+
+struct __align__(16) TileHdr {  // 16 bytes, first bytes of the blob
     uint16_t n_nodes, n_recs;
     uint16_t gmax;         // matrix code groups (8 codes) per node, padded to the chunk maximum
     uint16_t gvmax;        // vector code groups (4 codes) per node (scalar handles)
     uint16_t n_runs;       // runs of consecutive node ids
-    uint16_t pad_;
-    uint32_t pad2_;
+    uint16_t pad_[3];
 };
 
 struct __align__(8) TileNode {  // 8 bytes
-    uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileHdr::gbase
+    uint32_t gslot_rel;    // first value slot of the node's first dof row, relative to TileDir::gbase
     uint16_t aux;          // offset of the node's rows in the chunk's CSR image, in units (16 B for m = 2, 8 B for m = 1)
     uint16_t k;            // neighbour count: a dof row holds m * k values
 };
 
 struct __align__(8) TileRun {  // 8 bytes: one run of consecutive node ids, image -> CSR values
-    uint32_t gslot_rel;    // first value slot, relative to TileHdr::gbase
+    uint32_t gslot_rel;    // first value slot, relative to TileDir::gbase
     uint16_t out_off;      // image offset, in units
     uint16_t len;          // length, in units
 };
@@ -207,6 +218,9 @@ struct MeshDev {
     uint16_t* tile_codes_neutral = nullptr;  // (record << 2*lb | a << lb | b), lb = log2(nne)
     uint32_t* win_nodes = nullptr;     // node windows, chunk after chunk
     uint16_t* rec_local = nullptr;     // (nrecs, nne) window index of every record corner
+    uint8_t* rec_skip = nullptr;       // (nrecs) records of masked elements (pfg_mesh_set_element_mask), else null
+    int64_t ntemplates = 0;            // distinct chunk templates
+    int64_t plan_read_bytes = 0;       // directory + template tables: what one assembly reads of the plan
     int64_t nwin = 0;
     int max_chunk_win = 0;
     int64_t tile_blob_bytes = 0, tile_ncodes = 0;

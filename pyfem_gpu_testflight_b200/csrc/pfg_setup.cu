@@ -552,15 +552,131 @@ __global__ void k_tile_chunk_sizes(int64_t nchunks, const ChunkHdr* __restrict__
 }
 
 __global__ void k_tile_dir(int64_t nchunks, const ChunkHdr* __restrict__ chunks, const int64_t* __restrict__ blob_off,
-                           const int64_t* __restrict__ code_off, const uint32_t* __restrict__ win_begin, int64_t nrecs,
-                           int64_t nwin, TileDir* __restrict__ dir) {
+                           const int64_t* __restrict__ code_off, const uint32_t* __restrict__ blob_len16,
+                           const uint32_t* __restrict__ code_len16, const uint32_t* __restrict__ win_begin,
+                           const uint32_t* __restrict__ win_nodes_abs, const uint32_t* __restrict__ slot_node,
+                           const int64_t* __restrict__ blk_ptr, int m, int64_t nwin, TileDir* __restrict__ dir,
+                           int* __restrict__ err) {
     int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (c > nchunks) return;
     TileDir t;
-    t.blob_off16 = (uint32_t)blob_off[c];  // exclusive scans have nchunks + 1 entries: entry nchunks is the total
-    t.code_off16 = (uint32_t)code_off[c];
-    t.rec_begin = (c == nchunks) ? (uint32_t)nrecs : (uint32_t)chunks[c].rec_begin;
-    t.win_begin = (c == nchunks) ? (uint32_t)nwin : win_begin[c];
+    memset(&t, 0, sizeof(t));
+    if (c < nchunks) {  // entry nchunks is a zeroed sentinel (bulk copies of the directory may read it)
+        const ChunkHdr h = chunks[c];
+        const int64_t r_first = slot_node[h.node_begin];
+        const int64_t wend = (c + 1 < nchunks) ? win_begin[c + 1] : nwin;
+        t.gbase = blk_ptr[r_first] * m * m;
+        t.blob_off16 = (uint32_t)blob_off[c];
+        t.code_off16 = (uint32_t)code_off[c];
+        t.loc_off = (uint32_t)h.rec_begin;
+        t.win_off = win_begin[c];
+        t.rec_begin = (uint32_t)h.rec_begin;
+        t.node_base = win_nodes_abs[win_begin[c]];  // windows are sorted: the first id is the smallest
+        t.row_base = (uint32_t)r_first;
+        t.tmpl = (uint32_t)c;
+        t.blob_len16 = (uint16_t)blob_len16[c];
+        t.code_len16 = (uint16_t)code_len16[c];
+        t.n_recs = (uint16_t)h.n_recs;
+        t.n_win = (uint16_t)(wend - win_begin[c]);
+        if (blob_len16[c] > 0xFFFFu || code_len16[c] > 0xFFFFu || h.n_recs > 0xFFFFu || wend - win_begin[c] > 0xFFFF)
+            atomicExch(err, 1);
+    }
+    dir[c] = t;
+}
+
+// node ids of a window -> relative to the window's first (smallest) id
+__global__ void k_win_relative(int64_t nchunks, const TileDir* __restrict__ dir, int64_t nwin,
+                               const uint32_t* __restrict__ win_chunk, uint32_t* __restrict__ win_nodes) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= nwin) return;
+    win_nodes[i] -= dir[win_chunk[i]].node_base;
+}
+
+// ---- chunk templates: hash, group, verify -------------------------------------------------------------------
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {  // splitmix64 finaliser
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+    x ^= x >> 27; x *= 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
+}
+
+struct TileTables {  // the four tables of a chunk as 32-bit words (all offsets / lengths are multiples of 4 bytes)
+    const uint32_t* seg[4];
+    uint32_t words[4];
+};
+__device__ __forceinline__ TileTables tile_tables(const TileDir& t, const uint8_t* blob, const uint16_t* codes_neutral,
+                                                  const uint32_t* win, const uint16_t* loc, int nne) {
+    TileTables T;
+    T.seg[0] = reinterpret_cast<const uint32_t*>(blob + (size_t)t.blob_off16 * 16), T.words[0] = t.blob_len16 * 4u;
+    T.seg[1] = reinterpret_cast<const uint32_t*>(codes_neutral + (size_t)t.code_off16 * 8), T.words[1] = t.code_len16 * 4u;
+    T.seg[2] = win + t.win_off, T.words[2] = t.n_win;
+    T.seg[3] = reinterpret_cast<const uint32_t*>(loc + (size_t)t.loc_off * nne), T.words[3] = t.n_recs * (uint32_t)nne / 2u;
+    return T;
+}
+
+// one warp per chunk: position-aware 64-bit hash of its tables (sum of mixed words: lanes add in any order)
+__global__ void k_tile_hash(int64_t nchunks, const TileDir* __restrict__ dir, const uint8_t* __restrict__ blob,
+                            const uint16_t* __restrict__ codes_neutral, const uint32_t* __restrict__ win,
+                            const uint16_t* __restrict__ loc, int nne, uint64_t* __restrict__ hash,
+                            uint32_t* __restrict__ ids) {
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks) return;
+    const TileTables T = tile_tables(dir[c], blob, codes_neutral, win, loc, nne);
+    uint64_t h = 0;
+    for (int sgm = 0; sgm < 4; ++sgm) {
+        for (uint32_t w = lane; w < T.words[sgm]; w += 32)
+            h += mix64(((uint64_t)T.seg[sgm][w] << 32) | ((uint64_t)(sgm + 1) << 28) | w);
+        h += (lane == 0) ? mix64(0x9e3779b97f4a7c15ull * (sgm + 1) + T.words[sgm]) : 0ull;
+    }
+    for (int o = 16; o; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+    if (lane == 0) hash[c] = h, ids[c] = (uint32_t)c;
+}
+
+// along the hash-sorted order: position of the first chunk of every run of equal hashes (0 elsewhere, for a max-scan)
+__global__ void k_tile_group_heads(int64_t n, const uint64_t* __restrict__ sorted_hash, int64_t* __restrict__ head) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) head[i] = (i == 0 || sorted_hash[i] != sorted_hash[i - 1]) ? i : 0;
+}
+
+__global__ void k_tile_representative(int64_t n, const uint32_t* __restrict__ sorted_ids, const int64_t* __restrict__ head,
+                                      uint32_t* __restrict__ rep) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) rep[sorted_ids[i]] = sorted_ids[head[i]];  // stable sort: the run's first entry is its smallest chunk id
+}
+
+// one warp per chunk: the chunk's tables must equal its representative's word for word (a hash collision clears `same`)
+__global__ void k_tile_verify(int64_t nchunks, const TileDir* __restrict__ dir, const uint32_t* __restrict__ rep,
+                              const uint8_t* __restrict__ blob, const uint16_t* __restrict__ codes_neutral,
+                              const uint32_t* __restrict__ win, const uint16_t* __restrict__ loc, int nne,
+                              int* __restrict__ mismatch) {
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks || rep[c] == (uint32_t)c) return;
+    const TileTables A = tile_tables(dir[c], blob, codes_neutral, win, loc, nne);
+    const TileTables B = tile_tables(dir[rep[c]], blob, codes_neutral, win, loc, nne);
+    bool bad = false;
+    for (int sgm = 0; sgm < 4; ++sgm) {
+        if (A.words[sgm] != B.words[sgm]) { bad = true; break; }
+        for (uint32_t w = lane; w < A.words[sgm]; w += 32) bad |= A.seg[sgm][w] != B.seg[sgm][w];
+    }
+    if (bad) atomicExch(mismatch, 1);
+}
+
+// point every chunk at its template's tables; count templates and the bytes an assembly reads of the plan
+__global__ void k_tile_apply_templates(int64_t nchunks, const uint32_t* __restrict__ rep, TileDir* __restrict__ dir,
+                                       const TileDir* __restrict__ dir_in, int nne, unsigned long long* __restrict__ stats) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint32_t r = rep[c];
+    TileDir t = dir_in[c];
+    if (r == (uint32_t)c) {
+        atomicAdd(&stats[0], 1ull);
+        atomicAdd(&stats[1], (unsigned long long)(t.blob_len16 * 16u + t.code_len16 * 16u + t.n_win * 4u + t.n_recs * nne * 2u));
+    } else {
+        const TileDir tr = dir_in[r];
+        t.blob_off16 = tr.blob_off16, t.code_off16 = tr.code_off16, t.loc_off = tr.loc_off, t.win_off = tr.win_off;
+        t.tmpl = r;
+    }
     dir[c] = t;
 }
 
@@ -574,11 +690,12 @@ __global__ void k_win_keys(const uint64_t* __restrict__ rec_keys, const int32_t*
 }
 
 __global__ void k_win_fill(const uint64_t* __restrict__ win_keys, int64_t nwin, uint32_t* __restrict__ win_nodes,
-                           uint32_t* __restrict__ win_begin, int* __restrict__ max_win_scratch) {
+                           uint32_t* __restrict__ win_begin, uint32_t* __restrict__ win_chunk) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= nwin) return;
     const uint64_t k = win_keys[i];
     win_nodes[i] = (uint32_t)k;
+    win_chunk[i] = (uint32_t)(k >> 32);
     if (i == 0 || (win_keys[i - 1] >> 32) != (k >> 32)) win_begin[k >> 32] = (uint32_t)i;
 }
 
@@ -655,23 +772,19 @@ __global__ void k_tile_fill(TileFillArgs A) {
     }
     if (p == h.node_begin) {
         TileHdr th;
-        th.gbase = A.blk_ptr[r_first] * A.m * A.m;
-        th.rec_begin = (uint32_t)h.rec_begin;
-        th.pad0_ = 0;
         th.n_nodes = (uint16_t)h.n_nodes;
         th.n_recs = (uint16_t)h.n_recs;
         th.gmax = (uint16_t)gmax;
         th.gvmax = (uint16_t)gvmax;
         th.n_runs = (uint16_t)nruns;
-        th.pad_ = 0;
-        th.pad2_ = 0;
+        th.pad_[0] = th.pad_[1] = th.pad_[2] = 0;
         *reinterpret_cast<TileHdr*>(blob) = th;
     }
     TileNode* tn = reinterpret_cast<TileNode*>(blob + sizeof(TileHdr)) + pl;
     tn->gslot_rel = (uint32_t)grel;  // aux (image offset) is filled by k_tile_image_layout
     tn->k = (uint16_t)k;
     if (A.m == 1)
-        reinterpret_cast<uint32_t*>(blob + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes)[pl] = (uint32_t)r;
+        reinterpret_cast<uint32_t*>(blob + sizeof(TileHdr) + sizeof(TileNode) * h.n_nodes)[pl] = (uint32_t)(r - r_first);
     // counting sort of the valence*NNE contributions by neighbour rank
     uint8_t cnt[kMaxRowBlocks + 1];
     for (int t = 0; t <= k; ++t) cnt[t] = 0;
@@ -727,7 +840,7 @@ __global__ void k_tile_image_layout(int64_t nchunks, const ChunkHdr* __restrict_
     uint8_t* blob = blob_pool + (size_t)dir[c].blob_off16 * 16;
     TileNode* nodes = reinterpret_cast<TileNode*>(blob + sizeof(TileHdr));
     TileRun* runs = reinterpret_cast<TileRun*>(blob + tile_blob_tables(h.n_nodes, m));
-    const int64_t gbase = reinterpret_cast<const TileHdr*>(blob)->gbase;
+    const int64_t gbase = dir[c].gbase;
     const int unit_doubles = (m == 2) ? 2 : 1;
     int64_t off = 0;  // image offset in units
     int nrun = -1;
@@ -1114,7 +1227,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         // ---- tile plan: node windows, then blob (header, node table, runs) and contribution codes per chunk
         cudaFree(d.rec_dst);
         d.rec_dst = nullptr;
-        DBuf<uint32_t> win_begin;
+        DBuf<uint32_t> win_begin, win_chunk;
         DBuf<int> terr;
         PFG_CUDA_TRY(terr.alloc(1));
         PFG_CUDA_TRY(cudaMemsetAsync(terr.p, 0, sizeof(int), st));
@@ -1145,7 +1258,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
             PFG_CUDA_TRY(cudaMalloc(&d.win_nodes, d.nwin * sizeof(uint32_t) + 64));
             PFG_CUDA_TRY(cudaMalloc(&d.rec_local, ncorners * sizeof(uint16_t) + 64));
             PFG_CUDA_TRY(cudaMemsetAsync(win_begin.p, 0, (d.nchunks + 1) * sizeof(uint32_t), st));
-            k_win_fill<<<grid_for(d.nwin), kThreads, 0, st>>>(wuniq.p, d.nwin, d.win_nodes, win_begin.p, nullptr);
+            PFG_CUDA_TRY(win_chunk.alloc(d.nwin));
+            k_win_fill<<<grid_for(d.nwin), kThreads, 0, st>>>(wuniq.p, d.nwin, d.win_nodes, win_begin.p, win_chunk.p);
             k_win_max<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, win_begin.p, d.nwin, maxima.p);
             k_rec_local<NNE><<<grid_for(ncorners), kThreads, 0, st>>>(rec_keys.p, d.rec_nodes, wuniq.p, win_begin.p,
                                                                      d.nchunks, d.nwin, ncorners, d.rec_local, terr.p);
@@ -1200,8 +1314,10 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes, 0, d.tile_ncodes * 2 + 64, st));
         PFG_CUDA_TRY(cudaMemsetAsync(d.tile_codes_neutral, 0xFF, d.tile_ncodes * 2 + 64, st));  // 0xFFFF = padding
         PFG_CUDA_TRY(cudaMalloc(&d.cnode_id, nown * sizeof(int32_t)));
-        k_tile_dir<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.chunks, blob_off.p, code_off.p,
-                                                                 win_begin.p, d.nrecs, d.nwin, d.tile_dir);
+        k_tile_dir<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.chunks, blob_off.p, code_off.p, blob_len16.p,
+                                                                 code_len16.p, win_begin.p, d.win_nodes, slot_node.p,
+                                                                 d.blk_ptr, d.m, d.nwin, d.tile_dir, terr.p);
+        k_win_relative<<<grid_for(d.nwin), kThreads, 0, st>>>(d.nchunks, d.tile_dir, d.nwin, win_chunk.p, d.win_nodes);
         TileFillArgs fa;
         fa.slot_node = slot_node.p, fa.slot_chunk = slot_chunk.p;
         fa.inc_ptr = d.inc_ptr, fa.inc_list = d.inc_list, fa.rank = d.rank, fa.blk_ptr = d.blk_ptr;
@@ -1214,6 +1330,56 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         k_tile_image_layout<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, d.chunks, d.tile_dir, slot_node.p,
                                                                       d.blk_ptr, run_flag.p, d.m, d.tile_blob, maxima.p,
                                                                       terr.p);
+        // ---- chunk templates: chunks with byte-identical tables share the tables of the first of them
+        d.ntemplates = d.nchunks;
+        d.plan_read_bytes = 0;
+        if (!env_int("PFG_NO_TEMPLATES", 0)) {
+            DBuf<uint64_t> hash, hash_sorted;
+            DBuf<uint32_t> ids, ids_sorted, rep;
+            DBuf<int64_t> head;
+            DBuf<int> mismatch;
+            DBuf<unsigned long long> stats;
+            DBuf<TileDir> dir2;
+            PFG_CUDA_TRY(hash.alloc(d.nchunks));
+            PFG_CUDA_TRY(hash_sorted.alloc(d.nchunks));
+            PFG_CUDA_TRY(ids.alloc(d.nchunks));
+            PFG_CUDA_TRY(ids_sorted.alloc(d.nchunks));
+            PFG_CUDA_TRY(rep.alloc(d.nchunks));
+            PFG_CUDA_TRY(head.alloc(d.nchunks));
+            PFG_CUDA_TRY(mismatch.alloc(1));
+            PFG_CUDA_TRY(stats.alloc(2));
+            PFG_CUDA_TRY(dir2.alloc(d.nchunks + 1));
+            PFG_CUDA_TRY(cudaMemsetAsync(mismatch.p, 0, sizeof(int), st));
+            PFG_CUDA_TRY(cudaMemsetAsync(stats.p, 0, 2 * sizeof(unsigned long long), st));
+            const unsigned warp_grid = grid_for(d.nchunks * 32);
+            k_tile_hash<<<warp_grid, kThreads, 0, st>>>(d.nchunks, d.tile_dir, d.tile_blob, d.tile_codes_neutral, d.win_nodes,
+                                                        d.rec_local, NNE, hash.p, ids.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceRadixSort::SortPairs(d_temp_storage, temp_storage_bytes, (const uint64_t*)hash.p,
+                                                    hash_sorted.p, (const uint32_t*)ids.p, ids_sorted.p, d.nchunks, 0, 64,
+                                                    st));
+            k_tile_group_heads<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, hash_sorted.p, head.p);
+            PFG_CUB(scratch, st,
+                    cub::DeviceScan::InclusiveScan(d_temp_storage, temp_storage_bytes, head.p, head.p, cub::Max(),
+                                                   d.nchunks, st));
+            k_tile_representative<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, ids_sorted.p, head.p, rep.p);
+            k_tile_verify<<<warp_grid, kThreads, 0, st>>>(d.nchunks, d.tile_dir, rep.p, d.tile_blob, d.tile_codes_neutral,
+                                                          d.win_nodes, d.rec_local, NNE, mismatch.p);
+            int h_mismatch = 0;
+            PFG_CUDA_TRY(cudaMemcpyAsync(&h_mismatch, mismatch.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            PFG_CUDA_TRY(cudaStreamSynchronize(st));
+            if (!h_mismatch) {  // (a 64-bit hash collision between different tables: keep every chunk its own template)
+                PFG_CUDA_TRY(cudaMemcpyAsync(dir2.p, d.tile_dir, (d.nchunks + 1) * sizeof(TileDir),
+                                             cudaMemcpyDeviceToDevice, st));
+                k_tile_apply_templates<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, rep.p, d.tile_dir, dir2.p, NNE,
+                                                                                 stats.p);
+                unsigned long long h_stats[2] = {0, 0};
+                PFG_CUDA_TRY(cudaMemcpyAsync(h_stats, stats.p, sizeof(h_stats), cudaMemcpyDeviceToHost, st));
+                PFG_CUDA_TRY(cudaStreamSynchronize(st));
+                d.ntemplates = (int64_t)h_stats[0];
+                d.plan_read_bytes = (int64_t)h_stats[1];
+            }
+        }
         int h_terr = 0, h_max[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
         PFG_CUDA_TRY(cudaMemcpyAsync(&h_terr, terr.p, sizeof(int), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaMemcpyAsync(h_max, maxima.p, sizeof(h_max), cudaMemcpyDeviceToHost, st));
@@ -1241,6 +1407,9 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         cudaFree(d.rec_nodes);  // the tile kernels address record corners through the node windows
         d.rec_nodes = nullptr;
         d.plan_bytes = d.tile_blob_bytes + d.tile_ncodes * 2;
+        if (d.plan_read_bytes == 0)  // no template sharing: every chunk reads its own tables
+            d.plan_read_bytes = d.plan_bytes + d.nrecs * (NNE * 2) + d.nwin * 4;
+        d.plan_read_bytes += d.nchunks * (int64_t)sizeof(TileDir);
         d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * (NNE * 2 + 4) +
                           d.nwin * 4 + d.tile_blob_bytes + d.tile_ncodes * 4;
         return PFG_OK;
@@ -1307,7 +1476,7 @@ static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
                     d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip, d.hex_geo, d.inc_rec8, d.inc_ranks8,
-                    d.bc_fixed, d.bc_u0, d.cg_work};
+                    d.bc_fixed, d.bc_u0, d.cg_work, d.rec_skip};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }
@@ -1439,14 +1608,11 @@ extern "C" int pfg_mesh_create(pfg_mesh** out, int elem_type, int ndof_per_node,
     return PFG_OK;
 }
 
-// tile plan: the skip flag of a record rides in the top bit of its first corner's window index
+// tile plan: one skip flag per element record (chunk tables are shared between chunks, so the flag cannot ride in them)
 __global__ void k_mask_records(const int32_t* __restrict__ rec_elem, const uint8_t* __restrict__ skip, int64_t nrecs,
-                               int nne, uint16_t* __restrict__ rec_local) {
+                               uint8_t* __restrict__ rec_skip) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (r >= nrecs) return;
-    uint16_t v = rec_local[r * nne] & 0x7FFFu;
-    if (skip && skip[rec_elem[r]]) v |= 0x8000u;
-    rec_local[r * nne] = v;
+    if (r < nrecs) rec_skip[r] = skip[rec_elem[r]] ? 1 : 0;
 }
 
 extern "C" int pfg_mesh_set_element_mask(pfg_mesh* mesh, const uint8_t* elem_skip_dev, void* stream) {
@@ -1457,20 +1623,20 @@ extern "C" int pfg_mesh_set_element_mask(pfg_mesh* mesh, const uint8_t* elem_ski
     MeshDev& d = mesh->d;
     PFG_CUDA_TRY(cudaSetDevice(d.device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (d.tile_dir && d.max_chunk_win > 0x7FFF) {
-        set_error("node windows of %d entries leave no room for the record skip flag", d.max_chunk_win);
-        return PFG_ERR_UNSUPPORTED;
-    }
     if (elem_skip_dev) {
         if (!d.elem_skip) PFG_CUDA_TRY(cudaMalloc(&d.elem_skip, std::max<int64_t>(d.nelems, 1)));
         PFG_CUDA_TRY(cudaMemcpyAsync(d.elem_skip, elem_skip_dev, d.nelems, cudaMemcpyDeviceToDevice, st));
+        if (d.tile_dir && d.nrecs) {
+            if (!d.rec_skip) PFG_CUDA_TRY(cudaMalloc(&d.rec_skip, d.nrecs + 256));  // the kernels prefetch past the end
+            k_mask_records<<<grid_for(d.nrecs), kThreads, 0, st>>>(d.rec_elem, d.elem_skip, d.nrecs, d.rec_skip);
+        }
     } else if (d.elem_skip) {
         PFG_CUDA_TRY(cudaStreamSynchronize(st));
         cudaFree(d.elem_skip);
         d.elem_skip = nullptr;
+        if (d.rec_skip) cudaFree(d.rec_skip);
+        d.rec_skip = nullptr;
     }
-    if (d.tile_dir && d.nrecs)
-        k_mask_records<<<grid_for(d.nrecs), kThreads, 0, st>>>(d.rec_elem, d.elem_skip, d.nrecs, d.nne, d.rec_local);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
 }
@@ -1496,8 +1662,8 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_NCHUNKS: *value = d.nchunks; break;
         case PFG_INFO_CHUNK_ELEMS: *value = d.nrecs; break;
         case PFG_INFO_PLAN_BYTES:
-            if (d.tile_dir)
-                *value = (int64_t)(d.nchunks * sizeof(TileDir) + d.nrecs * (d.nne * 2) + d.nwin * 4 + d.plan_bytes);
+            if (d.tile_dir)  // what one assembly reads: the directory and the distinct chunk templates
+                *value = d.plan_read_bytes;
             else if (d.inc_rec8)  // hex8 chunk-row pass: chunk headers, node table, incidence tables, record elements
                 *value = (int64_t)(d.nchunks * sizeof(ChunkHdr) +
                                    (d.own_end - d.own_begin) * (sizeof(ChunkNode) + 8 * (4 + 8)) + d.nrecs * 4);
@@ -1510,6 +1676,7 @@ extern "C" int pfg_mesh_get(const pfg_mesh* mesh, int what, int64_t* value) {
         case PFG_INFO_MAX_ROW_BLOCKS: *value = d.max_k; break;
         case PFG_INFO_MAX_VALENCE: *value = d.max_valence; break;
         case PFG_INFO_HEX_ROWS: *value = (d.hex_rows_ok == 1 && d.nchunks > 0 && d.inc_rec8) ? 1 : 0; break;
+        case PFG_INFO_TEMPLATES: *value = d.tile_dir ? d.ntemplates : 0; break;
         default:
             set_error("pfg_mesh_get: unknown query %d", what);
             return PFG_ERR_INVALID;

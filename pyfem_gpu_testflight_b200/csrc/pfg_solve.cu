@@ -38,20 +38,24 @@ __global__ void __launch_bounds__(256) k_spmv_rows(const int64_t* __restrict__ b
     const int64_t nrows = nown * m;
     constexpr int RPB = 256 / kRowLanes;  // rows per CTA and step
     double dot = 0.0;                     // this row group's share of <dot_with, y>
-    for (int64_t row = blockIdx.x * (int64_t)RPB + threadIdx.x / kRowLanes; row < nrows; row += (int64_t)gridDim.x * RPB) {
-        const int64_t r = row / m;
-        const int alpha = (int)(row - r * m);
-        const int64_t p0 = blk_ptr[r];
-        const int k = (int)(blk_ptr[r + 1] - p0);
-        const double* __restrict__ v = vals + p0 * m * m + (int64_t)alpha * k * m;
+    // the trip count is uniform over the CTA (the loop runs on the CTA's first row), so every lane reaches the shuffles
+    for (int64_t row0 = blockIdx.x * (int64_t)RPB; row0 < nrows; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + threadIdx.x / kRowLanes;
         double s = 0.0;
-        for (int j = sub; j < k * m; j += kRowLanes) {
-            const int t = j / m, beta = j - t * m;
-            const int64_t cnode = nbr[p0 + t];
-            s = fma(v[j], x[(gid ? gid[cnode] : cnode) * m + beta], s);
+        if (row < nrows) {
+            const int64_t r = row / m;
+            const int alpha = (int)(row - r * m);
+            const int64_t p0 = blk_ptr[r];
+            const int k = (int)(blk_ptr[r + 1] - p0);
+            const double* __restrict__ v = vals + p0 * m * m + (int64_t)alpha * k * m;
+            for (int j = sub; j < k * m; j += kRowLanes) {
+                const int t = j / m, beta = j - t * m;
+                const int64_t cnode = nbr[p0 + t];
+                s = fma(v[j], x[(gid ? gid[cnode] : cnode) * m + beta], s);
+            }
         }
         s = group_sum(s);
-        if (sub == 0) {
+        if (sub == 0 && row < nrows) {
             y[row] = s;
             if (dot_with != nullptr) dot = fma(s, dot_with[row], dot);
         }

@@ -80,6 +80,7 @@ class DeviceMesh:
         self.nchunks = self.info(_lib.INFO_NCHUNKS)
         self.chunk_elems = self.info(_lib.INFO_CHUNK_ELEMS)
         self.plan_bytes = self.info(_lib.INFO_PLAN_BYTES)
+        self.ntemplates = self.info(_lib.INFO_TEMPLATES)
         self._pattern = None
         self._pattern_host = None
         self._host_pool = []  # pinned host buffers for to_scipy(reuse_host_buffers=True)
@@ -156,7 +157,7 @@ class DeviceMesh:
         if rho is None:
             return None, 1.0
         if np.ndim(rho) == 0:  # Python / numpy scalars and 0-d arrays: the reference's `not hasattr(rho, "__len__")`
-            if np.iscomplexobj(rho):
+            if rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho):
                 raise NotImplementedError("complex rho (complex-step verification) has no device path")
             return None, float(rho)
         return self._dev_f64(rho, self.nnodes, "rho"), 0.0

@@ -285,7 +285,8 @@ class _DensityFunctions:
 
 
 def _check_real(rho):
-    if np.iscomplexobj(rho):
+    is_complex = rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho)  # torch tensor or numpy
+    if is_complex:
         raise NotImplementedError("complex rho (complex-step verification, pyfem.py:1019-1020) has no device "
                                   "path and this engine has no CPU fallback")
 

@@ -98,3 +98,70 @@ def test_two_step_model_interface(pf):
     rhs = np.empty(X.shape[0])
     model._assemble_rhs(rhs_e, rhs)
     assert_values_close(rhs, orc.scatter_vector(rhs_e, conn, X.shape[0], 4), VAL_TOL, "_assemble_rhs")
+
+
+# ---- chunk templates (pfg_internal.cuh): chunks with the same local topology share one set of plan tables ------------
+def test_chunk_templates_share_tables_and_change_nothing(monkeypatch):
+    """On a lattice-like mesh the interior chunks are byte-identical once their tables are relative to per-chunk
+    bases: the plan read per assembly shrinks to the directory plus a few templates.  Sharing tables must not change
+    one bit of the result (PFG_NO_TEMPLATES=1 builds the same plan without sharing), with or without a nodal field,
+    for 2 x 2 blocks, scalar operators with a vector output, and hex8 scalar operators."""
+    import torch
+    import pyfem_gpu_testflight_b200 as pf
+    X, conn = orc.structured_mesh(301, 187)
+    # a graded tensor-product grid: still lattice-like for the chunking (nodes share coordinates along grid lines),
+    # but every element has its own Jacobian.  (Random jitter would make the coordinate-based chunking irregular:
+    # correct, but then hardly any two chunks share a topology.)
+    X = np.stack([X[:, 0] ** 1.3, np.sin(0.5 * np.pi * X[:, 1] / X[:, 1].max())], axis=1)
+    rho = 0.1 + 0.9 * np.random.default_rng(1).random(X.shape[0])
+    u = np.random.default_rng(2).random(X.shape[0])
+    xdv = np.ones(10) / 10.0
+    shared2, shared1 = pf.DeviceMesh(X, conn, 2), pf.DeviceMesh(X, conn, 1)
+    assert shared2.nchunks > 200 and shared2.ntemplates <= shared2.nchunks // 8
+    assert shared1.ntemplates <= shared1.nchunks // 8
+    monkeypatch.setenv("PFG_NO_TEMPLATES", "1")
+    plain2, plain1 = pf.DeviceMesh(X, conn, 2), pf.DeviceMesh(X, conn, 1)
+    monkeypatch.delenv("PFG_NO_TEMPLATES")
+    assert plain2.ntemplates == plain2.nchunks == shared2.nchunks
+    assert shared2.plan_bytes < plain2.plan_bytes // 4
+    for r, p in ((1.0, 0.0), (rho, 3.0)):
+        assert torch.equal(shared2.assemble_elasticity(r, p, mode="gather"), plain2.assemble_elasticity(r, p, mode="gather"))
+        assert torch.equal(shared1.assemble_poisson(r, p, mode="gather"), plain1.assemble_poisson(r, p, mode="gather"))
+    Ka, ra = shared1.assemble_nlpoisson(xdv, u, mode="gather")
+    Kb, rb = plain1.assemble_nlpoisson(xdv, u, mode="gather")
+    assert torch.equal(Ka, Kb) and torch.equal(ra, rb)
+    Ha, Ra = shared1.assemble_helmholtz(0.05, mode="gather")
+    Hb, Rb = plain1.assemble_helmholtz(0.05, mode="gather")
+    assert torch.equal(Ha, Hb) and torch.equal(Ra, Rb)
+    Kref = orc.assemble_elasticity(X, conn, rho, 3.0)
+    K = shared2.to_scipy(shared2.assemble_elasticity(rho, 3.0, mode="gather"))
+    assert np.array_equal(K.indices, Kref.indices)
+    assert_values_close(K.data, Kref.data, VAL_TOL)
+    # hex8, scalar operator
+    X3, c3 = orc.structured_mesh(23, 19, 17)
+    h3 = pf.DeviceMesh(X3, c3, 1)
+    assert h3.ntemplates < h3.nchunks
+    rho3 = 0.1 + 0.9 * np.random.default_rng(3).random(X3.shape[0])
+    K3 = h3.to_scipy(h3.assemble_poisson(rho3, 3.0, mode="gather"))
+    assert_values_close(K3.data, orc.assemble_poisson(X3, c3, rho3, 3.0).data, VAL_TOL)
+
+
+def test_element_mask_with_shared_templates():
+    """pfg_mesh_set_element_mask on a handle whose chunks share tables: the skip flags live beside the records, not in
+    the shared tables; masking every other element row and its complement adds up to the full matrix."""
+    import torch
+    import pyfem_gpu_testflight_b200 as pf
+    nx, ny = 97, 61
+    X, conn = orc.structured_mesh(nx, ny)
+    mesh = pf.DeviceMesh(X, conn, 2)
+    assert mesh.ntemplates < mesh.nchunks
+    full = mesh.assemble_elasticity(1.0, 0.0, mode="gather").clone()
+    rows = (np.arange(conn.shape[0]) // (nx - 1)) % 2
+    mesh.set_element_mask(rows.astype(np.uint8))
+    a = mesh.assemble_elasticity(1.0, 0.0, mode="gather").clone()
+    mesh.set_element_mask((1 - rows).astype(np.uint8))
+    b = mesh.assemble_elasticity(1.0, 0.0, mode="gather").clone()
+    mesh.set_element_mask(None)
+    assert torch.equal(mesh.assemble_elasticity(1.0, 0.0, mode="gather"), full)
+    assert float((a + b - full).abs().max()) <= 1e-13 * float(full.abs().max())
+    assert float(a.abs().max()) > 0 and float(b.abs().max()) > 0
