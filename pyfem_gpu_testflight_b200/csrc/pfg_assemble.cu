@@ -598,14 +598,31 @@ template <class Op, class = void>
 struct op_deep_prefetch : std::false_type {};
 template <class Op>
 struct op_deep_prefetch<Op, std::enable_if_t<Op::DEEP_PREFETCH>> : std::true_type {};
+// `static constexpr bool DEEP_X = true`: the operator MAY run the XD variant of the kernel, in which only the window
+// coordinates / field are double-buffered and gathered a whole chunk ahead (2-3 KB of shared memory for the 2 x 2-block
+// kernel; the corner indices keep their single stage).  With the plan tables resident (chunk templates) the coordinate
+// gather is the one transfer left on the critical path: 1.374 -> 1.349 ms on the 16.8 M-quad case.  The launcher takes
+// the variant only when the extra stage costs no resident CTA (with a nodal field it would: 3 -> 2 per SM).
+template <class Op, class = void>
+struct op_deep_x : std::false_type {};
+template <class Op>
+struct op_deep_x<Op, std::enable_if_t<Op::DEEP_X>> : std::true_type {};
 
-template <class Op, int THREADS, int MINB>
+// Operators with more than one nodal field (sensitivities: rho, phi, psi) declare `static constexpr int FW` doubles
+// per window node and a `gather_fields(prm, node, dst)` that issues the cp.async copies of one node.
+template <class Op, class = void>
+struct op_field_width : std::integral_constant<int, 1> {};
+template <class Op>
+struct op_field_width<Op, std::enable_if_t<(Op::FW > 1)>> : std::integral_constant<int, Op::FW> {};
+
+template <class Op, int THREADS, int MINB, bool XD>
 __global__ void __launch_bounds__(THREADS, MINB)
     k_tile(MeshView mv, typename Op::Params prm, Outputs out, TileCfg cfg) {
-    constexpr bool DEEP = op_deep_prefetch<Op>::value;
+    constexpr bool DEEP = op_deep_prefetch<Op>::value;  // corner indices double-buffered, fetched at the top
+    constexpr bool DEEPX = DEEP || XD;                  // window data double-buffered, gathered at the top
     extern __shared__ __align__(128) unsigned char smem[];
     using St = TileStage<Op>;
-    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
+    constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM, FW = op_field_width<Op>::value;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);  // [0] blob+codes, [1..2] window ids, [3] (and [5]) corner indices, [4] window data
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int64_t c_end = (int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x;
@@ -617,10 +634,10 @@ __global__ void __launch_bounds__(THREADS, MINB)
     uint16_t* codes_s = reinterpret_cast<uint16_t*>(smem + cfg.off_codes);
     auto loc_stage = [&](int j) -> unsigned char* { return smem + cfg.off_loc + (DEEP ? (j & 1) * cfg.loc_stride : 0); };
     auto x_stage = [&](int j) -> double* {
-        return reinterpret_cast<double*>(smem + cfg.off_x + (DEEP ? (j & 1) * cfg.x_stride : 0));
+        return reinterpret_cast<double*>(smem + cfg.off_x + (DEEPX ? (j & 1) * cfg.x_stride : 0));
     };
     auto f_stage = [&](int j) -> double* {
-        return reinterpret_cast<double*>(smem + cfg.off_field + (DEEP ? (j & 1) * cfg.field_stride : 0));
+        return reinterpret_cast<double*>(smem + cfg.off_field + (DEEPX ? (j & 1) * cfg.field_stride : 0));
     };
     double* stage = reinterpret_cast<double*>(smem + cfg.off_stage);
     double* image = reinterpret_cast<double*>(smem + cfg.off_image);
@@ -683,7 +700,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 cp_async_8(dst + 1, mv.X + node * 3 + 1);
                 cp_async_8(dst + 2, mv.X + node * 3 + 2);
             }
-            if (field != nullptr) cp_async_8(fs + t, field + node);
+            if constexpr (FW > 1) Op::gather_fields(prm, node, fs + (size_t)t * FW);
+            else if (field != nullptr) cp_async_8(fs + t, field + node);
         }
         cp_async_mbar_arrive(&bars[4]);
     };
@@ -722,17 +740,19 @@ __global__ void __launch_bounds__(THREADS, MINB)
         mbar_wait(&bars[4], i & 1);  // the window's coordinates have landed (all threads' copies)
         mbar_wait(loc_bar(i), loc_parity(i));  // and so have the corner indices
         // ---- prefetch: window ids two chunks ahead; corner indices and window coordinates one chunk ahead
-        auto prefetch_next = [&]() {
-            if (threadIdx.x == 0) {
-                if (i + 2 < nloc) issue_win(i + 2);
-                if (i + 1 < nloc) issue_loc(i + 1);
-            }
+        auto prefetch_window = [&]() {
+            if (threadIdx.x == 0 && i + 2 < nloc) issue_win(i + 2);
             if (i + 1 < nloc) {
                 mbar_wait(&bars[1 + ((i + 1) & 1)], ((i + 1) >> 1) & 1);
                 gather_window(i + 1);
             }
         };
-        if constexpr (DEEP) prefetch_next();  // into the other stage: phases A and B of this chunk to land
+        auto prefetch_corners = [&]() {
+            if (threadIdx.x == 0 && i + 1 < nloc) issue_loc(i + 1);
+        };
+        // into the other stage: phases A and B of this chunk to land
+        if constexpr (DEEPX) prefetch_window();
+        if constexpr (DEEP) prefetch_corners();
         // ---- phase A: one thread per element record -> staged element matrices
         const unsigned char* loc_i = loc_stage(i) + (((size_t)dir_s[i & 7].loc_off * NNE * 2) & 15);
         const double* xs = x_stage(i);
@@ -753,7 +773,7 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 loc[0] = v.x & 0xFFFFu, loc[1] = v.x >> 16, loc[2] = v.y & 0xFFFFu, loc[3] = v.y >> 16;
                 loc[4] = v.z & 0xFFFFu, loc[5] = v.z >> 16, loc[6] = v.w & 0xFFFFu, loc[7] = v.w >> 16;
             }
-            double xe[NNE][DIM], fe[NNE];
+            double xe[NNE][DIM], fe[NNE * FW];
 #pragma unroll
             for (int a = 0; a < NNE; ++a) {
                 const double* src = xs + (size_t)loc[a] * DIM;
@@ -763,7 +783,8 @@ __global__ void __launch_bounds__(THREADS, MINB)
                 } else {
                     xe[a][0] = src[0], xe[a][1] = src[1], xe[a][2] = src[2];
                 }
-                fe[a] = (field != nullptr) ? fs[loc[a]] : 0.0;
+#pragma unroll
+                for (int c = 0; c < FW; ++c) fe[a * FW + c] = (field != nullptr) ? fs[loc[a] * FW + c] : 0.0;
             }
             int64_t elem = 0;
             if constexpr (Op::NEEDS_ELEM) elem = __ldg(mv.rec_elem + dir_s[i & 7].rec_begin + r);
@@ -771,7 +792,9 @@ __global__ void __launch_bounds__(THREADS, MINB)
         }
         tma_store_wait_read();  // the previous chunk's bulk stores have read the image
         __syncthreads();
-        if constexpr (!DEEP) prefetch_next();  // single stage: free once phase A of this chunk has read it
+        // single stage: free once phase A of this chunk has read it
+        if constexpr (!DEEPX) prefetch_window();
+        if constexpr (!DEEP) prefetch_corners();
         // ---- phase B: plan-ordered sums into the CSR image, each CSR value written once
         mbar_wait(&bars[0], i & 1);
         {
@@ -1130,6 +1153,84 @@ __global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, do
         if (nodes[a] >= mv.own_begin && nodes[a] < mv.own_end) atomicAdd(out + (nodes[a] - mv.own_begin), inner[a]);
 }
 
+// The same sensitivities as a tile operator for scalar handles (one dof row per node): rho, phi and psi of the chunk's
+// window nodes are staged once in shared memory, every element record leaves its NNE nodal shares in the staging
+// area and phase B sums a node's shares in plan order -- no atomics, bitwise reproducible, every input read once.
+template <int NNE_, int M_>
+struct SensOp {
+    static constexpr int NNE = NNE_, M = 1, NMAT = 0, NVEC = 1, MF = M_;
+    static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    static constexpr int FW = 1 + 2 * M_;  // per window node: rho, phi[MF], psi[MF]
+    static constexpr bool NEEDS_ELEM = false, SYM = false;
+    using Params = SensParams;
+    __host__ __device__ __forceinline__ static const double* field(const Params& prm) { return prm.phi; }
+    PFG_DEV static void gather_fields(const Params& prm, size_t node, double* dst) {
+        if (prm.mat.rho != nullptr) cp_async_8(dst, prm.mat.rho + node);
+#pragma unroll
+        for (int c = 0; c < MF; ++c) {
+            cp_async_8(dst + 1 + c, prm.phi + node * MF + c);
+            cp_async_8(dst + 1 + MF + c, prm.psi + node * MF + c);
+        }
+    }
+    template <class Sink>
+    PFG_DEV static void run(const Params& prm, const double (&xe)[NNE][DIM], const double (&fe)[NNE * FW], int64_t,
+                            Sink& sink) {
+        double inner[NNE];
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) inner[a] = 0.0;
+        GeoCtx<NNE> geo(xe);
+        for_each_q<NQ>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[NNE][DIM];  // G = det * grad N
+            geo.template at<Q>(xe, det, G);
+            double rq = prm.mat.rho_const;
+            if (prm.mat.rho != nullptr) {
+                rq = 0.0;
+#pragma unroll
+                for (int a = 0; a < NNE; ++a) rq = fma(Elem<NNE>::N(Q, a), fe[a * FW], rq);
+            }
+            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);
+            const double dr = (1.0 + prm.mat.p) / (den * den);  // ramp'(rho_q), pyfem.py:1325
+            double gu[MF][DIM], gv[MF][DIM];                    // det * gradients of the two fields
+#pragma unroll
+            for (int c = 0; c < MF; ++c)
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) {
+                    double su = 0.0, sv = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NNE; ++a) {
+                        su = fma(G[a][l], fe[a * FW + 1 + c], su);
+                        sv = fma(G[a][l], fe[a * FW + 1 + MF + c], sv);
+                    }
+                    gu[c][l] = su, gv[c][l] = sv;
+                }
+            double energy;
+            if constexpr (MF == 1) {
+                energy = 0.0;
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) energy = fma(gu[0][l], gv[0][l], energy);
+            } else if constexpr (DIM == 2) {  // strains [ex, ey, gxy] (pyfem.py:1988-1998)
+                const double gxu = gu[0][1] + gu[1][0], gxv = gv[0][1] + gv[1][0];
+                energy = prm.c11 * (gu[0][0] * gv[0][0] + gu[1][1] * gv[1][1]) +
+                         prm.c12 * (gu[0][0] * gv[1][1] + gu[1][1] * gv[0][0]) + prm.c33 * gxu * gxv;
+            } else {  // [ex, ey, ez, gxy, gyz, gxz] (pyfem.py:2000-2011)
+                const double su = gu[0][0] + gu[1][1] + gu[2][2], sv = gv[0][0] + gv[1][1] + gv[2][2];
+                double diag = 0.0;
+#pragma unroll
+                for (int l = 0; l < 3; ++l) diag = fma(gu[l][l], gv[l][l], diag);
+                const double sh = (gu[0][1] + gu[1][0]) * (gv[0][1] + gv[1][0]) + (gu[1][2] + gu[2][1]) * (gv[1][2] + gv[2][1]) +
+                                  (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
+                energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
+            }
+            const double t = dr * energy / det;  // (gu / det) . (gv / det) * det * w, w = 1
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
+        });
+#pragma unroll
+        for (int a = 0; a < NNE; ++a) sink.vec(a, inner[a]);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1182,28 +1283,72 @@ static int zero_outputs(const MeshDev& d, const Outputs& out, cudaStream_t st) {
 }
 
 
-template <class Op, int THREADS, int MINB>
-static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params& prm, const Outputs& out,
-                       cudaStream_t st) {
+template <class Op, bool XD>
+static size_t tile_smem_layout(const MeshDev& d, const typename Op::Params& prm, TileCfg& cfg) {
     using St = TileStage<Op>;
     constexpr int NNE = Op::NNE, DIM = Elem<NNE>::DIM;
-    PFG_TRY(tile_prepare_layout(d, St::layout(), st));
-    TileCfg cfg;
     cfg.off_dir = 64;
     cfg.off_blob = cfg.off_dir + 8 * (int)sizeof(TileDir);
     cfg.off_codes = cfg.off_blob + align16(d.max_blob_bytes);
     cfg.off_win = cfg.off_codes + align16(d.max_code_bytes) + 16;  // slack: phase B may read a few codes past the end
     cfg.win_stride = align16(d.max_chunk_win * 4) + 16;            // copies start at the enclosing 16-byte boundary
-    constexpr int NST = op_deep_prefetch<Op>::value ? 2 : 1;  // stages of the corner-index / window-data buffers
+    constexpr int NSTL = op_deep_prefetch<Op>::value ? 2 : 1;  // stages of the corner-index buffer
+    constexpr int NSTX = (NSTL == 2 || XD) ? 2 : 1;            // stages of the window-data buffers
     cfg.off_loc = cfg.off_win + 2 * cfg.win_stride;
     cfg.loc_stride = align16(d.max_chunk_recs * NNE * 2) + 16;
-    cfg.off_x = cfg.off_loc + NST * cfg.loc_stride;
+    cfg.off_x = cfg.off_loc + NSTL * cfg.loc_stride;
     cfg.x_stride = align16(d.max_chunk_win * DIM * 8);
-    cfg.off_field = cfg.off_x + NST * cfg.x_stride;
-    cfg.field_stride = Op::field(prm) ? align16(d.max_chunk_win * 8) : 0;
-    cfg.off_stage = cfg.off_field + NST * cfg.field_stride;
+    cfg.off_field = cfg.off_x + NSTX * cfg.x_stride;
+    cfg.field_stride = Op::field(prm) ? align16(d.max_chunk_win * 8 * op_field_width<Op>::value) : 0;
+    cfg.off_stage = cfg.off_field + NSTX * cfg.field_stride;
     cfg.nchunks = (int)d.nchunks;
     cfg.off_image = align16(cfg.off_stage + (d.max_chunk_recs + 1) * St::S * 8);
+    cfg.image_stride = align16(d.max_out_bytes) / 8;
+    return (size_t)cfg.off_image + (size_t)Op::NMAT * cfg.image_stride * 8;
+}
+
+// attribute / occupancy queries cost more than a small assembly: repeated only when the configuration changes
+template <class Op, int THREADS, int MINB, bool XD>
+static int tile_resident_ctas(const MeshDev& d, size_t smem, int* per_sm) {
+    static thread_local size_t cached_smem = 0;
+    static thread_local int cached_device = -1, cached_per_sm = 0;
+    if (cached_smem != smem || cached_device != d.device) {
+        auto kern = k_tile<Op, THREADS, MINB, XD>;
+        int q = 0;
+        if (smem <= kMaxDynamicSmem) {
+            PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));
+        }
+        cached_per_sm = q;
+        cached_smem = smem;
+        cached_device = d.device;
+    }
+    *per_sm = cached_per_sm;
+    return PFG_OK;
+}
+
+template <class Op, int THREADS, int MINB, bool XD>
+static int launch_tile_variant(const MeshDev& d, const MeshView& mv, const typename Op::Params& prm, const Outputs& out,
+                               const TileCfg& cfg, size_t smem, int per_sm, cudaStream_t st) {
+    using St = TileStage<Op>;
+    const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)std::max(1, per_sm) * d.sm_count);
+    static const bool debug = getenv("PFG_DEBUG") != nullptr;
+    if (debug)
+        fprintf(stderr, "[pfg] k_tile%s: %d threads, %zu B smem (stage %d, image %d, blob %d, codes %d, win %d, recs<=%d), %d CTA/SM, grid %u\n",
+                XD ? " [window data a chunk ahead]" : "", THREADS, smem, (d.max_chunk_recs + 1) * St::S * 8,
+                Op::NMAT * cfg.image_stride * 8, d.max_blob_bytes, d.max_code_bytes, d.max_chunk_win, d.max_chunk_recs, per_sm,
+                grid);
+    k_tile<Op, THREADS, MINB, XD><<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+template <class Op, int THREADS, int MINB>
+static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params& prm, const Outputs& out,
+                       cudaStream_t st) {
+    using St = TileStage<Op>;
+    PFG_TRY(tile_prepare_layout(d, St::layout(), st));
     if ((Op::M == 2) != (d.m == 2)) {
         set_error("tile plan was built for %d dofs per node, the operator has %d", d.m, Op::M);
         return PFG_ERR_INVALID;
@@ -1215,35 +1360,25 @@ static int launch_tile(MeshDev& d, const MeshView& mv, const typename Op::Params
             set_error("CSR values buffer %p is not 16-byte aligned (bulk stores need it)", (void*)out.vals[mt]);
             return PFG_ERR_INVALID;
         }
-    cfg.image_stride = align16(d.max_out_bytes) / 8;
-    const size_t smem = (size_t)cfg.off_image + (size_t)Op::NMAT * cfg.image_stride * 8;
-    if (smem > 227 * 1024) {
+    TileCfg cfg;
+    const size_t smem = tile_smem_layout<Op, false>(d, prm, cfg);
+    if (smem > kMaxDynamicSmem) {
         set_error("chunk staging of %zu bytes exceeds shared memory", smem);
         return PFG_ERR_UNSUPPORTED;
     }
-    auto kern = k_tile<Op, THREADS, MINB>;
-    // attribute / occupancy queries cost more than a small assembly: repeat them only when the configuration changes
-    static thread_local size_t cached_smem = 0;
-    static thread_local int cached_device = -1, cached_per_sm = 1;
-    if (cached_smem != smem || cached_device != d.device) {
-        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PFG_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        int q = 1;
-        PFG_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&q, kern, THREADS, smem));
-        cached_per_sm = std::max(1, q);
-        cached_smem = smem;
-        cached_device = d.device;
+    int per_sm = 1;
+    PFG_TRY((tile_resident_ctas<Op, THREADS, MINB, false>(d, smem, &per_sm)));
+    if constexpr (op_deep_x<Op>::value) {
+        // the variant that gathers the window data a whole chunk ahead, if its second stage costs no resident CTA
+        static const bool no_xd = getenv("PFG_NO_DEEP_X") != nullptr;
+        TileCfg cfg_x;
+        const size_t smem_x = tile_smem_layout<Op, true>(d, prm, cfg_x);
+        int per_sm_x = 0;
+        PFG_TRY((tile_resident_ctas<Op, THREADS, MINB, true>(d, smem_x, &per_sm_x)));
+        if (!no_xd && per_sm_x >= per_sm)
+            return launch_tile_variant<Op, THREADS, MINB, true>(d, mv, prm, out, cfg_x, smem_x, per_sm_x, st);
     }
-    const int per_sm = cached_per_sm;
-    const unsigned grid = (unsigned)std::min<int64_t>(d.nchunks, (int64_t)per_sm * d.sm_count);
-    static const bool debug = getenv("PFG_DEBUG") != nullptr;
-    if (debug)
-        fprintf(stderr, "[pfg] k_tile: %d threads, %zu B smem (stage %d, image %d, blob %d, codes %d, win %d, recs<=%d), %d CTA/SM, grid %u\n",
-                THREADS, smem, (d.max_chunk_recs + 1) * St::S * 8, Op::NMAT * cfg.image_stride * 8, d.max_blob_bytes,
-                d.max_code_bytes, d.max_chunk_win, d.max_chunk_recs, per_sm, grid);
-    kern<<<grid, THREADS, smem, st>>>(mv, prm, out, cfg);
-    PFG_CUDA_TRY(cudaGetLastError());
-    return PFG_OK;
+    return launch_tile_variant<Op, THREADS, MINB, false>(d, mv, prm, out, cfg, smem, per_sm, st);
 }
 
 template <class Op, int THREADS, int MINB>
@@ -1550,11 +1685,14 @@ extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev,
         set_error("pfg_k_dv_sens: NULL argument");
         return PFG_ERR_INVALID;
     }
-    if ((physics == PFG_PHYS_POISSON && d.m != 1) || (physics == PFG_PHYS_ELASTICITY && d.m != d.ndims) ||
+    // elasticity: phi / psi carry ndims entries per node whatever the handle's own dof count -- a scalar handle of the
+    // same mesh is accepted too (and preferred: its tile plan has the nodal-vector codes the deterministic pass needs)
+    if ((physics == PFG_PHYS_POISSON && d.m != 1) || (physics == PFG_PHYS_ELASTICITY && d.m != d.ndims && d.m != 1) ||
         (physics != PFG_PHYS_POISSON && physics != PFG_PHYS_ELASTICITY)) {
         set_error("pfg_k_dv_sens: physics %d does not fit a handle with %d dofs per node", physics, d.m);
         return PFG_ERR_INVALID;
     }
+    const int mf = (physics == PFG_PHYS_POISSON) ? 1 : d.ndims;  // entries of phi / psi per node
     cudaStream_t st = (cudaStream_t)stream;
     SensParams prm{material_of(rho_dev, rho_const, p), phi_dev, psi_dev, 0.0, 0.0, 0.0};
     if (physics == PFG_PHYS_ELASTICITY) {
@@ -1568,12 +1706,22 @@ extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev,
             prm.c11 = f * (1.0 - nu), prm.c12 = f * nu, prm.c33 = f * (0.5 - nu);
         }
     }
-    PFG_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (d.own_end - d.own_begin) * sizeof(double), st));
     const MeshView mv = view_of(d);
+    static const bool force_atomic = getenv("PFG_SENS_ATOMIC") != nullptr;  // development aid
+    if (d.m == 1 && d.tile_dir != nullptr && !force_atomic) {
+        // deterministic pass on the tile plan of a scalar handle: window staging + plan-ordered nodal sums
+        Outputs out{{nullptr, nullptr}, out_dev};
+        MeshDev& dm = const_cast<MeshDev&>(d);
+        if (d.nne == 4 && mf == 1) return launch_tile<SensOp<4, 1>, 128, 4>(dm, mv, prm, out, st);
+        if (d.nne == 4) return launch_tile<SensOp<4, 2>, 128, 3>(dm, mv, prm, out, st);
+        if (mf == 1) return launch_tile<SensOp<8, 1>, 128, 2>(dm, mv, prm, out, st);
+        return launch_tile<SensOp<8, 3>, 128, 2>(dm, mv, prm, out, st);
+    }
+    PFG_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (d.own_end - d.own_begin) * sizeof(double), st));
     const unsigned grid = (unsigned)((d.nelems + 127) / 128);
-    if (d.nne == 4 && d.m == 1) k_dv_sens<4, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    if (d.nne == 4 && mf == 1) k_dv_sens<4, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
     else if (d.nne == 4) k_dv_sens<4, 2><<<grid, 128, 0, st>>>(mv, prm, out_dev);
-    else if (d.m == 1) k_dv_sens<8, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
+    else if (mf == 1) k_dv_sens<8, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
     else k_dv_sens<8, 3><<<grid, 128, 0, st>>>(mv, prm, out_dev);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;

@@ -252,6 +252,24 @@ PFG_DEV void load_field(const double* __restrict__ f, const int (&nodes)[NNE], d
     for (int a = 0; a < NNE; ++a) fe[a] = (f != nullptr) ? __ldg(f + nodes[a]) : 0.0;
 }
 
+// Partition of unity (sum_a grad N_a = 0): a gradient-gradient matrix K[a][b] = sum_q s G_a.G_b has zero row sums, so
+// its last row / column follow from the others.  Fills K[a][NNE-1] for a < NNE-1 and K[NNE-1][NNE-1] from the upper
+// triangle of the leading (NNE-1) x (NNE-1) block.
+template <int NNE>
+PFG_DEV void close_rows_upper(double (&K)[NNE][NNE]) {
+    constexpr int L = NNE - 1;
+    double last = 0.0;
+#pragma unroll
+    for (int a = 0; a < L; ++a) {
+        double sum = 0.0;
+#pragma unroll
+        for (int b = 0; b < L; ++b) sum += (a <= b) ? K[a][b] : K[b][a];
+        K[a][L] = -sum;
+        last += sum;
+    }
+    K[L][L] = last;  // = -sum_a K[a][L]
+}
+
 // emit a symmetric scalar matrix held as upper-triangular accumulators
 template <int NNE, class Sink>
 PFG_DEV void emit_sym_scalar(Sink& sink, int mat, const double (&K)[NNE][NNE]) {
@@ -293,16 +311,17 @@ struct PoissonOp {  // LinearPoisson._compute_element_jacobian (pyfem.py:1188-12
             geo.template at<Q>(xe, det, G);
             const double s = cq[Q] * fast_rcp(det);  // w = 1 (pyfem.py:92,110)
 #pragma unroll
-            for (int a = 0; a < NNE; ++a) {
+            for (int a = 0; a < NNE - 1; ++a) {  // the last node's row / column: close_rows_upper
                 double H[DIM];
 #pragma unroll
                 for (int l = 0; l < DIM; ++l) H[l] = s * G[a][l];
 #pragma unroll
-                for (int b = a; b < NNE; ++b)
+                for (int b = a; b < NNE - 1; ++b)
 #pragma unroll
                     for (int l = 0; l < DIM; ++l) K[a][b] = fma(H[l], G[b][l], K[a][b]);
             }
         });
+        close_rows_upper<NNE>(K);
         emit_sym_scalar<NNE>(sink, 0, K);
     }
 };
@@ -312,6 +331,7 @@ struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2
     static constexpr int NNE = NNE_, M = 1, NMAT = 2, NVEC = 0;  // matrix 0 = K, 1 = R
     static constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
     static constexpr bool NEEDS_ELEM = false, SYM = true;
+    static constexpr bool DEEP_X = (NNE_ == 4);  // quad4 Helmholtz: 1.079 -> 1.066 ms with the window data a chunk ahead
     struct Params {
         double r0sq;
     };
@@ -337,12 +357,15 @@ struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2
                 for (int l = 0; l < DIM; ++l) H[l] = s * G[a][l];
 #pragma unroll
                 for (int b = a; b < NNE; ++b) {
+                    if (b < NNE - 1) {  // stiffness part: the last node's row / column follows from the zero row sums
 #pragma unroll
-                    for (int l = 0; l < DIM; ++l) K[a][b] = fma(H[l], G[b][l], K[a][b]);
+                        for (int l = 0; l < DIM; ++l) K[a][b] = fma(H[l], G[b][l], K[a][b]);
+                    }
                     R[a][b] = fma(det, Elem<NNE>::N(Q, a) * Elem<NNE>::N(Q, b), R[a][b]);
                 }
             }
         });
+        close_rows_upper<NNE>(K);
 #pragma unroll
         for (int a = 0; a < NNE; ++a)
 #pragma unroll
@@ -355,6 +378,7 @@ struct HelmholtzOp {  // Helmholtz._compute_element_jacobian_and_rhs (pyfem.py:2
 struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_jacobian (pyfem.py:2029-2068)
     static constexpr int NNE = 4, M = 2, NMAT = 1, NVEC = 0, DIM = 2, NQ = 4;
     static constexpr bool NEEDS_ELEM = false, SYM = true;
+    static constexpr bool DEEP_X = true;  // may gather the window data a whole chunk ahead (pfg_assemble.cu, k_tile XD)
     struct Params {
         Material mat;
         double c11, c12, c33;  // C0 entries (pyfem.py:1746-1750)
@@ -364,12 +388,15 @@ struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_j
     PFG_DEV static void run(const Params& prm, const double (&xe)[4][2], const double (&fe)[4], int64_t, Sink& sink) {
         double cq[4];
         material_at_quads<4>(prm.mat, fe, cq);
-        // per node pair (a <= b): sums over q of s * {GxaGxb, GyaGyb, GxaGyb, GyaGxb}
-        double XX[4][4], YY[4][4], XY[4][4], YX[4][4];
+        // Partition of unity: sum_a grad N_a = 0 at every point, so every row of the element matrix sums to zero.  Only
+        // the node pairs among the first three nodes are integrated -- XX, YY (symmetric, 6 each) and XY (all 9;
+        // YX[a][b] = XY[b][a]) -- and the blocks of the fourth node follow from the row / column sums: 21 instead of
+        // 36 running sums per quadrature point, and no G / h for the fourth node.
+        double XX[4][4], YY[4][4], XY[4][4];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+        for (int a = 0; a < 3; ++a)
 #pragma unroll
-            for (int b = 0; b < 4; ++b) XX[a][b] = YY[a][b] = XY[a][b] = YX[a][b] = 0.0;
+            for (int b = 0; b < 3; ++b) XX[a][b] = YY[a][b] = XY[a][b] = 0.0;
         const Quad4Coef c = quad4_coef(xe);
         for_each_q<4>([&](auto qc) {
             constexpr int Q = decltype(qc)::value;
@@ -377,22 +404,37 @@ struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_j
             quad4_geo<Q>(c, det, G);
             const double s = cq[Q] * fast_rcp(det);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
+            for (int a = 0; a < 3; ++a) {
                 const double hx = s * G[a][0], hy = s * G[a][1];
 #pragma unroll
-                for (int b = a; b < 4; ++b) {
-                    XX[a][b] = fma(hx, G[b][0], XX[a][b]);
-                    YY[a][b] = fma(hy, G[b][1], YY[a][b]);
+                for (int b = 0; b < 3; ++b) {
                     XY[a][b] = fma(hx, G[b][1], XY[a][b]);
-                    if (b != a) YX[a][b] = fma(hy, G[b][0], YX[a][b]);
+                    if (b >= a) {
+                        XX[a][b] = fma(hx, G[b][0], XX[a][b]);
+                        YY[a][b] = fma(hy, G[b][1], YY[a][b]);
+                    }
                 }
             }
         });
 #pragma unroll
+        for (int a = 0; a < 3; ++a)
+#pragma unroll
+            for (int b = 0; b < a; ++b) XX[a][b] = XX[b][a], YY[a][b] = YY[b][a];
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {  // fourth node: minus the sums over the other three
+            XX[a][3] = -((XX[a][0] + XX[a][1]) + XX[a][2]);
+            YY[a][3] = -((YY[a][0] + YY[a][1]) + YY[a][2]);
+            XY[a][3] = -((XY[a][0] + XY[a][1]) + XY[a][2]);
+            XY[3][a] = -((XY[0][a] + XY[1][a]) + XY[2][a]);
+        }
+        XX[3][3] = -((XX[0][3] + XX[1][3]) + XX[2][3]);
+        YY[3][3] = -((YY[0][3] + YY[1][3]) + YY[2][3]);
+        XY[3][3] = -((XY[3][0] + XY[3][1]) + XY[3][2]);
+#pragma unroll
         for (int a = 0; a < 4; ++a)
 #pragma unroll
             for (int b = a; b < 4; ++b) {
-                const double yx = (a == b) ? XY[a][b] : YX[a][b];
+                const double yx = XY[b][a];  // sum_q s Gy_a Gx_b
                 double blk[4];  // [alpha][beta] for (row node a, col node b)
                 blk[0] = fma(prm.c11, XX[a][b], prm.c33 * YY[a][b]);
                 blk[1] = fma(prm.c12, XY[a][b], prm.c33 * yx);

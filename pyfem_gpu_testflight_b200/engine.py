@@ -315,15 +315,19 @@ class DeviceMesh:
 
     def k_dv_sens(self, physics, rho, p, phi, psi, E=10.0, nu=0.3, out=None):
         """d(phi^T K(rho) psi)/d rho at the owned nodes (the reference's _compute_K_dv_sens, pyfem.py:1239-1276 and
-        1872-1920), fused on the device.  physics: "poisson" (scalar handle) or "elasticity"."""
+        1872-1920), fused on the device.  physics: "poisson" (scalar handle) or "elasticity" (a handle with ndims dofs
+        per node: element-per-thread pass with atomic nodal adds; or a scalar handle of the same mesh: node-window
+        staging + plan-ordered nodal sums, deterministic)."""
         torch = _torch()
         code = {"poisson": _lib.PHYS_POISSON, "elasticity": _lib.PHYS_ELASTICITY}[physics]
         rho_t, rho_c = self._rho(rho)
-        ndof = self.nnodes * self.ndof_per_node
+        # phi / psi carry one entry per node (Poisson) or ndims entries (elasticity), whatever this handle's own dof
+        # count: a scalar handle of the mesh runs the deterministic tile-plan pass for both physics
+        ndof = self.nnodes * (1 if physics == "poisson" else self.ndims)
         phi_t, psi_t = self._dev_f64(phi, ndof, "phi"), self._dev_f64(psi, ndof, "psi")
         par = np.ascontiguousarray(np.asarray((E, nu), dtype=np.float64))
         if out is None:
-            out = torch.empty(self.nrows // self.ndof_per_node, dtype=torch.float64, device=self.device)
+            out = torch.empty(self.own_end - self.own_begin, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self._lib.pfg_k_dv_sens(self._handle, code, _ptr(rho_t), rho_c, float(p),
                                                par.ctypes.data_as(ctypes.POINTER(c_double)), 2, _ptr(phi_t),

@@ -276,12 +276,22 @@ class _DensityFunctions:
     def volume_grad(self, rho):
         return np.ones(self.nnodes) / self.nnodes
 
+    def _sens_mesh(self):
+        """The handle the sensitivity pass runs on: a scalar handle (one dof row per node), whose tile plan carries
+        the nodal-vector codes of the deterministic pass.  For elasticity it is a second handle of the same mesh,
+        built on first use (once per model)."""
+        if self.ndof_per_node == 1:
+            return self.mesh
+        if getattr(self, "_scalar_mesh", None) is None:
+            self._scalar_mesh = DeviceMesh(self.X, self.conn, 1, device=self.mesh.device)
+        return self._scalar_mesh
+
     def _k_dv_sens(self, physics, rho, phi, psi, **kw):
         _check_real(rho)
         if self.slab is not None:
             raise NotImplementedError("sensitivities of a slab-partitioned model are not implemented")
         rho = np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho
-        return self.mesh.k_dv_sens(physics, rho, self.p, phi, psi, **kw).cpu().numpy()
+        return self._sens_mesh().k_dv_sens(physics, rho, self.p, phi, psi, **kw).cpu().numpy()
 
 
 def _check_real(rho):

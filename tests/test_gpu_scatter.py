@@ -117,8 +117,8 @@ def test_chunk_templates_share_tables_and_change_nothing(monkeypatch):
     u = np.random.default_rng(2).random(X.shape[0])
     xdv = np.ones(10) / 10.0
     shared2, shared1 = pf.DeviceMesh(X, conn, 2), pf.DeviceMesh(X, conn, 1)
-    assert shared2.nchunks > 200 and shared2.ntemplates <= shared2.nchunks // 8
-    assert shared1.ntemplates <= shared1.nchunks // 8
+    assert shared2.nchunks > 200 and shared2.ntemplates <= shared2.nchunks // 4
+    assert shared1.ntemplates <= shared1.nchunks // 4
     monkeypatch.setenv("PFG_NO_TEMPLATES", "1")
     plain2, plain1 = pf.DeviceMesh(X, conn, 2), pf.DeviceMesh(X, conn, 1)
     monkeypatch.delenv("PFG_NO_TEMPLATES")

@@ -112,3 +112,38 @@ def test_sensitivities_on_row_slabs(pf, three_d):
         dof = (part.node_gid[:, None] * d + np.arange(d)[None, :]).ravel()
         out.append(mesh.k_dv_sens("elasticity", rho[part.node_gid], 3.0, phi[dof], psi[dof], E=8.0, nu=0.31).cpu().numpy())
     assert_values_close(np.concatenate(out), ref, VAL_TOL)
+
+
+@pytest.mark.parametrize("three_d", [False, True])
+def test_sensitivity_paths_agree_and_tile_path_is_reproducible(pf, three_d):
+    """Two device paths: the element-per-thread pass with atomic nodal adds (a handle with ndims dofs per node) and
+    the tile-plan pass on a scalar handle (node-window staging of rho / phi / psi, plan-ordered nodal sums).  They
+    agree to rounding; the tile pass repeats bit for bit; a row slab of the scalar handle yields the owned nodes."""
+    import torch
+    from pyfem_gpu_testflight_b200.partition import partition_mesh
+    if three_d:
+        X, conn = orc.structured_mesh(14, 11, 9)
+    else:
+        X, conn = orc.structured_mesh(131, 77)
+    nn, d = X.shape
+    rng = np.random.default_rng(11)
+    rho = 0.05 + 0.95 * rng.random(nn)
+    phi, psi = rng.random(nn * d) - 0.5, rng.random(nn * d) - 0.5
+    ref = orc.elasticity_K_dv_sens(X, conn, rho, 3.0, phi, psi, 8.0, 0.31)
+    vec, sca = pf.DeviceMesh(X, conn, d), pf.DeviceMesh(X, conn, 1)
+    ga = vec.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31)
+    gt = sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31)
+    assert torch.equal(gt, sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31))
+    assert_values_close(ga.cpu().numpy(), ref, VAL_TOL, "atomic pass")
+    assert_values_close(gt.cpu().numpy(), ref, VAL_TOL, "tile pass")
+    gc = sca.k_dv_sens("elasticity", 0.6, 3.0, phi, psi, E=8.0, nu=0.31)  # constant density
+    assert_values_close(gc.cpu().numpy(), orc.elasticity_K_dv_sens(X, conn, np.full(nn, 0.6), 3.0, phi, psi, 8.0, 0.31),
+                        VAL_TOL, "constant rho")
+    out = []
+    for r in range(3):
+        part = partition_mesh(X, conn, r, 3)
+        mesh = pf.DeviceMesh(part.X, part.conn, 1, own_range=part.own_range, node_gid=part.node_gid,
+                             ncols_nodes=part.nnodes_global)
+        dof = (part.node_gid[:, None] * d + np.arange(d)[None, :]).ravel()
+        out.append(mesh.k_dv_sens("elasticity", rho[part.node_gid], 3.0, phi[dof], psi[dof], E=8.0, nu=0.31).cpu().numpy())
+    assert_values_close(np.concatenate(out), ref, VAL_TOL, "slabs")

@@ -86,6 +86,18 @@ def main():
                         pass
         stalls.sort(reverse=True)
         lines.append("  top stalls: " + ", ".join(f"{n}={v:.2f}" for v, n in stalls[:8]))
+        # FP64 work of the launch from the sass op counters (rates per elapsed SMSP cycle, summed over the SMSPs)
+        try:
+            f = lambda op: float(rec[f"smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed"].replace(",", ""))
+            cyc = float(rec["smsp__cycles_elapsed.avg"].replace(",", ""))
+            insts = (f("dfma") + f("dmul") + f("dadd")) * cyc
+            flops = (2.0 * f("dfma") + f("dmul") + f("dadd")) * cyc
+            ms = float(rec["gpu__time_duration.sum"].replace(",", ""))
+            ms = ms * {"ms": 1.0, "us": 1e-3, "ns": 1e-6, "s": 1e3}.get(u["gpu__time_duration.sum"], 1.0)
+            lines.append(f"  fp64: {insts:.4e} thread instructions (DFMA + DMUL + DADD), {flops:.4e} flops "
+                         f"(DFMA = 2) -> {flops / (ms * 1e-3) / 1e12:.2f} TFLOP/s under ncu")
+        except (KeyError, ValueError):
+            pass
     text = "\n".join(lines)
     print(text)
     if len(sys.argv) > 2:
