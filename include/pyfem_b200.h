@@ -221,10 +221,23 @@ PFG_API int pfg_apply_dirichlet(pfg_mesh* mesh, const int64_t* fixed_dofs_dev, c
  *   rho_dev      nodal density or NULL for the constant rho_const; p is the RAMP parameter
  *   phi_dev, psi_dev   dof vectors (nnodes * ndof_per_node,), local node numbering
  *   out_dev      one entry per owned node; zeroed here, then accumulated with atomic adds
+ * For PFG_PHYS_ELASTICITY a scalar handle (1 dof per node) of the same mesh is accepted as well: phi / psi carry
+ * ndims entries per node whatever the handle's own dof count.
  */
 PFG_API int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
                           const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
                           double* out_dev, void* stream);
+
+/*
+ * The same sensitivities without atomics, bitwise reproducible: rho / phi / psi of a chunk's window nodes are staged
+ * once in shared memory and every node sums its elements' shares in plan order (the tile kernel's vector path).  Needs
+ * a SCALAR handle (1 dof per node) built with a gather plan, for either physics.  Same arguments as pfg_k_dv_sens.
+ * Measured slower than the atomic pass (the per-point arithmetic, not the scatter, is what bounds this operator, and
+ * the owner-computes plan integrates chunk-border elements twice): use it where run-to-run reproducibility matters.
+ */
+PFG_API int pfg_k_dv_sens_ordered(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
+                                  const double* params_host, int nparams, const double* phi_dev,
+                                  const double* psi_dev, double* out_dev, void* stream);
 
 /*
  * y = A x on the device CSR of the owned rows (Helmholtz.compute_rhs = R.dot(x), pyfem.py:2117-2120).

@@ -62,6 +62,8 @@ PROTOTYPES = {
                                      c_void_p, c_void_p]),
     "pfg_k_dv_sens": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, POINTER(c_double), c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
+    "pfg_k_dv_sens_ordered": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, POINTER(c_double), c_int, c_void_p,
+                                      c_void_p, c_void_p, c_void_p]),
     "pfg_probe_fp64": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),
     "pfg_mesh_set_element_mask": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pfg_add_indexed": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -1111,8 +1111,7 @@ __global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, do
         double det, G[NNE][DIM];  // G = det * grad N
         geo.template at<Q>(xe, det, G);
         const double rq = (prm.mat.rho != nullptr) ? interp<NNE, Q>(re) : prm.mat.rho_const;
-        const double den = fma(prm.mat.p, 1.0 - rq, 1.0);
-        const double dr = (1.0 + prm.mat.p) / (den * den);  // ramp'(rho_q), pyfem.py:1325
+        const double den = fma(prm.mat.p, 1.0 - rq, 1.0);  // ramp'(rho_q) = (1 + p) / den^2, pyfem.py:1325
         double gu[M][DIM], gv[M][DIM];                      // det * gradients of the two fields
 #pragma unroll
         for (int c = 0; c < M; ++c)
@@ -1144,7 +1143,8 @@ __global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, do
                               (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
             energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
         }
-        const double t = dr * energy / det;  // (gu / det) . (gv / det) * det * w, w = 1
+        // ramp' * (gu / det) . (gv / det) * det * w with w = 1: one reciprocal for both quotients
+        const double t = (1.0 + prm.mat.p) * energy * fast_rcp(den * den * det);
 #pragma unroll
         for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
     });
@@ -1189,8 +1189,7 @@ struct SensOp {
 #pragma unroll
                 for (int a = 0; a < NNE; ++a) rq = fma(Elem<NNE>::N(Q, a), fe[a * FW], rq);
             }
-            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);
-            const double dr = (1.0 + prm.mat.p) / (den * den);  // ramp'(rho_q), pyfem.py:1325
+            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);  // ramp'(rho_q) = (1 + p) / den^2, pyfem.py:1325
             double gu[MF][DIM], gv[MF][DIM];                    // det * gradients of the two fields
 #pragma unroll
             for (int c = 0; c < MF; ++c)
@@ -1222,7 +1221,7 @@ struct SensOp {
                                   (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
                 energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
             }
-            const double t = dr * energy / det;  // (gu / det) . (gv / det) * det * w, w = 1
+            const double t = (1.0 + prm.mat.p) * energy * fast_rcp(den * den * det);
 #pragma unroll
             for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
         });
@@ -1676,47 +1675,46 @@ extern "C" int pfg_element_matrices(pfg_mesh* mesh, int physics, const double* f
     return PFG_ERR_INVALID;
 }
 
-extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
-                             const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
-                             double* out_dev, void* stream) {
-    PFG_CHECK_MESH(mesh);
-    const MeshDev& d = mesh->d;
+static int sens_params(const MeshDev& d, int physics, const double* rho_dev, double rho_const, double p,
+                       const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
+                       const double* out_dev, const char* who, SensParams* prm, int* mf) {
     if (!phi_dev || !psi_dev || !out_dev) {
-        set_error("pfg_k_dv_sens: NULL argument");
+        set_error("%s: NULL argument", who);
         return PFG_ERR_INVALID;
     }
-    // elasticity: phi / psi carry ndims entries per node whatever the handle's own dof count -- a scalar handle of the
-    // same mesh is accepted too (and preferred: its tile plan has the nodal-vector codes the deterministic pass needs)
+    // elasticity: phi / psi carry ndims entries per node whatever the handle's own dof count
     if ((physics == PFG_PHYS_POISSON && d.m != 1) || (physics == PFG_PHYS_ELASTICITY && d.m != d.ndims && d.m != 1) ||
         (physics != PFG_PHYS_POISSON && physics != PFG_PHYS_ELASTICITY)) {
-        set_error("pfg_k_dv_sens: physics %d does not fit a handle with %d dofs per node", physics, d.m);
+        set_error("%s: physics %d does not fit a handle with %d dofs per node", who, physics, d.m);
         return PFG_ERR_INVALID;
     }
-    const int mf = (physics == PFG_PHYS_POISSON) ? 1 : d.ndims;  // entries of phi / psi per node
-    cudaStream_t st = (cudaStream_t)stream;
-    SensParams prm{material_of(rho_dev, rho_const, p), phi_dev, psi_dev, 0.0, 0.0, 0.0};
+    *mf = (physics == PFG_PHYS_POISSON) ? 1 : d.ndims;  // entries of phi / psi per node
+    *prm = SensParams{material_of(rho_dev, rho_const, p), phi_dev, psi_dev, 0.0, 0.0, 0.0};
     if (physics == PFG_PHYS_ELASTICITY) {
         const double E = (params_host && nparams > 0) ? params_host[0] : 10.0;
         const double nu = (params_host && nparams > 1) ? params_host[1] : 0.3;
         if (d.ndims == 2) {  // plane stress (pyfem.py:1746-1750)
             const double f = E / (1.0 - nu * nu);
-            prm.c11 = f, prm.c12 = f * nu, prm.c33 = f * 0.5 * (1.0 - nu);
+            prm->c11 = f, prm->c12 = f * nu, prm->c33 = f * 0.5 * (1.0 - nu);
         } else {  // pyfem.py:1752-1757
             const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
-            prm.c11 = f * (1.0 - nu), prm.c12 = f * nu, prm.c33 = f * (0.5 - nu);
+            prm->c11 = f * (1.0 - nu), prm->c12 = f * nu, prm->c33 = f * (0.5 - nu);
         }
     }
+    return PFG_OK;
+}
+
+extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
+                             const double* params_host, int nparams, const double* phi_dev, const double* psi_dev,
+                             double* out_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    SensParams prm;
+    int mf = 1;
+    PFG_TRY(sens_params(d, physics, rho_dev, rho_const, p, params_host, nparams, phi_dev, psi_dev, out_dev,
+                        "pfg_k_dv_sens", &prm, &mf));
+    cudaStream_t st = (cudaStream_t)stream;
     const MeshView mv = view_of(d);
-    static const bool force_atomic = getenv("PFG_SENS_ATOMIC") != nullptr;  // development aid
-    if (d.m == 1 && d.tile_dir != nullptr && !force_atomic) {
-        // deterministic pass on the tile plan of a scalar handle: window staging + plan-ordered nodal sums
-        Outputs out{{nullptr, nullptr}, out_dev};
-        MeshDev& dm = const_cast<MeshDev&>(d);
-        if (d.nne == 4 && mf == 1) return launch_tile<SensOp<4, 1>, 128, 4>(dm, mv, prm, out, st);
-        if (d.nne == 4) return launch_tile<SensOp<4, 2>, 128, 3>(dm, mv, prm, out, st);
-        if (mf == 1) return launch_tile<SensOp<8, 1>, 128, 2>(dm, mv, prm, out, st);
-        return launch_tile<SensOp<8, 3>, 128, 2>(dm, mv, prm, out, st);
-    }
     PFG_CUDA_TRY(cudaMemsetAsync(out_dev, 0, (d.own_end - d.own_begin) * sizeof(double), st));
     const unsigned grid = (unsigned)((d.nelems + 127) / 128);
     if (d.nne == 4 && mf == 1) k_dv_sens<4, 1><<<grid, 128, 0, st>>>(mv, prm, out_dev);
@@ -1725,6 +1723,30 @@ extern "C" int pfg_k_dv_sens(pfg_mesh* mesh, int physics, const double* rho_dev,
     else k_dv_sens<8, 3><<<grid, 128, 0, st>>>(mv, prm, out_dev);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
+}
+
+extern "C" int pfg_k_dv_sens_ordered(pfg_mesh* mesh, int physics, const double* rho_dev, double rho_const, double p,
+                                     const double* params_host, int nparams, const double* phi_dev,
+                                     const double* psi_dev, double* out_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    SensParams prm;
+    int mf = 1;
+    PFG_TRY(sens_params(d, physics, rho_dev, rho_const, p, params_host, nparams, phi_dev, psi_dev, out_dev,
+                        "pfg_k_dv_sens_ordered", &prm, &mf));
+    if (d.m != 1 || d.tile_dir == nullptr) {
+        set_error("pfg_k_dv_sens_ordered: needs a scalar handle (ndof_per_node == 1) with a gather plan: its tile plan "
+                  "carries the nodal-vector codes of the plan-ordered sums");
+        return PFG_ERR_UNSUPPORTED;
+    }
+    const MeshView mv = view_of(d);
+    Outputs out{{nullptr, nullptr}, out_dev};
+    MeshDev& dm = const_cast<MeshDev&>(d);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d.nne == 4 && mf == 1) return launch_tile<SensOp<4, 1>, 128, 4>(dm, mv, prm, out, st);
+    if (d.nne == 4) return launch_tile<SensOp<4, 2>, 128, 3>(dm, mv, prm, out, st);
+    if (mf == 1) return launch_tile<SensOp<8, 1>, 128, 2>(dm, mv, prm, out, st);
+    return launch_tile<SensOp<8, 3>, 128, 2>(dm, mv, prm, out, st);
 }
 
 extern "C" int pfg_scatter_matrix(pfg_mesh* mesh, const double* Ke_dev, double* vals_dev, int mode, void* stream) {

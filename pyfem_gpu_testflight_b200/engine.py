@@ -313,11 +313,12 @@ class DeviceMesh:
                 int(par.size), _ptr(Ke), _ptr(Ke2), _ptr(fe), self._stream()))
         return Ke, Ke2, fe
 
-    def k_dv_sens(self, physics, rho, p, phi, psi, E=10.0, nu=0.3, out=None):
+    def k_dv_sens(self, physics, rho, p, phi, psi, E=10.0, nu=0.3, out=None, deterministic=False):
         """d(phi^T K(rho) psi)/d rho at the owned nodes (the reference's _compute_K_dv_sens, pyfem.py:1239-1276 and
         1872-1920), fused on the device.  physics: "poisson" (scalar handle) or "elasticity" (a handle with ndims dofs
-        per node: element-per-thread pass with atomic nodal adds; or a scalar handle of the same mesh: node-window
-        staging + plan-ordered nodal sums, deterministic)."""
+        per node, or a scalar handle of the same mesh).  Default: element-per-thread pass with atomic nodal adds.
+        deterministic=True (scalar handles with a gather plan): node-window staging of rho / phi / psi and
+        plan-ordered nodal sums -- bitwise reproducible, measured ~1.5x slower (pfg_k_dv_sens_ordered)."""
         torch = _torch()
         code = {"poisson": _lib.PHYS_POISSON, "elasticity": _lib.PHYS_ELASTICITY}[physics]
         rho_t, rho_c = self._rho(rho)
@@ -329,9 +330,10 @@ class DeviceMesh:
         if out is None:
             out = torch.empty(self.own_end - self.own_begin, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            _lib.check(self._lib.pfg_k_dv_sens(self._handle, code, _ptr(rho_t), rho_c, float(p),
-                                               par.ctypes.data_as(ctypes.POINTER(c_double)), 2, _ptr(phi_t),
-                                               _ptr(psi_t), _ptr(out), self._stream()))
+            fn = self._lib.pfg_k_dv_sens_ordered if deterministic else self._lib.pfg_k_dv_sens
+            _lib.check(fn(self._handle, code, _ptr(rho_t), rho_c, float(p),
+                          par.ctypes.data_as(ctypes.POINTER(c_double)), 2, _ptr(phi_t), _ptr(psi_t), _ptr(out),
+                          self._stream()))
         return out
 
     # ---- multi-GPU reduce variant (halo.py) ---------------------------------------------------------

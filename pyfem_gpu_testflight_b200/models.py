@@ -276,10 +276,11 @@ class _DensityFunctions:
     def volume_grad(self, rho):
         return np.ones(self.nnodes) / self.nnodes
 
+    deterministic_sens = False  # True: plan-ordered nodal sums (bitwise reproducible) instead of atomic adds
+
     def _sens_mesh(self):
-        """The handle the sensitivity pass runs on: a scalar handle (one dof row per node), whose tile plan carries
-        the nodal-vector codes of the deterministic pass.  For elasticity it is a second handle of the same mesh,
-        built on first use (once per model)."""
+        """The handle of the deterministic sensitivity pass: a scalar handle (one dof row per node), whose tile plan
+        carries the nodal-vector codes.  For elasticity it is a second handle of the same mesh, built on first use."""
         if self.ndof_per_node == 1:
             return self.mesh
         if getattr(self, "_scalar_mesh", None) is None:
@@ -291,7 +292,8 @@ class _DensityFunctions:
         if self.slab is not None:
             raise NotImplementedError("sensitivities of a slab-partitioned model are not implemented")
         rho = np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho
-        return self._sens_mesh().k_dv_sens(physics, rho, self.p, phi, psi, **kw).cpu().numpy()
+        mesh = self._sens_mesh() if self.deterministic_sens else self.mesh
+        return mesh.k_dv_sens(physics, rho, self.p, phi, psi, deterministic=self.deterministic_sens, **kw).cpu().numpy()
 
 
 def _check_real(rho):

@@ -132,11 +132,13 @@ def test_sensitivity_paths_agree_and_tile_path_is_reproducible(pf, three_d):
     ref = orc.elasticity_K_dv_sens(X, conn, rho, 3.0, phi, psi, 8.0, 0.31)
     vec, sca = pf.DeviceMesh(X, conn, d), pf.DeviceMesh(X, conn, 1)
     ga = vec.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31)
-    gt = sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31)
-    assert torch.equal(gt, sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31))
+    gt = sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31, deterministic=True)
+    assert torch.equal(gt, sca.k_dv_sens("elasticity", rho, 3.0, phi, psi, E=8.0, nu=0.31, deterministic=True))
+    with pytest.raises(NotImplementedError):
+        vec.k_dv_sens("elasticity", rho, 3.0, phi, psi, deterministic=True)  # needs the scalar handle's plan
     assert_values_close(ga.cpu().numpy(), ref, VAL_TOL, "atomic pass")
     assert_values_close(gt.cpu().numpy(), ref, VAL_TOL, "tile pass")
-    gc = sca.k_dv_sens("elasticity", 0.6, 3.0, phi, psi, E=8.0, nu=0.31)  # constant density
+    gc = sca.k_dv_sens("elasticity", 0.6, 3.0, phi, psi, E=8.0, nu=0.31, deterministic=True)  # constant density
     assert_values_close(gc.cpu().numpy(), orc.elasticity_K_dv_sens(X, conn, np.full(nn, 0.6), 3.0, phi, psi, 8.0, 0.31),
                         VAL_TOL, "constant rho")
     out = []
@@ -145,5 +147,15 @@ def test_sensitivity_paths_agree_and_tile_path_is_reproducible(pf, three_d):
         mesh = pf.DeviceMesh(part.X, part.conn, 1, own_range=part.own_range, node_gid=part.node_gid,
                              ncols_nodes=part.nnodes_global)
         dof = (part.node_gid[:, None] * d + np.arange(d)[None, :]).ravel()
-        out.append(mesh.k_dv_sens("elasticity", rho[part.node_gid], 3.0, phi[dof], psi[dof], E=8.0, nu=0.31).cpu().numpy())
+        out.append(mesh.k_dv_sens("elasticity", rho[part.node_gid], 3.0, phi[dof], psi[dof], E=8.0, nu=0.31,
+                                  deterministic=True).cpu().numpy())
     assert_values_close(np.concatenate(out), ref, VAL_TOL, "slabs")
+    # through the model: deterministic_sens switches compliance_grad's kernel to the plan-ordered pass
+    q, b = _objs(pf, conn.shape[1])
+    model = pf.LinearElasticity(X, conn, [0], None, {0: [0.0] * d}, q, b, E=8.0, nu=0.31, p=3.0)
+    g_atomic = model._compute_K_dv_sens(rho, phi, psi)
+    model.deterministic_sens = True
+    g_ordered = model._compute_K_dv_sens(rho, phi, psi)
+    assert np.array_equal(g_ordered, model._compute_K_dv_sens(rho, phi, psi))
+    assert_values_close(g_atomic, ref, VAL_TOL)
+    assert_values_close(g_ordered, ref, VAL_TOL)
