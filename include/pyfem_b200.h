@@ -169,6 +169,20 @@ PFG_API int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, int n
  *   pfg_poisson_rhs  takes g at those points, (nelems, nquads), and writes
  *                    rhs[i] = sum_e sum_q detJ w N g for the owned rows.
  */
+/*
+ * K(rho) for a COMPLEX nodal density: the reference's complex-step checks (pyfem.py:1018-1020, 1289-1292, 1783-1785,
+ * 1933-1936; tests/test_linear_poisson.py:57-89, tests/test_elasticity.py:68-104) call compute_jacobian(rho + 1j h p)
+ * and read dK/drho . p off the imaginary part.  The element matrices are real multiples of the complex RAMP factor
+ * c(rho_q) = rho_q / (1 + p (1 - rho_q)), so Re K and Im K are two real assemblies, one per part of the factor.
+ *   rho_re_dev, rho_im_dev  (nnodes,) both parts of the nodal density
+ *   vals_re_dev, vals_im_dev (nnz,) CSR values of Re K and Im K (either may be NULL)
+ * Slot-indexed atomic scatter (this is a verification path, not a hot one); any mesh the handle was built for.
+ */
+PFG_API int pfg_assemble_poisson_complex(pfg_mesh* mesh, const double* rho_re_dev, const double* rho_im_dev, double p,
+                                         double* vals_re_dev, double* vals_im_dev, void* stream);
+PFG_API int pfg_assemble_elasticity_complex(pfg_mesh* mesh, const double* rho_re_dev, const double* rho_im_dev, double p,
+                                            double E, double nu, double* vals_re_dev, double* vals_im_dev, void* stream);
+
 PFG_API int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream);
 PFG_API int pfg_poisson_rhs(pfg_mesh* mesh, const double* gq_dev, double* rhs_dev, int mode, void* stream);
 

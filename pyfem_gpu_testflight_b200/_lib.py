@@ -49,6 +49,9 @@ PROTOTYPES = {
     "pfg_assemble_helmholtz": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_assemble_nlpoisson": (c_int, [c_void_p, POINTER(c_double), c_int, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]),
+    "pfg_assemble_poisson_complex": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
+    "pfg_assemble_elasticity_complex": (c_int, [c_void_p, c_void_p, c_void_p, c_double, c_double, c_double, c_void_p,
+                                                c_void_p, c_void_p]),
     "pfg_quad_points": (c_int, [c_void_p, c_void_p, c_void_p]),
     "pfg_poisson_rhs": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_apply_dirichlet": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p]),

@@ -149,6 +149,25 @@ __global__ void __launch_bounds__(128) k_assemble_atomic(MeshView mv, typename O
     Op::run(prm, xe, fe, e, sink);
 }
 
+// complex nodal density (complex-step verification, pyfem.py:1018-1020): the same scatter with one part of the
+// complex RAMP factor per pass (prm.mat.part); Poisson and quad4 elasticity operators
+template <class Op>
+__global__ void __launch_bounds__(128) k_assemble_atomic_complex(MeshView mv, typename Op::Params prm, Outputs out) {
+    const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (e >= mv.nelems) return;
+    if (mv.elem_skip != nullptr && mv.elem_skip[e]) return;
+    constexpr int NNE = Op::NNE;
+    int nodes[NNE];
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
+    AtomicSink<Op> sink(mv, out, nodes, e);
+    double xe[NNE][Elem<NNE>::DIM], fe[NNE], fi[NNE];
+    load_coords<NNE>(mv.X, nodes, xe);
+    load_field<NNE>(prm.mat.rho, nodes, fe);
+    load_field<NNE>(prm.mat.rho_im, nodes, fi);
+    Op::run_complex(prm, xe, fe, fi, sink);
+}
+
 // element matrices only (no scatter): one thread per element
 template <class Op>
 __global__ void __launch_bounds__(128) k_element_matrices(MeshView mv, typename Op::Params prm, double* Ke0, double* Ke1,
@@ -1570,6 +1589,70 @@ extern "C" int pfg_assemble_nlpoisson(pfg_mesh* mesh, const double* xdv_host, in
     }
     Outputs out{{K_vals_dev, nullptr}, res_dev};
     return launch<NlPoissonQuad4Op, 128, 3>(d, prm, out, gather, (cudaStream_t)stream);
+}
+
+// K(rho) for a COMPLEX nodal density (the reference's complex-step checks, pyfem.py:1018-1020 / 1783-1785 with
+// tests/test_linear_poisson.py:57-89, tests/test_elasticity.py:68-104): the element matrices are real multiples of the
+// complex RAMP factor, so the real and imaginary parts of K are two real assemblies, each with one part of the factor.
+template <class Op>
+static int launch_complex(const MeshDev& d, typename Op::Params prm, double* vals_re, double* vals_im, cudaStream_t st) {
+    const MeshView mv = view_of(d);
+    const unsigned grid = (unsigned)((d.nelems + 127) / 128);
+    double* outs[2] = {vals_re, vals_im};
+    for (int part = 0; part < 2; ++part) {
+        if (!outs[part]) continue;
+        Outputs out{{outs[part], nullptr}, nullptr};
+        PFG_TRY(zero_outputs(d, out, st));
+        prm.mat.part = part;
+        k_assemble_atomic_complex<Op><<<grid, 128, 0, st>>>(mv, prm, out);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+
+extern "C" int pfg_assemble_poisson_complex(pfg_mesh* mesh, const double* rho_re_dev, const double* rho_im_dev, double p,
+                                            double* vals_re_dev, double* vals_im_dev, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != 1 || !rho_re_dev || !rho_im_dev || (!vals_re_dev && !vals_im_dev)) {
+        set_error("pfg_assemble_poisson_complex: needs ndof_per_node == 1, both parts of rho and an output");
+        return PFG_ERR_INVALID;
+    }
+    Material mat = material_of(rho_re_dev, 0.0, p);
+    mat.rho_im = rho_im_dev;
+    if (d.nne == 4) return launch_complex<PoissonOp<4>>(d, {mat}, vals_re_dev, vals_im_dev, (cudaStream_t)stream);
+    return launch_complex<PoissonOp<8>>(d, {mat}, vals_re_dev, vals_im_dev, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_assemble_elasticity_complex(pfg_mesh* mesh, const double* rho_re_dev, const double* rho_im_dev,
+                                               double p, double E, double nu, double* vals_re_dev, double* vals_im_dev,
+                                               void* stream) {
+    PFG_CHECK_MESH(mesh);
+    const MeshDev& d = mesh->d;
+    if (d.m != d.ndims || !rho_re_dev || !rho_im_dev || (!vals_re_dev && !vals_im_dev)) {
+        set_error("pfg_assemble_elasticity_complex: needs ndof_per_node == ndims, both parts of rho and an output");
+        return PFG_ERR_INVALID;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    Material mat = material_of(rho_re_dev, 0.0, p);
+    mat.rho_im = rho_im_dev;
+    if (d.nne == 4) {
+        const double f = E / (1.0 - nu * nu);
+        return launch_complex<ElasticityQuad4Op>(d, {mat, f, f * nu, f * 0.5 * (1.0 - nu)}, vals_re_dev, vals_im_dev, st);
+    }
+    const double f = E / ((1.0 + nu) * (1.0 - 2.0 * nu));
+    ElasticityHex8Params prm{mat, f * (1.0 - nu), f * nu, f * (0.5 - nu)};
+    const MeshView mv = view_of(d);
+    double* outs[2] = {vals_re_dev, vals_im_dev};
+    for (int part = 0; part < 2; ++part) {
+        if (!outs[part]) continue;
+        Outputs out{{outs[part], nullptr}, nullptr};
+        PFG_TRY(zero_outputs(d, out, st));
+        prm.mat.part = part;
+        k_elasticity_hex8_atomic<<<(unsigned)((d.nelems + 15) / 16), 128, 0, st>>>(mv, prm, out);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
 }
 
 extern "C" int pfg_quad_points(pfg_mesh* mesh, double* Xq_dev, void* stream) {

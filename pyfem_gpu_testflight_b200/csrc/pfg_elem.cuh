@@ -229,7 +229,27 @@ struct Material {
     const double* rho;  // nodal field or nullptr
     double rho_const, p;
     double c_const;  // RAMP factor of the constant field, rho_const / (1 + p (1 - rho_const)), formed once on the host
+    // complex-step verification (pyfem.py:1018-1020, 1289-1292): imaginary part of a complex nodal field, and which
+    // part of the complex RAMP factor this pass integrates (0 real, 1 imaginary).  nullptr on the real path.
+    const double* rho_im = nullptr;
+    int part = 0;
 };
+
+// c = rho / (1 + p (1 - rho)) for complex rho = rr + i ri, real or imaginary part
+PFG_DEV double ramp_complex_part(double rr, double ri, double p, int part) {
+    const double dr = fma(p, 1.0 - rr, 1.0), di = -p * ri;  // denominator
+    const double inv = 1.0 / (dr * dr + di * di);
+    return (part == 0 ? (rr * dr + ri * di) : (ri * dr - rr * di)) * inv;
+}
+
+template <int NNE>
+PFG_DEV void material_at_quads_complex(const Material& mat, const double (&re)[NNE], const double (&im)[NNE],
+                                       double (&cq)[Elem<NNE>::NQ]) {
+    for_each_q<Elem<NNE>::NQ>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        cq[Q] = ramp_complex_part(interp<NNE, Q>(re), interp<NNE, Q>(im), mat.p, mat.part);
+    });
+}
 
 template <int NNE>
 PFG_DEV void material_at_quads(const Material& mat, const double (&re)[NNE], double (&cq)[Elem<NNE>::NQ]) {
@@ -299,6 +319,17 @@ struct PoissonOp {  // LinearPoisson._compute_element_jacobian (pyfem.py:1188-12
                             Sink& sink) {
         double cq[NQ];
         material_at_quads<NNE>(prm.mat, fe, cq);
+        integrate(xe, cq, sink);
+    }
+    template <class Sink>  // complex nodal density: one part of the complex RAMP factor per pass
+    PFG_DEV static void run_complex(const Params& prm, const double (&xe)[NNE][DIM], const double (&fe)[NNE],
+                                    const double (&fi)[NNE], Sink& sink) {
+        double cq[NQ];
+        material_at_quads_complex<NNE>(prm.mat, fe, fi, cq);
+        integrate(xe, cq, sink);
+    }
+    template <class Sink>
+    PFG_DEV static void integrate(const double (&xe)[NNE][DIM], const double (&cq)[NQ], Sink& sink) {
         double K[NNE][NNE];
 #pragma unroll
         for (int a = 0; a < NNE; ++a)
@@ -388,6 +419,17 @@ struct ElasticityQuad4Op {  // plane stress, LinearElasticity._compute_element_j
     PFG_DEV static void run(const Params& prm, const double (&xe)[4][2], const double (&fe)[4], int64_t, Sink& sink) {
         double cq[4];
         material_at_quads<4>(prm.mat, fe, cq);
+        integrate(prm, xe, cq, sink);
+    }
+    template <class Sink>  // complex nodal density: one part of the complex RAMP factor per pass
+    PFG_DEV static void run_complex(const Params& prm, const double (&xe)[4][2], const double (&fe)[4],
+                                    const double (&fi)[4], Sink& sink) {
+        double cq[4];
+        material_at_quads_complex<4>(prm.mat, fe, fi, cq);
+        integrate(prm, xe, cq, sink);
+    }
+    template <class Sink>
+    PFG_DEV static void integrate(const Params& prm, const double (&xe)[4][2], const double (&cq)[4], Sink& sink) {
         // Partition of unity: sum_a grad N_a = 0 at every point, so every row of the element matrix sums to zero.  Only
         // the node pairs among the first three nodes are integrated -- XX, YY (symmetric, 6 each) and XY (all 9;
         // YX[a][b] = XY[b][a]) -- and the blocks of the fourth node follow from the row / column sums: 21 instead of
@@ -698,7 +740,14 @@ PFG_DEV void elasticity_hex8_octet(const MeshView& mv, const ElasticityHex8Param
             double rq = 0.0;
 #pragma unroll
             for (int a = 0; a < 8; ++a) rq = fma(shape[a], __ldg(prm.mat.rho + nodes[a]), rq);
-            cq = rq * fast_rcp(fma(prm.mat.p, 1.0 - rq, 1.0));
+            if (prm.mat.rho_im == nullptr) {
+                cq = rq * fast_rcp(fma(prm.mat.p, 1.0 - rq, 1.0));
+            } else {  // complex-step verification: one part of the complex RAMP factor per pass
+                double iq = 0.0;
+#pragma unroll
+                for (int a = 0; a < 8; ++a) iq = fma(shape[a], __ldg(prm.mat.rho_im + nodes[a]), iq);
+                cq = ramp_complex_part(rq, iq, prm.mat.p, prm.mat.part);
+            }
         }
     }
     double* mine = stage + lane8 * 25;

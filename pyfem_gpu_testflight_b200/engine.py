@@ -162,8 +162,34 @@ class DeviceMesh:
             return None, float(rho)
         return self._dev_f64(rho, self.nnodes, "rho"), 0.0
 
+    def _complex_parts(self, rho):
+        """(real, imaginary) device tensors of a complex nodal density, or None for real input.  Complex scalars are
+        constant fields (pyfem.py:1015-1016)."""
+        torch = _torch()
+        is_complex = rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho)
+        if not is_complex:
+            return None
+        t = torch.as_tensor(rho).to(device=self.device, dtype=torch.complex128).reshape(-1)
+        if t.numel() == 1:
+            t = t.expand(self.nnodes)
+        if t.numel() != self.nnodes:
+            raise ValueError(f"rho must have {self.nnodes} entries, got {t.numel()}")
+        return t.real.contiguous(), t.imag.contiguous()
+
+    def _assemble_complex(self, fn, parts, *args):
+        """K for complex rho (complex-step verification): Re K and Im K as two real assemblies, returned as one
+        complex128 tensor of CSR values."""
+        torch = _torch()
+        re, im = self.new_values(), self.new_values()
+        with torch.cuda.device(self.device):
+            _lib.check(fn(self._handle, _ptr(parts[0]), _ptr(parts[1]), *args, _ptr(re), _ptr(im), self._stream()))
+        return torch.complex(re, im)
+
     def assemble_poisson(self, rho=1.0, p=0.0, out=None, mode="auto"):
         torch = _torch()
+        parts = self._complex_parts(rho)
+        if parts is not None:
+            return self._assemble_complex(self._lib.pfg_assemble_poisson_complex, parts, float(p))
         rho_t, rho_c = self._rho(rho)
         out = self.new_values() if out is None else out
         with torch.cuda.device(self.device):
@@ -173,6 +199,9 @@ class DeviceMesh:
 
     def assemble_elasticity(self, rho=1.0, p=0.0, E=10.0, nu=0.3, out=None, mode="auto"):
         torch = _torch()
+        parts = self._complex_parts(rho)
+        if parts is not None:
+            return self._assemble_complex(self._lib.pfg_assemble_elasticity_complex, parts, float(p), float(E), float(nu))
         rho_t, rho_c = self._rho(rho)
         out = self.new_values() if out is None else out
         with torch.cuda.device(self.device):
@@ -388,7 +417,9 @@ class DeviceMesh:
         torch = _torch()
         from scipy import sparse
         indptr, indices = self.pattern_host()
-        if out is None:
+        if vals.is_complex():  # complex-step verification: a fresh complex128 array
+            out = np.empty(self.nnz, dtype=np.complex128)
+        elif out is None:
             out = self._pinned_values() if reuse_host_buffers else np.empty(self.nnz, dtype=np.float64)
         data = out
         torch.from_numpy(data).copy_(vals)

@@ -296,9 +296,12 @@ class _DensityFunctions:
         return mesh.k_dv_sens(physics, rho, self.p, phi, psi, deterministic=self.deterministic_sens, **kw).cpu().numpy()
 
 
+def _is_complex(rho):
+    return bool(rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho))  # torch tensor or numpy
+
+
 def _check_real(rho):
-    is_complex = rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho)  # torch tensor or numpy
-    if is_complex:
+    if _is_complex(rho):
         raise NotImplementedError("complex rho (complex-step verification, pyfem.py:1019-1020) has no device "
                                   "path and this engine has no CPU fallback")
 
@@ -313,7 +316,10 @@ class LinearPoisson(_DensityFunctions, ModelBase):
         self.p = p
 
     def compute_jacobian_device(self, rho=1.0, out=None):
-        _check_real(rho)
+        """CSR values on the device.  A complex rho (the reference's complex-step checks, pyfem.py:1018-1020) yields
+        complex128 values: Re K and Im K from two real assemblies (single-GPU handles)."""
+        if _is_complex(rho) and self._reducer is not None:
+            raise NotImplementedError("complex rho with the reduce variant of a slab partition")
         return self._asm.assemble_poisson(self._local(rho), self.p, out=out, mode=self.scatter)
 
     def compute_jacobian(self, rho=1.0):
@@ -419,7 +425,9 @@ class LinearElasticity(_DensityFunctions, ModelBase):
         return self._owned(self.rhs)
 
     def compute_jacobian_device(self, rho=1.0, out=None):
-        _check_real(rho)
+        """CSR values on the device; complex rho (complex-step checks, pyfem.py:1783-1785) yields complex128 values."""
+        if _is_complex(rho) and self._reducer is not None:
+            raise NotImplementedError("complex rho with the reduce variant of a slab partition")
         return self._asm.assemble_elasticity(self._local(rho), self.p, self.E, self.nu, out=out, mode=self.scatter)
 
     def _compute_element_jacobian(self, Ke_mat, rho=1.0):

@@ -187,8 +187,8 @@ def test_bad_inputs_raise(pf):
     q, b = _objs(pf, 4)
     with pytest.raises(AssertionError):  # reference asserts conn.max() == nnodes-1 (pyfem.py:681)
         pf.LinearPoisson(np.vstack([X, [[9.0, 9.0]]]), conn, [0], None, q, b, gfunc)
-    with pytest.raises(NotImplementedError):  # complex-step rho has no device path and no CPU fallback
-        pf.LinearPoisson(X, conn, [0], None, q, b, gfunc).compute_jacobian(np.ones(16, dtype=complex))
+    with pytest.raises(NotImplementedError):  # sensitivities take a real density (the reference's do too)
+        pf.LinearPoisson(X, conn, [0], None, q, b, gfunc)._compute_K_dv_sens(np.ones(16, dtype=complex), X[:, 0], X[:, 1])
     with pytest.raises(NotImplementedError):
         pf.LinearPoisson(X, conn[:, :3], [0], None, q, b, gfunc)
 
@@ -324,3 +324,53 @@ def test_host_buffers_are_reused_but_never_aliased(pf):
     assert K3.nnz < nnz and K2.nnz == nnz and K2.indices.flags.writeable is False
     K4 = model.compute_jacobian(1.0)
     assert K4.nnz == nnz and np.array_equal(K4.indices, K2.indices)
+
+
+# ---- complex nodal density: the reference's complex-step checks run against the drop-in ------------------------------
+@pytest.mark.parametrize("kind", ["quad", "hex"])
+def test_complex_step_derivative_like_reference_tests(pf, kind):
+    """tests/test_linear_poisson.py:57-89 and tests/test_elasticity.py:68-104 (run_dKdx): K(rho + 1j h p) assembled with
+    a complex density, phi^T K psi read off the imaginary part, against _compute_K_dv_sens . p -- same seeds, same
+    h = 1e-30, same 1e-12 bound.  The complex matrix itself is checked against the oracle evaluated in complex
+    arithmetic (pattern bit-exact, both parts within 1e-12)."""
+    creator = pf.ProblemCreator(nnodes_x=13, nnodes_y=11) if kind == "quad" else pf.ProblemCreator(7, 7, 7)
+    q, b = _objs(pf, 4 if kind == "quad" else 8)
+    h = 1e-30
+    conn, X, dof_fixed = creator.create_poisson_problem()
+    model = pf.LinearPoisson(X, conn, dof_fixed, None, q, b, gfunc, p=5.0)
+    np.random.seed(0)
+    nn = X.shape[0]
+    phi, psi = np.random.rand(nn), np.random.rand(nn)
+    rho, pert = np.random.rand(nn), np.random.rand(nn)
+    dfdrho = pert.dot(model._compute_K_dv_sens(rho, phi, psi))
+    K = model.compute_jacobian(rho + 1j * pert * h)
+    assert K.dtype == np.complex128
+    dfdrho_cs = phi.dot(K.dot(psi)).imag / h
+    assert abs((dfdrho - dfdrho_cs) / dfdrho) <= 1e-12
+    Kref = orc.assemble_poisson(X, conn, rho + 1j * pert * 0.25, 5.0)  # a finite imaginary part for the value check
+    K = model.compute_jacobian(rho + 1j * pert * 0.25)
+    assert_pattern_equal(K.indptr, K.indices, Kref.indptr, Kref.indices)
+    assert_values_close(K.data.real, Kref.data.real, VAL_TOL, "Re K")
+    assert_values_close(K.data.imag, Kref.data.imag, VAL_TOL, "Im K")
+    # a real density through the same call stays real and takes the gather path
+    assert model.compute_jacobian(rho).dtype == np.float64
+
+    conn, X, dof_fixed, nodal_force = creator.create_linear_elasticity_problem()
+    model = pf.LinearElasticity(X, conn, dof_fixed, None, nodal_force, q, b, p=5.0)
+    np.random.seed(0)
+    ndof = X.shape[0] * X.shape[1]
+    phi, psi = np.random.rand(ndof), np.random.rand(ndof)
+    rho, pert = np.random.rand(nn), np.random.rand(nn)
+    dfdrho = pert.dot(model._compute_K_dv_sens(rho, phi, psi))
+    K = model.compute_jacobian(rho + 1j * pert * h)
+    dfdrho_cs = phi.dot(K.dot(psi)).imag / h
+    assert abs((dfdrho - dfdrho_cs) / dfdrho) <= 1e-12
+    Kref = orc.assemble_elasticity(X, conn, rho + 1j * pert * 0.25, 5.0)
+    K = model.compute_jacobian(rho + 1j * pert * 0.25)
+    assert_pattern_equal(K.indptr, K.indices, Kref.indptr, Kref.indices)
+    assert_values_close(K.data.real, Kref.data.real, VAL_TOL, "Re K")
+    assert_values_close(K.data.imag, Kref.data.imag, VAL_TOL, "Im K")
+    # a complex scalar is a constant complex field (pyfem.py:1015-1016)
+    Kc = model.compute_jacobian(0.7 + 0.1j)
+    Kcr = orc.assemble_elasticity(X, conn, np.full(nn, 0.7 + 0.1j), 5.0)
+    assert_values_close(Kc.data.imag, Kcr.data.imag, VAL_TOL, "constant complex rho")

@@ -133,3 +133,30 @@ def test_dirichlet_host_matches_reference(symmetric, with_vals):
     assert np.array_equal(Km.indptr, Kr.indptr) and np.array_equal(Km.indices, Kr.indices)
     assert_values_close(Km.data, Kr.data, 1e-15)
     assert_values_close(rm2, rr, 1e-14)
+
+
+@pytest.mark.skipif(not ref_import.available(), reason="reference tree not present (GPU box)")
+def test_oracle_complex_density_matches_reference():
+    """The oracle evaluated in complex arithmetic is what the GPU's complex-rho assembly is checked against
+    (tests/test_gpu_parity.py::test_complex_step_derivative_like_reference_tests): pin it to the unmodified reference's
+    complex-step path (pyfem.py:1018-1020, 1289-1292, 1783-1785, 1933-1936) on quad and hex meshes."""
+    ref = ref_import.load()
+    for dims in ((9, 7), (5, 4, 6)):
+        three_d = len(dims) == 3
+        c = ref.ProblemCreator(*dims, element_type="block" if three_d else "quad")
+        q = ref.QuadratureBlock3D() if three_d else ref.QuadratureBilinear2D()
+        b = ref.BasisBlock3D(q) if three_d else ref.BasisBilinear2D(q)
+        rng = np.random.default_rng(0)
+        conn, X, dof_fixed = c.create_poisson_problem()
+        rho = rng.random(X.shape[0]) + 1j * 0.25 * rng.random(X.shape[0])
+        Kr = ref.LinearPoisson(X, conn, dof_fixed, None, q, b, lambda xq: 1.0, p=5.0).compute_jacobian(rho)
+        Ko = orc.assemble_poisson(np.asarray(X, dtype=float), np.asarray(conn), rho, 5.0)
+        assert np.array_equal(Kr.indices, Ko.indices) and Kr.dtype == Ko.dtype == np.complex128
+        assert_values_close(Ko.data.real, Kr.data.real, 1e-13)
+        assert_values_close(Ko.data.imag, Kr.data.imag, 1e-13)
+        conn, X, dof_fixed, force = c.create_linear_elasticity_problem()
+        Kr = ref.LinearElasticity(X, conn, dof_fixed, None, force, q, b, p=5.0).compute_jacobian(rho)
+        Ko = orc.assemble_elasticity(np.asarray(X, dtype=float), np.asarray(conn), rho, 5.0)
+        assert np.array_equal(Kr.indices, Ko.indices)
+        assert_values_close(Ko.data.real, Kr.data.real, 1e-13)
+        assert_values_close(Ko.data.imag, Kr.data.imag, 1e-13)
