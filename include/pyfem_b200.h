@@ -285,6 +285,16 @@ PFG_API int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, 
                    void* stream);
 
 /*
+ * Jacobi-preconditioned BiCGStab on the device CSR, for NON-SYMMETRIC systems: the Newton step of
+ * Assembler.solve_nonlinear (pyfem.py:2337-2353: K is the Jacobian of NonlinearPoisson2D, the reference solves it with
+ * gmres + pyamg or spsolve).  Same arguments and stopping rule as pfg_cg; x_dev is zero-filled here (x0 = 0).  Scalars
+ * stay on the device (one-thread kernels between the vector kernels); the host reads |r|^2 every check_every
+ * iterations (<= 0: 8).  PFG_ERR_NOCONV when max_iter is reached first.
+ */
+PFG_API int pfg_bicgstab(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, double rtol,
+                         double atol, int max_iter, int check_every, int* iters_out, double* resid_out, void* stream);
+
+/*
  * Diagnostics for the bench's roofline: sustained FP64 FMA throughput of `device` in TFLOP/s (a DFMA-bound kernel,
  * 8 CTAs of 256 threads per SM, 16 independent chains per thread, best of 4 timed launches with CUDA events).  The
  * assembly kernels run their quadrature on the FP64 CUDA cores, so this is the second roof next to HBM bandwidth

@@ -65,6 +65,8 @@ PROTOTYPES = {
                                      c_void_p, c_void_p]),
     "pfg_k_dv_sens": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, POINTER(c_double), c_int, c_void_p,
                               c_void_p, c_void_p, c_void_p]),
+    "pfg_bicgstab": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_double, c_double, c_int, c_int, POINTER(c_int),
+                             POINTER(c_double), c_void_p]),
     "pfg_k_dv_sens_ordered": (c_int, [c_void_p, c_int, c_void_p, c_double, c_double, POINTER(c_double), c_int, c_void_p,
                                       c_void_p, c_void_p, c_void_p]),
     "pfg_probe_fp64": (c_int, [c_int, c_int, POINTER(c_double), POINTER(c_double)]),

@@ -28,9 +28,13 @@ class Assembler:
         K, rhs = self.model.apply_dirichlet_bcs(K, rhs, enforce_symmetric_K=True)
         return self._solve_linear_system(K, rhs, method)
 
-    def solve_nonlinear(self, method="gmres", xdv=None, u0=None, tol=1e-10, atol=1e-12, max_iter=10):
-        """Newton iteration with Jacobian + residual re-assembled every step (pyfem.py:2319-2355)."""
+    def solve_nonlinear(self, method="gmres", xdv=None, u0=None, tol=1e-10, atol=1e-12, max_iter=10, device=False):
+        """Newton iteration with Jacobian + residual re-assembled every step (pyfem.py:2319-2355).  device=True: the
+        whole loop stays in HBM -- one fused assembly of Jacobian and residual, boundary conditions on the device CSR
+        (pattern kept), the step solved by Jacobi-preconditioned BiCGStab; only the residual norm crosses PCIe."""
         assert method in ("direct", "cg", "gmres")
+        if device:
+            return self._solve_nonlinear_device(xdv, u0, tol, atol, max_iter)
         u = np.zeros(self.model.nnodes) if u0 is None else u0
         res_norm_init = None
         for k in range(max_iter):
@@ -45,6 +49,27 @@ class Assembler:
                 break
             u -= self._solve_linear_system(K, res, method)
         return u
+
+    def _solve_nonlinear_device(self, xdv, u0, tol, atol, max_iter):
+        import torch
+        model, mesh = self.model, self.model.mesh
+        u = torch.zeros(model.nnodes, dtype=torch.float64, device=mesh.device) if u0 is None else \
+            torch.as_tensor(u0, dtype=torch.float64).to(mesh.device).clone()
+        res_norm_init = None
+        self.last_iterations = []
+        for k in range(max_iter):
+            K, res = model.assemble_device(xdv, u)  # Jacobian and residual from one pass over the elements
+            mesh.apply_dirichlet(K, res, model.dof_fixed, None, enforce_symmetric=False)
+            res_norm = float(torch.linalg.vector_norm(res))
+            print("pyfem", "{0:5d} {1:25.15e}".format(k, res_norm))
+            if k == 0:
+                res_norm_init = res_norm
+            elif res_norm < tol * res_norm_init or res_norm < atol:
+                break
+            du, iters, _ = mesh.bicgstab(K, res, rtol=1e-8)
+            self.last_iterations.append(iters)
+            u -= du
+        return u.cpu().numpy()
 
     def _setup_amg(self, K):
         try:

@@ -256,6 +256,85 @@ __global__ void k_apply_dirichlet(const int64_t* __restrict__ blk_ptr, const int
     }
 }
 
+// ---- BiCGStab (non-symmetric systems: the Newton Jacobian of NonlinearPoisson2D, pyfem.py:1595-1609) ---------------
+// Right-preconditioned with Jacobi.  Scalars live in a small device array `sc`: [0] rho, [1] alpha, [2] omega, [3] beta;
+// one-thread kernels turn the fixed-order partial sums into the next scalar, so an iteration never syncs with the host.
+__device__ __forceinline__ double serial_sum(const double* __restrict__ part, int n) {
+    double s = 0.0;
+    for (int i = 0; i < n; ++i) s += part[i];
+    return s;
+}
+__global__ void k_bicg_scalar(int which, int n_a, const double* __restrict__ part_a, int n_b,
+                              const double* __restrict__ part_b, double* __restrict__ sc) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) {  // start: rho = rhat . r, alpha = omega = 1, beta = 0
+        sc[0] = serial_sum(part_a, n_a), sc[1] = 1.0, sc[2] = 1.0, sc[3] = 0.0;
+    } else if (which == 1) {  // alpha = rho / (rhat . v)
+        const double d = serial_sum(part_a, n_a);
+        sc[1] = (d != 0.0) ? sc[0] / d : 0.0;
+    } else if (which == 2) {  // omega = (t . s) / (t . t)
+        const double tt = serial_sum(part_b, n_b);
+        sc[2] = (tt != 0.0) ? serial_sum(part_a, n_a) / tt : 0.0;
+    } else {  // beta = (rho_new / rho) (alpha / omega); rho = rho_new
+        const double rho_new = serial_sum(part_a, n_a);
+        sc[3] = (sc[0] != 0.0 && sc[2] != 0.0) ? (rho_new / sc[0]) * (sc[1] / sc[2]) : 0.0;
+        sc[0] = rho_new;
+    }
+}
+
+// p = r + beta (p - omega v); y = dinv p
+__global__ void __launch_bounds__(kVecThreads) k_bicg_p(int64_t n, const double* __restrict__ sc, const double* __restrict__ dinv,
+                                                        const double* __restrict__ r, const double* __restrict__ v,
+                                                        double* __restrict__ p, double* __restrict__ y) {
+    const double beta = sc[3], omega = sc[2];
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        const double pi = fma(beta, fma(-omega, v[i], p[i]), r[i]);
+        p[i] = pi, y[i] = dinv[i] * pi;
+    }
+}
+
+// s = r - alpha v; z = dinv s
+__global__ void __launch_bounds__(kVecThreads) k_bicg_s(int64_t n, const double* __restrict__ sc, const double* __restrict__ dinv,
+                                                        const double* __restrict__ r, const double* __restrict__ v,
+                                                        double* __restrict__ s_, double* __restrict__ z) {
+    const double alpha = sc[1];
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        const double si = fma(-alpha, v[i], r[i]);
+        s_[i] = si, z[i] = dinv[i] * si;
+    }
+}
+
+// partial sums of a . b and a . a
+__global__ void __launch_bounds__(kVecThreads) k_dot2_partials(int64_t n, const double* __restrict__ a, const double* __restrict__ b,
+                                                               double* __restrict__ part_ab, double* __restrict__ part_aa) {
+    __shared__ double red[kVecThreads / 32];
+    double ab = 0.0, aa = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        ab = fma(a[i], b[i], ab), aa = fma(a[i], a[i], aa);
+    }
+    const double x = block_sum(ab, red), y = block_sum(aa, red);
+    if (threadIdx.x == 0) part_ab[blockIdx.x] = x, part_aa[blockIdx.x] = y;
+}
+
+// x += alpha y + omega z; r = s - omega t; partial sums of rhat . r and r . r
+__global__ void __launch_bounds__(kVecThreads) k_bicg_x(int64_t n, const double* __restrict__ sc, const double* __restrict__ y,
+                                                        const double* __restrict__ z, const double* __restrict__ s_,
+                                                        const double* __restrict__ t, const double* __restrict__ rhat,
+                                                        double* __restrict__ x, double* __restrict__ r,
+                                                        double* __restrict__ part_rho, double* __restrict__ part_rr) {
+    __shared__ double red[kVecThreads / 32];
+    const double alpha = sc[1], omega = sc[2];
+    double rho = 0.0, rr = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)kVecThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kVecThreads) {
+        x[i] = fma(alpha, y[i], fma(omega, z[i], x[i]));
+        const double ri = fma(-omega, t[i], s_[i]);
+        r[i] = ri;
+        rho = fma(rhat[i], ri, rho), rr = fma(ri, ri, rr);
+    }
+    const double a = block_sum(rho, red), b = block_sum(rr, red);
+    if (threadIdx.x == 0) part_rho[blockIdx.x] = a, part_rr[blockIdx.x] = b;
+}
+
 static int ensure_solve_scratch(MeshDev& d, bool cg) {
     const int64_t ncols = d.ncols_nodes * d.m;
     if (!d.bc_fixed) {
@@ -265,8 +344,9 @@ static int ensure_solve_scratch(MeshDev& d, bool cg) {
     }
     if (cg && !d.cg_work) {
         const int64_t n = (d.own_end - d.own_begin) * d.m;
-        PFG_CUDA_TRY(cudaMalloc(&d.cg_work, (5 * std::max<int64_t>(n, 1) + 5 * kMaxPartials) * sizeof(double)));
-        d.device_bytes += (5 * n + 5 * kMaxPartials) * (int64_t)sizeof(double);
+        // CG uses five vectors, BiCGStab nine; then the partial-sum arrays and a few device scalars
+        PFG_CUDA_TRY(cudaMalloc(&d.cg_work, (9 * std::max<int64_t>(n, 1) + 8 * kMaxPartials + 16) * sizeof(double)));
+        d.device_bytes += (9 * n + 8 * kMaxPartials + 16) * (int64_t)sizeof(double);
     }
     return PFG_OK;
 }
@@ -366,7 +446,7 @@ extern "C" int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_de
     const int64_t n = d.nnodes * d.m, nown = d.nnodes;
     double* r = d.cg_work;
     double *z = r + n, *p = z + n, *Ap = p + n, *dinv = Ap + n;
-    double* parts = dinv + n;  // [0] p.Ap (one per SpMV CTA, capped), [1..2] r.z ping-pong, [3] r.r, [4] |b|^2
+    double* parts = r + 9 * n;  // [0] p.Ap (one per SpMV CTA, capped), [1..2] r.z ping-pong, [3] r.r, [4] |b|^2
     const unsigned gs = spmv_grid(n, d.sm_count);  // persistent SpMV grid: one p.Ap partial per CTA
     double* part_pAp = parts;
     double* part_rz[2] = {parts + 1 * kMaxPartials, parts + 2 * kMaxPartials};
@@ -413,6 +493,76 @@ extern "C" int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_de
         PFG_TRY(host_sum(part_rr, &rr));
         if (!(rr == rr)) {
             set_error("pfg_cg: the residual became NaN after %d iterations (matrix not positive definite?)", it);
+            return PFG_ERR_INVALID;
+        }
+    }
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = std::sqrt(rr);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return (std::sqrt(rr) <= target) ? PFG_OK : PFG_ERR_NOCONV;
+}
+
+extern "C" int pfg_bicgstab(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, double rtol,
+                            double atol, int max_iter, int check_every, int* iters_out, double* resid_out, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    MeshDev& d = mesh->d;
+    if (!vals_dev || !b_dev || !x_dev || max_iter < 0) {
+        set_error("pfg_bicgstab: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(whole_matrix(d, "pfg_bicgstab"));
+    PFG_TRY(ensure_solve_scratch(d, true));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = d.nnodes * d.m, nown = d.nnodes;
+    double* r = d.cg_work;
+    double *rhat = r + n, *p = rhat + n, *v = p + n, *s_ = v + n, *t = s_ + n, *y = t + n, *z = y + n, *dinv = z + n;
+    double* parts = r + 9 * n;
+    double *part_a = parts, *part_b = parts + kMaxPartials, *part_rho = parts + 2 * kMaxPartials,
+           *part_rr = parts + 3 * kMaxPartials, *part_bb = parts + 4 * kMaxPartials, *sc = parts + 8 * kMaxPartials;
+    const unsigned gs = spmv_grid(n, d.sm_count);
+    const int gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
+    k_inv_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, nown, d.m, vals_dev, dinv);
+    // x0 = 0: r = rhat = b, p = v = 0
+    PFG_CUDA_TRY(cudaMemsetAsync(x_dev, 0, n * sizeof(double), st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(rhat, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PFG_CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(double), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(double), st));
+    k_norm2_partials<<<gv, kVecThreads, 0, st>>>(n, b_dev, part_bb);
+    k_dot2_partials<<<gv, kVecThreads, 0, st>>>(n, r, rhat, part_rho, part_rr);
+    k_bicg_scalar<<<1, 32, 0, st>>>(0, gv, part_rho, 0, nullptr, sc);
+    std::vector<double> h(kMaxPartials);
+    auto host_sum = [&](const double* dev, double* out) -> int {
+        PFG_CUDA_TRY(cudaMemcpyAsync(h.data(), dev, gv * sizeof(double), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        double sum = 0.0;
+        for (int i = 0; i < gv; ++i) sum += h[i];
+        *out = sum;
+        return PFG_OK;
+    };
+    double bb = 0.0, rr = 0.0;
+    PFG_TRY(host_sum(part_bb, &bb));
+    rr = bb;
+    const double target = std::max(rtol * std::sqrt(bb), atol);
+    int it = 0;
+    if (check_every <= 0) check_every = 8;
+    while (std::sqrt(rr) > target && it < max_iter) {
+        const int batch = std::min(check_every, max_iter - it);
+        for (int j = 0; j < batch; ++j, ++it) {
+            k_bicg_p<<<gv, kVecThreads, 0, st>>>(n, sc, dinv, r, v, p, y);
+            k_spmv_rows<<<gs, 256, 0, st>>>(d.blk_ptr, d.nbr, nullptr, nown, d.m, vals_dev, y, v, rhat, part_a);
+            k_bicg_scalar<<<1, 32, 0, st>>>(1, (int)gs, part_a, 0, nullptr, sc);
+            k_bicg_s<<<gv, kVecThreads, 0, st>>>(n, sc, dinv, r, v, s_, z);
+            k_spmv_rows<<<gs, 256, 0, st>>>(d.blk_ptr, d.nbr, nullptr, nown, d.m, vals_dev, z, t, nullptr, nullptr);
+            k_dot2_partials<<<gv, kVecThreads, 0, st>>>(n, t, s_, part_a, part_b);
+            k_bicg_scalar<<<1, 32, 0, st>>>(2, gv, part_a, gv, part_b, sc);
+            k_bicg_x<<<gv, kVecThreads, 0, st>>>(n, sc, y, z, s_, t, rhat, x_dev, r, part_rho, part_rr);
+            k_bicg_scalar<<<1, 32, 0, st>>>(3, gv, part_rho, 0, nullptr, sc);
+        }
+        PFG_CUDA_TRY(cudaGetLastError());
+        PFG_TRY(host_sum(part_rr, &rr));
+        if (!(rr == rr)) {
+            set_error("pfg_bicgstab: the residual became NaN after %d iterations (breakdown)", it);
             return PFG_ERR_INVALID;
         }
     }

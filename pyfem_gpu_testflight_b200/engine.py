@@ -169,6 +169,8 @@ class DeviceMesh:
         is_complex = rho.is_complex() if hasattr(rho, "is_complex") else np.iscomplexobj(rho)
         if not is_complex:
             return None
+        if not hasattr(rho, "is_complex"):  # (a Python complex would become complex64 through torch.as_tensor)
+            rho = np.asarray(rho, dtype=np.complex128)
         t = torch.as_tensor(rho).to(device=self.device, dtype=torch.complex128).reshape(-1)
         if t.numel() == 1:
             t = t.expand(self.nnodes)
@@ -293,6 +295,23 @@ class DeviceMesh:
                                   float(atol), max_iter, int(check_every), byref(iters), byref(resid), self._stream())
         if st == _lib.PFG_ERR_NOCONV:
             raise RuntimeError(f"cg failed with code {iters.value}")  # scipy reports the iteration count as the code
+        _lib.check(st)
+        return x, int(iters.value), float(resid.value)
+
+    def bicgstab(self, vals, b, rtol=1e-8, atol=0.0, max_iter=None, check_every=8):
+        """Jacobi-preconditioned BiCGStab on the device CSR for non-symmetric systems (the Newton Jacobian of
+        NonlinearPoisson2D): the device stand-in for Assembler._solve_linear_system(method="gmres").  Returns
+        (x, iterations, |r|)."""
+        torch = _torch()
+        b = self._dev_f64(b, self.nrows, "b")
+        x = torch.empty_like(b)
+        iters, resid = ctypes.c_int(0), c_double(0.0)
+        max_iter = 10 * self.nrows if max_iter is None else int(max_iter)
+        with torch.cuda.device(self.device):
+            st = self._lib.pfg_bicgstab(self._handle, _ptr(vals), _ptr(b), _ptr(x), float(rtol), float(atol), max_iter,
+                                        int(check_every), byref(iters), byref(resid), self._stream())
+        if st == _lib.PFG_ERR_NOCONV:
+            raise RuntimeError(f"bicgstab failed with code {iters.value}")
         _lib.check(st)
         return x, int(iters.value), float(resid.value)
 

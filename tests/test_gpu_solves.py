@@ -191,3 +191,58 @@ def test_hex_spmv_transpose_three_dofs(pf):
     g = np.random.default_rng(5).random(mesh.nrows)
     assert np.max(np.abs(mesh.spmv(vals, g).cpu().numpy() - A @ g)) <= 1e-13 * np.max(np.abs(A @ g))
     assert np.max(np.abs(mesh.spmv_t(vals, g).cpu().numpy() - A.T @ g)) <= 1e-13 * np.max(np.abs(A.T @ g))
+
+
+def test_newton_loop_on_the_device(pf, capsys):
+    """Assembler.solve_nonlinear(device=True): Jacobian + residual from one fused assembly, boundary conditions on the
+    device CSR, the step by Jacobi-preconditioned BiCGStab (pfg_bicgstab) -- against the host Newton loop with a direct
+    solve (tests/test_nonlinear_poisson.py:12-42 compares at 1e-8)."""
+    creator = pf.ProblemCreator(nnodes_x=32, nnodes_y=32)
+    conn, X, dof_fixed = creator.create_poisson_problem()
+    X = X / X.max(axis=0)
+    q = pf.QuadratureBilinear2D()
+    model = pf.NonlinearPoisson2D(X, conn, dof_fixed, None, q, pf.BasisBilinear2D(q))
+    xdv = np.ones(10) / 10.0
+    asm = pf.Assembler(model)
+    u_dev = asm.solve_nonlinear(xdv=xdv, device=True)
+    assert "pyfem" in capsys.readouterr().out and len(asm.last_iterations) >= 2
+    u_host = pf.Assembler(model).solve_nonlinear(method="direct", xdv=xdv)
+    assert abs(_ptu(u_dev) - _ptu(u_host)) <= 1e-8 * abs(_ptu(u_host))
+    assert np.max(np.abs(u_dev - u_host)) <= 1e-7 * np.max(np.abs(u_host))
+
+
+def test_bicgstab_nonsymmetric_system(pf):
+    """pfg_bicgstab on a diagonally dominant non-symmetric matrix in the mesh pattern, against scipy's direct solve."""
+    import torch
+    from scipy.sparse.linalg import spsolve
+    X, conn = orc.structured_mesh(23, 19)
+    mesh = pf.DeviceMesh(X, conn, 2)
+    g = torch.Generator(mesh.device).manual_seed(5)
+    vals = torch.rand(mesh.nnz, dtype=torch.float64, device=mesh.device, generator=g) - 0.5
+    A = mesh.to_scipy(vals)
+    A.setdiag(np.abs(A).sum(axis=1).A1 + 1.0)  # diagonally dominant
+    vals = torch.as_tensor(A.data, device=mesh.device)
+    b = np.random.default_rng(2).random(mesh.nrows) - 0.5
+    x, iters, resid = mesh.bicgstab(vals, b, rtol=1e-12)
+    ref = spsolve(A.tocsc(), b)
+    assert np.max(np.abs(x.cpu().numpy() - ref)) <= 1e-9 * np.max(np.abs(ref)) and iters > 0
+
+
+def test_compliance_on_the_device_at_1024(pf):
+    """SURVEY 8f #4 at a size where the host path would move 300 MB per call: compliance(rho, device=True) on 1024^2
+    quads -- assembly, Dirichlet conditions and CG in HBM -- against the residual of the solved system."""
+    import torch
+    n = 1024
+    creator = pf.ProblemCreator(nnodes_x=n + 1, nnodes_y=n + 1)
+    conn, X, dof_fixed = creator.create_poisson_problem()
+    q = pf.QuadratureBilinear2D()
+    model = pf.LinearPoisson(X, conn, dof_fixed, None, q, pf.BasisBilinear2D(q), gfunc, p=3.0)
+    rho = 0.3 + 0.7 * np.random.default_rng(0).random(X.shape[0])
+    c, u = model.compliance(rho, solver="cg", device=True)
+    assert np.isfinite(c) and c > 0
+    # residual of the boundary-conditioned system, evaluated on the device
+    vals = model.compute_jacobian_device(rho)
+    rhs = torch.as_tensor(model.compute_rhs()).to(model.mesh.device)
+    model.mesh.apply_dirichlet(vals, rhs, model.dof_fixed, None, enforce_symmetric=True)
+    r = model.mesh.spmv(vals, u) - rhs
+    assert float(torch.linalg.vector_norm(r)) <= 2e-8 * float(torch.linalg.vector_norm(rhs))
