@@ -868,6 +868,55 @@ __global__ void k_tile_image_layout(int64_t nchunks, const ChunkHdr* __restrict_
     atomicMax(&maxima[7], (int)((off + 1) * unit_doubles * 8));
 }
 
+// ---- compaction: only the tables of the templates (the representative chunks) are kept -----------------------
+// sizes of a chunk's four tables if it is a template, zero otherwise (inputs of four exclusive scans)
+__global__ void k_tile_template_sizes(int64_t nchunks, const TileDir* __restrict__ dir, int nne, int64_t* __restrict__ blob16,
+                                      int64_t* __restrict__ code16, int64_t* __restrict__ win, int64_t* __restrict__ recs) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > nchunks) return;
+    const bool keep = c < nchunks && dir[c].tmpl == (uint32_t)c;
+    blob16[c] = keep ? dir[c].blob_len16 : 0;
+    code16[c] = keep ? dir[c].code_len16 : 0;
+    win[c] = keep ? dir[c].n_win : 0;  // (windows / corner tables may start anywhere: the kernel fetches them from the
+    recs[c] = keep ? dir[c].n_recs : 0;  // enclosing 16-byte boundary)
+}
+
+// one warp per template: copy its tables to their compact places
+__global__ void k_tile_compact_copy(int64_t nchunks, const TileDir* __restrict__ dir, int nne, const int64_t* __restrict__ blob16,
+                                    const int64_t* __restrict__ code16, const int64_t* __restrict__ win,
+                                    const int64_t* __restrict__ recs, const uint8_t* __restrict__ blob_in,
+                                    const uint16_t* __restrict__ codes_in, const uint32_t* __restrict__ win_in,
+                                    const uint16_t* __restrict__ loc_in, uint8_t* __restrict__ blob_out,
+                                    uint16_t* __restrict__ codes_out, uint32_t* __restrict__ win_out,
+                                    uint16_t* __restrict__ loc_out) {
+    const int64_t c = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (c >= nchunks || dir[c].tmpl != (uint32_t)c) return;
+    const TileDir t = dir[c];
+    const uint32_t* bi = reinterpret_cast<const uint32_t*>(blob_in + (size_t)t.blob_off16 * 16);
+    uint32_t* bo = reinterpret_cast<uint32_t*>(blob_out + (size_t)blob16[c] * 16);
+    for (uint32_t w = lane; w < t.blob_len16 * 4u; w += 32) bo[w] = bi[w];
+    const uint32_t* ci = reinterpret_cast<const uint32_t*>(codes_in + (size_t)t.code_off16 * 8);
+    uint32_t* co = reinterpret_cast<uint32_t*>(codes_out + (size_t)code16[c] * 8);
+    for (uint32_t w = lane; w < t.code_len16 * 4u; w += 32) co[w] = ci[w];
+    for (uint32_t w = lane; w < t.n_win; w += 32) win_out[win[c] + w] = win_in[t.win_off + w];
+    const uint16_t* li = loc_in + (size_t)t.loc_off * nne;
+    uint16_t* lo = loc_out + (size_t)recs[c] * nne;
+    for (uint32_t w = lane; w < t.n_recs * (uint32_t)nne; w += 32) lo[w] = li[w];
+}
+
+__global__ void k_tile_compact_dir(int64_t nchunks, const int64_t* __restrict__ blob16, const int64_t* __restrict__ code16,
+                                   const int64_t* __restrict__ win, const int64_t* __restrict__ recs,
+                                   TileDir* __restrict__ dir) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c >= nchunks) return;
+    const uint32_t r = dir[c].tmpl;
+    dir[c].blob_off16 = (uint32_t)blob16[r];
+    dir[c].code_off16 = (uint32_t)code16[r];
+    dir[c].win_off = (uint32_t)win[r];
+    dir[c].loc_off = (uint32_t)recs[r];
+}
+
 // neutral codes -> staging offsets of one operator layout (record slot 0 is the zero record; padding -> 0)
 __host__ __device__ inline uint32_t tile_encode(const TileLayout& L, uint32_t neutral) {
     if (neutral == 0xFFFFu) return 0;
@@ -1331,6 +1380,7 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                                                                       d.blk_ptr, run_flag.p, d.m, d.tile_blob, maxima.p,
                                                                       terr.p);
         // ---- chunk templates: chunks with byte-identical tables share the tables of the first of them
+        int64_t compact_win = -1, compact_recs = -1;  // entries kept after compaction (-1: pools not compacted)
         d.ntemplates = d.nchunks;
         d.plan_read_bytes = 0;
         if (!env_int("PFG_NO_TEMPLATES", 0)) {
@@ -1378,6 +1428,51 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
                 PFG_CUDA_TRY(cudaStreamSynchronize(st));
                 d.ntemplates = (int64_t)h_stats[0];
                 d.plan_read_bytes = (int64_t)h_stats[1];
+                // ---- keep only the templates' tables: compact pools, directory re-pointed, the rest freed
+                if (d.ntemplates * 2 <= d.nchunks && !env_int("PFG_NO_COMPACT", 0)) {
+                    DBuf<int64_t> sz[4], off[4];
+                    for (int k = 0; k < 4; ++k) {
+                        PFG_CUDA_TRY(sz[k].alloc(d.nchunks + 1));
+                        PFG_CUDA_TRY(off[k].alloc(d.nchunks + 1));
+                    }
+                    k_tile_template_sizes<<<grid_for(d.nchunks + 1), kThreads, 0, st>>>(d.nchunks, d.tile_dir, NNE, sz[0].p,
+                                                                                        sz[1].p, sz[2].p, sz[3].p);
+                    int64_t total[4] = {0, 0, 0, 0};
+                    for (int k = 0; k < 4; ++k) {
+                        PFG_CUB(scratch, st,
+                                cub::DeviceScan::ExclusiveSum(d_temp_storage, temp_storage_bytes, sz[k].p, off[k].p,
+                                                              d.nchunks + 1, st));
+                        PFG_CUDA_TRY(cudaMemcpyAsync(&total[k], off[k].p + d.nchunks, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+                    }
+                    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+                    uint8_t* blob2 = nullptr;
+                    uint16_t *codes2 = nullptr, *neutral2 = nullptr, *loc2 = nullptr;
+                    uint32_t* win2 = nullptr;
+                    PFG_CUDA_TRY(cudaMalloc(&blob2, total[0] * 16 + 64));
+                    PFG_CUDA_TRY(cudaMalloc(&codes2, total[1] * 16 + 64));
+                    PFG_CUDA_TRY(cudaMalloc(&neutral2, total[1] * 16 + 64));
+                    PFG_CUDA_TRY(cudaMalloc(&win2, total[2] * 4 + 64));
+                    PFG_CUDA_TRY(cudaMalloc(&loc2, total[3] * NNE * 2 + 64));
+                    PFG_CUDA_TRY(cudaMemsetAsync(blob2, 0, total[0] * 16 + 64, st));
+                    PFG_CUDA_TRY(cudaMemsetAsync(codes2, 0, total[1] * 16 + 64, st));
+                    PFG_CUDA_TRY(cudaMemsetAsync(neutral2, 0xFF, total[1] * 16 + 64, st));
+                    PFG_CUDA_TRY(cudaMemsetAsync(win2, 0, total[2] * 4 + 64, st));
+                    PFG_CUDA_TRY(cudaMemsetAsync(loc2, 0, total[3] * NNE * 2 + 64, st));
+                    k_tile_compact_copy<<<warp_grid, kThreads, 0, st>>>(d.nchunks, d.tile_dir, NNE, off[0].p, off[1].p, off[2].p,
+                                                                        off[3].p, d.tile_blob, d.tile_codes_neutral, d.win_nodes,
+                                                                        d.rec_local, blob2, neutral2, win2, loc2);
+                    k_tile_compact_dir<<<grid_for(d.nchunks), kThreads, 0, st>>>(d.nchunks, off[0].p, off[1].p, off[2].p,
+                                                                                 off[3].p, d.tile_dir);
+                    PFG_CUDA_TRY(cudaStreamSynchronize(st));
+                    PFG_CUDA_TRY(cudaGetLastError());
+                    cudaFree(d.tile_blob), cudaFree(d.tile_codes), cudaFree(d.tile_codes_neutral);
+                    cudaFree(d.win_nodes), cudaFree(d.rec_local);
+                    d.tile_blob = blob2, d.tile_codes = codes2, d.tile_codes_neutral = neutral2;
+                    d.win_nodes = win2, d.rec_local = loc2;
+                    d.tile_blob_bytes = total[0] * 16;
+                    d.tile_ncodes = total[1] * 8;
+                    compact_win = total[2], compact_recs = total[3];
+                }
             }
         }
         int h_terr = 0, h_max[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -1410,8 +1505,9 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         if (d.plan_read_bytes == 0)  // no template sharing: every chunk reads its own tables
             d.plan_read_bytes = d.plan_bytes + d.nrecs * (NNE * 2) + d.nwin * 4;
         d.plan_read_bytes += d.nchunks * (int64_t)sizeof(TileDir);
-        d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * (NNE * 2 + 4) +
-                          d.nwin * 4 + d.tile_blob_bytes + d.tile_ncodes * 4;
+        d.device_bytes += d.nchunks * (sizeof(ChunkHdr) + sizeof(TileDir)) + nown * 4 + d.nrecs * 4 +
+                          (compact_recs >= 0 ? compact_recs : d.nrecs) * (NNE * 2) +
+                          (compact_win >= 0 ? compact_win : d.nwin) * 4 + d.tile_blob_bytes + d.tile_ncodes * 4;
         return PFG_OK;
     }
     k_fill_dst<NNE><<<grid_for(nown), kThreads, 0, st>>>(slot_node.p, slot_chunk.p, d.inc_ptr, d.inc_list, inc_excl.p,

@@ -124,6 +124,9 @@ def test_chunk_templates_share_tables_and_change_nothing(monkeypatch):
     monkeypatch.delenv("PFG_NO_TEMPLATES")
     assert plain2.ntemplates == plain2.nchunks == shared2.nchunks
     assert shared2.plan_bytes < plain2.plan_bytes // 4
+    # only the templates' tables are kept: the handle itself shrinks
+    from pyfem_gpu_testflight_b200 import _lib
+    assert shared2.info(_lib.INFO_DEVICE_BYTES) < plain2.info(_lib.INFO_DEVICE_BYTES)
     for r, p in ((1.0, 0.0), (rho, 3.0)):
         assert torch.equal(shared2.assemble_elasticity(r, p, mode="gather"), plain2.assemble_elasticity(r, p, mode="gather"))
         assert torch.equal(shared1.assemble_poisson(r, p, mode="gather"), plain1.assemble_poisson(r, p, mode="gather"))
