@@ -906,13 +906,29 @@ __global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHe
 // tables of the next chunk are fetched while the current one is computed.  No atomics, no zero-fill of the
 // output, every CSR value written once, bitwise reproducible.
 #ifndef PFG_HEX_NB
-#define PFG_HEX_NB 4  // column nodes per pass over the quadrature points: two passes with 36 running sums each
-#endif                // (no spills, 3.98 ms for 128^3 hex) beat one pass with 72 (4.16 ms)
+#define PFG_HEX_NB 7  // 7: one pass over the quadrature points for seven column nodes (63 running sums), the eighth block
+#endif                // from the zero row sums -- 128^3 hex 3.997 -> 3.894 ms; 4: two passes of four column nodes (36
+                      // sums each, geometry read twice); 8: one pass with 72 sums (spills: 4.16 ms)
 constexpr int kHexRowsThreads = (kHexRowWarps + 1) * 32;
 constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
 constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
                                                        // consecutive records on different banks
 static_assert(kHexGeoRecordBytes == (8 * kHexGeoDoubles + 2) * 8, "hex8 geometry record layout");
+
+PFG_DEV void hex8_add_block(const ElasticityHex8Params& prm, const double (&P)[3][3], int b, bool active,
+                            double* __restrict__ rows, int k3, uint2 ranks) {
+    if (active) {
+        double blk[9];
+        hex8_apply_c0(prm, P, blk);
+        const unsigned rk = (b < 4) ? ranks.x : ranks.y;  // four 8-bit ranks per word
+        double* dst = rows + 3 * (int)((rk >> (8 * (b & 3))) & 0xFFu);
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) dst[i * k3 + j] += blk[i * 3 + j];
+    }
+    __syncwarp();  // the next column index may land on a block another lane of the node has just updated
+}
 
 template <int B0, int NB>
 PFG_DEV void hex8_rows_part(const ElasticityHex8Params& prm, const double* __restrict__ geo_e, double sx8, double sy8,
@@ -920,19 +936,30 @@ PFG_DEV void hex8_rows_part(const ElasticityHex8Params& prm, const double* __res
     double P[NB][3][3];
     if (active) hex8_row_products<B0, NB>(geo_e, sx8, sy8, sz8, P);
 #pragma unroll
-    for (int bb = 0; bb < NB; ++bb) {
-        if (active) {
-            double blk[9];
-            hex8_apply_c0(prm, P[bb], blk);
-            const unsigned rk = (B0 + bb < 4) ? ranks.x : ranks.y;  // four 8-bit ranks per word
-            double* dst = rows + 3 * (int)((rk >> (8 * ((B0 + bb) & 3))) & 0xFFu);
+    for (int bb = 0; bb < NB; ++bb) hex8_add_block(prm, P[bb], B0 + bb, active, rows, k3, ranks);
+}
+
+// One pass over the quadrature points for seven column nodes; the eighth block follows from the zero row sums of the
+// element matrix (sum_b grad N_b = 0 at every point): 63 running sums fit the register file where 72 do not, and the
+// element's geometry is read from shared memory once instead of twice.
+PFG_DEV void hex8_rows_closed(const ElasticityHex8Params& prm, const double* __restrict__ geo_e, double sx8, double sy8,
+                              double sz8, bool active, double* __restrict__ rows, int k3, uint2 ranks) {
+    double P[7][3][3], L[3][3];
+    if (active) {
+        hex8_row_products<0, 7>(geo_e, sx8, sy8, sz8, P);
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i)
 #pragma unroll
-                for (int j = 0; j < 3; ++j) dst[i * k3 + j] += blk[i * 3 + j];
-        }
-        __syncwarp();  // the next column index may land on a block another lane of the node has just updated
+            for (int j = 0; j < 3; ++j) {
+                double sum = P[0][i][j];
+#pragma unroll
+                for (int bb = 1; bb < 7; ++bb) sum += P[bb][i][j];
+                L[i][j] = -sum;
+            }
     }
+#pragma unroll
+    for (int bb = 0; bb < 7; ++bb) hex8_add_block(prm, P[bb], bb, active, rows, k3, ranks);
+    hex8_add_block(prm, L, 7, active, rows, k3, ranks);
 }
 
 struct HexRowsCfg {
@@ -1046,7 +1073,9 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
             if (!waited) mbar_wait(&bars[s], f & 1);  // the chunk's geometry has landed
             waited = true;
             __syncwarp();
-#if PFG_HEX_NB == 8
+#if PFG_HEX_NB == 7
+            hex8_rows_closed(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
+#elif PFG_HEX_NB == 8
             hex8_rows_part<0, 8>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
 #else
             hex8_rows_part<0, 4>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
