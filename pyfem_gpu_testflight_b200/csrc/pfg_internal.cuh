@@ -238,6 +238,7 @@ struct MeshDev {
     uint8_t* bc_fixed = nullptr;       // (ncols) flags of the fixed dofs
     double* bc_u0 = nullptr;           // (ncols) prescribed values, defined at the fixed dofs
     double* cg_work = nullptr;         // r, z, p, Ap, 1/diag and the dot-product partial sums
+    uint8_t* trank = nullptr;          // (nblocks) transposed-slot map of pfg_spmv_t, built on first use
 
     int64_t device_bytes = 0;
     int sm_count = 148;

@@ -1572,7 +1572,7 @@ static void free_all(MeshDev& d) {
     void* ptrs[] = {d.X, d.conn, d.gid, d.inc_ptr, d.inc_list, d.blk_ptr, d.nbr, d.rank, d.chunks, d.cnodes,
                     d.cnode_id, d.rec_nodes, d.rec_dst, d.rec_elem, d.plan_pool, d.tile_dir, d.tile_blob,
                     d.tile_codes, d.tile_codes_neutral, d.win_nodes, d.rec_local, d.elem_skip, d.hex_geo, d.inc_rec8, d.inc_ranks8,
-                    d.bc_fixed, d.bc_u0, d.cg_work, d.rec_skip};
+                    d.bc_fixed, d.bc_u0, d.cg_work, d.rec_skip, d.trank};
     for (void* p : ptrs)
         if (p) cudaFree(p);
 }

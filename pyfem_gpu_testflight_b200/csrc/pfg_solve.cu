@@ -93,35 +93,58 @@ static void launch_spmv_rows(unsigned grid, cudaStream_t st, const MeshDev& d, c
     else k_spmv_rows<3, 8><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, gid, nown, vals, x, y, dot_with, partial);
 }
 
-// y = A^T x for a handle that owns every row: entry (c, r) of A sits in row c at the rank of r in c's sorted column
-// list (the node-level pattern is symmetric: c is a neighbour of r exactly when r is a neighbour of c).
-__global__ void __launch_bounds__(256) k_spmv_t_rows(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
-                                                     int64_t nown, int m, const double* __restrict__ vals,
-                                                     const double* __restrict__ x, double* __restrict__ y) {
-    const int64_t row = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) / kRowLanes;
-    const int sub = threadIdx.x & (kRowLanes - 1);
-    const int64_t nrows = nown * m;
-    double s = 0.0;
-    if (row < nrows) {
-        const int64_t r = row / m;
-        const int alpha = (int)(row - r * m);
-        const int64_t p0 = blk_ptr[r];
-        const int k = (int)(blk_ptr[r + 1] - p0);
-        for (int t = sub; t < k; t += kRowLanes) {
-            const int64_t c = nbr[p0 + t];
-            const int64_t q0 = blk_ptr[c];
-            const int kc = (int)(blk_ptr[c + 1] - q0);
-            int lo = 0, hi = kc;  // rank of r among c's neighbours
-            while (lo < hi) {
-                const int mid = (lo + hi) >> 1;
-                if (nbr[q0 + mid] < r) lo = mid + 1; else hi = mid;
-            }
-            const double* __restrict__ v = vals + q0 * m * m + (int64_t)lo * m + alpha;
-            for (int beta = 0; beta < m; ++beta) s = fma(v[(int64_t)beta * kc * m], x[c * m + beta], s);
+// Transposed-slot map, built on the first transposed product and kept in the handle: for node block (r, t) with
+// column node c, the rank of r among c's sorted neighbours -- where entry (c, r) of the matrix sits in row c (the
+// node-level pattern is symmetric: c is a neighbour of r exactly when r is a neighbour of c).
+__global__ void k_transpose_ranks(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr, int64_t nown,
+                                  uint8_t* __restrict__ trank) {
+    const int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= nown) return;
+    const int64_t p0 = blk_ptr[r], p1 = blk_ptr[r + 1];
+    for (int64_t p = p0; p < p1; ++p) {
+        const int64_t c = nbr[p];
+        const int64_t q0 = blk_ptr[c];
+        int lo = 0, hi = (int)(blk_ptr[c + 1] - q0);
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (nbr[q0 + mid] < r) lo = mid + 1; else hi = mid;
         }
+        trank[p] = (uint8_t)lo;  // a row has at most kMaxRowBlocks = 255 blocks
     }
-    s = group_sum(s);
-    if (row < nrows && sub == 0) y[row] = s;
+}
+
+// y = A^T x for a handle that owns every row: the same lanes-per-row layout as k_spmv_rows; lane j of row (r, alpha)
+// takes column dof (c, beta) = j and reads A[(c, beta), (r, alpha)] from row c at the mapped rank.
+template <int M, int LANES>
+__global__ void __launch_bounds__(256) k_spmv_t_rows(const int64_t* __restrict__ blk_ptr, const int32_t* __restrict__ nbr,
+                                                     const uint8_t* __restrict__ trank, int64_t nown,
+                                                     const double* __restrict__ vals, const double* __restrict__ x,
+                                                     double* __restrict__ y) {
+    const int sub = threadIdx.x & (LANES - 1);
+    const int64_t nrows = nown * M;
+    constexpr int RPB = 256 / LANES;
+    for (int64_t row0 = blockIdx.x * (int64_t)RPB; row0 < nrows; row0 += (int64_t)gridDim.x * RPB) {
+        const int64_t row = row0 + threadIdx.x / LANES;
+        double s = 0.0;
+        if (row < nrows) {
+            const int64_t r = row / M;
+            const int alpha = (int)(row - r * M);
+            const int64_t p0 = __ldg(blk_ptr + r);
+            const int km = (int)(__ldg(blk_ptr + r + 1) - p0) * M;
+#pragma unroll 4
+            for (int j = sub; j < km; j += LANES) {
+                const int t = j / M, beta = j - t * M;
+                const int64_t c = __ldg(nbr + p0 + t);
+                const int64_t q0 = __ldg(blk_ptr + c);
+                const int kc = (int)(__ldg(blk_ptr + c + 1) - q0);
+                const int rk = __ldg(trank + p0 + t);
+                s = fma(__ldg(vals + q0 * (M * M) + (int64_t)beta * kc * M + rk * M + alpha), __ldg(x + c * M + beta), s);
+            }
+        }
+#pragma unroll
+        for (int o = LANES / 2; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (sub == 0 && row < nrows) y[row] = s;
+    }
 }
 
 // 1 / diag(A) of the owned rows (Jacobi preconditioner); a zero diagonal maps to 1
@@ -438,15 +461,26 @@ static int whole_matrix(const MeshDev& d, const char* who) {
 
 extern "C" int pfg_spmv_t(pfg_mesh* mesh, const double* vals_dev, const double* x_dev, double* y_dev, void* stream) {
     PFG_CHECK_MESH(mesh);
-    const MeshDev& d = mesh->d;
+    MeshDev& d = mesh->d;
     if (!vals_dev || !x_dev || !y_dev) {
         set_error("pfg_spmv_t: NULL argument");
         return PFG_ERR_INVALID;
     }
     PFG_TRY(whole_matrix(d, "pfg_spmv_t"));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d.trank) {  // once per handle
+        PFG_CUDA_TRY(cudaMalloc(&d.trank, std::max<int64_t>(d.nblocks, 1)));
+        d.device_bytes += d.nblocks;
+        k_transpose_ranks<<<(unsigned)((d.nnodes + 127) / 128), 128, 0, st>>>(d.blk_ptr, d.nbr, d.nnodes, d.trank);
+    }
     const int64_t nrows = d.nnodes * d.m;
-    k_spmv_t_rows<<<(unsigned)((nrows * kRowLanes + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d.blk_ptr, d.nbr, d.nnodes, d.m, vals_dev, x_dev,
-                                                                     y_dev);
+    const unsigned grid = spmv_grid(nrows, d.sm_count);
+    const bool short_rows = d.max_k * d.m <= 24;
+    if (d.m == 1 && short_rows) k_spmv_t_rows<1, 4><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, d.trank, d.nnodes, vals_dev, x_dev, y_dev);
+    else if (d.m == 1) k_spmv_t_rows<1, 8><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, d.trank, d.nnodes, vals_dev, x_dev, y_dev);
+    else if (d.m == 2 && short_rows) k_spmv_t_rows<2, 4><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, d.trank, d.nnodes, vals_dev, x_dev, y_dev);
+    else if (d.m == 2) k_spmv_t_rows<2, 8><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, d.trank, d.nnodes, vals_dev, x_dev, y_dev);
+    else k_spmv_t_rows<3, 8><<<grid, 256, 0, st>>>(d.blk_ptr, d.nbr, d.trank, d.nnodes, vals_dev, x_dev, y_dev);
     PFG_CUDA_TRY(cudaGetLastError());
     return PFG_OK;
 }

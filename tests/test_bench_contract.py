@@ -24,6 +24,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["dtype"] == "f64" and line["vs_baseline"] is None and "workload" in line["config"]
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    # the CPU arm runs a bounded sample of the named workload: its size is stated in the line
+    assert line["config"]["cpu_sample_elements"] > 0 and line["scaling"] == "strong"
 
 
 def test_reference_arm_other_ranks_exit_quietly():
