@@ -64,6 +64,13 @@ def _worker(rank, world, port, transport, out_dir):
             K, res = rs.assemble_nlpoisson(xdv, u[part.node_gid])
             ok &= slab_ok(K, Kg, 1)
             ok &= np.max(np.abs(res.cpu().numpy() - rg[gb:ge])) <= 1e-12 * np.max(np.abs(rg))
+            # Helmholtz K and R (two value arrays per handle; their halo shares travel by send / recv)
+            Hk, Hr = orc.assemble_helmholtz(X, conn, 0.05)
+            for _ in range(2):
+                Kh, Rh = rs.assemble_helmholtz(0.05)
+                ok &= slab_ok(Kh, Hk, 1) and slab_ok(Rh, Hr, 1)
+            K2, res2 = rs.assemble_nlpoisson(xdv, u[part.node_gid])  # the inboxes still work afterwards
+            ok &= slab_ok(K2, Kg, 1)
     # the same through the model API: LinearElasticity(..., group=WORLD, halo=transport) is one rank of the partition,
     # compute_jacobian returns its row slab and gather() rebuilds the reference's global matrix on rank 0
     import pyfem_gpu_testflight_b200 as pf
