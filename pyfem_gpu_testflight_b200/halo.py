@@ -16,8 +16,8 @@ Transport "p2p" fuses the halo assembly with its transfer: every rank keeps an i
 (torch.distributed._symmetric_memory, NVLink peer mappings), and a sender's halo handle assembles STRAIGHT INTO the
 owner's inbox -- the tile kernel's TMA bulk stores (or the atomic kernel's red.global) target the peer's HBM through
 NVLink / NVSwitch, chunk by chunk as they complete; no staging copy, no send/recv launch.  A device-side barrier on the
-symmetric-memory signal pads orders "all halo kernels done" before the owners' indexed adds, a second one frees the
-inboxes for the next assembly.
+symmetric-memory signal pads orders "all halo kernels done" before the owners' indexed adds; every rank keeps two inboxes
+and alternates between them, so that this one barrier per assembly also frees the inbox of the assembly before.
 
 The planning below is numpy and runs anywhere (gloo test on CPU); `ReduceAssembler` is the device part.
 """
@@ -144,19 +144,22 @@ class ReduceAssembler:
         def offset(q, d):
             return off_table[q][d]
 
-        self.inbox = symm_mem.empty(n, dtype=torch.float64, device=self.device)  # same size on every rank
+        # TWO inboxes per rank, used alternately: the sender of assembly k writes the half its owner consumed in
+        # assembly k - 2, and the one barrier of assembly k - 1 (which the owner joins only after enqueueing those
+        # adds) already orders the two -- so an assembly needs a single device-side barrier, not two
+        n = _even(n)
+        self.inbox = symm_mem.empty(2 * n, dtype=torch.float64, device=self.device)  # same size on every rank
         self.symm = symm_mem.rendezvous(self.inbox, self.group if self.group is not None else self.dist.group.WORLD)
-        self.peer_out = []
-        for s, hm, _ in self.halo:
-            off = offset(rank, s.dest)
-            self.peer_out.append((self.symm.get_buffer(s.dest, (hm.nnz,), torch.float64, off),
-                                  self.symm.get_buffer(s.dest, (hm.nrows,), torch.float64, off + _even(hm.nnz))))
-        recv = []
-        for q, slots, rows, _, _ in self.recv:
-            off = offset(q, rank)
-            v0 = off + _even(len(slots))
-            recv.append((q, slots, rows, self.inbox[off:off + len(slots)], self.inbox[v0:v0 + len(rows)]))
-        self.recv = recv
+        self.peer_out, self.recv_p2p, self._phase = [[], []], [[], []], 0
+        for par in (0, 1):
+            for s, hm, _ in self.halo:
+                off = par * n + offset(rank, s.dest)
+                self.peer_out[par].append((self.symm.get_buffer(s.dest, (hm.nnz,), torch.float64, off),
+                                           self.symm.get_buffer(s.dest, (hm.nrows,), torch.float64, off + _even(hm.nnz))))
+            for q, slots, rows, _, _ in self.recv:
+                off = par * n + offset(q, rank)
+                v0 = off + _even(len(slots))
+                self.recv_p2p[par].append((q, slots, rows, self.inbox[off:off + len(slots)], self.inbox[v0:v0 + len(rows)]))
         self.symm.barrier()
 
     # ---- setup: halo patterns travel to the owners, owners build their index maps --------------------------------
@@ -219,21 +222,21 @@ class ReduceAssembler:
     # ---- every assembly ---------------------------------------------------------------------------------------------
     def _halo_out(self, i):
         """(values, vector) outputs of halo handle i: the owner's inbox for the p2p transport, else fresh tensors."""
-        return self.peer_out[i] if self.transport == "p2p" else (None, None)
+        return self.peer_out[self._phase & 1][i] if self.transport == "p2p" else (None, None)
 
     def _before_halo(self):
-        if self.transport == "p2p":
-            self.symm.barrier()  # every owner has consumed the previous assembly's inbox contents
+        pass  # (the p2p inboxes alternate: no barrier is needed before the halo kernels, see _setup_p2p)
 
     def _reduce(self, main_vals, halo_vals, main_vec=None, halo_vecs=None):
         dist = self.dist
         if self.transport == "p2p":
             self.symm.barrier()  # every rank's halo kernels have written their peers' inboxes
-            for q, slots, rows, vbuf, rbuf in self.recv:
+            for q, slots, rows, vbuf, rbuf in self.recv_p2p[self._phase & 1]:
                 if halo_vals is not None:
                     self.mesh.add_indexed(main_vals, slots, vbuf)
                 if halo_vecs is not None:
                     self.mesh.add_indexed(main_vec, rows, rbuf)
+            self._phase += 1
             return
         ops = []
         for i, (s, _, _) in enumerate(self.halo):

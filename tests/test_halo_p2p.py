@@ -54,7 +54,7 @@ def _worker(rank, world, port, transport, out_dir):
 
         ra = ReduceAssembler(part, m_el, ranges, device=torch.device("cuda", rank), transport=transport)
         Kg = orc.assemble_elasticity(X, conn, rho, 3.0)
-        for _ in range(2):  # twice: the inboxes are reused
+        for _ in range(4):  # the two inboxes of the p2p transport alternate: each is reused
             ok &= slab_ok(ra.assemble_elasticity(rho[part.node_gid], 3.0), Kg, m_el)
         if dims[2] is None:
             rs = ReduceAssembler(part, 1, ranges, device=torch.device("cuda", rank), transport=transport)
