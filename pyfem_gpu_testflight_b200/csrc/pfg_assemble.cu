@@ -909,7 +909,6 @@ __global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHe
 #define PFG_HEX_NB 7  // 7: one pass over the quadrature points for seven column nodes (63 running sums), the eighth block
 #endif                // from the zero row sums -- 128^3 hex 3.997 -> 3.894 ms; 4: two passes of four column nodes (36
                       // sums each, geometry read twice); 8: one pass with 72 sums (spills: 4.16 ms)
-constexpr int kHexRowsThreads = (kHexRowWarps + 1) * 32;
 constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
 constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
                                                        // consecutive records on different banks
@@ -966,6 +965,7 @@ struct HexRowsCfg {
     int off_geo, geo_stage_bytes;  // two geometry stages
     int off_image, image_stride;   // per consumer warp: four nodes x image_stride doubles (9 * max neighbours)
     int off_meta;                  // per consumer thread 2 x 32 B of node / incidence tables, per warp 2 x 8 B
+    int off_feed;                  // self-feeding ring: per warp four chunk headers + two record-id lists
     int nchunks;
 };
 
@@ -982,31 +982,72 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
                       double* __restrict__ vals, HexRowsCfg cfg) {
     extern __shared__ __align__(128) unsigned char hex_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(hex_smem);  // [0..1] stage full, [2..3] stage empty
+    unsigned* left = reinterpret_cast<unsigned*>(hex_smem + 64);  // self-feeding ring: warps that have left stage 0 / 1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int nloc = (int)((int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x - c_begin);
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
         mbar_init(&bars[2], kHexRowWarps), mbar_init(&bars[3], kHexRowWarps);
+        left[0] = left[1] = 0u;
     }
     __syncthreads();
-    if (warp == kHexRowWarps) {
-        // ---- producer warp: geometry of chunk i's records -> stage i & 1
-        for (int i = 0; i < nloc; ++i) {
-            const int s = i & 1, f = i >> 1;
-            const ChunkHdr h = mv.chunks[c_begin + i];
-            const int e_lo = ((int)h.n_recs > lane) ? __ldg(mv.rec_elem + h.rec_begin + lane) : 0;
-            mbar_wait(&bars[2 + s], (f & 1) ^ 1);  // consumers have left the stage's previous chunk
-            if (lane == 0) mbar_expect_tx(&bars[s], h.n_recs * (uint32_t)kHexGeoBytes);
-            __syncwarp();
-            unsigned char* stage = hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes;
-            for (int r = lane; r < (int)h.n_recs; r += 32) {
-                const int e = (r < 32) ? e_lo : __ldg(mv.rec_elem + h.rec_begin + r);
-                tma_load_1d(stage + (size_t)r * (kHexGeoStride * 8), geo + (size_t)e * (8 * kHexGeoDoubles),
-                            (uint32_t)kHexGeoBytes, &bars[s]);
+    // whole warp: bulk copies of the geometry of `n_recs` element records (ids through `elem_of`) into stage s
+    auto feed_stage = [&](int s, uint32_t n_recs, auto&& elem_of) {
+        if (lane == 0) mbar_expect_tx(&bars[s], n_recs * (uint32_t)kHexGeoBytes);
+        __syncwarp();
+        unsigned char* stage = hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes;
+        for (int r = lane; r < (int)n_recs; r += 32)
+            tma_load_1d(stage + (size_t)r * (kHexGeoStride * 8), geo + (size_t)elem_of(r) * (8 * kHexGeoDoubles),
+                        (uint32_t)kHexGeoBytes, &bars[s]);
+    };
+    if constexpr (!kHexSelfFeed) {
+        if (warp == kHexRowWarps) {
+            // ---- producer warp: geometry of chunk i's records -> stage i & 1
+            for (int i = 0; i < nloc; ++i) {
+                const int s = i & 1, f = i >> 1;
+                const ChunkHdr h = mv.chunks[c_begin + i];
+                const int e_lo = ((int)h.n_recs > lane) ? __ldg(mv.rec_elem + h.rec_begin + lane) : 0;
+                mbar_wait(&bars[2 + s], (f & 1) ^ 1);  // consumers have left the stage's previous chunk
+                feed_stage(s, h.n_recs, [&](int r) { return (r < 32) ? e_lo : __ldg(mv.rec_elem + h.rec_begin + r); });
             }
+            return;
         }
-        return;
+    }
+    // Self-feeding ring (eight consumer warps, no producer warp): every warp keeps, in its own shared-memory slots,
+    // the header of the chunk after next and that chunk's record ids (cp.async, a chunk ahead); the warp that leaves
+    // chunk i LAST -- elected with a counter, so nobody waits -- issues the bulk copies of chunk i + 2 into the stage
+    // all warps have just left.
+    struct FeedHdr {  // the first 24 bytes of a ChunkHdr
+        uint32_t node_begin, n_nodes, n_recs, n_inc;
+        int64_t rec_begin;
+    };
+    unsigned char* feed_s = hex_smem + cfg.off_feed + (size_t)warp * kHexFeedBytes;
+    auto feed_hdr = [&](int i_chunk) { return reinterpret_cast<FeedHdr*>(feed_s + (i_chunk & 3) * 32); };
+    auto feed_recs = [&](int i_chunk) { return reinterpret_cast<int32_t*>(feed_s + 128 + (i_chunk & 1) * (kHexFeedRecs * 4)); };
+    auto feed_prefetch = [&](int i) {  // at the start of local chunk i: header of i + 3, record ids of i + 2
+        if (i + 3 < nloc && lane == 0) {
+            cp_async_16(feed_hdr(i + 3), mv.chunks + c_begin + i + 3);
+            cp_async_8(reinterpret_cast<unsigned char*>(feed_hdr(i + 3)) + 16, &mv.chunks[c_begin + i + 3].rec_begin);
+        }
+        if (i + 2 < nloc) {
+            const FeedHdr h = *feed_hdr(i + 2);
+            int32_t* dst = feed_recs(i + 2);
+            for (int r = lane; r < min((int)h.n_recs, kHexFeedRecs); r += 32) cp_async_4(dst + r, mv.rec_elem + h.rec_begin + r);
+        }
+    };
+    if constexpr (kHexSelfFeed) {
+        if (warp < 2 && warp < nloc) {  // the first two chunks: direct loads
+            const ChunkHdr h = mv.chunks[c_begin + warp];
+            feed_stage(warp, h.n_recs, [&](int r) { return __ldg(mv.rec_elem + h.rec_begin + r); });
+        }
+        if (lane == 0 && 2 < nloc) {
+            const ChunkHdr h = mv.chunks[c_begin + 2];
+            FeedHdr* dst = feed_hdr(2);
+            dst->node_begin = h.node_begin, dst->n_nodes = h.n_nodes, dst->n_recs = h.n_recs, dst->n_inc = h.n_inc;
+            dst->rec_begin = h.rec_begin;
+        }
+        __syncwarp();
     }
     // ---- consumer warps
     const int j = lane & 7;
@@ -1059,6 +1100,7 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
         __syncwarp();
         const uint2 hd = *reinterpret_cast<const uint2*>(hd_s + s * 8);  // (node_begin, n_nodes)
         HexLaneMeta meta = read_meta(hd, s);
+        if constexpr (kHexSelfFeed) feed_prefetch(i);  // (joins the cp.async group issue_meta commits)
         issue_meta((int64_t)hd.x + hd.y, i + 1);
         const double* geo_s = reinterpret_cast<const double*>(hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes);
         bool waited = false;
@@ -1093,7 +1135,26 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
         }
         if (!waited) mbar_wait(&bars[s], f & 1);  // keep the ring in step even without a node in this chunk
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[2 + s]);
+        if constexpr (kHexSelfFeed) {
+            int last = 0;
+            if (lane == 0) {
+                __threadfence_block();  // this warp's reads of the stage come before the count
+                last = (atomicAdd(&left[s], 1u) == (unsigned)(kHexRowWarps - 1));
+                if (last) left[s] = 0u;  // nobody counts on this stage again before the copies issued below have landed
+                __threadfence_block();
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last && i + 2 < nloc) {
+                cp_async_wait<0>();  // issued at the start of this chunk: long since landed
+                __syncwarp();
+                const FeedHdr h = *feed_hdr(i + 2);
+                const int32_t* ids = feed_recs(i + 2);
+                feed_stage(s, h.n_recs,
+                           [&](int r) { return (r < kHexFeedRecs) ? ids[r] : __ldg(mv.rec_elem + h.rec_begin + r); });
+            }
+        } else {
+            if (lane == 0) mbar_arrive(&bars[2 + s]);
+        }
     }
     cp_async_wait<0>();
 }
@@ -1132,70 +1193,142 @@ struct SensParams {
     double c11, c12, c33;  // elasticity: C0 diagonal, off-diagonal and shear entries
 };
 
+// energy density phi-strain : C0 : psi-strain (times det^2) from the det-scaled gradients of the two fields
+template <int M, int DIM>
+PFG_DEV double sens_energy(const SensParams& prm, const double (&gu)[M][DIM], const double (&gv)[M][DIM]) {
+    if constexpr (M == 1) {
+        double energy = 0.0;
+#pragma unroll
+        for (int l = 0; l < DIM; ++l) energy = fma(gu[0][l], gv[0][l], energy);
+        return energy;
+    } else if constexpr (DIM == 2) {  // strains [ex, ey, gxy] (pyfem.py:1988-1998)
+        const double gxu = gu[0][1] + gu[1][0], gxv = gv[0][1] + gv[1][0];
+        return prm.c11 * (gu[0][0] * gv[0][0] + gu[1][1] * gv[1][1]) +
+               prm.c12 * (gu[0][0] * gv[1][1] + gu[1][1] * gv[0][0]) + prm.c33 * gxu * gxv;
+    } else {  // [ex, ey, ez, gxy, gyz, gxz] (pyfem.py:2000-2011)
+        const double su = gu[0][0] + gu[1][1] + gu[2][2], sv = gv[0][0] + gv[1][1] + gv[2][2];
+        double diag = 0.0;
+#pragma unroll
+        for (int l = 0; l < 3; ++l) diag = fma(gu[l][l], gv[l][l], diag);
+        const double sh = (gu[0][1] + gu[1][0]) * (gv[0][1] + gv[1][0]) + (gu[1][2] + gu[2][1]) * (gv[1][2] + gv[2][1]) +
+                          (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
+        return prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
+    }
+}
+
+// Nodal shares inner[o] = sum_q N[q, o] ramp'(rho_q) (strain(phi) : C0 : strain(psi)) detJ_q of one element
+// (pyfem.py:1239-1276, 1872-1920).  hex8: gradients through G_a = det grad N_a.  quad4: the fields are bilinear like
+// the map, so det * df/dx = y_eta f_xi - y_xi f_eta and det * df/dy = x_xi f_eta - x_eta f_xi with f_xi = a + c eta,
+// f_eta = b + c xi -- six flops per field component and point, and no G_a at all (30 instead of 54 flops per point
+// ahead of the energy for two components; 285 instead of 325 FP64 instructions per element, 78 instead of 128 registers).
+template <int NNE, int M>
+PFG_DEV void sens_element(const SensParams& prm, const double (&xe)[NNE][Elem<NNE>::DIM], const double (&re)[NNE],
+                          const double (&ue)[NNE][M], const double (&ve)[NNE][M], double (&inner)[NNE]) {
+    constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+#pragma unroll
+    for (int a = 0; a < NNE; ++a) inner[a] = 0.0;
+    const double scale = 1.0 + prm.mat.p;
+    if constexpr (NNE == 4) {
+        const Quad4Coef c = quad4_coef(xe);
+        Quad4Field fu[M], fv[M];
+#pragma unroll
+        for (int k = 0; k < M; ++k) {
+            fu[k] = quad4_field4(ue[0][k], ue[1][k], ue[2][k], ue[3][k]);
+            fv[k] = quad4_field4(ve[0][k], ve[1][k], ve[2][k], ve[3][k]);
+        }
+        const Quad4Field fr = quad4_field4(re[0], re[1], re[2], re[3]);
+        const double scale16 = 0.0625 * scale;  // the two field gradients carry a factor 4 each
+        for_each_q<4>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            constexpr double xi = Elem<4>::qp(Q, 0), eta = Elem<4>::qp(Q, 1);
+            const double xxi = fma(c.cx, eta, c.ax), xeta = fma(c.cx, xi, c.bx);
+            const double yxi = fma(c.cy, eta, c.ay), yeta = fma(c.cy, xi, c.by);
+            const double det = xxi * yeta - xeta * yxi;
+            const double rq = (prm.mat.rho != nullptr)
+                                  ? fma(fr.c, 0.25 * xi * eta, fma(fr.b, 0.25 * eta, fma(fr.a, 0.25 * xi, 0.25 * fr.m)))
+                                  : prm.mat.rho_const;
+            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);  // ramp'(rho_q) = (1 + p) / den^2, pyfem.py:1325
+            double gu[M][2], gv[M][2];                          // det * gradients of the two fields
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const double uxi = fma(fu[k].c, eta, fu[k].a), ueta = fma(fu[k].c, xi, fu[k].b);
+                const double vxi = fma(fv[k].c, eta, fv[k].a), veta = fma(fv[k].c, xi, fv[k].b);
+                gu[k][0] = yeta * uxi - yxi * ueta, gu[k][1] = xxi * ueta - xeta * uxi;
+                gv[k][0] = yeta * vxi - yxi * veta, gv[k][1] = xxi * veta - xeta * vxi;
+            }
+            // ramp' * (gu / det) . (gv / det) * det * w with w = 1: one reciprocal for both quotients
+            const double t = scale16 * sens_energy<M, 2>(prm, gu, gv) * fast_rcp(den * den * det);
+#pragma unroll
+            for (int a = 0; a < 4; ++a) inner[a] = fma(Elem<4>::N(Q, a), t, inner[a]);
+        });
+    } else {
+        GeoCtx<NNE> geo(xe);
+        for_each_q<NQ>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            double det, G[NNE][DIM];  // G = det * grad N
+            geo.template at<Q>(xe, det, G);
+            const double rq = (prm.mat.rho != nullptr) ? interp<NNE, Q>(re) : prm.mat.rho_const;
+            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);
+            double gu[M][DIM], gv[M][DIM];
+#pragma unroll
+            for (int k = 0; k < M; ++k)
+#pragma unroll
+                for (int l = 0; l < DIM; ++l) {
+                    double su = 0.0, sv = 0.0;
+#pragma unroll
+                    for (int a = 0; a < NNE; ++a) {
+                        su = fma(G[a][l], ue[a][k], su);
+                        sv = fma(G[a][l], ve[a][k], sv);
+                    }
+                    gu[k][l] = su, gv[k][l] = sv;
+                }
+            const double t = scale * sens_energy<M, DIM>(prm, gu, gv) * fast_rcp(den * den * det);
+#pragma unroll
+            for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
+        });
+    }
+}
+
 template <int NNE, int M>
 __global__ void __launch_bounds__(128) k_dv_sens(MeshView mv, SensParams prm, double* __restrict__ out) {
     const int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (e >= mv.nelems) return;
-    if (mv.elem_skip != nullptr && mv.elem_skip[e]) return;  // integrated by another rank
-    constexpr int DIM = Elem<NNE>::DIM, NQ = Elem<NNE>::NQ;
+    // (whole warps stay in the kernel for the shuffles below; a masked element is integrated by another rank)
+    const bool active = e < mv.nelems && !(mv.elem_skip != nullptr && mv.elem_skip[e]);
+    constexpr int DIM = Elem<NNE>::DIM;
     int nodes[NNE];
+    double inner[NNE];
 #pragma unroll
-    for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
-    double xe[NNE][DIM], re[NNE], ue[NNE][M], ve[NNE][M], inner[NNE];
-    load_coords<NNE>(mv.X, nodes, xe);
-    load_field<NNE>(prm.mat.rho, nodes, re);
+    for (int a = 0; a < NNE; ++a) nodes[a] = -1 - a, inner[a] = 0.0;
+    if (active) {
 #pragma unroll
-    for (int a = 0; a < NNE; ++a) {
+        for (int a = 0; a < NNE; ++a) nodes[a] = __ldg(mv.conn + e * NNE + a);
+        double xe[NNE][DIM], re[NNE], ue[NNE][M], ve[NNE][M];
+        load_coords<NNE>(mv.X, nodes, xe);
+        load_field<NNE>(prm.mat.rho, nodes, re);
 #pragma unroll
-        for (int c = 0; c < M; ++c) {
-            ue[a][c] = __ldg(prm.phi + (int64_t)nodes[a] * M + c);
-            ve[a][c] = __ldg(prm.psi + (int64_t)nodes[a] * M + c);
-        }
-        inner[a] = 0.0;
-    }
-    GeoCtx<NNE> geo(xe);
-    for_each_q<NQ>([&](auto qc) {
-        constexpr int Q = decltype(qc)::value;
-        double det, G[NNE][DIM];  // G = det * grad N
-        geo.template at<Q>(xe, det, G);
-        const double rq = (prm.mat.rho != nullptr) ? interp<NNE, Q>(re) : prm.mat.rho_const;
-        const double den = fma(prm.mat.p, 1.0 - rq, 1.0);  // ramp'(rho_q) = (1 + p) / den^2, pyfem.py:1325
-        double gu[M][DIM], gv[M][DIM];                      // det * gradients of the two fields
+        for (int a = 0; a < NNE; ++a) {
 #pragma unroll
-        for (int c = 0; c < M; ++c)
-#pragma unroll
-            for (int l = 0; l < DIM; ++l) {
-                double su = 0.0, sv = 0.0;
-#pragma unroll
-                for (int a = 0; a < NNE; ++a) {
-                    su = fma(G[a][l], ue[a][c], su);
-                    sv = fma(G[a][l], ve[a][c], sv);
-                }
-                gu[c][l] = su, gv[c][l] = sv;
+            for (int c = 0; c < M; ++c) {
+                ue[a][c] = __ldg(prm.phi + (int64_t)nodes[a] * M + c);
+                ve[a][c] = __ldg(prm.psi + (int64_t)nodes[a] * M + c);
             }
-        double energy;
-        if constexpr (M == 1) {
-            energy = 0.0;
-#pragma unroll
-            for (int l = 0; l < DIM; ++l) energy = fma(gu[0][l], gv[0][l], energy);
-        } else if constexpr (DIM == 2) {  // strains [ex, ey, gxy] (pyfem.py:1988-1998)
-            const double gxu = gu[0][1] + gu[1][0], gxv = gv[0][1] + gv[1][0];
-            energy = prm.c11 * (gu[0][0] * gv[0][0] + gu[1][1] * gv[1][1]) +
-                     prm.c12 * (gu[0][0] * gv[1][1] + gu[1][1] * gv[0][0]) + prm.c33 * gxu * gxv;
-        } else {  // [ex, ey, ez, gxy, gyz, gxz] (pyfem.py:2000-2011)
-            const double su = gu[0][0] + gu[1][1] + gu[2][2], sv = gv[0][0] + gv[1][1] + gv[2][2];
-            double diag = 0.0;
-#pragma unroll
-            for (int l = 0; l < 3; ++l) diag = fma(gu[l][l], gv[l][l], diag);
-            const double sh = (gu[0][1] + gu[1][0]) * (gv[0][1] + gv[1][0]) + (gu[1][2] + gu[2][1]) * (gv[1][2] + gv[2][1]) +
-                              (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
-            energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
         }
-        // ramp' * (gu / det) . (gv / det) * det * w with w = 1: one reciprocal for both quotients
-        const double t = (1.0 + prm.mat.p) * energy * fast_rcp(den * den * det);
+        sens_element<NNE, M>(prm, xe, re, ue, ve, inner);
+    }
+    // Elements that follow each other along a mesh line share an edge (quad4) or a face (hex8): local nodes
+    // (1, 2[, 5, 6]) of one are nodes (0, 3[, 4, 7]) of the next.  Where the ids say so (checked per lane pair, any mesh)
+    // the next lane's share travels by shuffle and one atomic serves both: half the atomics on a lattice.
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
-    });
+    for (int k = 0; k < NNE / 2; ++k) {
+        const int mine = (k & 1) ? (k / 2) * 4 + 2 : (k / 2) * 4 + 1;    // 1, 2, 5, 6
+        const int theirs = (k & 1) ? (k / 2) * 4 + 3 : (k / 2) * 4 + 0;  // 0, 3, 4, 7
+        const int next_id = __shfl_down_sync(0xffffffffu, nodes[theirs], 1);
+        const double next_val = __shfl_down_sync(0xffffffffu, inner[theirs], 1);
+        const int prev_id = __shfl_up_sync(0xffffffffu, nodes[mine], 1);
+        if (lane < 31 && next_id == nodes[mine]) inner[mine] += next_val;
+        if (lane > 0 && prev_id == nodes[theirs]) nodes[theirs] = -1;  // taken by the previous lane
+    }
 #pragma unroll
     for (int a = 0; a < NNE; ++a)
         if (nodes[a] >= mv.own_begin && nodes[a] < mv.own_end) atomicAdd(out + (nodes[a] - mv.own_begin), inner[a]);
@@ -1223,56 +1356,14 @@ struct SensOp {
     template <class Sink>
     PFG_DEV static void run(const Params& prm, const double (&xe)[NNE][DIM], const double (&fe)[NNE * FW], int64_t,
                             Sink& sink) {
-        double inner[NNE];
+        double inner[NNE], re[NNE], ue[NNE][MF], ve[NNE][MF];
 #pragma unroll
-        for (int a = 0; a < NNE; ++a) inner[a] = 0.0;
-        GeoCtx<NNE> geo(xe);
-        for_each_q<NQ>([&](auto qc) {
-            constexpr int Q = decltype(qc)::value;
-            double det, G[NNE][DIM];  // G = det * grad N
-            geo.template at<Q>(xe, det, G);
-            double rq = prm.mat.rho_const;
-            if (prm.mat.rho != nullptr) {
-                rq = 0.0;
+        for (int a = 0; a < NNE; ++a) {
+            re[a] = fe[a * FW];
 #pragma unroll
-                for (int a = 0; a < NNE; ++a) rq = fma(Elem<NNE>::N(Q, a), fe[a * FW], rq);
-            }
-            const double den = fma(prm.mat.p, 1.0 - rq, 1.0);  // ramp'(rho_q) = (1 + p) / den^2, pyfem.py:1325
-            double gu[MF][DIM], gv[MF][DIM];                    // det * gradients of the two fields
-#pragma unroll
-            for (int c = 0; c < MF; ++c)
-#pragma unroll
-                for (int l = 0; l < DIM; ++l) {
-                    double su = 0.0, sv = 0.0;
-#pragma unroll
-                    for (int a = 0; a < NNE; ++a) {
-                        su = fma(G[a][l], fe[a * FW + 1 + c], su);
-                        sv = fma(G[a][l], fe[a * FW + 1 + MF + c], sv);
-                    }
-                    gu[c][l] = su, gv[c][l] = sv;
-                }
-            double energy;
-            if constexpr (MF == 1) {
-                energy = 0.0;
-#pragma unroll
-                for (int l = 0; l < DIM; ++l) energy = fma(gu[0][l], gv[0][l], energy);
-            } else if constexpr (DIM == 2) {  // strains [ex, ey, gxy] (pyfem.py:1988-1998)
-                const double gxu = gu[0][1] + gu[1][0], gxv = gv[0][1] + gv[1][0];
-                energy = prm.c11 * (gu[0][0] * gv[0][0] + gu[1][1] * gv[1][1]) +
-                         prm.c12 * (gu[0][0] * gv[1][1] + gu[1][1] * gv[0][0]) + prm.c33 * gxu * gxv;
-            } else {  // [ex, ey, ez, gxy, gyz, gxz] (pyfem.py:2000-2011)
-                const double su = gu[0][0] + gu[1][1] + gu[2][2], sv = gv[0][0] + gv[1][1] + gv[2][2];
-                double diag = 0.0;
-#pragma unroll
-                for (int l = 0; l < 3; ++l) diag = fma(gu[l][l], gv[l][l], diag);
-                const double sh = (gu[0][1] + gu[1][0]) * (gv[0][1] + gv[1][0]) + (gu[1][2] + gu[2][1]) * (gv[1][2] + gv[2][1]) +
-                                  (gu[0][2] + gu[2][0]) * (gv[0][2] + gv[2][0]);
-                energy = prm.c11 * diag + prm.c12 * (su * sv - diag) + prm.c33 * sh;
-            }
-            const double t = (1.0 + prm.mat.p) * energy * fast_rcp(den * den * det);
-#pragma unroll
-            for (int a = 0; a < NNE; ++a) inner[a] = fma(Elem<NNE>::N(Q, a), t, inner[a]);
-        });
+            for (int c = 0; c < MF; ++c) ue[a][c] = fe[a * FW + 1 + c], ve[a][c] = fe[a * FW + 1 + MF + c];
+        }
+        sens_element<NNE, MF>(prm, xe, re, ue, ve, inner);
 #pragma unroll
         for (int a = 0; a < NNE; ++a) sink.vec(a, inner[a]);
     }
@@ -1544,6 +1635,7 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         cfg.geo_stage_bytes = L.geo_stage_bytes;
         cfg.off_image = L.off_image;
         cfg.off_meta = L.off_meta;
+        cfg.off_feed = L.off_feed;
         const size_t smem = L.total;
         static thread_local size_t cached_smem = 0;
         static thread_local int cached_device = -1;  // function attributes are per device

@@ -156,6 +156,21 @@ PFG_DEV void quad4_geo(const Quad4Coef& c, double& det, double (&G)[4][2]) {
     }
 }
 
+// bilinear nodal field on the reference square: f = (m + a xi + b eta + c xi eta) / 4 (the form quad4_coef gives the
+// map, without its factor 1/4: the callers fold it into their scale)
+struct Quad4Field {
+    double m, a, b, c;
+};
+PFG_DEV Quad4Field quad4_field4(double f0, double f1, double f2, double f3) {
+    const double d10 = f1 - f0, d23 = f2 - f3;
+    Quad4Field r;
+    r.m = (f0 + f1) + (f2 + f3);
+    r.a = d10 + d23;
+    r.b = (f3 - f0) + (f2 - f1);
+    r.c = d23 - d10;
+    return r;
+}
+
 template <int Q>
 PFG_DEV void hex8_geo(const double (&xe)[8][3], double& det, double (&G)[8][3]) {
     double J[3][3];
@@ -502,69 +517,134 @@ struct NlPoissonQuad4Op {  // NonlinearPoisson2D: Jacobian (pyfem.py:1541-1610) 
         int nxdv;
         double coef[kMaxXdv];  // xdv[k] * binom(nxdv-1, k)  (pyfem.py:1466-1470)
     };
-    PFG_DEV static double hfun(const Params& prm, double x, double y) {
-        // h = 1 + 4y(1-y) sum_k coef_k (1-x)^(n-1-k) x^k.  Two-variable Horner: S_k = (1-x) S_{k-1} + coef_k x^k
-        // needs no power table (three flops per term, coefficients straight from the constant bank).
-        const int n = prm.nxdv;
-        const double om = 1.0 - x;
-        double s = prm.coef[0], xp = 1.0;
-        for (int k = 1; k < n; ++k) {
-            xp *= x;
-            s = fma(s, om, prm.coef[k] * xp);
-        }
-        return fma(s, 4.0 * y * (1.0 - y), 1.0);
-    }
     PFG_DEV static double gfun(double x, double y) {  // pyfem.py:1438-1446
         return 1e4 * x * (1.0 - x) * (1.0 - 2.0 * x) * y * (1.0 - y) * (1.0 - 2.0 * y);
     }
     __host__ __device__ __forceinline__ static const double* field(const Params& prm) { return prm.u; }
+    // h = 1 + 4y(1-y) sum_k coef_k (1-x)^(n-1-k) x^k (pyfem.py:1450-1472).  Two-variable Horner: S_k = (1-x) S_{k-1} +
+    // coef_k x^k needs no power table (three flops per term, coefficients straight from the constant bank).  The four
+    // quadrature points share ONE coefficient loop: four independent Horner chains instead of four
+    // dependent ones run one after the other (the loop bound is a run-time value, so the compiler cannot interleave
+    // the per-point loops itself).
+    PFG_DEV static void hfun4(const Params& prm, const double (&x)[4], const double (&y)[4], double (&h)[4]) {
+        const int n = prm.nxdv;
+        double om[4], s[4], xp[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) om[q] = 1.0 - x[q], s[q] = prm.coef[0], xp[q] = 1.0;
+        for (int k = 1; k < n; ++k) {
+            const double ck = prm.coef[k];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                xp[q] *= x[q];
+                s[q] = fma(s[q], om[q], ck * xp[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = fma(s[q], 4.0 * y[q] * (1.0 - y[q]), 1.0);
+    }
+    static constexpr int qidx(int sx, int sy) {  // node / quadrature point with local coordinate signs (sx, sy), 1 = plus
+        return sy ? (sx ? 2 : 3) : (sx ? 1 : 0);
+    }
     template <class Sink>
     PFG_DEV static void run(const Params& prm, const double (&xe)[4][2], const double (&ue)[4], int64_t, Sink& sink) {
-        double K[4][4], res[4];
+        // K = S + T.  S[a][b] = sum_q c1 G_a.G_b is symmetric with zero row sums (partition of unity): only the six
+        // node pairs among the first three nodes are integrated, the fourth node follows from close_rows_upper, and
+        // the gradient part of the residual is S u.  T[a][b] = sum_q c2 (G_a.grad u) N_b, the non-symmetric Newton
+        // term, is linear in eight numbers per element: G_a.grad u = dN_a/dxi P + dN_a/deta R with
+        // P = y_eta gux - x_eta guy, R = x_xi guy - y_xi gux, and both basis tables are tensor products of the
+        // one-dimensional values (1 +- g), so T is formed after the quadrature loop from (P_q, R_q) by two
+        // one-dimensional contractions each (56 flops per element instead of 28 per point).
+        double S[4][4], res[4], Pq[4], Rq[4];
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
             res[a] = 0.0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) K[a][b] = 0.0;
+            for (int b = 0; b < 4; ++b) S[a][b] = 0.0;
         }
-        const Quad4Coef c = quad4_coef(xe);
+        double xq[4], yq[4], hq[4];
         for_each_q<4>([&](auto qc) {
             constexpr int Q = decltype(qc)::value;
-            double det, G[4][2];
-            quad4_geo<Q>(c, det, G);
-            double xq = 0.0, yq = 0.0, uq = 0.0, gux = 0.0, guy = 0.0;
+            double x = 0.0, y = 0.0;
 #pragma unroll
             for (int a = 0; a < 4; ++a) {
-                xq = fma(Elem<4>::N(Q, a), xe[a][0], xq);
-                yq = fma(Elem<4>::N(Q, a), xe[a][1], yq);
-                uq = fma(Elem<4>::N(Q, a), ue[a], uq);
-                gux = fma(G[a][0], ue[a], gux);  // det * du/dx
-                guy = fma(G[a][1], ue[a], guy);
+                x = fma(Elem<4>::N(Q, a), xe[a][0], x);
+                y = fma(Elem<4>::N(Q, a), xe[a][1], y);
             }
-            const double h = hfun(prm, xq, yq);
+            xq[Q] = x, yq[Q] = y;
+        });
+        hfun4(prm, xq, yq, hq);
+        const Quad4Coef c = quad4_coef(xe);
+        const Quad4Field fu = quad4_field4(ue[0], ue[1], ue[2], ue[3]);  // 4 u = m + a xi + b eta + c xi eta
+        for_each_q<4>([&](auto qc) {
+            constexpr int Q = decltype(qc)::value;
+            constexpr double xi = Elem<4>::qp(Q, 0), eta = Elem<4>::qp(Q, 1);
+            const double xxi = fma(c.cx, eta, c.ax), xeta = fma(c.cx, xi, c.bx);
+            const double yxi = fma(c.cy, eta, c.ay), yeta = fma(c.cy, xi, c.by);
+            const double det = xxi * yeta - xeta * yxi;
+            const double uq = fma(fu.c, 0.25 * xi * eta, fma(fu.b, 0.25 * eta, fma(fu.a, 0.25 * xi, 0.25 * fu.m)));
+            const double uxi = fma(fu.c, eta, fu.a), ueta = fma(fu.c, xi, fu.b);  // 4 du/dxi, 4 du/deta
+            const double P4 = yeta * uxi - yxi * ueta;   // 4 det du/dx
+            const double R4 = xxi * ueta - xeta * uxi;   // 4 det du/dy
+            const double h = hq[Q];
             const double inv = fast_rcp(det);
             const double c1 = h * fma(uq, uq, 1.0) * inv;  // detJ h (1+u^2) w / det^2
-            const double c2 = 2.0 * h * uq * inv;
-            const double gsrc = det * gfun(xq, yq);
+            const double c2 = 0.03125 * h * uq * inv;      // 2 h u / det, with 1/4 of the field gradient and 1/16 of T's tables
+            const double gsrc = det * gfun(xq[Q], yq[Q]);
+            Pq[Q] = c2 * (yeta * P4 - xeta * R4);
+            Rq[Q] = c2 * (xxi * R4 - yxi * P4);
 #pragma unroll
-            for (int a = 0; a < 4; ++a) {
-                const double da = fma(G[a][0], gux, G[a][1] * guy);  // det^2 gradN_a . grad u
-                res[a] = fma(c1, da, res[a]);
-                res[a] = fma(-gsrc, Elem<4>::N(Q, a), res[a]);
-                const double hx = c1 * G[a][0], hy = c1 * G[a][1], na = c2 * da;
+            for (int a = 0; a < 4; ++a) res[a] = fma(-gsrc, Elem<4>::N(Q, a), res[a]);
+            double G[3][2];
 #pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    double v = fma(hx, G[b][0], K[a][b]);
-                    v = fma(hy, G[b][1], v);
-                    K[a][b] = fma(na, Elem<4>::N(Q, b), v);
+            for (int a = 0; a < 3; ++a) {
+                const double dxi = Elem<4>::dN(Q, a, 0), deta = Elem<4>::dN(Q, a, 1);
+                G[a][0] = dxi * yeta - deta * yxi;
+                G[a][1] = deta * xxi - dxi * xeta;
+            }
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const double hx = c1 * G[a][0], hy = c1 * G[a][1];
+#pragma unroll
+                for (int b = a; b < 3; ++b) {
+                    S[a][b] = fma(hx, G[b][0], S[a][b]);
+                    S[a][b] = fma(hy, G[b][1], S[a][b]);
                 }
             }
         });
+        close_rows_upper<4>(S);
+        // T[a][b] = sx_a B[sx_b][sy_a][sy_b] + sy_a B'[sy_b][sx_a][sx_b]:
+        //   dN_a/dxi (q) = sx_a f(sy_a sy_q) / 4, dN_a/deta (q) = sy_a f(sx_a sx_q) / 4, N_b(q) = f(sx_b sx_q) f(sy_b sy_q) / 4,
+        //   f(+1) = 1 + g, f(-1) = 1 - g (signs as indices: 0 = minus, 1 = plus)
+        constexpr double fp = 1.0 + PFG_G, fm = 1.0 - PFG_G;
+        double Bs[2][2], Bm[2], Cs[2][2], Cm[2];  // B / B' for equal (by sign) and for unequal second indices
+#pragma unroll
+        for (int sb = 0; sb < 2; ++sb) {
+            const double a0 = fma(fp, Pq[qidx(sb, 0)], fm * Pq[qidx(1 - sb, 0)]);  // sum over sx_q, sy_q = minus
+            const double a1 = fma(fp, Pq[qidx(sb, 1)], fm * Pq[qidx(1 - sb, 1)]);  // sy_q = plus
+            Bs[sb][0] = fma(fp * fp, a0, (fm * fm) * a1);
+            Bs[sb][1] = fma(fm * fm, a0, (fp * fp) * a1);
+            Bm[sb] = (fp * fm) * (a0 + a1);
+            const double d0 = fma(fp, Rq[qidx(0, sb)], fm * Rq[qidx(0, 1 - sb)]);  // sum over sy_q, sx_q = minus
+            const double d1 = fma(fp, Rq[qidx(1, sb)], fm * Rq[qidx(1, 1 - sb)]);  // sx_q = plus
+            Cs[sb][0] = fma(fp * fp, d0, (fm * fm) * d1);
+            Cs[sb][1] = fma(fm * fm, d0, (fp * fp) * d1);
+            Cm[sb] = (fp * fm) * (d0 + d1);
+        }
 #pragma unroll
         for (int a = 0; a < 4; ++a) {
+            constexpr int sxs[4] = {0, 1, 1, 0}, sys[4] = {0, 0, 1, 1};
+            double r = res[a];
 #pragma unroll
-            for (int b = 0; b < 4; ++b) sink.block(0, a, b, &K[a][b]);
-            sink.vec(a, res[a]);
+            for (int b = 0; b < 4; ++b) {
+                const double pb = (sys[a] == sys[b]) ? Bs[sxs[b]][sys[a]] : Bm[sxs[b]];
+                const double rb = (sxs[a] == sxs[b]) ? Cs[sys[b]][sxs[a]] : Cm[sys[b]];
+                const double tab = (sxs[a] ? pb : -pb) + (sys[a] ? rb : -rb);
+                const double sab = (a <= b) ? S[a][b] : S[b][a];
+                r = fma(sab, ue[b], r);  // gradient part of the residual: S u
+                const double v = tab + sab;
+                sink.block(0, a, b, &v);
+            }
+            sink.vec(a, r);
         }
     }
 };
