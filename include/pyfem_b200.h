@@ -285,6 +285,27 @@ PFG_API int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, 
                    void* stream);
 
 /*
+ * The same conjugate gradients over the row slabs of several ranks (handles built with own_range / node_gid, one per
+ * rank and GPU): what Assembler._solve_linear_system(K, rhs, method="cg") (pyfem.py:2403-2423) becomes when the
+ * matrix is distributed by rows.  The library does not link NCCL: the two collective steps are the caller's
+ * callbacks, which enqueue their work on `stream` (torch.distributed in the Python binding, slab_solve.py).
+ *   x_full_dev  work vector of ncols doubles (global dof numbering): the search direction; entries of the owned rows
+ *               are written here, `halo(user)` must make the ghost entries (columns of owned rows owned by other
+ *               ranks) current before every product
+ *   scal_dev    8 doubles; `reduce(user, offset, count)` must sum scal_dev[offset .. offset + count) over the ranks
+ *   row0        global dof index of the rank's first owned row (rows are contiguous)
+ *   b_dev, x_dev   the rank's rows of the right-hand side / the solution
+ * Both callbacks return 0 on success.  Norms in the stopping rule are global, so every rank runs the same number of
+ * iterations and returns the same status.
+ */
+typedef int (*pfg_reduce_fn)(void* user, int offset, int count);
+typedef int (*pfg_halo_fn)(void* user);
+PFG_API int pfg_cg_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, int x_is_zero,
+                        double* x_full_dev, double* scal_dev, int64_t row0, double rtol, double atol, int max_iter,
+                        int check_every, pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, int* iters_out,
+                        double* resid_out, void* stream);
+
+/*
  * Jacobi-preconditioned BiCGStab on the device CSR, for NON-SYMMETRIC systems: the Newton step of
  * Assembler.solve_nonlinear (pyfem.py:2337-2353: K is the Jacobian of NonlinearPoisson2D, the reference solves it with
  * gmres + pyamg or spsolve).  Same arguments and stopping rule as pfg_cg; x_dev is zero-filled here (x0 = 0).  Scalars

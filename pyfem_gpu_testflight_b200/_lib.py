@@ -34,6 +34,9 @@ PHYS_POISSON, PHYS_ELASTICITY, PHYS_HELMHOLTZ, PHYS_NLPOISSON = 1, 2, 3, 4
 CREATE_NO_GATHER_PLAN = 1
 CREATE_NO_REORDER = 2
 
+REDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_int)  # pfg_reduce_fn(user, offset, count)
+HALO_FN = ctypes.CFUNCTYPE(c_int, c_void_p)                 # pfg_halo_fn(user)
+
 # name -> (restype, argtypes); must list every PFG_API symbol of include/pyfem_b200.h
 PROTOTYPES = {
     "pfg_abi_version": (c_int, []),
@@ -59,6 +62,9 @@ PROTOTYPES = {
     "pfg_spmv_t": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfg_cg": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_double, c_double, c_int, c_int,
                        POINTER(c_int), POINTER(c_double), c_void_p]),
+    "pfg_cg_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_double,
+                            c_double, c_int, c_int, REDUCE_FN, HALO_FN, c_void_p, POINTER(c_int), POINTER(c_double),
+                            c_void_p]),
     "pfg_scatter_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_scatter_vector": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_element_matrices": (c_int, [c_void_p, c_int, c_void_p, c_double, POINTER(c_double), c_int, c_void_p, c_void_p,

@@ -187,6 +187,13 @@ __device__ __forceinline__ double sum_partials(const double* __restrict__ partia
     return bcast;
 }
 
+// out[0] = sum of n partial sums, in a fixed order (one CTA): the value a rank contributes to an all-reduce
+__global__ void __launch_bounds__(kVecThreads) k_sum_into(const double* __restrict__ partial, int n, double* __restrict__ out) {
+    __shared__ double red[kVecThreads / 32];
+    const double t = sum_partials(partial, n, red);
+    if (threadIdx.x == 0) out[0] = t;
+}
+
 // r = b - A x0 is formed by the caller as r = b (x0 = 0) or through k_spmv_rows; this kernel starts the recurrences:
 // z = dinv r, p = z, partial sums of r.z and r.r
 __global__ void __launch_bounds__(kVecThreads) k_cg_init(int64_t n, const double* __restrict__ dinv, const double* __restrict__ r,
@@ -547,6 +554,96 @@ extern "C" int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_de
         PFG_TRY(host_sum(part_rr, &rr));
         if (!(rr == rr)) {
             set_error("pfg_cg: the residual became NaN after %d iterations (matrix not positive definite?)", it);
+            return PFG_ERR_INVALID;
+        }
+    }
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = std::sqrt(rr);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return (std::sqrt(rr) <= target) ? PFG_OK : PFG_ERR_NOCONV;
+}
+
+// Conjugate gradients over the row slabs of several ranks: the same kernels as pfg_cg; every dot product is summed
+// on the rank in a fixed order, written to one slot of scal_dev and all-reduced by the caller's callback (the library
+// itself does not link NCCL), the search direction lives in a global-length vector whose ghost entries the halo
+// callback refreshes before every product.
+extern "C" int pfg_cg_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, int x_is_zero,
+                           double* x_full_dev, double* scal_dev, int64_t row0, double rtol, double atol, int max_iter,
+                           int check_every, pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, int* iters_out,
+                           double* resid_out, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    MeshDev& d = mesh->d;
+    const int64_t nown = d.own_end - d.own_begin, n = nown * d.m, ncols = d.ncols_nodes * d.m;
+    if (!vals_dev || !b_dev || !x_dev || !x_full_dev || !scal_dev || !reduce || !halo || max_iter < 0 || row0 < 0 ||
+        row0 + n > ncols) {
+        set_error("pfg_cg_dist: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(ensure_solve_scratch(d, true));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* r = d.cg_work;
+    double *z = r + n, *Ap = z + 2 * n, *dinv = Ap + n;  // (the slot pfg_cg uses for p stays free: p lives in x_full)
+    double* p = x_full_dev + row0;
+    double* parts = r + 9 * n;
+    double *part_a = parts, *part_b = parts + kMaxPartials, *part_c = parts + 2 * kMaxPartials;
+    const unsigned gs = spmv_grid(std::max<int64_t>(n, 1), d.sm_count);
+    const int gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
+    // scal_dev: [0] p.Ap  [1] / [3] r.z (alternating)  [2] r.r  [4] |b|^2
+    auto cb = [&](int rc, const char* what) -> int {
+        if (rc != 0) {
+            set_error("pfg_cg_dist: the %s callback failed (%d)", what, rc);
+            return PFG_ERR_INVALID;
+        }
+        return PFG_OK;
+    };
+    auto read_scal = [&](int slot, double* out) -> int {
+        PFG_CUDA_TRY(cudaMemcpyAsync(out, scal_dev + slot, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        return PFG_OK;
+    };
+    if (n) k_inv_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, nown, d.m, vals_dev, dinv);
+    if (x_is_zero) {
+        PFG_CUDA_TRY(cudaMemsetAsync(x_dev, 0, n * sizeof(double), st));
+        PFG_CUDA_TRY(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        PFG_CUDA_TRY(cudaMemcpyAsync(p, x_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        PFG_TRY(cb(halo(user), "halo"));
+        if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, x_full_dev, Ap, nullptr, nullptr);
+        k_residual<<<gv, kVecThreads, 0, st>>>(n, b_dev, Ap, r);
+    }
+    k_norm2_partials<<<gv, kVecThreads, 0, st>>>(n, b_dev, part_a);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(part_a, gv, scal_dev + 4);
+    k_cg_init<<<gv, kVecThreads, 0, st>>>(n, dinv, r, z, p, part_b, part_c);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(part_b, gv, scal_dev + 1);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(part_c, gv, scal_dev + 2);
+    PFG_CUDA_TRY(cudaGetLastError());
+    PFG_TRY(cb(reduce(user, 1, 2), "reduce"));
+    PFG_TRY(cb(reduce(user, 4, 1), "reduce"));
+    double bb = 0.0, rr = 0.0;
+    PFG_TRY(read_scal(4, &bb));
+    PFG_TRY(read_scal(2, &rr));
+    const double target = std::max(rtol * std::sqrt(bb), atol);  // scipy's cg: |r| <= max(rtol |b|, atol), global norms
+    int it = 0;
+    if (check_every <= 0) check_every = 16;
+    while (std::sqrt(rr) > target && it < max_iter) {  // rr is the same number on every rank: so is the trip count
+        const int batch = std::min(check_every, max_iter - it);
+        for (int j = 0; j < batch; ++j, ++it) {
+            const int rz_old = (it & 1) ? 3 : 1, rz_new = (it & 1) ? 1 : 3;
+            PFG_TRY(cb(halo(user), "halo"));
+            if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, x_full_dev, Ap, p, part_a);
+            k_sum_into<<<1, kVecThreads, 0, st>>>(part_a, n ? (int)gs : 0, scal_dev + 0);
+            PFG_TRY(cb(reduce(user, 0, 1), "reduce"));
+            k_cg_update<<<gv, kVecThreads, 0, st>>>(n, 1, 1, scal_dev + 0, scal_dev + rz_old, dinv, p, Ap, x_dev, r, z,
+                                                    part_b, part_c);
+            k_sum_into<<<1, kVecThreads, 0, st>>>(part_b, gv, scal_dev + rz_new);
+            k_sum_into<<<1, kVecThreads, 0, st>>>(part_c, gv, scal_dev + 2);
+            PFG_TRY(cb(reduce(user, std::min(rz_new, 2), 2), "reduce"));  // slots (1, 2) or (2, 3)
+            k_cg_direction<<<gv, kVecThreads, 0, st>>>(n, 1, scal_dev + rz_new, scal_dev + rz_old, z, p);
+        }
+        PFG_CUDA_TRY(cudaGetLastError());
+        PFG_TRY(read_scal(2, &rr));
+        if (!(rr == rr)) {
+            set_error("pfg_cg_dist: the residual became NaN after %d iterations (matrix not positive definite?)", it);
             return PFG_ERR_INVALID;
         }
     }

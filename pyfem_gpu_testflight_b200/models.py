@@ -51,7 +51,7 @@ class ModelBase:
         self.ndof = self.nnodes * self.ndof_per_node
 
         # device: H2D of X / conn, the conn.min()/max() asserts of pyfem.py:680-681, CSR pattern, plans
-        self.slab = self._reducer = None
+        self.slab = self._reducer = self._slab_cg = None
         if group is not None or partition is not None:
             self._init_slab(group, partition, node_ranges, halo, device)
         else:
@@ -193,8 +193,26 @@ class ModelBase:
         torch = _torch()
         rhs_d = torch.as_tensor(rhs).to(device=self.mesh.device, dtype=torch.float64).clone()
         self.mesh.apply_dirichlet(vals, rhs_d, self.dof_fixed, self.dof_fixed_vals, enforce_symmetric=True)
-        u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
+        if self.slab is not None and self.slab.size > 1:
+            # one rank of a row-slab partition: `rhs` / `u` are the rank's rows, the solve runs over all ranks
+            # (slab_solve.py: halo exchange of the search direction + three all-reduced scalars per iteration)
+            if self._slab_cg is None:
+                from .slab_solve import SlabCG
+                self._slab_cg = SlabCG(self.mesh, self.slab.part, self.slab.ranges, self.slab.rank, self.slab.group)
+            u, iters, _ = self._slab_cg.solve(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
+        else:
+            u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         return u, rhs_d, iters
+
+    def _global_sum(self, v):
+        """Sum of a per-rank scalar over the ranks of a slab partition (the value itself otherwise)."""
+        if self.slab is None or self.slab.size == 1:
+            return v
+        import torch.distributed as dist
+        on_host = dist.get_backend(self.slab.group) == "gloo"  # gloo reduces host memory
+        t = _torch().tensor([float(v)], dtype=_torch().float64, device="cpu" if on_host else self.mesh.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.slab.group)
+        return float(t.item())
 
     def apply_dirichlet_bcs(self, K, rhs, enforce_symmetric_K=True):
         """Host-side Dirichlet conditions with the reference's semantics (pyfem.py:780-835): rows (and, if
@@ -363,7 +381,9 @@ class LinearPoisson(_DensityFunctions, ModelBase):
         """Thermal compliance and the solution (pyfem.py:1033-1073).  device=True: Dirichlet conditions and a
         Jacobi-preconditioned CG run on the device CSR (homogeneous or symmetric-eliminated conditions)."""
         _, rhs, u = self._solve_compliance_system(rho, solver, device)
-        return (rhs.dot(u) if weighted else np.sum(u) / len(u)), u
+        if weighted:
+            return self._global_sum(rhs.dot(u)), u  # slab mode: u and rhs are the rank's rows
+        return self._global_sum(np.sum(u)) / self.ndof, u
 
     def compliance_grad(self, rho, u, weighted=True):
         """pyfem.py:1075-1101."""
@@ -447,7 +467,7 @@ class LinearElasticity(_DensityFunctions, ModelBase):
     def compliance(self, rho, solver="cg", device=False):
         """Compliance and the solution (pyfem.py:1796-1833); device=True keeps the system and the CG solve in HBM."""
         _, rhs, u = self._solve_compliance_system(rho, solver, device)
-        return rhs.dot(u), u
+        return self._global_sum(rhs.dot(u)), u  # slab mode: u and rhs are the rank's rows
 
     def compliance_grad(self, rho, u):
         """pyfem.py:1835-1847."""

@@ -1,0 +1,176 @@
+"""Krylov solves on a matrix distributed by row slabs (one rank = one GPU = one slab): the multi-GPU form of
+Assembler._solve_linear_system(K, rhs, method="cg") (pyfem.py:2403-2423) and of the solves inside compliance
+(pyfem.py:1050-1068, 1814-1828).
+
+The device work is the library's (pfg_cg_dist: SpMV on the rank's slab, fused vector kernels, fixed-order dot
+products); what crosses ranks is (a) the ghost entries of the search direction -- the columns of a rank's rows that
+belong to other ranks' nodes, one mesh layer either side of a slab -- exchanged with batched send / recv before every
+product, and (b) three all-reduced scalars per iteration.  `HaloExchange` is host logic over torch.distributed only
+(it runs under gloo on CPU tensors as well, tests/test_partition_gloo.py); `SlabCG` binds it to a slab handle.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+class HaloExchange:
+    """Who needs which entries of a row-distributed dof vector.
+
+    ghost_gid  global ids of the nodes this rank reads but does not own (sorted)
+    ranges     [(begin, end)] global node range of every rank
+    m          dofs per node
+    The lists are agreed on once (one all_gather_object of the requests); `refresh(x_full)` then copies, for every
+    neighbour, the owned entries it asked for into a send buffer and scatters what arrives into the ghost entries.
+    """
+
+    def __init__(self, ghost_gid, ranges, m, rank, group=None, device=None):
+        import torch
+        import torch.distributed as dist
+        self.group, self.rank, self.m = group, int(rank), int(m)
+        ghost_gid = np.asarray(ghost_gid, dtype=np.int64)
+        begins = np.array([b for b, _ in ranges], dtype=np.int64)
+        owner = np.searchsorted(begins, ghost_gid, side="right") - 1
+        need = {int(q): ghost_gid[owner == q] for q in np.unique(owner)}  # what this rank asks of rank q
+        if self.rank in need:
+            raise ValueError("ghost nodes must not include owned nodes")
+        everyone = [None] * len(ranges)
+        dist.all_gather_object(everyone, need, group=group)
+        dofs = lambda nodes: (np.asarray(nodes, dtype=np.int64)[:, None] * self.m + np.arange(self.m)).ravel()
+        self.peers = sorted(set(need) | {q for q, asks in enumerate(everyone) if self.rank in asks})
+        dev = torch.device("cpu") if device is None else torch.device(device)
+        # gloo moves host memory only: device vectors are staged through the host then (two processes sharing one
+        # GPU in the tests; under NCCL everything stays on the device and on the stream)
+        self.staged = dev.type == "cuda" and dist.get_backend(group) == "gloo"
+        self.send_idx, self.recv_idx, self.send_buf, self.recv_buf = {}, {}, {}, {}
+        for q in self.peers:
+            s = dofs(everyone[q].get(self.rank, np.empty(0, dtype=np.int64)))
+            r = dofs(need.get(q, np.empty(0, dtype=np.int64)))
+            self.send_idx[q] = torch.as_tensor(s, device=dev)
+            self.recv_idx[q] = torch.as_tensor(r, device=dev)
+            self.send_buf[q] = torch.empty(len(s), dtype=torch.float64, device=dev)
+            self.recv_buf[q] = torch.empty(len(r), dtype=torch.float64, device=dev)
+        self.bytes_per_refresh = 8 * sum(len(v) for v in self.send_idx.values())
+
+    def _peer(self, q):
+        import torch.distributed as dist
+        return q if self.group is None else dist.get_global_rank(self.group, q)
+
+    def refresh(self, x_full):
+        """x_full: global-length dof vector whose owned entries are current; on return the ghost entries are too."""
+        import torch
+        import torch.distributed as dist
+        ops, landing = [], {}
+        for q in self.peers:
+            if len(self.send_idx[q]):
+                torch.index_select(x_full, 0, self.send_idx[q], out=self.send_buf[q])
+                out = self.send_buf[q].cpu() if self.staged else self.send_buf[q]
+                ops.append(dist.P2POp(dist.isend, out, self._peer(q), group=self.group))
+            if len(self.recv_idx[q]):
+                landing[q] = torch.empty(len(self.recv_idx[q]), dtype=torch.float64) if self.staged else self.recv_buf[q]
+                ops.append(dist.P2POp(dist.irecv, landing[q], self._peer(q), group=self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for q, buf in landing.items():
+            x_full.index_copy_(0, self.recv_idx[q], buf.to(x_full.device) if self.staged else buf)
+        return x_full
+
+    def all_reduce(self, t):
+        import torch.distributed as dist
+        if self.staged:
+            host = t.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=self.group)
+            t.copy_(host)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t
+
+
+def cg_reference(matvec, exchange, b_owned, row0, ncols, dinv, rtol=1e-8, atol=0.0, max_iter=1000):
+    """The recurrence pfg_cg_dist runs, with torch tensors and a caller-supplied slab product: the CPU model of the
+    distributed solve used by the gloo tests (this is test support for the HOST logic -- the product path is SlabCG)."""
+    import torch
+    n = b_owned.numel()
+    x = torch.zeros_like(b_owned)
+    p_full = torch.zeros(ncols, dtype=torch.float64, device=b_owned.device)
+    p = p_full[row0:row0 + n]
+    r = b_owned.clone()
+    z = dinv * r
+    p.copy_(z)
+    rz = exchange.all_reduce(torch.dot(r, z).reshape(1))
+    rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
+    bb = exchange.all_reduce(torch.dot(b_owned, b_owned).reshape(1))
+    target = max(rtol * float(bb.sqrt()), atol)
+    it = 0
+    while float(rr.sqrt()) > target and it < max_iter:
+        exchange.refresh(p_full)
+        Ap = matvec(p_full)
+        pAp = exchange.all_reduce(torch.dot(p, Ap).reshape(1))
+        alpha = rz / pAp
+        x += alpha * p
+        r -= alpha * Ap
+        z = dinv * r
+        rz_new = exchange.all_reduce(torch.dot(r, z).reshape(1))
+        rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
+        p.copy_(z + (rz_new / rz) * p)
+        rz = rz_new
+        it += 1
+    return x, it, float(rr.sqrt())
+
+
+class SlabCG:
+    """Jacobi-preconditioned conjugate gradients on the device CSR of a row-slab model (models.py, `group=`)."""
+
+    def __init__(self, mesh, part, ranges, rank, group=None):
+        import torch
+        self.mesh, self.group = mesh, group
+        m = mesh.ndof_per_node
+        lb, le = part.own_range
+        gid = np.asarray(part.node_gid, dtype=np.int64)
+        ghost = np.concatenate([gid[:lb], gid[le:]])
+        self.exchange = HaloExchange(ghost, ranges, m, rank, group=group, device=mesh.device)
+        self.row0 = int(part.owned_global_range[0]) * m
+        self.x_full = torch.zeros(mesh.ncols, dtype=torch.float64, device=mesh.device)
+        self.scal = torch.zeros(8, dtype=torch.float64, device=mesh.device)
+        self._error = None
+
+        def reduce_cb(_user, offset, count):
+            try:
+                self.exchange.all_reduce(self.scal[offset:offset + count])
+                return 0
+            except BaseException as exc:  # must not propagate through the C frames
+                self._error = exc
+                return 1
+
+        def halo_cb(_user):
+            try:
+                self.exchange.refresh(self.x_full)
+                return 0
+            except BaseException as exc:
+                self._error = exc
+                return 1
+
+        self._reduce_cb, self._halo_cb = _lib.REDUCE_FN(reduce_cb), _lib.HALO_FN(halo_cb)  # kept alive with self
+
+    def solve(self, vals, b_owned, x0=None, rtol=1e-8, atol=0.0, max_iter=None, check_every=16):
+        """(x_owned, iterations, |r| over all ranks); RuntimeError like the reference when max_iter is reached."""
+        import torch
+        mesh = self.mesh
+        b = mesh._dev_f64(b_owned, mesh.nrows, "b")
+        x = torch.empty_like(b) if x0 is None else mesh._dev_f64(x0, mesh.nrows, "x0").clone()
+        iters, resid = ctypes.c_int(0), ctypes.c_double(0.0)
+        max_iter = 10 * mesh.ncols if max_iter is None else int(max_iter)  # scipy's default, on the global size
+        self._error = None
+        with torch.cuda.device(mesh.device):
+            st = mesh._lib.pfg_cg_dist(mesh._handle, vals.data_ptr(), b.data_ptr(), x.data_ptr(), 1 if x0 is None else 0,
+                                       self.x_full.data_ptr(), self.scal.data_ptr(), self.row0, float(rtol),
+                                       float(atol), max_iter, int(check_every), self._reduce_cb, self._halo_cb, None,
+                                       ctypes.byref(iters), ctypes.byref(resid), mesh._stream())
+        if self._error is not None:
+            raise self._error
+        if st == _lib.PFG_ERR_NOCONV:
+            raise RuntimeError(f"cg failed with code {iters.value}")
+        _lib.check(st)
+        return x, int(iters.value), float(resid.value)

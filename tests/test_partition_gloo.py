@@ -134,3 +134,74 @@ def test_index_bytes_rule():
     assert index_bytes_rule(16777216 * 2, 8, 2 * 33570818) == 8
     assert index_bytes_rule(16777216, 24, 50923779) == 8       # C5
     assert index_bytes_rule(10, 4, 2 ** 31) == 8               # many columns alone switch the width
+
+
+def _cg_worker(rank, world, port, out_dir):
+    for p in (ROOT, os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from pyfem_gpu_testflight_b200.partition import SlabContext
+    from pyfem_gpu_testflight_b200.slab_solve import HaloExchange, cg_reference
+    from scipy import sparse
+    from scipy.sparse.linalg import spsolve
+    ok = True
+    for dims, m in (((17, 12, None), 1), ((6, 5, 7), 3)):
+        X, conn = orc.structured_mesh(*dims)
+        X = X + np.random.default_rng(3).uniform(-0.01, 0.01, size=X.shape)
+        N = X.shape[0]
+        rho = 0.2 + np.random.default_rng(1).random(N)
+        Kg = (orc.assemble_poisson(X, conn, rho, 3.0) if m == 1 else orc.assemble_elasticity(X, conn, rho, 3.0)).tolil()
+        fixed = np.arange(m * dims[0])  # the first mesh line / its dofs
+        b = np.random.default_rng(2).random(N * m)
+        for f in fixed:  # symmetric elimination with zero values
+            Kg[f, :] = 0.0
+            Kg[:, f] = 0.0
+            Kg[f, f] = 1.0
+            b[f] = 0.0
+        Kg = Kg.tocsr()
+        ctx = SlabContext(X, conn, group=dist.group.WORLD)
+        part = ctx.part
+        gb, ge = ctx.owned_nodes
+        lb, le = part.own_range
+        gid = np.asarray(part.node_gid)
+        ghost = np.concatenate([gid[:lb], gid[le:]])
+        ex = HaloExchange(ghost, ctx.ranges, m, rank, group=dist.group.WORLD)
+        rows = Kg[gb * m: ge * m]
+        # the slab reads owned + ghost columns only
+        used = np.unique(rows.indices // m)
+        ok &= bool(np.all(np.isin(used, np.concatenate([np.arange(gb, ge), ghost]))))
+        A = torch.sparse_csr_tensor(torch.from_numpy(rows.indptr.astype(np.int64)), torch.from_numpy(rows.indices.astype(np.int64)),
+                                    torch.from_numpy(rows.data), size=rows.shape)
+        dinv = torch.from_numpy(1.0 / Kg.diagonal()[gb * m: ge * m])
+
+        def matvec(p_full):  # poison what this rank neither owns nor asked for: the product must not read it
+            masked = torch.full_like(p_full, float("nan"))
+            for nodes in (np.arange(gb, ge), ghost):
+                idx = torch.from_numpy((nodes[:, None] * m + np.arange(m)).ravel())
+                masked[idx] = p_full[idx]
+            masked = torch.nan_to_num(masked, nan=1e300)
+            return (A @ masked.unsqueeze(1)).squeeze(1)
+
+        x, iters, resid = cg_reference(matvec, ex, torch.from_numpy(b[gb * m: ge * m]), gb * m, N * m, dinv, rtol=1e-12,
+                                       max_iter=4000)
+        xs = ctx.gather_vector(x.numpy())
+        if rank == 0:
+            ref = spsolve(Kg.tocsc(), b)
+            ok &= iters > 3 and np.max(np.abs(xs - ref)) <= 1e-8 * np.max(np.abs(ref))
+    flag = torch.tensor([1 if ok else 0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        open(os.path.join(out_dir, "ok"), "w").write(str(int(flag.item())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_distributed_cg_host_logic(tmp_path, world):
+    """Halo plan + exchange + the conjugate-gradient recurrence of pfg_cg_dist over row slabs (gloo, CPU tensors, a
+    scipy slab standing in for the device SpMV): the gathered solution equals the direct solve of the global system,
+    and no rank reads an entry it neither owns nor requested."""
+    port = _free_port()
+    mp.spawn(_cg_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    assert open(tmp_path / "ok").read() == "1"
