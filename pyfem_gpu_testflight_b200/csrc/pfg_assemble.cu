@@ -909,6 +909,7 @@ __global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHe
 #define PFG_HEX_NB 7  // 7: one pass over the quadrature points for seven column nodes (63 running sums), the eighth block
 #endif                // from the zero row sums -- 128^3 hex 3.997 -> 3.894 ms; 4: two passes of four column nodes (36
                       // sums each, geometry read twice); 8: one pass with 72 sums (spills: 4.16 ms)
+constexpr int kHexRowsThreads = (kHexRowWarps + 1) * 32;
 constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
 constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
                                                        // consecutive records on different banks
@@ -965,7 +966,6 @@ struct HexRowsCfg {
     int off_geo, geo_stage_bytes;  // two geometry stages
     int off_image, image_stride;   // per consumer warp: four nodes x image_stride doubles (9 * max neighbours)
     int off_meta;                  // per consumer thread 2 x 32 B of node / incidence tables, per warp 2 x 8 B
-    int off_feed;                  // self-feeding ring: per warp four chunk headers + two record-id lists
     int nchunks;
 };
 
@@ -982,72 +982,31 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
                       double* __restrict__ vals, HexRowsCfg cfg) {
     extern __shared__ __align__(128) unsigned char hex_smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(hex_smem);  // [0..1] stage full, [2..3] stage empty
-    unsigned* left = reinterpret_cast<unsigned*>(hex_smem + 64);  // self-feeding ring: warps that have left stage 0 / 1
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t c_begin = (int64_t)cfg.nchunks * blockIdx.x / gridDim.x;
     const int nloc = (int)((int64_t)cfg.nchunks * (blockIdx.x + 1) / gridDim.x - c_begin);
     if (threadIdx.x == 0) {
         mbar_init(&bars[0], 1), mbar_init(&bars[1], 1);
         mbar_init(&bars[2], kHexRowWarps), mbar_init(&bars[3], kHexRowWarps);
-        left[0] = left[1] = 0u;
     }
     __syncthreads();
-    // whole warp: bulk copies of the geometry of `n_recs` element records (ids through `elem_of`) into stage s
-    auto feed_stage = [&](int s, uint32_t n_recs, auto&& elem_of) {
-        if (lane == 0) mbar_expect_tx(&bars[s], n_recs * (uint32_t)kHexGeoBytes);
-        __syncwarp();
-        unsigned char* stage = hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes;
-        for (int r = lane; r < (int)n_recs; r += 32)
-            tma_load_1d(stage + (size_t)r * (kHexGeoStride * 8), geo + (size_t)elem_of(r) * (8 * kHexGeoDoubles),
-                        (uint32_t)kHexGeoBytes, &bars[s]);
-    };
-    if constexpr (!kHexSelfFeed) {
-        if (warp == kHexRowWarps) {
-            // ---- producer warp: geometry of chunk i's records -> stage i & 1
-            for (int i = 0; i < nloc; ++i) {
-                const int s = i & 1, f = i >> 1;
-                const ChunkHdr h = mv.chunks[c_begin + i];
-                const int e_lo = ((int)h.n_recs > lane) ? __ldg(mv.rec_elem + h.rec_begin + lane) : 0;
-                mbar_wait(&bars[2 + s], (f & 1) ^ 1);  // consumers have left the stage's previous chunk
-                feed_stage(s, h.n_recs, [&](int r) { return (r < 32) ? e_lo : __ldg(mv.rec_elem + h.rec_begin + r); });
+    if (warp == kHexRowWarps) {
+        // ---- producer warp: geometry of chunk i's records -> stage i & 1
+        for (int i = 0; i < nloc; ++i) {
+            const int s = i & 1, f = i >> 1;
+            const ChunkHdr h = mv.chunks[c_begin + i];
+            const int e_lo = ((int)h.n_recs > lane) ? __ldg(mv.rec_elem + h.rec_begin + lane) : 0;
+            mbar_wait(&bars[2 + s], (f & 1) ^ 1);  // consumers have left the stage's previous chunk
+            if (lane == 0) mbar_expect_tx(&bars[s], h.n_recs * (uint32_t)kHexGeoBytes);
+            __syncwarp();
+            unsigned char* stage = hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes;
+            for (int r = lane; r < (int)h.n_recs; r += 32) {
+                const int e = (r < 32) ? e_lo : __ldg(mv.rec_elem + h.rec_begin + r);
+                tma_load_1d(stage + (size_t)r * (kHexGeoStride * 8), geo + (size_t)e * (8 * kHexGeoDoubles),
+                            (uint32_t)kHexGeoBytes, &bars[s]);
             }
-            return;
         }
-    }
-    // Self-feeding ring (eight consumer warps, no producer warp): every warp keeps, in its own shared-memory slots,
-    // the header of the chunk after next and that chunk's record ids (cp.async, a chunk ahead); the warp that leaves
-    // chunk i LAST -- elected with a counter, so nobody waits -- issues the bulk copies of chunk i + 2 into the stage
-    // all warps have just left.
-    struct FeedHdr {  // the first 24 bytes of a ChunkHdr
-        uint32_t node_begin, n_nodes, n_recs, n_inc;
-        int64_t rec_begin;
-    };
-    unsigned char* feed_s = hex_smem + cfg.off_feed + (size_t)warp * kHexFeedBytes;
-    auto feed_hdr = [&](int i_chunk) { return reinterpret_cast<FeedHdr*>(feed_s + (i_chunk & 3) * 32); };
-    auto feed_recs = [&](int i_chunk) { return reinterpret_cast<int32_t*>(feed_s + 128 + (i_chunk & 1) * (kHexFeedRecs * 4)); };
-    auto feed_prefetch = [&](int i) {  // at the start of local chunk i: header of i + 3, record ids of i + 2
-        if (i + 3 < nloc && lane == 0) {
-            cp_async_16(feed_hdr(i + 3), mv.chunks + c_begin + i + 3);
-            cp_async_8(reinterpret_cast<unsigned char*>(feed_hdr(i + 3)) + 16, &mv.chunks[c_begin + i + 3].rec_begin);
-        }
-        if (i + 2 < nloc) {
-            const FeedHdr h = *feed_hdr(i + 2);
-            int32_t* dst = feed_recs(i + 2);
-            for (int r = lane; r < min((int)h.n_recs, kHexFeedRecs); r += 32) cp_async_4(dst + r, mv.rec_elem + h.rec_begin + r);
-        }
-    };
-    if constexpr (kHexSelfFeed) {
-        if (warp < 2 && warp < nloc) {  // the first two chunks: direct loads
-            const ChunkHdr h = mv.chunks[c_begin + warp];
-            feed_stage(warp, h.n_recs, [&](int r) { return __ldg(mv.rec_elem + h.rec_begin + r); });
-        }
-        if (lane == 0 && 2 < nloc) {
-            const ChunkHdr h = mv.chunks[c_begin + 2];
-            FeedHdr* dst = feed_hdr(2);
-            dst->node_begin = h.node_begin, dst->n_nodes = h.n_nodes, dst->n_recs = h.n_recs, dst->n_inc = h.n_inc;
-            dst->rec_begin = h.rec_begin;
-        }
-        __syncwarp();
+        return;
     }
     // ---- consumer warps
     const int j = lane & 7;
@@ -1100,7 +1059,6 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
         __syncwarp();
         const uint2 hd = *reinterpret_cast<const uint2*>(hd_s + s * 8);  // (node_begin, n_nodes)
         HexLaneMeta meta = read_meta(hd, s);
-        if constexpr (kHexSelfFeed) feed_prefetch(i);  // (joins the cp.async group issue_meta commits)
         issue_meta((int64_t)hd.x + hd.y, i + 1);
         const double* geo_s = reinterpret_cast<const double*>(hex_smem + cfg.off_geo + s * cfg.geo_stage_bytes);
         bool waited = false;
@@ -1135,26 +1093,7 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
         }
         if (!waited) mbar_wait(&bars[s], f & 1);  // keep the ring in step even without a node in this chunk
         __syncwarp();
-        if constexpr (kHexSelfFeed) {
-            int last = 0;
-            if (lane == 0) {
-                __threadfence_block();  // this warp's reads of the stage come before the count
-                last = (atomicAdd(&left[s], 1u) == (unsigned)(kHexRowWarps - 1));
-                if (last) left[s] = 0u;  // nobody counts on this stage again before the copies issued below have landed
-                __threadfence_block();
-            }
-            last = __shfl_sync(0xffffffffu, last, 0);
-            if (last && i + 2 < nloc) {
-                cp_async_wait<0>();  // issued at the start of this chunk: long since landed
-                __syncwarp();
-                const FeedHdr h = *feed_hdr(i + 2);
-                const int32_t* ids = feed_recs(i + 2);
-                feed_stage(s, h.n_recs,
-                           [&](int r) { return (r < kHexFeedRecs) ? ids[r] : __ldg(mv.rec_elem + h.rec_begin + r); });
-            }
-        } else {
-            if (lane == 0) mbar_arrive(&bars[2 + s]);
-        }
+        if (lane == 0) mbar_arrive(&bars[2 + s]);
     }
     cp_async_wait<0>();
 }
@@ -1635,7 +1574,6 @@ extern "C" int pfg_assemble_elasticity(pfg_mesh* mesh, const double* rho_dev, do
         cfg.geo_stage_bytes = L.geo_stage_bytes;
         cfg.off_image = L.off_image;
         cfg.off_meta = L.off_meta;
-        cfg.off_feed = L.off_feed;
         const size_t smem = L.total;
         static thread_local size_t cached_smem = 0;
         static thread_local int cached_device = -1;  // function attributes are per device

@@ -153,20 +153,10 @@ struct TileLayout {  // how an operator stages one record; decides the code enco
 
 // hex8 chunk-row pass (k_hex8_chunk_rows): shared-memory layout shared by the plan builder (does a mesh fit?) and
 // the launch
-#ifndef PFG_HEX_WARPS
-#define PFG_HEX_WARPS 7
-#endif
-constexpr int kHexRowWarps = PFG_HEX_WARPS;         // consumer warps, four chunk nodes each
-// 7: plus one producer warp that feeds the geometry ring; 8: no producer warp -- the consumer warp that leaves a chunk
-// last issues the bulk copies of the chunk after next (self-feeding ring), all four SM sub-partitions hold two warps
-constexpr bool kHexSelfFeed = (kHexRowWarps == 8);
-constexpr int kHexRowsThreads = (kHexRowWarps + (kHexSelfFeed ? 0 : 1)) * 32;
-constexpr int kHexChunkNodes = kHexSelfFeed ? 32 : 27;
-constexpr int kHexFeedRecs = 128;                                      // record ids prefetched per chunk (more: direct loads)
-constexpr int kHexFeedBytes = 4 * 32 + 2 * kHexFeedRecs * 4;           // per warp: four chunk headers + two record lists
+constexpr int kHexRowWarps = 7;                     // consumer warps, four chunk nodes each (+ one producer warp)
 constexpr int kHexGeoRecordBytes = (8 * 10 + 2) * 8; // staged geometry of one element record: 640 B + 16 B bank shift
 struct HexRowsSmem {
-    int off_geo, geo_stage_bytes, off_image, image_stride, off_meta, off_feed;
+    int off_geo, geo_stage_bytes, off_image, image_stride, off_meta;
     size_t total;
 };
 inline HexRowsSmem hex_rows_smem(int max_chunk_recs, int max_k) {
@@ -176,8 +166,7 @@ inline HexRowsSmem hex_rows_smem(int max_chunk_recs, int max_k) {
     L.geo_stage_bytes = (max_chunk_recs * kHexGeoRecordBytes + 15) & ~15;
     L.off_image = L.off_geo + 2 * L.geo_stage_bytes;
     L.off_meta = L.off_image + kHexRowWarps * 4 * L.image_stride * 8;
-    L.off_feed = L.off_meta + kHexRowWarps * (32 * 64 + 16);
-    L.total = (size_t)L.off_feed + (kHexSelfFeed ? (size_t)kHexRowWarps * kHexFeedBytes : 0);
+    L.total = (size_t)L.off_meta + (size_t)kHexRowWarps * (32 * 64 + 16);
     return L;
 }
 constexpr size_t kMaxDynamicSmem = 227 * 1024;

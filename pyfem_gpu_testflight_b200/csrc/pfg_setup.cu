@@ -1089,8 +1089,8 @@ static int build_gather_plan(MeshDev& d, cudaStream_t st, Scratch& scratch) {
         int budget = env_int("PFG_CHUNK_SMEM_BYTES", 160 * 1024);
         int per_node = std::max(1, d.max_valence) * worst_rb_doubles(NNE, d.m) * 8;
         C = budget / per_node * 4 / 5;  // tie-aware cuts may overshoot the target by up to 1/4
-        // chunk-row pass of hex8 elasticity (k_hex8_chunk_rows): consumer warps x four nodes per round
-        if (d.hex_rows_ok) C = env_int("PFG_HEX_CHUNK_NODES", kHexChunkNodes);
+        // chunk-row pass of hex8 elasticity (k_hex8_chunk_rows): seven consumer warps x four nodes per round
+        if (d.hex_rows_ok) C = env_int("PFG_HEX_CHUNK_NODES", 27);
     }
     C = env_int("PFG_CHUNK_NODES", (int)C);
     C = std::max<int64_t>(4, std::min<int64_t>(C, 1024));
