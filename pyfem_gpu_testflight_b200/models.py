@@ -196,10 +196,7 @@ class ModelBase:
         if self.slab is not None and self.slab.size > 1:
             # one rank of a row-slab partition: `rhs` / `u` are the rank's rows, the solve runs over all ranks
             # (slab_solve.py: halo exchange of the search direction + three all-reduced scalars per iteration)
-            if self._slab_cg is None:
-                from .slab_solve import SlabCG
-                self._slab_cg = SlabCG(self.mesh, self.slab.part, self.slab.ranges, self.slab.rank, self.slab.group)
-            u, iters, _ = self._slab_cg.solve(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
+            u, iters, _ = self._slab_solver().solve(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         else:
             u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         return u, rhs_d, iters
@@ -305,10 +302,49 @@ class _DensityFunctions:
             self._scalar_mesh = DeviceMesh(self.X, self.conn, 1, device=self.mesh.device)
         return self._scalar_mesh
 
+    def _slab_solver(self):
+        if self._slab_cg is None:
+            from .slab_solve import SlabCG
+            self._slab_cg = SlabCG(self.mesh, self.slab.part, self.slab.ranges, self.slab.rank, self.slab.group)
+        return self._slab_cg
+
+    def _local_dofs(self, v):
+        """A dof vector on this rank's LOCAL nodes (owned + ghost) from the global vector or from the rank's own rows
+        (then the ghost entries come from their owners: one halo exchange, slab_solve.HaloExchange)."""
+        torch = _torch()
+        m = self.ndof_per_node
+        part = self.slab.part
+        dof = torch.as_tensor((np.asarray(part.node_gid)[:, None] * m + np.arange(m)).ravel(), device=self.mesh.device)
+        v = torch.as_tensor(np.asarray(v) if not hasattr(v, "device") else v).to(device=self.mesh.device, dtype=torch.float64)
+        if v.numel() == self.ndof:
+            return v[dof]
+        if v.numel() != self.mesh.nrows:
+            raise ValueError(f"dof vector has {v.numel()} entries, expected {self.ndof} (global) or {self.mesh.nrows} "
+                             "(this rank's rows)")
+        solver = self._slab_solver()
+        full = torch.zeros(self.ndof, dtype=torch.float64, device=self.mesh.device)
+        full[solver.row0: solver.row0 + v.numel()] = v
+        return solver.exchange.refresh(full)[dof]
+
+    def _k_dv_sens_slab(self, physics, rho, phi, psi, **kw):
+        """Sensitivities at this rank's owned nodes: every element touching an owned node is local (ghost layer), so
+        no value crosses ranks; phi / psi may be global vectors or the rank's rows (e.g. the u of solve_device)."""
+        if self.deterministic_sens:
+            raise NotImplementedError("the plan-ordered sensitivity pass is single-GPU; slab models use the atomic pass")
+        rho_l = self._local(np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho)
+        phi_l, psi_l = self._local_dofs(phi), self._local_dofs(psi)
+        if self._reducer is not None:  # the reduce variant masks the ghost elements: integrate them here too
+            self.mesh.set_element_mask(None)
+        try:
+            return self.mesh.k_dv_sens(physics, rho_l, self.p, phi_l, psi_l, **kw).cpu().numpy()
+        finally:
+            if self._reducer is not None:
+                self.mesh.set_element_mask(self._reducer.plan.skip_mask)
+
     def _k_dv_sens(self, physics, rho, phi, psi, **kw):
         _check_real(rho)
-        if self.slab is not None:
-            raise NotImplementedError("sensitivities of a slab-partitioned model are not implemented")
+        if self.slab is not None and self.slab.size > 1:
+            return self._k_dv_sens_slab(physics, rho, phi, psi, **kw)
         rho = np.ones(self.nnodes) * rho if not hasattr(rho, "__len__") else rho
         mesh = self._sens_mesh() if self.deterministic_sens else self.mesh
         return mesh.k_dv_sens(physics, rho, self.p, phi, psi, deterministic=self.deterministic_sens, **kw).cpu().numpy()

@@ -78,6 +78,13 @@ def _worker(rank, world, port, backend, halo, out_dir):
                                 group=dist.group.WORLD, halo=halo, device=dev)
     c_dev, u_own = model.compliance(rho, solver="cg", device=True)
     u = model.gather_vector(u_own)
+    # the gradient from the rank's own rows of u (ghost entries travel in one halo exchange) and from the global u
+    grad = model.gather_vector(model.compliance_grad(rho, u_own))
+    u_all = [None]
+    if rank == 0:
+        u_all = [u]
+    dist.broadcast_object_list(u_all, src=0)
+    grad_g = model.gather_vector(model.compliance_grad(rho, u_all[0]))
     if rank == 0:
         fixed = np.asarray(dof_fixed)
         rhs = orc.elasticity_point_loads(2 * X.shape[0], 2, nodal_force)
@@ -86,6 +93,9 @@ def _worker(rank, world, port, backend, halo, out_dir):
         b[fixed] = 0.0
         ok &= np.max(np.abs(u - u_ref)) <= 1e-6 * np.max(np.abs(u_ref))
         ok &= abs(c_dev - b @ u_ref) <= 1e-6 * abs(b @ u_ref)
+        g_ref = -orc.elasticity_K_dv_sens(X, conn, rho, 3.0, u, u)  # pyfem.py:1835-1847 on the same u
+        ok &= np.max(np.abs(grad - g_ref)) <= 1e-10 * np.max(np.abs(g_ref))
+        ok &= np.max(np.abs(grad_g - g_ref)) <= 1e-10 * np.max(np.abs(g_ref))
 
     # hex8, three dofs per node: the slab solve against the single-handle device solve of the same system
     X3, conn3 = orc.structured_mesh(7, 6, 9)
