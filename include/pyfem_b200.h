@@ -316,6 +316,18 @@ PFG_API int pfg_bicgstab(pfg_mesh* mesh, const double* vals_dev, const double* b
                          double atol, int max_iter, int check_every, int* iters_out, double* resid_out, void* stream);
 
 /*
+ * pfg_bicgstab over the row slabs of several ranks (the Newton step of Assembler.solve_nonlinear, pyfem.py:2337-2353,
+ * on a matrix distributed by rows).  As pfg_cg_dist, except that x_full_dev holds TWO global-length work vectors
+ * (2 * ncols doubles: the preconditioned direction and the preconditioned residual) and halo(user, which) refreshes
+ * the ghost entries of vector `which` (0 / 1, at x_full_dev + which * ncols) before the product that reads it.
+ */
+typedef int (*pfg_halo2_fn)(void* user, int which);
+PFG_API int pfg_bicgstab_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev,
+                              double* x_full_dev, double* scal_dev, int64_t row0, double rtol, double atol, int max_iter,
+                              int check_every, pfg_reduce_fn reduce, pfg_halo2_fn halo, void* user, int* iters_out,
+                              double* resid_out, void* stream);
+
+/*
  * Diagnostics for the bench's roofline: sustained FP64 FMA throughput of `device` in TFLOP/s (a DFMA-bound kernel,
  * 8 CTAs of 256 threads per SM, 16 independent chains per thread, best of 4 timed launches with CUDA events).  The
  * assembly kernels run their quadrature on the FP64 CUDA cores, so this is the second roof next to HBM bandwidth

@@ -36,6 +36,7 @@ CREATE_NO_REORDER = 2
 
 REDUCE_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_int)  # pfg_reduce_fn(user, offset, count)
 HALO_FN = ctypes.CFUNCTYPE(c_int, c_void_p)                 # pfg_halo_fn(user)
+HALO2_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_int)         # pfg_halo2_fn(user, which)
 
 # name -> (restype, argtypes); must list every PFG_API symbol of include/pyfem_b200.h
 PROTOTYPES = {
@@ -65,6 +66,9 @@ PROTOTYPES = {
     "pfg_cg_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_double,
                             c_double, c_int, c_int, REDUCE_FN, HALO_FN, c_void_p, POINTER(c_int), POINTER(c_double),
                             c_void_p]),
+    "pfg_bicgstab_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
+                                  c_int, c_int, REDUCE_FN, HALO2_FN, c_void_p, POINTER(c_int), POINTER(c_double),
+                                  c_void_p]),
     "pfg_scatter_matrix": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_scatter_vector": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "pfg_element_matrices": (c_int, [c_void_p, c_int, c_void_p, c_double, POINTER(c_double), c_int, c_void_p, c_void_p,

@@ -53,23 +53,35 @@ class Assembler:
     def _solve_nonlinear_device(self, xdv, u0, tol, atol, max_iter):
         import torch
         model, mesh = self.model, self.model.mesh
+        # one rank of a row-slab partition: u is kept on the global numbering (the assembly reads the rank's local
+        # nodes from it), the rank updates its own rows and fetches the ghost entries from their owners; the step
+        # comes from the BiCGStab over all ranks and the residual norm is the global one.  Returns the rank's rows.
+        solver = model._slab_solver() if (model.slab is not None and model.slab.size > 1) else None
         u = torch.zeros(model.nnodes, dtype=torch.float64, device=mesh.device) if u0 is None else \
             torch.as_tensor(u0, dtype=torch.float64).to(mesh.device).clone()
+        if u.numel() != model.nnodes:
+            raise ValueError(f"u0 must have {model.nnodes} entries (the global mesh)")
+        own = slice(solver.row0, solver.row0 + mesh.nrows) if solver is not None else slice(None)
         res_norm_init = None
         self.last_iterations = []
         for k in range(max_iter):
             K, res = model.assemble_device(xdv, u)  # Jacobian and residual from one pass over the elements
             mesh.apply_dirichlet(K, res, model.dof_fixed, None, enforce_symmetric=False)
-            res_norm = float(torch.linalg.vector_norm(res))
+            rr = torch.dot(res, res).reshape(1)
+            if solver is not None:
+                solver.exchange.all_reduce(rr)
+            res_norm = float(torch.sqrt(rr))
             print("pyfem", "{0:5d} {1:25.15e}".format(k, res_norm))
             if k == 0:
                 res_norm_init = res_norm
             elif res_norm < tol * res_norm_init or res_norm < atol:
                 break
-            du, iters, _ = mesh.bicgstab(K, res, rtol=1e-8)
+            du, iters, _ = (solver if solver is not None else mesh).bicgstab(K, res, rtol=1e-8)
             self.last_iterations.append(iters)
-            u -= du
-        return u.cpu().numpy()
+            u[own] -= du
+            if solver is not None:
+                solver.exchange.refresh(u)
+        return u[own].cpu().numpy()
 
     def _setup_amg(self, K):
         try:

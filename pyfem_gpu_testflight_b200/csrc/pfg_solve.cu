@@ -722,3 +722,95 @@ extern "C" int pfg_bicgstab(pfg_mesh* mesh, const double* vals_dev, const double
     PFG_CUDA_TRY(cudaGetLastError());
     return (std::sqrt(rr) <= target) ? PFG_OK : PFG_ERR_NOCONV;
 }
+
+// BiCGStab over the row slabs of several ranks: pfg_bicgstab's kernels; the two preconditioned vectors y and z live in
+// global-length vectors (x_full_dev holds both, ncols doubles each) whose ghost entries halo(user, which) refreshes
+// before the product that reads them, the five dot products per iteration travel in three all-reduces.
+extern "C" int pfg_bicgstab_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev,
+                                 double* x_full_dev, double* scal_dev, int64_t row0, double rtol, double atol,
+                                 int max_iter, int check_every, pfg_reduce_fn reduce, pfg_halo2_fn halo, void* user,
+                                 int* iters_out, double* resid_out, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    MeshDev& d = mesh->d;
+    const int64_t nown = d.own_end - d.own_begin, n = nown * d.m, ncols = d.ncols_nodes * d.m;
+    if (!vals_dev || !b_dev || !x_dev || !x_full_dev || !scal_dev || !reduce || !halo || max_iter < 0 || row0 < 0 ||
+        row0 + n > ncols) {
+        set_error("pfg_bicgstab_dist: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(ensure_solve_scratch(d, true));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* r = d.cg_work;
+    double *rhat = r + n, *p = rhat + n, *v = p + n, *s_ = v + n, *t = s_ + n, *dinv = t + 3 * n;
+    double *y_full = x_full_dev, *z_full = x_full_dev + ncols;
+    double *y = y_full + row0, *z = z_full + row0;
+    double* parts = r + 9 * n;
+    double *part_a = parts, *part_b = parts + kMaxPartials, *sc = parts + 8 * kMaxPartials;
+    const unsigned gs = spmv_grid(std::max<int64_t>(n, 1), d.sm_count);
+    const int gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
+    // scal_dev: [0] rhat.v  [1] t.s  [2] t.t  [3] rhat.r  [4] r.r  [5] |b|^2
+    auto cb = [&](int rc, const char* what) -> int {
+        if (rc != 0) {
+            set_error("pfg_bicgstab_dist: the %s callback failed (%d)", what, rc);
+            return PFG_ERR_INVALID;
+        }
+        return PFG_OK;
+    };
+    auto sum_into = [&](const double* part, int np, int slot) { k_sum_into<<<1, kVecThreads, 0, st>>>(part, np, scal_dev + slot); };
+    auto read_scal = [&](int slot, double* out) -> int {
+        PFG_CUDA_TRY(cudaMemcpyAsync(out, scal_dev + slot, sizeof(double), cudaMemcpyDeviceToHost, st));
+        PFG_CUDA_TRY(cudaStreamSynchronize(st));
+        return PFG_OK;
+    };
+    if (n) k_inv_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, nown, d.m, vals_dev, dinv);
+    PFG_CUDA_TRY(cudaMemsetAsync(x_dev, 0, n * sizeof(double), st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PFG_CUDA_TRY(cudaMemcpyAsync(rhat, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    PFG_CUDA_TRY(cudaMemsetAsync(p, 0, n * sizeof(double), st));
+    PFG_CUDA_TRY(cudaMemsetAsync(v, 0, n * sizeof(double), st));
+    k_norm2_partials<<<gv, kVecThreads, 0, st>>>(n, b_dev, part_a);
+    sum_into(part_a, gv, 5);
+    k_dot2_partials<<<gv, kVecThreads, 0, st>>>(n, r, rhat, part_a, part_b);
+    sum_into(part_a, gv, 3), sum_into(part_b, gv, 4);
+    PFG_CUDA_TRY(cudaGetLastError());
+    PFG_TRY(cb(reduce(user, 3, 3), "reduce"));
+    k_bicg_scalar<<<1, 32, 0, st>>>(0, 1, scal_dev + 3, 0, nullptr, sc);
+    double bb = 0.0, rr = 0.0;
+    PFG_TRY(read_scal(5, &bb));
+    rr = bb;
+    const double target = std::max(rtol * std::sqrt(bb), atol);
+    int it = 0;
+    if (check_every <= 0) check_every = 8;
+    while (std::sqrt(rr) > target && it < max_iter) {
+        const int batch = std::min(check_every, max_iter - it);
+        for (int j = 0; j < batch; ++j, ++it) {
+            k_bicg_p<<<gv, kVecThreads, 0, st>>>(n, sc, dinv, r, v, p, y);
+            PFG_TRY(cb(halo(user, 0), "halo"));
+            if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, y_full, v, rhat, part_a);
+            sum_into(part_a, n ? (int)gs : 0, 0);
+            PFG_TRY(cb(reduce(user, 0, 1), "reduce"));
+            k_bicg_scalar<<<1, 32, 0, st>>>(1, 1, scal_dev + 0, 0, nullptr, sc);
+            k_bicg_s<<<gv, kVecThreads, 0, st>>>(n, sc, dinv, r, v, s_, z);
+            PFG_TRY(cb(halo(user, 1), "halo"));
+            if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, z_full, t, nullptr, nullptr);
+            k_dot2_partials<<<gv, kVecThreads, 0, st>>>(n, t, s_, part_a, part_b);
+            sum_into(part_a, gv, 1), sum_into(part_b, gv, 2);
+            PFG_TRY(cb(reduce(user, 1, 2), "reduce"));
+            k_bicg_scalar<<<1, 32, 0, st>>>(2, 1, scal_dev + 1, 1, scal_dev + 2, sc);
+            k_bicg_x<<<gv, kVecThreads, 0, st>>>(n, sc, y, z, s_, t, rhat, x_dev, r, part_a, part_b);
+            sum_into(part_a, gv, 3), sum_into(part_b, gv, 4);
+            PFG_TRY(cb(reduce(user, 3, 2), "reduce"));
+            k_bicg_scalar<<<1, 32, 0, st>>>(3, 1, scal_dev + 3, 0, nullptr, sc);
+        }
+        PFG_CUDA_TRY(cudaGetLastError());
+        PFG_TRY(read_scal(4, &rr));
+        if (!(rr == rr)) {
+            set_error("pfg_bicgstab_dist: the residual became NaN after %d iterations (breakdown)", it);
+            return PFG_ERR_INVALID;
+        }
+    }
+    if (iters_out) *iters_out = it;
+    if (resid_out) *resid_out = std::sqrt(rr);
+    PFG_CUDA_TRY(cudaGetLastError());
+    return (std::sqrt(rr) <= target) ? PFG_OK : PFG_ERR_NOCONV;
+}

@@ -201,6 +201,30 @@ class ModelBase:
             u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         return u, rhs_d, iters
 
+    def _slab_solver(self):
+        if self._slab_cg is None:
+            from .slab_solve import SlabKrylov
+            self._slab_cg = SlabKrylov(self.mesh, self.slab.part, self.slab.ranges, self.slab.rank, self.slab.group)
+        return self._slab_cg
+
+    def _local_dofs(self, v):
+        """A dof vector on this rank's LOCAL nodes (owned + ghost) from the global vector or from the rank's own rows
+        (then the ghost entries come from their owners: one halo exchange, slab_solve.HaloExchange)."""
+        torch = _torch()
+        m = self.ndof_per_node
+        part = self.slab.part
+        dof = torch.as_tensor((np.asarray(part.node_gid)[:, None] * m + np.arange(m)).ravel(), device=self.mesh.device)
+        v = torch.as_tensor(np.asarray(v) if not hasattr(v, "device") else v).to(device=self.mesh.device, dtype=torch.float64)
+        if v.numel() == self.ndof:
+            return v[dof]
+        if v.numel() != self.mesh.nrows:
+            raise ValueError(f"dof vector has {v.numel()} entries, expected {self.ndof} (global) or {self.mesh.nrows} "
+                             "(this rank's rows)")
+        solver = self._slab_solver()
+        full = torch.zeros(self.ndof, dtype=torch.float64, device=self.mesh.device)
+        full[solver.row0: solver.row0 + v.numel()] = v
+        return solver.exchange.refresh(full)[dof]
+
     def _global_sum(self, v):
         """Sum of a per-rank scalar over the ranks of a slab partition (the value itself otherwise)."""
         if self.slab is None or self.slab.size == 1:
@@ -301,30 +325,6 @@ class _DensityFunctions:
         if getattr(self, "_scalar_mesh", None) is None:
             self._scalar_mesh = DeviceMesh(self.X, self.conn, 1, device=self.mesh.device)
         return self._scalar_mesh
-
-    def _slab_solver(self):
-        if self._slab_cg is None:
-            from .slab_solve import SlabCG
-            self._slab_cg = SlabCG(self.mesh, self.slab.part, self.slab.ranges, self.slab.rank, self.slab.group)
-        return self._slab_cg
-
-    def _local_dofs(self, v):
-        """A dof vector on this rank's LOCAL nodes (owned + ghost) from the global vector or from the rank's own rows
-        (then the ghost entries come from their owners: one halo exchange, slab_solve.HaloExchange)."""
-        torch = _torch()
-        m = self.ndof_per_node
-        part = self.slab.part
-        dof = torch.as_tensor((np.asarray(part.node_gid)[:, None] * m + np.arange(m)).ravel(), device=self.mesh.device)
-        v = torch.as_tensor(np.asarray(v) if not hasattr(v, "device") else v).to(device=self.mesh.device, dtype=torch.float64)
-        if v.numel() == self.ndof:
-            return v[dof]
-        if v.numel() != self.mesh.nrows:
-            raise ValueError(f"dof vector has {v.numel()} entries, expected {self.ndof} (global) or {self.mesh.nrows} "
-                             "(this rank's rows)")
-        solver = self._slab_solver()
-        full = torch.zeros(self.ndof, dtype=torch.float64, device=self.mesh.device)
-        full[solver.row0: solver.row0 + v.numel()] = v
-        return solver.exchange.refresh(full)[dof]
 
     def _k_dv_sens_slab(self, physics, rho, phi, psi, **kw):
         """Sensitivities at this rank's owned nodes: every element touching an owned node is local (ghost layer), so

@@ -120,8 +120,9 @@ def cg_reference(matvec, exchange, b_owned, row0, ncols, dinv, rtol=1e-8, atol=0
     return x, it, float(rr.sqrt())
 
 
-class SlabCG:
-    """Jacobi-preconditioned conjugate gradients on the device CSR of a row-slab model (models.py, `group=`)."""
+class SlabKrylov:
+    """Jacobi-preconditioned conjugate gradients (symmetric systems) and BiCGStab (the Newton Jacobian) on the device
+    CSR of a row-slab model (models.py, `group=`)."""
 
     def __init__(self, mesh, part, ranges, rank, group=None):
         import torch
@@ -132,7 +133,8 @@ class SlabCG:
         ghost = np.concatenate([gid[:lb], gid[le:]])
         self.exchange = HaloExchange(ghost, ranges, m, rank, group=group, device=mesh.device)
         self.row0 = int(part.owned_global_range[0]) * m
-        self.x_full = torch.zeros(mesh.ncols, dtype=torch.float64, device=mesh.device)
+        self.x_full2 = torch.zeros(2 * mesh.ncols, dtype=torch.float64, device=mesh.device)  # BiCGStab uses both halves
+        self.x_full = self.x_full2[:mesh.ncols]
         self.scal = torch.zeros(8, dtype=torch.float64, device=mesh.device)
         self._error = None
 
@@ -152,9 +154,19 @@ class SlabCG:
                 self._error = exc
                 return 1
 
-        self._reduce_cb, self._halo_cb = _lib.REDUCE_FN(reduce_cb), _lib.HALO_FN(halo_cb)  # kept alive with self
+        def halo2_cb(_user, which):
+            try:
+                n = self.mesh.ncols
+                self.exchange.refresh(self.x_full2[which * n:(which + 1) * n])
+                return 0
+            except BaseException as exc:
+                self._error = exc
+                return 1
 
-    def solve(self, vals, b_owned, x0=None, rtol=1e-8, atol=0.0, max_iter=None, check_every=16):
+        # (the ctypes thunks are kept alive with self)
+        self._reduce_cb, self._halo_cb, self._halo2_cb = _lib.REDUCE_FN(reduce_cb), _lib.HALO_FN(halo_cb), _lib.HALO2_FN(halo2_cb)
+
+    def cg(self, vals, b_owned, x0=None, rtol=1e-8, atol=0.0, max_iter=None, check_every=16):
         """(x_owned, iterations, |r| over all ranks); RuntimeError like the reference when max_iter is reached."""
         import torch
         mesh = self.mesh
@@ -174,3 +186,29 @@ class SlabCG:
             raise RuntimeError(f"cg failed with code {iters.value}")
         _lib.check(st)
         return x, int(iters.value), float(resid.value)
+
+    solve = cg
+
+    def bicgstab(self, vals, b_owned, rtol=1e-8, atol=0.0, max_iter=None, check_every=8):
+        """Non-symmetric systems (x0 = 0): (x_owned, iterations, |r| over all ranks)."""
+        import torch
+        mesh = self.mesh
+        b = mesh._dev_f64(b_owned, mesh.nrows, "b")
+        x = torch.empty_like(b)
+        iters, resid = ctypes.c_int(0), ctypes.c_double(0.0)
+        max_iter = 10 * mesh.ncols if max_iter is None else int(max_iter)
+        self._error = None
+        with torch.cuda.device(mesh.device):
+            st = mesh._lib.pfg_bicgstab_dist(mesh._handle, vals.data_ptr(), b.data_ptr(), x.data_ptr(),
+                                             self.x_full2.data_ptr(), self.scal.data_ptr(), self.row0, float(rtol),
+                                             float(atol), max_iter, int(check_every), self._reduce_cb, self._halo2_cb,
+                                             None, ctypes.byref(iters), ctypes.byref(resid), mesh._stream())
+        if self._error is not None:
+            raise self._error
+        if st == _lib.PFG_ERR_NOCONV:
+            raise RuntimeError(f"bicgstab failed with code {iters.value}")
+        _lib.check(st)
+        return x, int(iters.value), float(resid.value)
+
+
+SlabCG = SlabKrylov  # first name of the class

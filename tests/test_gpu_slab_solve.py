@@ -110,6 +110,23 @@ def _worker(rank, world, port, backend, halo, out_dir):
         rhs = orc.elasticity_point_loads(3 * X3.shape[0], 3, force3)
         u_ref = _dense_solve(orc.assemble_elasticity(X3, conn3), rhs, fixed3)
         ok &= np.max(np.abs(u - u_ref)) <= 1e-6 * np.max(np.abs(u_ref))
+    # Newton loop of the nonlinear Poisson problem over the slabs (BiCGStab over all ranks) against the host loop of
+    # a single handle with a direct solve, as tests/test_nonlinear_poisson.py:12-42 compares p.u
+    import contextlib
+    import io
+    creator = pf.ProblemCreator(nnodes_x=24, nnodes_y=19)
+    conn, X, dof_fixed = creator.create_poisson_problem()
+    X = X / X.max(axis=0)
+    xdv = 0.2 + np.random.default_rng(7).random(10)
+    model = pf.NonlinearPoisson2D(X, conn, dof_fixed, None, q, pf.BasisBilinear2D(q), group=dist.group.WORLD, halo=halo,
+                                  device=dev)
+    with contextlib.redirect_stdout(io.StringIO()):
+        u = model.gather_vector(pf.Assembler(model).solve_nonlinear(xdv=xdv, device=True))
+    if rank == 0:
+        single = pf.NonlinearPoisson2D(X, conn, dof_fixed, None, q, pf.BasisBilinear2D(q), device=dev)
+        with contextlib.redirect_stdout(io.StringIO()):
+            u_ref = pf.Assembler(single).solve_nonlinear(method="direct", xdv=xdv)
+        ok &= np.max(np.abs(u - u_ref)) <= 1e-6 * np.max(np.abs(u_ref)) and np.max(np.abs(u_ref)) > 0
     flag = torch.tensor([1 if ok else 0])
     if backend == "nccl":
         flag = flag.to(dev)
