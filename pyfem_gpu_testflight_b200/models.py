@@ -220,10 +220,17 @@ class ModelBase:
         if v.numel() != self.mesh.nrows:
             raise ValueError(f"dof vector has {v.numel()} entries, expected {self.ndof} (global) or {self.mesh.nrows} "
                              "(this rank's rows)")
+        return self._global_dofs(v)[dof]
+
+    def _global_dofs(self, v_owned):
+        """The rank's rows placed in a global-length device vector with the ghost entries fetched from their owners
+        (what a slab product reads); other entries are zero."""
+        torch = _torch()
         solver = self._slab_solver()
+        v = torch.as_tensor(v_owned).to(device=self.mesh.device, dtype=torch.float64)
         full = torch.zeros(self.ndof, dtype=torch.float64, device=self.mesh.device)
         full[solver.row0: solver.row0 + v.numel()] = v
-        return solver.exchange.refresh(full)[dof]
+        return solver.exchange.refresh(full)
 
     def _global_sum(self, v):
         """Sum of a per-rank scalar over the ranks of a slab partition (the value itself otherwise)."""
@@ -549,13 +556,24 @@ class Helmholtz(ModelBase):
     def compute_rhs_device(self, x, out=None):
         return self.mesh.spmv(self.R_device, x, out=out)
 
+    def _cg_device(self, b, rtol):
+        if self.slab is not None and self.slab.size > 1:
+            return self._slab_solver().cg(self.K_device, b, rtol=rtol)[0]
+        return self.mesh.cg(self.K_device, b, rtol=rtol)[0]
+
     def apply_device(self, x, rtol=1e-8):
-        """Filtered field K^-1 R x with R.x and the CG solve on the device (pyfem.py:2102-2107)."""
-        return self.mesh.cg(self.K_device, self.compute_rhs_device(x), rtol=rtol)[0]
+        """Filtered field K^-1 R x with R.x and the CG solve on the device (pyfem.py:2102-2107).  Slab mode: x is the
+        global field, the result the rank's rows (the solve runs over all ranks)."""
+        return self._cg_device(self.compute_rhs_device(x), rtol)
 
     def apply_gradient_device(self, gradrho, rtol=1e-8):
-        """R^T K^-1 g on the device (pyfem.py:2109-2115): CG solve, then the transposed product."""
-        y = self.mesh.cg(self.K_device, gradrho, rtol=rtol)[0]
+        """R^T K^-1 g on the device (pyfem.py:2109-2115): CG solve, then the transposed product.  Slab mode: g and the
+        result are the rank's rows; a slab does not hold the transposed entries, so the product uses R itself with the
+        ghost entries of K^-1 g fetched from their owners (R is the mass matrix: its (i, j) and (j, i) entries sum the
+        same element integrals, in possibly different order)."""
+        y = self._cg_device(gradrho, rtol)
+        if self.slab is not None and self.slab.size > 1:
+            return self.mesh.spmv(self.R_device, self._global_dofs(y))
         return self.mesh.spmv_t(self.R_device, y)
 
     def compute_jacobian(self):

@@ -110,6 +110,20 @@ def _worker(rank, world, port, backend, halo, out_dir):
         rhs = orc.elasticity_point_loads(3 * X3.shape[0], 3, force3)
         u_ref = _dense_solve(orc.assemble_elasticity(X3, conn3), rhs, fixed3)
         ok &= np.max(np.abs(u - u_ref)) <= 1e-6 * np.max(np.abs(u_ref))
+    # Helmholtz filter and its transposed application over the slabs (tests/test_helmholtz.py:11-44 compares the
+    # filtered field at 1e-8)
+    creator = pf.ProblemCreator(nnodes_x=32, nnodes_y=17)
+    conn, X = creator.create_helmhotz_problem()[:2]
+    hm = pf.Helmholtz(0.07, X, conn, q, pf.BasisBilinear2D(q), group=dist.group.WORLD, halo=halo, device=dev)
+    xf = np.random.default_rng(11).random(X.shape[0])
+    gb, ge = hm.slab.owned_nodes
+    rho_f = hm.gather_vector(hm.apply_device(xf).cpu().numpy())
+    grad_f = hm.gather_vector(hm.apply_gradient_device(xf[gb:ge]).cpu().numpy())
+    if rank == 0:
+        Kh, Rh = orc.assemble_helmholtz(X, conn, 0.07)
+        Kd = np.array(Kh.todense())
+        ok &= np.max(np.abs(rho_f - np.linalg.solve(Kd, Rh @ xf))) <= 1e-7
+        ok &= np.max(np.abs(grad_f - Rh.T @ np.linalg.solve(Kd, xf))) <= 1e-7
     # Newton loop of the nonlinear Poisson problem over the slabs (BiCGStab over all ranks) against the host loop of
     # a single handle with a direct solve, as tests/test_nonlinear_poisson.py:12-42 compares p.u
     import contextlib
