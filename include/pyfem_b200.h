@@ -306,6 +306,21 @@ PFG_API int pfg_cg_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_
                         double* resid_out, void* stream);
 
 /*
+ * The two phases of pfg_cg_dist on their own.  Both only ENQUEUE work on `stream` (no host synchronisation), so a
+ * caller can capture pfg_cg_dist_steps -- kernels and the callbacks' collectives -- in a CUDA graph and replay it
+ * (slab_solve.py does, two iterations per graph), reading scal_dev[2] = |r|^2 (global) whenever it wants to test
+ * convergence.  After pfg_cg_dist_begin: scal_dev[4] = |b|^2, scal_dev[2] = |r0|^2, both global.
+ *   first_iter   index of the first of the n_steps iterations (its parity selects the r.z slot: iterations must be
+ *                numbered consecutively from 0 across calls)
+ */
+PFG_API int pfg_cg_dist_begin(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev,
+                              int x_is_zero, double* x_full_dev, double* scal_dev, int64_t row0, pfg_reduce_fn reduce,
+                              pfg_halo_fn halo, void* user, void* stream);
+PFG_API int pfg_cg_dist_steps(pfg_mesh* mesh, const double* vals_dev, double* x_dev, double* x_full_dev,
+                              double* scal_dev, int64_t row0, int first_iter, int n_steps, pfg_reduce_fn reduce,
+                              pfg_halo_fn halo, void* user, void* stream);
+
+/*
  * Jacobi-preconditioned BiCGStab on the device CSR, for NON-SYMMETRIC systems: the Newton step of
  * Assembler.solve_nonlinear (pyfem.py:2337-2353: K is the Jacobian of NonlinearPoisson2D, the reference solves it with
  * gmres + pyamg or spsolve).  Same arguments and stopping rule as pfg_cg; x_dev is zero-filled here (x0 = 0).  Scalars

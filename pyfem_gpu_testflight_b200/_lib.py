@@ -66,6 +66,10 @@ PROTOTYPES = {
     "pfg_cg_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_double,
                             c_double, c_int, c_int, REDUCE_FN, HALO_FN, c_void_p, POINTER(c_int), POINTER(c_double),
                             c_void_p]),
+    "pfg_cg_dist_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, REDUCE_FN,
+                                  HALO_FN, c_void_p, c_void_p]),
+    "pfg_cg_dist_steps": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int, REDUCE_FN,
+                                  HALO_FN, c_void_p, c_void_p]),
     "pfg_bicgstab_dist": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double,
                                   c_int, c_int, REDUCE_FN, HALO2_FN, c_void_p, POINTER(c_int), POINTER(c_double),
                                   c_void_p]),

@@ -566,59 +566,139 @@ extern "C" int pfg_cg(pfg_mesh* mesh, const double* vals_dev, const double* b_de
 // Conjugate gradients over the row slabs of several ranks: the same kernels as pfg_cg; every dot product is summed
 // on the rank in a fixed order, written to one slot of scal_dev and all-reduced by the caller's callback (the library
 // itself does not link NCCL), the search direction lives in a global-length vector whose ghost entries the halo
-// callback refreshes before every product.
+// callback refreshes before every product.  Two phases that only ENQUEUE work (no host synchronisation, so a caller
+// may capture the steps in a CUDA graph and replay them), and pfg_cg_dist = begin + steps + the convergence check.
+namespace {
+struct CgDist {  // scal_dev: [0] p.Ap  [1] / [3] r.z (alternating by iteration parity)  [2] r.r  [4] |b|^2
+    MeshDev* d;
+    int64_t n, nown;
+    double *r, *z, *Ap, *dinv, *p, *part_a, *part_b, *part_c;
+    unsigned gs;
+    int gv;
+};
+
+int cg_dist_setup(pfg_mesh* mesh, const void* vals, const void* x, double* x_full, const void* scal, int64_t row0,
+                  const void* reduce, const void* halo, const char* who, CgDist* c) {
+    MeshDev& d = mesh->d;
+    const int64_t nown = d.own_end - d.own_begin, n = nown * d.m, ncols = d.ncols_nodes * d.m;
+    if (!vals || !x || !x_full || !scal || !reduce || !halo || row0 < 0 || row0 + n > ncols) {
+        set_error("%s: invalid argument", who);
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(ensure_solve_scratch(d, true));
+    c->d = &d, c->n = n, c->nown = nown;
+    c->r = d.cg_work;
+    c->z = c->r + n, c->Ap = c->r + 3 * n, c->dinv = c->r + 4 * n;  // (the slot pfg_cg uses for p stays free: p lives in x_full)
+    c->p = x_full + row0;
+    double* parts = c->r + 9 * n;
+    c->part_a = parts, c->part_b = parts + kMaxPartials, c->part_c = parts + 2 * kMaxPartials;
+    c->gs = spmv_grid(std::max<int64_t>(n, 1), d.sm_count);
+    c->gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
+    return PFG_OK;
+}
+
+int cg_dist_cb(int rc, const char* what) {
+    if (rc != 0) {
+        set_error("pfg_cg_dist: the %s callback failed (%d)", what, rc);
+        return PFG_ERR_INVALID;
+    }
+    return PFG_OK;
+}
+
+int cg_dist_begin(const CgDist& c, const double* vals, const double* b, double* x, int x_is_zero, double* x_full,
+                  double* scal, pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, cudaStream_t st) {
+    const MeshDev& d = *c.d;
+    const int64_t n = c.n;
+    if (n) k_inv_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, c.nown, d.m, vals, c.dinv);
+    if (x_is_zero) {
+        PFG_CUDA_TRY(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+        PFG_CUDA_TRY(cudaMemcpyAsync(c.r, b, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+        PFG_CUDA_TRY(cudaMemcpyAsync(c.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        PFG_TRY(cg_dist_cb(halo(user), "halo"));
+        if (n) launch_spmv_rows(c.gs, st, d, d.gid, vals, x_full, c.Ap, nullptr, nullptr);
+        k_residual<<<c.gv, kVecThreads, 0, st>>>(n, b, c.Ap, c.r);
+    }
+    k_norm2_partials<<<c.gv, kVecThreads, 0, st>>>(n, b, c.part_a);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_a, c.gv, scal + 4);
+    k_cg_init<<<c.gv, kVecThreads, 0, st>>>(n, c.dinv, c.r, c.z, c.p, c.part_b, c.part_c);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_b, c.gv, scal + 1);
+    k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_c, c.gv, scal + 2);
+    PFG_CUDA_TRY(cudaGetLastError());
+    PFG_TRY(cg_dist_cb(reduce(user, 1, 2), "reduce"));
+    PFG_TRY(cg_dist_cb(reduce(user, 4, 1), "reduce"));
+    return PFG_OK;
+}
+
+int cg_dist_steps(const CgDist& c, const double* vals, double* x, double* x_full, double* scal, int first_iter,
+                  int n_steps, pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, cudaStream_t st) {
+    const MeshDev& d = *c.d;
+    const int64_t n = c.n;
+    for (int it = first_iter; it < first_iter + n_steps; ++it) {
+        const int rz_old = (it & 1) ? 3 : 1, rz_new = (it & 1) ? 1 : 3;
+        PFG_TRY(cg_dist_cb(halo(user), "halo"));
+        if (n) launch_spmv_rows(c.gs, st, d, d.gid, vals, x_full, c.Ap, c.p, c.part_a);
+        k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_a, n ? (int)c.gs : 0, scal + 0);
+        PFG_TRY(cg_dist_cb(reduce(user, 0, 1), "reduce"));
+        k_cg_update<<<c.gv, kVecThreads, 0, st>>>(n, 1, 1, scal + 0, scal + rz_old, c.dinv, c.p, c.Ap, x, c.r, c.z,
+                                                  c.part_b, c.part_c);
+        k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_b, c.gv, scal + rz_new);
+        k_sum_into<<<1, kVecThreads, 0, st>>>(c.part_c, c.gv, scal + 2);
+        PFG_TRY(cg_dist_cb(reduce(user, std::min(rz_new, 2), 2), "reduce"));  // slots (1, 2) or (2, 3)
+        k_cg_direction<<<c.gv, kVecThreads, 0, st>>>(n, 1, scal + rz_new, scal + rz_old, c.z, c.p);
+    }
+    PFG_CUDA_TRY(cudaGetLastError());
+    return PFG_OK;
+}
+}  // namespace
+
+extern "C" int pfg_cg_dist_begin(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev,
+                                 int x_is_zero, double* x_full_dev, double* scal_dev, int64_t row0,
+                                 pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    CgDist c;
+    if (!b_dev) {
+        set_error("pfg_cg_dist_begin: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(cg_dist_setup(mesh, vals_dev, x_dev, x_full_dev, scal_dev, row0, (const void*)reduce, (const void*)halo,
+                          "pfg_cg_dist_begin", &c));
+    return cg_dist_begin(c, vals_dev, b_dev, x_dev, x_is_zero, x_full_dev, scal_dev, reduce, halo, user, (cudaStream_t)stream);
+}
+
+extern "C" int pfg_cg_dist_steps(pfg_mesh* mesh, const double* vals_dev, double* x_dev, double* x_full_dev,
+                                 double* scal_dev, int64_t row0, int first_iter, int n_steps, pfg_reduce_fn reduce,
+                                 pfg_halo_fn halo, void* user, void* stream) {
+    PFG_CHECK_MESH(mesh);
+    CgDist c;
+    if (first_iter < 0 || n_steps < 0) {
+        set_error("pfg_cg_dist_steps: invalid argument");
+        return PFG_ERR_INVALID;
+    }
+    PFG_TRY(cg_dist_setup(mesh, vals_dev, x_dev, x_full_dev, scal_dev, row0, (const void*)reduce, (const void*)halo,
+                          "pfg_cg_dist_steps", &c));
+    return cg_dist_steps(c, vals_dev, x_dev, x_full_dev, scal_dev, first_iter, n_steps, reduce, halo, user, (cudaStream_t)stream);
+}
+
 extern "C" int pfg_cg_dist(pfg_mesh* mesh, const double* vals_dev, const double* b_dev, double* x_dev, int x_is_zero,
                            double* x_full_dev, double* scal_dev, int64_t row0, double rtol, double atol, int max_iter,
                            int check_every, pfg_reduce_fn reduce, pfg_halo_fn halo, void* user, int* iters_out,
                            double* resid_out, void* stream) {
     PFG_CHECK_MESH(mesh);
-    MeshDev& d = mesh->d;
-    const int64_t nown = d.own_end - d.own_begin, n = nown * d.m, ncols = d.ncols_nodes * d.m;
-    if (!vals_dev || !b_dev || !x_dev || !x_full_dev || !scal_dev || !reduce || !halo || max_iter < 0 || row0 < 0 ||
-        row0 + n > ncols) {
+    CgDist c;
+    if (!b_dev || max_iter < 0) {
         set_error("pfg_cg_dist: invalid argument");
         return PFG_ERR_INVALID;
     }
-    PFG_TRY(ensure_solve_scratch(d, true));
+    PFG_TRY(cg_dist_setup(mesh, vals_dev, x_dev, x_full_dev, scal_dev, row0, (const void*)reduce, (const void*)halo,
+                          "pfg_cg_dist", &c));
     cudaStream_t st = (cudaStream_t)stream;
-    double* r = d.cg_work;
-    double *z = r + n, *Ap = z + 2 * n, *dinv = Ap + n;  // (the slot pfg_cg uses for p stays free: p lives in x_full)
-    double* p = x_full_dev + row0;
-    double* parts = r + 9 * n;
-    double *part_a = parts, *part_b = parts + kMaxPartials, *part_c = parts + 2 * kMaxPartials;
-    const unsigned gs = spmv_grid(std::max<int64_t>(n, 1), d.sm_count);
-    const int gv = (int)std::min<int64_t>(kMaxPartials, std::max<int64_t>(1, (n + kVecThreads - 1) / kVecThreads));
-    // scal_dev: [0] p.Ap  [1] / [3] r.z (alternating)  [2] r.r  [4] |b|^2
-    auto cb = [&](int rc, const char* what) -> int {
-        if (rc != 0) {
-            set_error("pfg_cg_dist: the %s callback failed (%d)", what, rc);
-            return PFG_ERR_INVALID;
-        }
-        return PFG_OK;
-    };
     auto read_scal = [&](int slot, double* out) -> int {
         PFG_CUDA_TRY(cudaMemcpyAsync(out, scal_dev + slot, sizeof(double), cudaMemcpyDeviceToHost, st));
         PFG_CUDA_TRY(cudaStreamSynchronize(st));
         return PFG_OK;
     };
-    if (n) k_inv_diag<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(d.blk_ptr, d.nbr, d.own_begin, nown, d.m, vals_dev, dinv);
-    if (x_is_zero) {
-        PFG_CUDA_TRY(cudaMemsetAsync(x_dev, 0, n * sizeof(double), st));
-        PFG_CUDA_TRY(cudaMemcpyAsync(r, b_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    } else {
-        PFG_CUDA_TRY(cudaMemcpyAsync(p, x_dev, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
-        PFG_TRY(cb(halo(user), "halo"));
-        if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, x_full_dev, Ap, nullptr, nullptr);
-        k_residual<<<gv, kVecThreads, 0, st>>>(n, b_dev, Ap, r);
-    }
-    k_norm2_partials<<<gv, kVecThreads, 0, st>>>(n, b_dev, part_a);
-    k_sum_into<<<1, kVecThreads, 0, st>>>(part_a, gv, scal_dev + 4);
-    k_cg_init<<<gv, kVecThreads, 0, st>>>(n, dinv, r, z, p, part_b, part_c);
-    k_sum_into<<<1, kVecThreads, 0, st>>>(part_b, gv, scal_dev + 1);
-    k_sum_into<<<1, kVecThreads, 0, st>>>(part_c, gv, scal_dev + 2);
-    PFG_CUDA_TRY(cudaGetLastError());
-    PFG_TRY(cb(reduce(user, 1, 2), "reduce"));
-    PFG_TRY(cb(reduce(user, 4, 1), "reduce"));
+    PFG_TRY(cg_dist_begin(c, vals_dev, b_dev, x_dev, x_is_zero, x_full_dev, scal_dev, reduce, halo, user, st));
     double bb = 0.0, rr = 0.0;
     PFG_TRY(read_scal(4, &bb));
     PFG_TRY(read_scal(2, &rr));
@@ -627,20 +707,8 @@ extern "C" int pfg_cg_dist(pfg_mesh* mesh, const double* vals_dev, const double*
     if (check_every <= 0) check_every = 16;
     while (std::sqrt(rr) > target && it < max_iter) {  // rr is the same number on every rank: so is the trip count
         const int batch = std::min(check_every, max_iter - it);
-        for (int j = 0; j < batch; ++j, ++it) {
-            const int rz_old = (it & 1) ? 3 : 1, rz_new = (it & 1) ? 1 : 3;
-            PFG_TRY(cb(halo(user), "halo"));
-            if (n) launch_spmv_rows(gs, st, d, d.gid, vals_dev, x_full_dev, Ap, p, part_a);
-            k_sum_into<<<1, kVecThreads, 0, st>>>(part_a, n ? (int)gs : 0, scal_dev + 0);
-            PFG_TRY(cb(reduce(user, 0, 1), "reduce"));
-            k_cg_update<<<gv, kVecThreads, 0, st>>>(n, 1, 1, scal_dev + 0, scal_dev + rz_old, dinv, p, Ap, x_dev, r, z,
-                                                    part_b, part_c);
-            k_sum_into<<<1, kVecThreads, 0, st>>>(part_b, gv, scal_dev + rz_new);
-            k_sum_into<<<1, kVecThreads, 0, st>>>(part_c, gv, scal_dev + 2);
-            PFG_TRY(cb(reduce(user, std::min(rz_new, 2), 2), "reduce"));  // slots (1, 2) or (2, 3)
-            k_cg_direction<<<gv, kVecThreads, 0, st>>>(n, 1, scal_dev + rz_new, scal_dev + rz_old, z, p);
-        }
-        PFG_CUDA_TRY(cudaGetLastError());
+        PFG_TRY(cg_dist_steps(c, vals_dev, x_dev, x_full_dev, scal_dev, it, batch, reduce, halo, user, st));
+        it += batch;
         PFG_TRY(read_scal(2, &rr));
         if (!(rr == rr)) {
             set_error("pfg_cg_dist: the residual became NaN after %d iterations (matrix not positive definite?)", it);

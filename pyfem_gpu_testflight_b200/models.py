@@ -196,7 +196,7 @@ class ModelBase:
         if self.slab is not None and self.slab.size > 1:
             # one rank of a row-slab partition: `rhs` / `u` are the rank's rows, the solve runs over all ranks
             # (slab_solve.py: halo exchange of the search direction + three all-reduced scalars per iteration)
-            u, iters, _ = self._slab_solver().solve(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
+            u, iters, _ = self._slab_solver().cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         else:
             u, iters, _ = self.mesh.cg(vals, rhs_d, rtol=rtol, atol=atol, max_iter=max_iter)
         return u, rhs_d, iters

@@ -1,5 +1,5 @@
 """Timing probe of the row-slab conjugate gradients (development aid):
-    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/probe_slab_solve.py [n] [iters]
+    torchrun --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P tools/probe_slab_solve.py [n] [iters] [graph|eager]
 Poisson on an n x n quad mesh split into N row slabs (structured_slab, no global mesh on any rank), the first mesh
 line fixed; a fixed number of iterations (the tolerance is unreachable on purpose) timed with CUDA events."""
 import os, sys, time
@@ -25,6 +25,12 @@ model = pf.LinearPoisson(part.X, part.conn, fixed, None, q, pf.BasisBilinear2D(q
                          node_ranges=ranges, device=dev)
 vals = model.compute_jacobian_device(1.0)
 rhs = model.compute_rhs()
+graph = None if len(sys.argv) <= 3 else (sys.argv[3] == "graph")
+if graph is not None and model._slab_cg is None and world > 1:
+    model._slab_solver()
+if graph is not None and world > 1:
+    import functools
+    model._slab_cg.cg = functools.partial(model._slab_cg.cg, graph=graph)
 for rep in range(2):
     torch.cuda.synchronize()
     if world > 1:
@@ -42,7 +48,8 @@ for rep in range(2):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     if rank == 0 and rep == 1:
         ex = model._slab_cg.exchange.bytes_per_refresh if model._slab_cg is not None else 0
-        print(f"slab cg poisson n={n} ranks={world}: {iters} iterations {ms.item():.2f} ms -> {ms.item() / iters:.4f} ms / iteration, "
+        mode = "" if graph is None else (" [graph replay]" if graph and model._slab_cg._graph_ok else " [eager]")
+        print(f"slab cg poisson n={n} ranks={world}{mode}: {iters} iterations {ms.item():.2f} ms -> {ms.item() / iters:.4f} ms / iteration, "
               f"{(n + 1) ** 2 / 1e6:.1f} M unknowns, halo {ex} B sent per rank and iteration", flush=True)
 if world > 1:
     dist.barrier()
