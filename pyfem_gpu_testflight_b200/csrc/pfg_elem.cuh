@@ -171,6 +171,33 @@ PFG_DEV Quad4Field quad4_field4(double f0, double f1, double f2, double f3) {
     return r;
 }
 
+// trilinear nodal field on the reference cube: 8 f = m + cx xi + cy eta + cz zeta + cxy xi eta + cyz eta zeta +
+// cxz xi zeta + cxyz xi eta zeta; coefficients by a three-stage butterfly over the corner values (node order of
+// Elem<8>: (-,-,-), (+,-,-), (+,+,-), (-,+,-), then the same with zeta = +1)
+struct Hex8Field {
+    double m, cx, cy, cz, cxy, cyz, cxz, cxyz;
+};
+PFG_DEV Hex8Field hex8_field8(double f0, double f1, double f2, double f3, double f4, double f5, double f6, double f7) {
+    const double s00 = f1 + f0, d00 = f1 - f0, s10 = f2 + f3, d10 = f2 - f3;  // along xi, at (eta, zeta) = (-,-), (+,-)
+    const double s01 = f5 + f4, d01 = f5 - f4, s11 = f6 + f7, d11 = f6 - f7;  // ... (-,+), (+,+)
+    const double ss0 = s10 + s00, sd0 = s10 - s00, ds0 = d10 + d00, dd0 = d10 - d00;  // along eta, zeta = -1
+    const double ss1 = s11 + s01, sd1 = s11 - s01, ds1 = d11 + d01, dd1 = d11 - d01;  // zeta = +1
+    Hex8Field r;
+    r.m = ss1 + ss0, r.cz = ss1 - ss0;
+    r.cy = sd1 + sd0, r.cyz = sd1 - sd0;
+    r.cx = ds1 + ds0, r.cxz = ds1 - ds0;
+    r.cxy = dd1 + dd0, r.cxyz = dd1 - dd0;
+    return r;
+}
+// 8 * (df/dxi, df/deta, df/dzeta) at quadrature point Q
+template <int Q>
+PFG_DEV void hex8_field_grad8(const Hex8Field& f, double (&g)[3]) {
+    constexpr double xi = Elem<8>::qp(Q, 0), eta = Elem<8>::qp(Q, 1), zeta = Elem<8>::qp(Q, 2);
+    g[0] = fma(f.cxyz, eta * zeta, fma(f.cxz, zeta, fma(f.cxy, eta, f.cx)));
+    g[1] = fma(f.cxyz, xi * zeta, fma(f.cyz, zeta, fma(f.cxy, xi, f.cy)));
+    g[2] = fma(f.cxyz, xi * eta, fma(f.cxz, xi, fma(f.cyz, eta, f.cz)));
+}
+
 template <int Q>
 PFG_DEV void hex8_geo(const double (&xe)[8][3], double& det, double (&G)[8][3]) {
     double J[3][3];
