@@ -906,9 +906,12 @@ __global__ void __launch_bounds__(256) k_hex8_geometry(MeshView mv, ElasticityHe
 // tables of the next chunk are fetched while the current one is computed.  No atomics, no zero-fill of the
 // output, every CSR value written once, bitwise reproducible.
 #ifndef PFG_HEX_NB
-#define PFG_HEX_NB 7  // 7: one pass over the quadrature points for seven column nodes (63 running sums), the eighth block
-#endif                // from the zero row sums -- 128^3 hex 3.997 -> 3.894 ms; 4: two passes of four column nodes (36
-                      // sums each, geometry read twice); 8: one pass with 72 sums (spills: 4.16 ms)
+#define PFG_HEX_NB 0  // row products of a (node, element) lane.  0: through the modes of the trilinear basis -- 63 running sums
+#endif                // against seven modes whose values cost 15 additions per point, node blocks by a butterfly at the end
+                      // (244 registers, no spills): 128^3 hex 3.890 -> 3.281 ms.  7: seven column nodes with their
+                      // gradients (63 FMAs per point), the eighth block from the zero row sums (255 registers, 116 B of
+                      // spills); 4: two passes of four column nodes (36 sums each, geometry read twice); 8: one pass with
+                      // 72 sums (spills: 4.16 ms)
 constexpr int kHexRowsThreads = (kHexRowWarps + 1) * 32;
 constexpr int kHexGeoBytes = 8 * kHexGeoDoubles * (int)sizeof(double);  // 640 B per element
 constexpr int kHexGeoStride = kHexGeoRecordBytes / 8;  // doubles per staged record: 656 B keeps 16-byte reads of
@@ -962,6 +965,20 @@ PFG_DEV void hex8_rows_closed(const ElasticityHex8Params& prm, const double* __r
     hex8_add_block(prm, L, 7, active, rows, k3, ranks);
 }
 
+// The same through the modes of the trilinear basis (pfg_elem.cuh: hex8_row_modes): 15 additions per point instead of
+// the 63 FMAs of seven column gradients, a butterfly per entry at the end; `prm` carries C0 / 8.
+PFG_DEV void hex8_rows_modal(const ElasticityHex8Params& prm, const double* __restrict__ geo_e, double sx8, double sy8,
+                             double sz8, bool active, double* __restrict__ rows, int k3, uint2 ranks) {
+    double P[8][3][3];
+    if (active) {
+        double V[7][3][3];
+        hex8_row_modes(geo_e, sx8, sy8, sz8, V);
+        hex8_modes_to_nodes(V, P);
+    }
+#pragma unroll
+    for (int bb = 0; bb < 8; ++bb) hex8_add_block(prm, P[bb], bb, active, rows, k3, ranks);
+}
+
 struct HexRowsCfg {
     int off_geo, geo_stage_bytes;  // two geometry stages
     int off_image, image_stride;   // per consumer warp: four nodes x image_stride doubles (9 * max neighbours)
@@ -1009,6 +1026,10 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
         return;
     }
     // ---- consumer warps
+#if PFG_HEX_NB == 0
+    ElasticityHex8Params prm8 = prm;  // the modal row products carry a factor 8
+    prm8.c11 *= 0.125, prm8.c12 *= 0.125, prm8.c44 *= 0.125;
+#endif
     const int j = lane & 7;
     const int64_t nown = mv.own_end - mv.own_begin;
     double* image = reinterpret_cast<double*>(hex_smem + cfg.off_image) + (size_t)warp * 4 * cfg.image_stride;
@@ -1073,7 +1094,9 @@ __global__ void __launch_bounds__(kHexRowsThreads, 1)
             if (!waited) mbar_wait(&bars[s], f & 1);  // the chunk's geometry has landed
             waited = true;
             __syncwarp();
-#if PFG_HEX_NB == 7
+#if PFG_HEX_NB == 0
+            hex8_rows_modal(prm8, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
+#elif PFG_HEX_NB == 7
             hex8_rows_closed(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);
 #elif PFG_HEX_NB == 8
             hex8_rows_part<0, 8>(prm, geo_e, sx8, sy8, sz8, active, rows, meta.k9 / 3, meta.ranks);

@@ -1012,6 +1012,77 @@ PFG_DEV void hex8_row_products(const double* __restrict__ geo_e, double sx8, dou
     });
 }
 
+// The same row block through the modes of the trilinear basis.  8 grad N_b = sum over the seven non-constant
+// monomials sigma_k(b) of the node's corner signs (x, y, z, xy, xz, yz, xyz) of M_k, with
+//   M_x = A[0], M_y = A[1], M_z = A[2], M_xy = eta A[0] + xi A[1], M_xz = zeta A[0] + xi A[2],
+//   M_yz = zeta A[1] + eta A[2], M_xyz = eta zeta A[0] + xi zeta A[1] + xi eta A[2]     (rows of the adjugate),
+// and (xi, eta, zeta) = (+-g, +-g, +-g) at a quadrature point: the modes cost 15 additions per point (the factors g, g^2
+// leave the sum over the points) where the seven column gradients cost 63 FMAs.  V[k][i][j] = sum_q s_q G_a,i M'_k,j;
+// the node blocks are P_ab = (1/8) sum_k sigma_k(b) scale_k V_k -- a three-stage butterfly per entry, which also yields
+// the eighth block that hex8_rows_closed takes from the zero row sums (there is no constant mode).
+PFG_DEV void hex8_row_modes(const double* __restrict__ geo_e, double sx8, double sy8, double sz8, double (&V)[7][3][3]) {
+#pragma unroll
+    for (int k = 0; k < 7; ++k)
+#pragma unroll
+        for (int i = 0; i < 3; ++i)
+#pragma unroll
+            for (int j = 0; j < 3; ++j) V[k][i][j] = 0.0;
+    for_each_q<8>([&](auto qc) {
+        constexpr int Q = decltype(qc)::value;
+        const double2* g = reinterpret_cast<const double2*>(geo_e + Q * kHexGeoDoubles);
+        const double2 g0 = g[0], g1 = g[1], g2 = g[2], g3 = g[3], g4 = g[4];
+        const double A[3][3] = {{g0.x, g0.y, g1.x}, {g1.y, g2.x, g2.y}, {g3.x, g3.y, g4.x}};
+        const double s = g4.y;
+        const double ax = fma(sx8, 8.0 * Elem<8>::qp(Q, 0), 1.0), ay = fma(sy8, 8.0 * Elem<8>::qp(Q, 1), 1.0),
+                     az = fma(sz8, 8.0 * Elem<8>::qp(Q, 2), 1.0);
+        const double d0 = sx8 * (ay * az), d1 = sy8 * (ax * az), d2 = sz8 * (ax * ay);
+        double h[3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) h[l] = s * (d0 * A[0][l] + d1 * A[1][l] + d2 * A[2][l]);
+        constexpr bool px = Elem<8>::qp(Q, 0) > 0, py = Elem<8>::qp(Q, 1) > 0, pz = Elem<8>::qp(Q, 2) > 0;  // signs of the point
+        double M[7][3];
+#pragma unroll
+        for (int l = 0; l < 3; ++l) {
+            const double a0 = A[0][l], a1 = A[1][l], a2 = A[2][l];
+            M[0][l] = a0, M[1][l] = a1, M[2][l] = a2;
+            M[3][l] = (py ? a0 : -a0) + (px ? a1 : -a1);  // xy / g
+            M[4][l] = (pz ? a0 : -a0) + (px ? a2 : -a2);  // xz / g
+            M[5][l] = (pz ? a1 : -a1) + (py ? a2 : -a2);  // yz / g
+            M[6][l] = ((py == pz) ? a0 : -a0) + ((px == pz) ? a1 : -a1) + ((px == py) ? a2 : -a2);  // xyz / g^2
+        }
+#pragma unroll
+        for (int k = 0; k < 7; ++k)
+#pragma unroll
+            for (int i = 0; i < 3; ++i)
+#pragma unroll
+                for (int j = 0; j < 3; ++j) V[k][i][j] = fma(h[i], M[k][j], V[k][i][j]);
+    });
+}
+
+// modes -> the eight node blocks, entry by entry: 8 P_b = sx Vx + sy Vy + sz Vz + sx sy g Vxy + sx sz g Vxz + sy sz g Vyz +
+// sx sy sz g^2 Vxyz with (sx, sy, sz) the corner signs of node b (the factor 1/8 is left to the caller's constants)
+PFG_DEV void hex8_modes_to_nodes(const double (&V)[7][3][3], double (&P)[8][3][3]) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double vx = V[0][i][j], vy = V[1][i][j], vz = V[2][i][j];
+            const double vxy = PFG_G * V[3][i][j], vxz = PFG_G * V[4][i][j], vyz = PFG_G * V[5][i][j];
+            const double vxyz = (PFG_G * PFG_G) * V[6][i][j];
+            // along z: index [sz] with 0 = minus, 1 = plus
+            const double a10[2] = {vx - vxz, vx + vxz}, a01[2] = {vy - vyz, vy + vyz}, a11[2] = {vxy - vxyz, vxy + vxyz};
+            const double a00[2] = {-vz, vz};
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int sx = Elem<8>::sgn(b, 0) > 0 ? 1 : 0, sy = Elem<8>::sgn(b, 1) > 0 ? 1 : 0,
+                          sz = Elem<8>::sgn(b, 2) > 0 ? 1 : 0;
+                const double b0 = sy ? a00[sz] + a01[sz] : a00[sz] - a01[sz];
+                const double b1 = sy ? a10[sz] + a11[sz] : a10[sz] - a11[sz];
+                P[b][i][j] = sx ? b0 + b1 : b0 - b1;
+            }
+        }
+}
+
 // C0 applied to one summed product block (pyfem.py:1752-1757, 2017-2026)
 PFG_DEV void hex8_apply_c0(const ElasticityHex8Params& prm, const double (&P)[3][3], double (&blk)[9]) {
 #pragma unroll
