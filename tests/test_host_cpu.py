@@ -160,3 +160,83 @@ def test_oracle_complex_density_matches_reference():
         assert np.array_equal(Kr.indices, Ko.indices)
         assert_values_close(Ko.data.real, Kr.data.real, 1e-13)
         assert_values_close(Ko.data.imag, Kr.data.imag, 1e-13)
+
+
+# ---- the algebraic identities the re-derived element operators rest on (csrc/pfg_elem.cuh), checked in numpy ---------
+def test_hex8_gradients_through_the_trilinear_modes():
+    """hex8_row_modes / hex8_modes_to_nodes: 8 grad N_b = sum over the seven non-constant sign monomials sigma_k(b) of
+    M_k with M_x, M_y, M_z the rows of the adjugate and M_xy = eta A0 + xi A1, ..., M_xyz = eta zeta A0 + xi zeta A1 +
+    xi eta A2; hence sum_q s_q G_a (x) G_b = (1/8) sum_k sigma_k(b) V_k with V_k = sum_q s_q G_a (x) M_k, including the
+    eighth node (no constant mode: the zero row sums)."""
+    pts, _, _, dN = orc.hex8_tables()
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((8, 3, 3))  # one adjugate per quadrature point
+    s = rng.random(8) + 0.5
+    sx = np.array([-1.0, 1.0, 1.0, -1.0, -1.0, 1.0, 1.0, -1.0])
+    sy = np.array([-1.0, -1.0, 1.0, 1.0, -1.0, -1.0, 1.0, 1.0])
+    sz = np.array([-1.0, -1.0, -1.0, -1.0, 1.0, 1.0, 1.0, 1.0])
+    sigma = np.stack([sx, sy, sz, sx * sy, sx * sz, sy * sz, sx * sy * sz])  # (7, node)
+    G = np.einsum("qbk,qkl->qbl", dN, A)  # G_b,l = sum_k dN_b,k A[k][l]  (hex8_geo)
+    M = np.zeros((8, 7, 3))
+    for q, (xi, eta, zeta) in enumerate(pts):
+        M[q] = [A[q, 0], A[q, 1], A[q, 2], eta * A[q, 0] + xi * A[q, 1], zeta * A[q, 0] + xi * A[q, 2],
+                zeta * A[q, 1] + eta * A[q, 2], eta * zeta * A[q, 0] + xi * zeta * A[q, 1] + xi * eta * A[q, 2]]
+    assert np.allclose(8.0 * G, np.einsum("kb,qkl->qbl", sigma, M), rtol=0, atol=1e-13)
+    for a in range(8):
+        P = np.einsum("q,qi,qbj->bij", s, G[:, a], G)            # the row blocks of node a
+        V = np.einsum("q,qi,qkj->kij", s, G[:, a], M)            # the seven running sums of a lane
+        assert np.allclose(P, np.einsum("kb,kij->bij", sigma, V) / 8.0, rtol=0, atol=1e-12)
+    assert np.allclose(sigma.sum(axis=1), 0.0)  # every mode sums to zero over the nodes: the rows of Ke do too
+
+
+def test_nlpoisson_newton_term_from_eight_numbers():
+    """NlPoissonQuad4Op: T[a][b] = sum_q c2 (G_a . grad u) N_b with G_a . grad u = dN_a/dxi P + dN_a/deta R, formed from
+    (P_q, R_q) by two one-dimensional contractions (the basis tables are tensor products of 1 +- g)."""
+    pts, _, N, dN = orc.quad4_tables()
+    rng = np.random.default_rng(1)
+    Pq, Rq = rng.standard_normal(4), rng.standard_normal(4)
+    T_ref = np.einsum("qa,q,qb->ab", dN[:, :, 0], Pq, N) + np.einsum("qa,q,qb->ab", dN[:, :, 1], Rq, N)
+    g = 1.0 / np.sqrt(3.0)
+    fp, fm = 1.0 + g, 1.0 - g
+    sxs, sys = [0, 1, 1, 0], [0, 0, 1, 1]          # sign bits of node / point 0..3
+    qidx = lambda sx, sy: (2 if sx else 3) if sy else (1 if sx else 0)
+    Bs, Bm, Cs, Cm = np.zeros((2, 2)), np.zeros(2), np.zeros((2, 2)), np.zeros(2)
+    for sb in range(2):
+        a0 = fp * Pq[qidx(sb, 0)] + fm * Pq[qidx(1 - sb, 0)]
+        a1 = fp * Pq[qidx(sb, 1)] + fm * Pq[qidx(1 - sb, 1)]
+        Bs[sb] = [fp * fp * a0 + fm * fm * a1, fm * fm * a0 + fp * fp * a1]
+        Bm[sb] = fp * fm * (a0 + a1)
+        d0 = fp * Rq[qidx(0, sb)] + fm * Rq[qidx(0, 1 - sb)]
+        d1 = fp * Rq[qidx(1, sb)] + fm * Rq[qidx(1, 1 - sb)]
+        Cs[sb] = [fp * fp * d0 + fm * fm * d1, fm * fm * d0 + fp * fp * d1]
+        Cm[sb] = fp * fm * (d0 + d1)
+    T = np.zeros((4, 4))
+    for a in range(4):
+        for b in range(4):
+            pb = Bs[sxs[b]][sys[a]] if sys[a] == sys[b] else Bm[sxs[b]]
+            rb = Cs[sys[b]][sxs[a]] if sxs[a] == sxs[b] else Cm[sys[b]]
+            T[a, b] = ((pb if sxs[a] else -pb) + (rb if sys[a] else -rb)) / 16.0
+    assert np.allclose(T, T_ref, rtol=0, atol=1e-14)
+
+
+def test_bilinear_and_trilinear_coefficient_forms():
+    """quad4_field4 / hex8_field8: nodal values -> monomial coefficients; the reference-space derivatives they give at
+    the quadrature points equal sum_a dN_a f_a (the form the sensitivity kernels and the nonlinear operator use)."""
+    rng = np.random.default_rng(2)
+    pts, _, N, dN = orc.quad4_tables()
+    f = rng.standard_normal(4)
+    m, a, b, c = f.sum(), (f[1] - f[0]) + (f[2] - f[3]), (f[3] - f[0]) + (f[2] - f[1]), (f[2] - f[3]) - (f[1] - f[0])
+    for q, (xi, eta) in enumerate(pts):
+        assert np.allclose([0.25 * (m + a * xi + b * eta + c * xi * eta), 0.25 * (a + c * eta), 0.25 * (b + c * xi)],
+                           [N[q] @ f, dN[q, :, 0] @ f, dN[q, :, 1] @ f], rtol=0, atol=1e-14)
+    pts, _, N, dN = orc.hex8_tables()
+    f = rng.standard_normal(8)
+    s00, d00, s10, d10 = f[1] + f[0], f[1] - f[0], f[2] + f[3], f[2] - f[3]
+    s01, d01, s11, d11 = f[5] + f[4], f[5] - f[4], f[6] + f[7], f[6] - f[7]
+    ss0, sd0, ds0, dd0 = s10 + s00, s10 - s00, d10 + d00, d10 - d00
+    ss1, sd1, ds1, dd1 = s11 + s01, s11 - s01, d11 + d01, d11 - d01
+    cz, cy, cyz, cx, cxz, cxy, cxyz = ss1 - ss0, sd1 + sd0, sd1 - sd0, ds1 + ds0, ds1 - ds0, dd1 + dd0, dd1 - dd0
+    for q, (xi, eta, zeta) in enumerate(pts):
+        grad8 = [cx + cxy * eta + cxz * zeta + cxyz * eta * zeta, cy + cxy * xi + cyz * zeta + cxyz * xi * zeta,
+                 cz + cyz * eta + cxz * xi + cxyz * xi * eta]
+        assert np.allclose(np.array(grad8) / 8.0, dN[q].T @ f, rtol=0, atol=1e-14)
