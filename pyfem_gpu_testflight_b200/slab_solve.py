@@ -6,7 +6,7 @@ The device work is the library's (pfg_cg_dist: SpMV on the rank's slab, fused ve
 products); what crosses ranks is (a) the ghost entries of the search direction -- the columns of a rank's rows that
 belong to other ranks' nodes, one mesh layer either side of a slab -- exchanged with batched send / recv before every
 product, and (b) three all-reduced scalars per iteration.  `HaloExchange` is host logic over torch.distributed only
-(it runs under gloo on CPU tensors as well, tests/test_partition_gloo.py); `SlabCG` binds it to a slab handle.
+(it runs under gloo on CPU tensors as well, tests/test_partition_gloo.py); `SlabKrylov` binds it to a slab handle.
 """
 import ctypes
 
@@ -86,38 +86,6 @@ class HaloExchange:
         else:
             dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
         return t
-
-
-def cg_reference(matvec, exchange, b_owned, row0, ncols, dinv, rtol=1e-8, atol=0.0, max_iter=1000):
-    """The recurrence pfg_cg_dist runs, with torch tensors and a caller-supplied slab product: the CPU model of the
-    distributed solve used by the gloo tests (this is test support for the HOST logic -- the product path is SlabCG)."""
-    import torch
-    n = b_owned.numel()
-    x = torch.zeros_like(b_owned)
-    p_full = torch.zeros(ncols, dtype=torch.float64, device=b_owned.device)
-    p = p_full[row0:row0 + n]
-    r = b_owned.clone()
-    z = dinv * r
-    p.copy_(z)
-    rz = exchange.all_reduce(torch.dot(r, z).reshape(1))
-    rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
-    bb = exchange.all_reduce(torch.dot(b_owned, b_owned).reshape(1))
-    target = max(rtol * float(bb.sqrt()), atol)
-    it = 0
-    while float(rr.sqrt()) > target and it < max_iter:
-        exchange.refresh(p_full)
-        Ap = matvec(p_full)
-        pAp = exchange.all_reduce(torch.dot(p, Ap).reshape(1))
-        alpha = rz / pAp
-        x += alpha * p
-        r -= alpha * Ap
-        z = dinv * r
-        rz_new = exchange.all_reduce(torch.dot(r, z).reshape(1))
-        rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
-        p.copy_(z + (rz_new / rz) * p)
-        rz = rz_new
-        it += 1
-    return x, it, float(rr.sqrt())
 
 
 class SlabKrylov:

@@ -136,13 +136,46 @@ def test_index_bytes_rule():
     assert index_bytes_rule(10, 4, 2 ** 31) == 8               # many columns alone switch the width
 
 
+def cg_reference(matvec, exchange, b_owned, row0, ncols, dinv, rtol=1e-8, atol=0.0, max_iter=1000):
+    """The recurrence pfg_cg_dist runs, with torch tensors and a caller-supplied slab product: the CPU model of the
+    distributed solve (test support for the HOST logic -- halo plan, exchange, collectives; the product path is
+    slab_solve.SlabKrylov on the device)."""
+    import torch
+    n = b_owned.numel()
+    x = torch.zeros_like(b_owned)
+    p_full = torch.zeros(ncols, dtype=torch.float64, device=b_owned.device)
+    p = p_full[row0:row0 + n]
+    r = b_owned.clone()
+    z = dinv * r
+    p.copy_(z)
+    rz = exchange.all_reduce(torch.dot(r, z).reshape(1))
+    rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
+    bb = exchange.all_reduce(torch.dot(b_owned, b_owned).reshape(1))
+    target = max(rtol * float(bb.sqrt()), atol)
+    it = 0
+    while float(rr.sqrt()) > target and it < max_iter:
+        exchange.refresh(p_full)
+        Ap = matvec(p_full)
+        pAp = exchange.all_reduce(torch.dot(p, Ap).reshape(1))
+        alpha = rz / pAp
+        x += alpha * p
+        r -= alpha * Ap
+        z = dinv * r
+        rz_new = exchange.all_reduce(torch.dot(r, z).reshape(1))
+        rr = exchange.all_reduce(torch.dot(r, r).reshape(1))
+        p.copy_(z + (rz_new / rz) * p)
+        rz = rz_new
+        it += 1
+    return x, it, float(rr.sqrt())
+
+
 def _cg_worker(rank, world, port, out_dir):
     for p in (ROOT, os.path.join(ROOT, "oracle")):
         sys.path.insert(0, p)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from pyfem_gpu_testflight_b200.partition import SlabContext
-    from pyfem_gpu_testflight_b200.slab_solve import HaloExchange, cg_reference
+    from pyfem_gpu_testflight_b200.slab_solve import HaloExchange
     from scipy import sparse
     from scipy.sparse.linalg import spsolve
     ok = True
